@@ -1,0 +1,155 @@
+/*
+ * vitb200.h -- C ABI of the B200-native ViT forward (libvitb200.so).
+ *
+ * Drop-in boundary for ONE path of conceptofmind/vit-flax: the forward pass of
+ * vit_flax/vit.py (ViT.__call__, vit.py:127-167, reached through
+ * Module.apply at vit.py:192).  The reference has no FFI seam of its own
+ * (SURVEY.md section 8b): its boundary is the Flax Module API.  These entry points are
+ * what a jax.ffi / XLA custom-call target (or any ctypes/cgo/JNI binding)
+ * would bind for that path; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, <0 on error; the message for the
+ *     calling thread is returned by vitb200_last_error().  Nothing aborts.
+ *   - a handle is NOT thread-safe; one handle per (device, stream).
+ *   - caller owns image / logits buffers; the library owns packed weights and
+ *     the activation workspace (sized for cfg.max_batch images at create).
+ *   - no hidden synchronisation in vitb200_forward(): work is enqueued on the
+ *     caller's stream.  vitb200_forward_host() is the end-to-end variant with
+ *     the H2D / D2H copies and a final stream synchronise.
+ *   - there is NO CPU fallback: every compute entry point needs an sm_100a GPU.
+ */
+#ifndef VITB200_H_
+#define VITB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITB200_ABI_VERSION 1
+
+/* error codes */
+#define VITB200_OK                 0
+#define VITB200_ERR_INVALID       -1   /* bad argument / shape / config          */
+#define VITB200_ERR_CUDA          -2   /* CUDA runtime or driver error           */
+#define VITB200_ERR_PARAM_MISSING -3   /* finalize/forward before all params set */
+#define VITB200_ERR_UNSUPPORTED   -4   /* valid for the reference, not built yet */
+#define VITB200_ERR_NO_DEVICE     -5   /* no sm_100 device visible               */
+
+/* cfg.precision */
+#define VITB200_PREC_BF16 0   /* bf16 operands, fp32 accumulate, fp32 residual stream (tcgen05) */
+#define VITB200_PREC_FP32 1   /* fp32 everywhere (SIMT validation mode, tolerance 1e-4)        */
+
+/* cfg.pool -- vit.py:121,159 */
+#define VITB200_POOL_CLS  0
+#define VITB200_POOL_MEAN 1
+
+/* Mirrors the dataclass fields of `class ViT` (vit.py:115-125); dim_head is the
+ * reference's class constant 64 (vit.py:123) and is therefore not a field.     */
+typedef struct vitb200_config {
+  int32_t image_h, image_w;     /* pair(image_size)  vit.py:130 */
+  int32_t patch_h, patch_w;     /* pair(patch_size)  vit.py:131 */
+  int32_t channels;             /* last axis of x (3 in every reference use) */
+  int32_t num_classes;
+  int32_t dim;
+  int32_t depth;
+  int32_t heads;
+  int32_t mlp_dim;
+  int32_t pool;                 /* VITB200_POOL_*  */
+  int32_t precision;            /* VITB200_PREC_*  */
+  int32_t max_batch;            /* workspace is sized for this many images   */
+  int32_t reserved[3];
+} vitb200_config;
+
+typedef struct vitb200_model vitb200_model;   /* opaque */
+
+/* ---- library ---------------------------------------------------------- */
+int         vitb200_abi_version(void);
+const char* vitb200_last_error(void);
+/* number of CUDA devices with compute capability 10.x, or <0 */
+int         vitb200_device_count(void);
+/* total kernels launched by this library in this process (bench "gpu_launches") */
+int64_t     vitb200_launch_count(void);
+
+/* ---- model lifecycle (replaces Module.init/apply plumbing, vit.py:187-192) */
+int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out);
+int vitb200_destroy(vitb200_model* m);
+
+/* Number of parameter leaves the config implies and the i-th leaf's path
+ * ("Transformer_0/Attention_3/Dense_0/kernel") and shape -- the Flax pytree of
+ * SURVEY.md section 8c.  `shape` receives up to 4 dims; returns ndim or <0. */
+int vitb200_num_params(const vitb200_model* m);
+int vitb200_param_info(const vitb200_model* m, int index, const char** path, int64_t shape[4]);
+
+/* Upload one fp32 leaf (HOST pointer) by path; shape is checked against the
+ * config like Flax's ScopeParamShapeError would.                            */
+int vitb200_set_param(vitb200_model* m, const char* path, const float* host_data,
+                      const int64_t* shape, int ndim);
+/* Pack weights for the kernels (bf16 K-major transposes etc.); must be called
+ * after all leaves are set and before forward.                              */
+int vitb200_finalize_params(vitb200_model* m, void* stream);
+
+/* ViT.__call__ (vit.py:127-167): images [batch, H, W, C] fp32 NHWC on DEVICE,
+ * logits [batch, num_classes] fp32 on DEVICE.  batch <= cfg.max_batch.       */
+int vitb200_forward(vitb200_model* m, void* stream, const float* images_dev, int batch,
+                    float* logits_dev);
+/* Same call with HOST buffers (pinned or pageable): H2D, forward, D2H, sync. */
+int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_host, int batch,
+                         float* logits_host);
+/* Copy the token stream after the last block ([batch, T, dim] fp32, device to
+ * host) -- parity checks of Transformer.__call__ (vit.py:98-112).            */
+int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int batch);
+
+/* ---- per-kernel entry points (unit parity tests, ncu) -------------------
+ * All pointers are DEVICE pointers.                                         */
+
+/* gemm epilogues */
+#define VITB200_EPI_STORE_BF16      0  /* C_bf16 = acc                         (to_qkv, vit.py:68)   */
+#define VITB200_EPI_BIAS_GELU_BF16  1  /* C_bf16 = gelu_tanh(acc + bias)       (vit.py:48-49)        */
+#define VITB200_EPI_BIAS_RESID_F32  2  /* C_f32 += acc + bias  (in place)      (vit.py:51/82 + 39)   */
+#define VITB200_EPI_BIAS_F32        3  /* C_f32 = acc + bias                   (head, vit.py:165)    */
+#define VITB200_EPI_PATCH_F32       4  /* C_f32[b*T+1+t] = acc + bias + pos[1+t]  (vit.py:147-153)   */
+
+/* tcgen05 bf16 GEMM: acc[M,N] = A[M,K] (bf16 row-major) x Wt[N,K]^T (bf16,
+ * row-major, i.e. the transposed Flax kernel).  K % 8 == 0, N % 8 == 0.
+ * `aux` = pos_embedding [T, N] fp32 and `tokens_per_image` = T-1 for EPI_PATCH. */
+int vitb200_gemm_bf16(void* stream, const void* A, const void* Wt, const float* bias,
+                      void* C, int M, int N, int K, int epilogue,
+                      const float* aux, int tokens_per_image);
+/* SIMT fp32 GEMM (validation mode): acc = A[M,K] x W[K,N] (Flax layout).
+ * Epilogues: STORE writes fp32 here; GELU writes fp32.                      */
+int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias,
+                     float* C, int M, int N, int K, int epilogue,
+                     const float* aux, int tokens_per_image);
+
+/* nn.LayerNorm() (vit.py:31,163): x [rows, dim] fp32 -> y (bf16 if out_bf16 else fp32) */
+int vitb200_layernorm(void* stream, const float* x, const float* scale, const float* bias,
+                      void* y, int rows, int dim, int out_bf16);
+
+/* softmax(Q K^T * 64^-0.5) V per (image, head) (vit.py:69-79).  qkv is the
+ * to_qkv output [batch*T, 3*heads*64] (q | k | v, head-major inside each),
+ * out is [batch*T, heads*64].  bf16 flavour = flash-style tensor-core kernel. */
+int vitb200_attention_bf16(void* stream, const void* qkv, void* out, int batch, int T, int heads);
+int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads);
+
+/* patchify (vit.py:146): images [batch,H,W,C] fp32 -> patches [batch*Np, Kpad]
+ * (bf16 if out_bf16 else fp32), feature f = (p1*pw + p2)*C + c, zero padded to Kpad. */
+int vitb200_patchify(void* stream, const float* images, void* patches, int batch,
+                     int H, int W, int C, int ph, int pw, int Kpad, int out_bf16);
+/* cls rows (vit.py:151-153): x[b*T + 0, :] = cls + pos[0] */
+int vitb200_cls_rows(void* stream, const float* cls, const float* pos, float* x,
+                     int batch, int T, int dim);
+/* pool (vit.py:159) + head LayerNorm (vit.py:163): x [batch,T,dim] fp32 ->
+ * y [batch, dim] (bf16 if out_bf16 else fp32) */
+int vitb200_pool_layernorm(void* stream, const float* x, const float* scale, const float* bias,
+                           void* y, int batch, int T, int dim, int pool, int out_bf16);
+/* fp32 [K,N] (Flax kernel) -> bf16 [N,Kpad] transposed pack used by gemm_bf16 */
+int vitb200_pack_weight_bf16(void* stream, const float* W, void* Wt, int K, int N, int Kpad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITB200_H_ */

@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE ONLY -- torch-CPU float32 twin of ``vit_flax/vit.py``.
+
+PARITY UNPINNED (see ``oracle/__init__.py``).  Written independently of
+``vit_numpy.py`` (torch library ops instead of hand-written formulas) so the
+two restatements cross-check each other; also the timed CPU baseline
+(``bench.py`` ``cpu_baseline`` / ``--impl reference``) because its GEMMs run on
+all host cores through MKL/oneDNN, like XLA:CPU's Eigen pool would.
+
+Reference lines restated: vit.py:41-53 (FeedForward), 55-87 (Attention),
+89-112 (Transformer), 114-167 (ViT).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+DIM_HEAD = 64  # vit.py:123
+
+
+def _t(a, dtype):
+    return torch.as_tensor(a).to(dtype)
+
+
+def tree_to_torch(tree, dtype=torch.float32):
+    if isinstance(tree, dict) or hasattr(tree, "items"):
+        return {k: tree_to_torch(v, dtype) for k, v in tree.items()}
+    return _t(tree, dtype)
+
+
+def _ln(x, p):
+    # nn.LayerNorm(): eps 1e-6, scale+bias (vit.py:31,163)
+    return F.layer_norm(x, (x.shape[-1],), p["scale"], p["bias"], eps=1e-6)
+
+
+def _attention(x, p, heads, dim):
+    b, n, _ = x.shape
+    qkv = x @ p["Dense_0"]["kernel"]                                       # vit.py:68
+    q, k, v = qkv.chunk(3, dim=-1)                                         # vit.py:69
+    q, k, v = (t.view(b, n, heads, DIM_HEAD).transpose(1, 2) for t in (q, k, v))  # vit.py:71
+    # vit.py:73-78; SDPA's default scale is 1/sqrt(dim_head) = dim_head ** -0.5
+    o = F.scaled_dot_product_attention(q, k, v)
+    o = o.transpose(1, 2).reshape(b, n, heads * DIM_HEAD)                  # vit.py:79
+    if not (heads == 1 and DIM_HEAD == dim):                               # vit.py:65
+        o = F.linear(o, p["Dense_1"]["kernel"].t(), p["Dense_1"]["bias"])  # vit.py:82
+    return o
+
+
+def _ff(x, p):
+    h = F.gelu(x @ p["Dense_0"]["kernel"] + p["Dense_0"]["bias"], approximate="tanh")  # vit.py:48-49
+    return h @ p["Dense_1"]["kernel"] + p["Dense_1"]["bias"]                           # vit.py:51
+
+
+@torch.no_grad()
+def vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, depth,
+                heads, mlp_dim, pool="cls"):
+    """``params_t``: the ``params`` sub-tree already converted by ``tree_to_torch``."""
+    p = params_t["params"] if "params" in params_t else params_t
+    ph, pw = (patch_size, patch_size) if not isinstance(patch_size, tuple) else patch_size
+    x = torch.as_tensor(images).to(p["cls"].dtype)
+    b, H, W, c = x.shape
+    # vit.py:146 -- unfold-free patchify through view/permute
+    x = x.view(b, H // ph, ph, W // pw, pw, c).permute(0, 1, 3, 2, 4, 5).reshape(b, -1, ph * pw * c)
+    x = x @ p["Dense_0"]["kernel"] + p["Dense_0"]["bias"]                  # vit.py:147
+    x = torch.cat([p["cls"].expand(b, -1, -1), x], dim=1)                  # vit.py:151-152
+    x = x + p["pos_embedding"][:, : x.shape[1]]                            # vit.py:153
+    tp = p["Transformer_0"]
+    for l in range(depth):                                                 # vit.py:108-110
+        x = _attention(_ln(x, tp[f"PreNorm_{2 * l}"]["LayerNorm_0"]), tp[f"Attention_{l}"], heads, dim) + x
+        x = _ff(_ln(x, tp[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"]), tp[f"FeedForward_{l}"]) + x
+    x = x.mean(dim=1) if pool == "mean" else x[:, 0]                       # vit.py:159
+    x = _ln(x, p["LayerNorm_0"])                                           # vit.py:163
+    return x @ p["Dense_1"]["kernel"] + p["Dense_1"]["bias"]               # vit.py:165

@@ -1,0 +1,62 @@
+"""N>1 host logic on CPU: world_size-2 gloo -- shard bounds and the logits all-gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vit_flax_b200.dist import shard_range, sharded_logits
+
+
+def test_shard_range_partitions_the_batch():
+    for b in (0, 1, 7, 8, 256, 2048):
+        for w in (1, 2, 3, 4, 8):
+            spans = [shard_range(b, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == b
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, global_batch, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        classes = 5
+        full = torch.arange(global_batch * 12, dtype=torch.float32).view(global_batch, 12)
+        w = torch.linspace(-1, 1, 12 * classes).view(12, classes)
+        s, e = shard_range(global_batch, world, rank)
+
+        def forward_local(x, out):      # stand-in for Engine.forward: writes into its slot
+            out.copy_(x @ w)
+
+        got = sharded_logits(forward_local, full[s:e], global_batch, classes)
+        q.put((rank, torch.allclose(got, full @ w), tuple(got.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("global_batch", [8, 7])
+def test_sharded_logits_world2_gloo(global_batch):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, global_batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, (global_batch, 5)), (1, True, (global_batch, 5))]

@@ -1,0 +1,155 @@
+"""End-to-end parity of ViT.apply on a real B200 against the CPU oracle.
+
+Tolerances are BASELINE.json's: logits max-abs 1e-4 in fp32 mode, 2e-2 in bf16 mode; top-1
+agreement is reported on images whose oracle top-1 margin exceeds twice the tolerance
+(on random-init weights the raw metric measures luck, not kernels)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_numpy, vit_torch
+from vit_flax_b200 import ViT, init_params, perturb_params
+from vit_flax_b200._lib import VitB200Error
+from vit_flax_b200.engine import Engine, launch_count
+from vit_flax_b200.runtime import clear_cache
+from _util import C1, C2, C3, C4, C5, TINY, TINY_MEAN, images_for, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def oracle_logits(variables, images, cfg, pool="cls"):
+    return vit_torch.vit_forward(vit_torch.tree_to_torch(variables), images, pool=pool, **cfg).numpy()
+
+
+@pytest.fixture(autouse=True)
+def _fresh_cache():
+    yield
+    clear_cache()
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,cfg,pool", [("tiny_cls.npz", TINY, "cls"), ("tiny_mean.npz", TINY_MEAN, "mean")])
+def test_golden_tiny(name, cfg, pool, precision):
+    variables, meta = load_golden(name)
+    before = launch_count()
+    y = ViT(pool=pool, **cfg).apply(variables, meta["images"], precision=precision)
+    assert launch_count() > before, "no kernels of libvitb200 were launched"
+    assert y.shape == meta["logits"].shape and y.dtype == np.float32
+    assert np.abs(y - meta["logits"]).max() < TOL[precision]
+
+
+def test_golden_tiny_tokens_fp32():
+    variables, meta = load_golden("tiny_cls.npz")
+    eng = Engine(precision="fp32", max_batch=3, **TINY)
+    eng.load_params(variables)
+    eng.forward_host(meta["images"])
+    tok = eng.tokens_after_transformer(3)                       # Transformer.__call__ output, vit.py:157
+    assert np.abs(tok - meta["tokens"]).max() < 1e-4
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_readme_config_c1(precision):
+    """BASELINE configs[0]: image 256, patch 32, dim 1024, depth 6, heads 16, mlp 2048, batch 1."""
+    _, meta = load_golden("c1_logits.npz")
+    variables = perturb_params(init_params(seed=int(meta["init_seed"]), **C1), seed=int(meta["perturb_seed"]))
+    img = images_for(C1, 1, seed=int(meta["image_seed"]))
+    y = ViT(**C1).apply(variables, img, precision=precision)
+    assert y.shape == (1, 1000)                                 # README.md:34
+    assert np.abs(y - meta["logits"]).max() < TOL[precision]
+
+
+def test_reference_init_zero_image_gives_zero_logits():
+    v = ViT(**TINY)
+    variables = v.init({"params": 1}, np.zeros((2, 32, 32, 3), np.float32))
+    for precision in ("fp32", "bf16"):
+        y = v.apply(variables, np.zeros((2, 32, 32, 3), np.float32), precision=precision)
+        assert np.all(y == 0.0)
+
+
+def _check_bf16(cfg, batch, depth=None, pool="cls", seed=0):
+    cfg = dict(cfg)
+    if depth is not None:
+        cfg["depth"] = depth
+    variables = perturb_params(init_params(seed=seed + 1, **cfg), seed=seed + 2)
+    img = images_for(cfg, batch, seed=seed)
+    want = oracle_logits(variables, img, cfg, pool)
+    got = ViT(pool=pool, **cfg).apply(variables, img, precision="bf16")
+    err = np.abs(got - want).max()
+    assert err < TOL["bf16"], f"max abs logit error {err}"
+    srt = np.sort(want, axis=1)
+    confident = (srt[:, -1] - srt[:, -2]) > 2 * TOL["bf16"]
+    assert np.array_equal(got.argmax(1)[confident], want.argmax(1)[confident])
+    return err
+
+
+def test_vit_b16_full_depth_bf16():
+    """BASELINE configs[1] (ViT-B/16 224, all 12 layers) on a sub-batch the CPU oracle finishes in seconds."""
+    _check_bf16(C2, batch=8)
+
+
+def test_vit_l16_bf16_reduced_depth():
+    _check_bf16(C3, batch=4, depth=3)
+
+
+def test_vit_h14_bf16_reduced_depth():
+    """configs[3]: K0 = 588 (zero-padded to 640), inner_dim 1024 != dim 1280 (vit.py:64,123)."""
+    _check_bf16(C4, batch=3, depth=2)
+
+
+def test_vit_l16_512px_bf16_reduced_depth():
+    """configs[4]: T = 1025 tokens stresses the streamed-KV attention."""
+    _check_bf16(C5, batch=2, depth=2)
+
+
+def test_mean_pool_bf16():
+    _check_bf16(C2, batch=4, depth=2, pool="mean")
+
+
+def test_vit_b16_fp32_mode_reduced_depth():
+    cfg = dict(C2, depth=2)
+    variables = perturb_params(init_params(seed=3, **cfg), seed=4)
+    img = images_for(cfg, 2, seed=5)
+    want = vit_numpy.vit_forward(variables, img, **cfg)
+    got = ViT(**cfg).apply(variables, img, precision="fp32")
+    assert np.abs(got - want).max() < TOL["fp32"]
+
+
+def test_device_path_equals_host_path_and_is_batch_independent():
+    """Full BASELINE batch (256) properties that need no oracle: device tensors in/out give the
+    same logits as the host path, and an image's logits do not depend on its batch neighbours."""
+    cfg = C2
+    variables = perturb_params(init_params(seed=1, **cfg), seed=2)
+    img = images_for(cfg, 256, seed=0)
+    v = ViT(**cfg)
+    y_host = v.apply(variables, img)
+    x_dev = torch.as_tensor(img, device="cuda")
+    y_dev = v.apply(variables, x_dev)
+    assert isinstance(y_dev, torch.Tensor) and y_dev.is_cuda
+    np.testing.assert_array_equal(y_host, y_dev.cpu().numpy())
+    perm = np.random.default_rng(0).permutation(256)
+    y_perm = v.apply(variables, img[perm])
+    assert np.abs(y_perm - y_host[perm]).max() < 1e-4            # same kernels, same per-row arithmetic
+    y_small = v.apply(variables, img[:8])
+    assert np.abs(y_small - y_host[:8]).max() < 1e-4
+    want = oracle_logits(variables, img[:8], cfg)
+    assert np.abs(y_host[:8] - want).max() < TOL["bf16"]
+
+
+def test_error_behaviour():
+    eng = Engine(precision="bf16", max_batch=2, **TINY)
+    variables = perturb_params(init_params(seed=0, **TINY))
+    with pytest.raises(VitB200Error, match="finalize_params"):   # forward before params
+        eng.forward(torch.zeros((1, 32, 32, 3), device="cuda"))
+    bad = perturb_params(init_params(seed=0, **dict(TINY, mlp_dim=64)))
+    with pytest.raises(VitB200Error, match="shape mismatch"):    # flax: ScopeParamShapeError
+        eng.load_params(bad)
+    eng.load_params(variables)
+    with pytest.raises(ValueError, match="max_batch"):
+        eng.forward_host(np.zeros((3, 32, 32, 3), np.float32))
+    with pytest.raises(ValueError, match="NHWC"):
+        eng.forward_host(np.zeros((1, 3, 32, 32), np.float32))
+    eng.close()

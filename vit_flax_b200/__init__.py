@@ -1,0 +1,9 @@
+"""vit_flax_b200 -- B200-native forward pass of conceptofmind/vit-flax's ``vit_flax/vit.py``.
+
+Public surface = the reference's: ``ViT(...)``, ``.init(rngs, x)``, ``.apply(variables, x)``.
+Importing this package does not need a GPU; computing anything does (no CPU fallback).
+"""
+from .params import count_params, flatten_params, init_params, perturb_params  # noqa: F401
+from .vit import ViT  # noqa: F401
+
+__all__ = ["ViT", "init_params", "perturb_params", "flatten_params", "count_params"]

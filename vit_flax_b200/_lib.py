@@ -1,0 +1,94 @@
+"""ctypes binding of ``libvitb200.so`` (the C ABI declared in ``include/vitb200.h``).
+
+There is no CPU fallback: if the shared object is missing, ``load()`` raises.
+Build it with ``python -m vit_flax_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libvitb200.so"
+
+# error codes / enums (keep in sync with include/vitb200.h)
+OK = 0
+PREC_BF16, PREC_FP32 = 0, 1
+POOL_CLS, POOL_MEAN = 0, 1
+EPI_STORE_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32 = range(5)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("image_h", C.c_int32), ("image_w", C.c_int32),
+        ("patch_h", C.c_int32), ("patch_w", C.c_int32),
+        ("channels", C.c_int32), ("num_classes", C.c_int32),
+        ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
+        ("mlp_dim", C.c_int32), ("pool", C.c_int32), ("precision", C.c_int32),
+        ("max_batch", C.c_int32), ("reserved", C.c_int32 * 3),
+    ]
+
+
+class VitB200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"vitb200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+_fp = C.c_void_p  # float* passed as raw addresses
+
+# name -> (restype, argtypes); every symbol include/vitb200.h declares
+SIGNATURES = {
+    "vitb200_abi_version": (_i, []),
+    "vitb200_last_error": (C.c_char_p, []),
+    "vitb200_device_count": (_i, []),
+    "vitb200_launch_count": (_i64, []),
+    "vitb200_create": (_i, [C.POINTER(Config), _i, C.POINTER(_vp)]),
+    "vitb200_destroy": (_i, [_vp]),
+    "vitb200_num_params": (_i, [_vp]),
+    "vitb200_param_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_i64)]),
+    "vitb200_set_param": (_i, [_vp, C.c_char_p, _fp, C.POINTER(_i64), _i]),
+    "vitb200_finalize_params": (_i, [_vp, _vp]),
+    "vitb200_forward": (_i, [_vp, _vp, _fp, _i, _fp]),
+    "vitb200_forward_host": (_i, [_vp, _vp, _fp, _i, _fp]),
+    "vitb200_debug_tokens": (_i, [_vp, _vp, _fp, _i]),
+    "vitb200_gemm_bf16": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i]),
+    "vitb200_gemm_f32": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i]),
+    "vitb200_layernorm": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i]),
+    "vitb200_attention_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "vitb200_attention_f32": (_i, [_vp, _fp, _fp, _i, _i, _i]),
+    "vitb200_patchify": (_i, [_vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "vitb200_cls_rows": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i]),
+    "vitb200_pool_layernorm": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i]),
+    "vitb200_pack_weight_bf16": (_i, [_vp, _fp, _vp, _i, _i, _i]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA extension is not built and vit_flax_b200 has no "
+                "CPU fallback. Run `python -m vit_flax_b200.build` (needs nvcc) first.")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        got = lib.vitb200_abi_version()
+        if got != 1:
+            raise ImportError(f"libvitb200.so ABI version {got}, expected 1")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        msg = load().vitb200_last_error()
+        raise VitB200Error(rc, msg.decode() if msg else "unknown error")
+    return rc

@@ -1,0 +1,535 @@
+// api.cu -- the C ABI of include/vitb200.h: model handle, parameter registry
+// (the Flax pytree of vit.py, looked up by path), weight packing, the forward
+// schedule of ViT.__call__ (vit.py:127-167) and the per-kernel entry points.
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace vb {
+namespace {
+
+constexpr int DIM_HEAD = 64;   // vit.py:123
+
+struct Leaf {
+  std::string path;
+  std::vector<int64_t> shape;
+  float* dev = nullptr;        // fp32 copy on device
+  bool set = false;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// One Dense layer as the kernels want it.
+struct DenseW {
+  int leaf_kernel = -1, leaf_bias = -1;   // indices into leaves
+  int K = 0, N = 0, Kpad = 0;
+  __nv_bfloat16* wt = nullptr;            // bf16 [N, Kpad] (bf16 mode)
+  CUtensorMap tm{};                       // box 256 x 64 over wt
+};
+
+struct Layer {
+  int ln1_scale, ln1_bias, ln2_scale, ln2_bias;
+  DenseW qkv, out, ff1, ff2;
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct ActMaps {   // TMA descriptors over the activation workspace for one batch size
+  CUtensorMap patches, xn, o, h, pooled;
+};
+
+}  // namespace
+}  // namespace vb
+
+using namespace vb;
+
+struct vitb200_model {
+  vitb200_config cfg{};
+  int device = 0;
+  int Np = 0, T = 0, K0 = 0, K0pad = 0, inner = 0;
+  bool project_out = true;
+  bool bf16 = true;
+  bool finalized = false;
+  bool head_tc = false;
+
+  std::vector<Leaf> leaves;
+  std::map<std::string, int> index;
+  int leaf_pos = -1, leaf_cls = -1, leaf_head_scale = -1, leaf_head_bias = -1;
+  DenseW patch, head;
+  std::vector<Layer> layers;
+
+  // activation workspace (bf16 mode uses the bf16 buffers, fp32 mode the f32 ones)
+  DevBuf<float> x;                                   // residual stream [B*T, D] fp32 (both modes)
+  DevBuf<__nv_bfloat16> patches_h, xn_h, qkv_h, o_h, hid_h, pooled_h;
+  DevBuf<float> patches_f, xn_f, qkv_f, o_f, hid_f, pooled_f;
+  DevBuf<float> img_stage, logit_stage;              // forward_host staging
+  std::map<int, ActMaps> act_maps;
+
+  ~vitb200_model() {
+    for (auto& l : leaves)
+      if (l.dev) cudaFree(l.dev);
+    auto free_dense = [](DenseW& d) { if (d.wt) cudaFree(d.wt); d.wt = nullptr; };
+    free_dense(patch);
+    free_dense(head);
+    for (auto& L : layers) { free_dense(L.qkv); free_dense(L.out); free_dense(L.ff1); free_dense(L.ff2); }
+    x.release();
+    patches_h.release(); xn_h.release(); qkv_h.release(); o_h.release(); hid_h.release(); pooled_h.release();
+    patches_f.release(); xn_f.release(); qkv_f.release(); o_f.release(); hid_f.release(); pooled_f.release();
+    img_stage.release(); logit_stage.release();
+  }
+};
+
+namespace vb_api {
+
+int add_leaf(vitb200_model* m, const std::string& path, std::vector<int64_t> shape) {
+  Leaf l;
+  l.path = path;
+  l.shape = std::move(shape);
+  m->leaves.push_back(std::move(l));
+  m->index[path] = int(m->leaves.size()) - 1;
+  return int(m->leaves.size()) - 1;
+}
+
+DenseW add_dense(vitb200_model* m, const std::string& prefix, int K, int N, bool bias) {
+  DenseW d;
+  d.K = K;
+  d.N = N;
+  d.Kpad = int(round_up(K, GEMM_BK));
+  d.leaf_kernel = add_leaf(m, prefix + "/kernel", {K, N});
+  if (bias) d.leaf_bias = add_leaf(m, prefix + "/bias", {N});
+  return d;
+}
+
+// The params pytree of `ViT` (flax compact auto-naming).
+void build_registry(vitb200_model* m) {
+  const auto& c = m->cfg;
+  const int D = c.dim, I = m->inner;
+  m->leaf_pos = add_leaf(m, "pos_embedding", {1, m->T, D});          // vit.py:142
+  m->leaf_cls = add_leaf(m, "cls", {1, 1, D});                       // vit.py:144
+  m->patch = add_dense(m, "Dense_0", m->K0, D, true);                // vit.py:147
+  m->layers.resize(c.depth);
+  for (int l = 0; l < c.depth; ++l) {                                // vit.py:102-106
+    Layer& L = m->layers[l];
+    const std::string tp = "Transformer_0/";
+    const std::string att = tp + "Attention_" + std::to_string(l);
+    L.qkv = add_dense(m, att + "/Dense_0", D, 3 * I, false);         // vit.py:68
+    if (m->project_out) L.out = add_dense(m, att + "/Dense_1", I, D, true);   // vit.py:82
+    const std::string ff = tp + "FeedForward_" + std::to_string(l);
+    L.ff1 = add_dense(m, ff + "/Dense_0", D, c.mlp_dim, true);       // vit.py:48
+    L.ff2 = add_dense(m, ff + "/Dense_1", c.mlp_dim, D, true);       // vit.py:51
+    const std::string p1 = tp + "PreNorm_" + std::to_string(2 * l) + "/LayerNorm_0";
+    const std::string p2 = tp + "PreNorm_" + std::to_string(2 * l + 1) + "/LayerNorm_0";
+    L.ln1_scale = add_leaf(m, p1 + "/scale", {D});                   // vit.py:31
+    L.ln1_bias = add_leaf(m, p1 + "/bias", {D});
+    L.ln2_scale = add_leaf(m, p2 + "/scale", {D});
+    L.ln2_bias = add_leaf(m, p2 + "/bias", {D});
+  }
+  m->leaf_head_scale = add_leaf(m, "LayerNorm_0/scale", {D});        // vit.py:163
+  m->leaf_head_bias = add_leaf(m, "LayerNorm_0/bias", {D});
+  m->head = add_dense(m, "Dense_1", D, c.num_classes, true);         // vit.py:165
+}
+
+int alloc_workspace(vitb200_model* m) {
+  const auto& c = m->cfg;
+  const size_t B = size_t(c.max_batch);
+  const size_t R = B * m->T, Rp = B * m->Np;
+  int rc;
+  if ((rc = m->x.alloc(R * c.dim))) return rc;
+  if (m->bf16) {
+    if ((rc = m->patches_h.alloc(Rp * m->K0pad))) return rc;
+    if ((rc = m->xn_h.alloc(R * c.dim))) return rc;
+    if ((rc = m->qkv_h.alloc(R * 3 * m->inner))) return rc;
+    if ((rc = m->o_h.alloc(R * m->inner))) return rc;
+    if ((rc = m->hid_h.alloc(R * c.mlp_dim))) return rc;
+    if (m->head_tc) { if ((rc = m->pooled_h.alloc(B * c.dim))) return rc; }
+    else { if ((rc = m->pooled_f.alloc(B * c.dim))) return rc; }
+  } else {
+    if ((rc = m->patches_f.alloc(Rp * m->K0pad))) return rc;
+    if ((rc = m->xn_f.alloc(R * c.dim))) return rc;
+    if ((rc = m->qkv_f.alloc(R * 3 * m->inner))) return rc;
+    if ((rc = m->o_f.alloc(R * m->inner))) return rc;
+    if ((rc = m->hid_f.alloc(R * c.mlp_dim))) return rc;
+    if ((rc = m->pooled_f.alloc(B * c.dim))) return rc;
+  }
+  return 0;
+}
+
+int get_act_maps(vitb200_model* m, int batch, const ActMaps** out) {
+  auto it = m->act_maps.find(batch);
+  if (it == m->act_maps.end()) {
+    const auto& c = m->cfg;
+    const int64_t R = int64_t(batch) * m->T, Rp = int64_t(batch) * m->Np;
+    ActMaps am;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&am.patches, m->patches_h.p, Rp, m->K0pad, m->K0pad, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16_2d(&am.xn, m->xn_h.p, R, c.dim, c.dim, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16_2d(&am.o, m->o_h.p, R, m->inner, m->inner, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16_2d(&am.h, m->hid_h.p, R, c.mlp_dim, c.mlp_dim, GEMM_BM))) return rc;
+    if (m->head_tc)
+      if ((rc = make_tmap_bf16_2d(&am.pooled, m->pooled_h.p, batch, c.dim, c.dim, GEMM_BM))) return rc;
+    it = m->act_maps.emplace(batch, am).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+int pack_dense(vitb200_model* m, DenseW& d, cudaStream_t st) {
+  if (d.leaf_kernel < 0) return 0;
+  if (d.wt == nullptr)
+    VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.wt), size_t(d.N) * d.Kpad * sizeof(__nv_bfloat16)));
+  int rc = launch_pack_weight_bf16(st, m->leaves[d.leaf_kernel].dev, d.wt, d.K, d.N, d.Kpad);
+  if (rc) return rc;
+  return make_tmap_bf16_2d(&d.tm, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN);
+}
+
+inline const float* leaf_ptr(const vitb200_model* m, int idx) { return idx >= 0 ? m->leaves[idx].dev : nullptr; }
+
+__global__ void add_bf16_into_f32_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ x, int64_t n) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i < n) x[i] += __bfloat162float(a[i]);
+}
+__global__ void add_f32_into_f32_kernel(const float* __restrict__ a, float* __restrict__ x, int64_t n) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i < n) x[i] += a[i];
+}
+
+// ---- the forward schedule, bf16 / tcgen05 flavour ---------------------------
+int forward_bf16(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
+  const auto& c = m->cfg;
+  const int D = c.dim, I = m->inner, T = m->T, Np = m->Np;
+  const int R = batch * T, Rp = batch * Np;
+  const ActMaps* am;
+  int rc;
+  if ((rc = get_act_maps(m, batch, &am))) return rc;
+  // vit.py:146  patchify (+ fp32->bf16 cast, zero pad to K0pad)
+  if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
+                            c.patch_h, c.patch_w, m->K0pad, true))) return rc;
+  // vit.py:147-153  Dense_0 + bias, placed at row b*T+1+t, + pos_embedding[1+t]
+  if ((rc = launch_gemm_bf16(st, am->patches, m->patch.tm, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+                             Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np))) return rc;
+  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
+  for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
+    Layer& L = m->layers[l];
+    // Residual(PreNorm(Attention))  vit.py:31,39,62-87
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, true))) return rc;
+    if ((rc = launch_gemm_bf16(st, am->xn, L.qkv.tm, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_BF16, nullptr, 0))) return rc;
+    if ((rc = launch_attention_bf16(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads))) return rc;
+    if (m->project_out) {
+      if ((rc = launch_gemm_bf16(st, am->o, L.out.tm, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+    } else {   // heads == 1 and dim == 64: to_out is the identity (vit.py:65,85)
+      const int64_t n = int64_t(R) * D;
+      add_bf16_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_h.p, m->x.p, n);
+      VB_LAUNCH_CHECK("add_bf16_into_f32_kernel");
+    }
+    // Residual(PreNorm(FeedForward))  vit.py:31,39,47-53
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, true))) return rc;
+    if ((rc = launch_gemm_bf16(st, am->xn, L.ff1.tm, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_BF16, nullptr, 0))) return rc;
+    if ((rc = launch_gemm_bf16(st, am->h, L.ff2.tm, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+  }
+  // vit.py:159-165  pool, LayerNorm_0, Dense_1
+  if (m->head_tc) {
+    if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, true))) return rc;
+    if ((rc = launch_gemm_bf16(st, am->pooled, m->head.tm, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
+  } else {
+    if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, false))) return rc;
+    if ((rc = launch_gemm_f32(st, m->pooled_f.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
+  }
+  return 0;
+}
+
+// ---- the forward schedule, fp32 validation flavour --------------------------
+int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
+  const auto& c = m->cfg;
+  const int D = c.dim, I = m->inner, T = m->T, Np = m->Np;
+  const int R = batch * T, Rp = batch * Np;
+  int rc;
+  if ((rc = launch_patchify(st, images, m->patches_f.p, batch, c.image_h, c.image_w, c.channels,
+                            c.patch_h, c.patch_w, m->K0pad, false))) return rc;
+  // K = K0pad with zero-padded A columns; W rows beyond K0 are never read (A there is 0,
+  // and the kernel guards k < K with K = K0): use the true K0 and the padded lda via a copy-free trick:
+  // the SIMT kernel takes a dense [M,K] A, so run it on K0pad only when K0pad == K0.
+  if (m->K0pad != m->K0) return fail(VITB200_ERR_UNSUPPORTED, "internal: fp32 path expects K0pad == K0");
+  if ((rc = launch_gemm_f32(st, m->patches_f.p, leaf_ptr(m, m->patch.leaf_kernel), leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+                            Rp, D, m->K0, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np))) return rc;
+  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
+  for (int l = 0; l < c.depth; ++l) {
+    Layer& L = m->layers[l];
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_f.p, R, D, false))) return rc;
+    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.qkv.leaf_kernel), nullptr, m->qkv_f.p, R, 3 * I, D, VITB200_EPI_STORE_BF16, nullptr, 0))) return rc;
+    if ((rc = launch_attention_f32(st, m->qkv_f.p, m->o_f.p, batch, T, c.heads))) return rc;
+    if (m->project_out) {
+      if ((rc = launch_gemm_f32(st, m->o_f.p, leaf_ptr(m, L.out.leaf_kernel), leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+    } else {
+      const int64_t n = int64_t(R) * D;
+      add_f32_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_f.p, m->x.p, n);
+      VB_LAUNCH_CHECK("add_f32_into_f32_kernel");
+    }
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_f.p, R, D, false))) return rc;
+    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.ff1.leaf_kernel), leaf_ptr(m, L.ff1.leaf_bias), m->hid_f.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_BF16, nullptr, 0))) return rc;
+    if ((rc = launch_gemm_f32(st, m->hid_f.p, leaf_ptr(m, L.ff2.leaf_kernel), leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+  }
+  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, false))) return rc;
+  return launch_gemm_f32(st, m->pooled_f.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace vb_api
+using namespace vb_api;
+
+// =============================================================== C ABI ======
+extern "C" {
+
+int vitb200_abi_version(void) { return VITB200_ABI_VERSION; }
+const char* vitb200_last_error(void) { return last_error_ref().c_str(); }
+int64_t vitb200_launch_count(void) { return launch_count(); }
+
+int vitb200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(VITB200_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out) {
+  if (!cfg || !out) return fail(VITB200_ERR_INVALID, "create: null argument");
+  *out = nullptr;
+  const vitb200_config& c = *cfg;
+  if (c.image_h <= 0 || c.image_w <= 0 || c.patch_h <= 0 || c.patch_w <= 0 || c.channels <= 0 ||
+      c.num_classes <= 0 || c.dim <= 0 || c.depth < 0 || c.heads <= 0 || c.mlp_dim <= 0 || c.max_batch <= 0)
+    return fail(VITB200_ERR_INVALID, "create: non-positive field in config");
+  if (c.image_h % c.patch_h != 0 || c.image_w % c.patch_w != 0)      // vit.py:133-134
+    return fail(VITB200_ERR_INVALID, "create: image dimensions must be divisible by the patch size");
+  if (c.pool != VITB200_POOL_CLS && c.pool != VITB200_POOL_MEAN)     // vit.py:137
+    return fail(VITB200_ERR_INVALID, "create: pool must be cls or mean");
+  if (c.precision != VITB200_PREC_BF16 && c.precision != VITB200_PREC_FP32)
+    return fail(VITB200_ERR_INVALID, "create: unknown precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(VITB200_ERR_NO_DEVICE, "create: no CUDA device visible (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail(VITB200_ERR_INVALID, "create: device index out of range");
+  int major = 0;
+  VB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fail(VITB200_ERR_NO_DEVICE, "create: device is not sm_100 (B200); kernels are sm_100a only");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(VITB200_ERR_CUDA, "create: cudaSetDevice failed");
+
+  std::unique_ptr<vitb200_model> m(new vitb200_model());
+  m->cfg = c;
+  m->device = device;
+  m->Np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
+  m->T = m->Np + 1;
+  m->K0 = c.patch_h * c.patch_w * c.channels;
+  m->bf16 = c.precision == VITB200_PREC_BF16;
+  m->K0pad = m->bf16 ? int(round_up(m->K0, GEMM_BK)) : m->K0 + (m->K0 & 1);
+  m->inner = DIM_HEAD * c.heads;
+  m->project_out = !(c.heads == 1 && DIM_HEAD == c.dim);             // vit.py:65
+  m->head_tc = m->bf16 && (c.num_classes % 8 == 0);
+  if (m->bf16 && (c.dim % 8 != 0 || c.mlp_dim % 8 != 0))
+    return fail(VITB200_ERR_UNSUPPORTED, "create: bf16 mode needs dim and mlp_dim to be multiples of 8");
+  if (!m->bf16 && m->K0pad != m->K0)
+    return fail(VITB200_ERR_UNSUPPORTED, "create: fp32 mode needs an even patch feature count");
+  build_registry(m.get());
+  int rc = alloc_workspace(m.get());
+  if (rc) return rc;
+  *out = m.release();
+  return 0;
+}
+
+int vitb200_destroy(vitb200_model* m) {
+  if (!m) return 0;
+  DeviceGuard guard(m->device);
+  delete m;
+  return 0;
+}
+
+int vitb200_num_params(const vitb200_model* m) {
+  if (!m) return fail(VITB200_ERR_INVALID, "num_params: null model");
+  return int(m->leaves.size());
+}
+
+int vitb200_param_info(const vitb200_model* m, int index, const char** path, int64_t shape[4]) {
+  if (!m || index < 0 || index >= int(m->leaves.size())) return fail(VITB200_ERR_INVALID, "param_info: bad index");
+  const Leaf& l = m->leaves[index];
+  if (path) *path = l.path.c_str();
+  if (shape) for (size_t i = 0; i < 4; ++i) shape[i] = i < l.shape.size() ? l.shape[i] : 0;
+  return int(l.shape.size());
+}
+
+int vitb200_set_param(vitb200_model* m, const char* path, const float* host_data, const int64_t* shape, int ndim) {
+  if (!m || !path || !host_data || !shape) return fail(VITB200_ERR_INVALID, "set_param: null argument");
+  auto it = m->index.find(path);
+  if (it == m->index.end()) return fail(VITB200_ERR_INVALID, std::string("set_param: unknown parameter path '") + path + "'");
+  Leaf& l = m->leaves[it->second];
+  bool same = ndim == int(l.shape.size());
+  for (int i = 0; same && i < ndim; ++i) same = shape[i] == l.shape[i];
+  if (!same) {
+    std::string want, got;
+    for (auto s : l.shape) want += std::to_string(s) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    return fail(VITB200_ERR_INVALID, std::string("set_param: shape mismatch for '") + path + "': expected (" + want + ") got (" + got + ")");
+  }
+  DeviceGuard guard(m->device);
+  if (!l.dev) VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&l.dev), size_t(l.numel()) * sizeof(float)));
+  VB_CUDA(cudaMemcpy(l.dev, host_data, size_t(l.numel()) * sizeof(float), cudaMemcpyHostToDevice));
+  l.set = true;
+  m->finalized = false;
+  return 0;
+}
+
+int vitb200_finalize_params(vitb200_model* m, void* stream) {
+  if (!m) return fail(VITB200_ERR_INVALID, "finalize_params: null model");
+  for (const auto& l : m->leaves)
+    if (!l.set) return fail(VITB200_ERR_PARAM_MISSING, "finalize_params: parameter '" + l.path + "' was never set");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (m->bf16) {
+    int rc;
+    if ((rc = pack_dense(m, m->patch, st))) return rc;
+    for (auto& L : m->layers) {
+      if ((rc = pack_dense(m, L.qkv, st))) return rc;
+      if ((rc = pack_dense(m, L.out, st))) return rc;
+      if ((rc = pack_dense(m, L.ff1, st))) return rc;
+      if ((rc = pack_dense(m, L.ff2, st))) return rc;
+    }
+    if (m->head_tc && (rc = pack_dense(m, m->head, st))) return rc;
+  }
+  VB_CUDA(cudaStreamSynchronize(st));
+  m->finalized = true;
+  return 0;
+}
+
+int vitb200_forward(vitb200_model* m, void* stream, const float* images_dev, int batch, float* logits_dev) {
+  if (!m || !images_dev || !logits_dev) return fail(VITB200_ERR_INVALID, "forward: null argument");
+  if (!m->finalized) return fail(VITB200_ERR_PARAM_MISSING, "forward: call finalize_params first");
+  if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "forward: batch must be in [1, max_batch]");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return m->bf16 ? forward_bf16(m, st, images_dev, batch, logits_dev) : forward_f32(m, st, images_dev, batch, logits_dev);
+}
+
+int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_host, int batch, float* logits_host) {
+  if (!m || !images_host || !logits_host) return fail(VITB200_ERR_INVALID, "forward_host: null argument");
+  if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "forward_host: batch must be in [1, max_batch]");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto& c = m->cfg;
+  const size_t img_elems = size_t(c.max_batch) * c.image_h * c.image_w * c.channels;
+  int rc;
+  if (m->img_stage.n < img_elems && (rc = m->img_stage.alloc(img_elems))) return rc;
+  if (m->logit_stage.n < size_t(c.max_batch) * c.num_classes && (rc = m->logit_stage.alloc(size_t(c.max_batch) * c.num_classes))) return rc;
+  const size_t in_bytes = size_t(batch) * c.image_h * c.image_w * c.channels * sizeof(float);
+  const size_t out_bytes = size_t(batch) * c.num_classes * sizeof(float);
+  VB_CUDA(cudaMemcpyAsync(m->img_stage.p, images_host, in_bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = vitb200_forward(m, stream, m->img_stage.p, batch, m->logit_stage.p))) return rc;
+  VB_CUDA(cudaMemcpyAsync(logits_host, m->logit_stage.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  VB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int batch) {
+  if (!m || !tokens_host) return fail(VITB200_ERR_INVALID, "debug_tokens: null argument");
+  if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "debug_tokens: bad batch");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VB_CUDA(cudaMemcpyAsync(tokens_host, m->x.p, size_t(batch) * m->T * m->cfg.dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- per-kernel entry points ------------------------------------------------
+int vitb200_gemm_bf16(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
+                      int K, int epilogue, const float* aux, int tokens_per_image) {
+  if (!A || !Wt || !C) return fail(VITB200_ERR_INVALID, "gemm_bf16: null pointer");
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&ta, A, M, K, K, GEMM_BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tb, Wt, N, K, K, GEMM_BN))) return rc;
+  return launch_gemm_bf16(static_cast<cudaStream_t>(stream), ta, tb, bias, C, M, N, K, epilogue, aux, tokens_per_image);
+}
+
+int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias, float* C, int M, int N,
+                     int K, int epilogue, const float* aux, int tokens_per_image) {
+  if (!A || !W || !C) return fail(VITB200_ERR_INVALID, "gemm_f32: null pointer");
+  return launch_gemm_f32(static_cast<cudaStream_t>(stream), A, W, bias, C, M, N, K, epilogue, aux, tokens_per_image);
+}
+
+int vitb200_layernorm(void* stream, const float* x, const float* scale, const float* bias, void* y, int rows,
+                      int dim, int out_bf16) {
+  if (!x || !scale || !bias || !y) return fail(VITB200_ERR_INVALID, "layernorm: null pointer");
+  return launch_layernorm(static_cast<cudaStream_t>(stream), x, scale, bias, y, rows, dim, out_bf16 != 0);
+}
+
+int vitb200_attention_bf16(void* stream, const void* qkv, void* out, int batch, int T, int heads) {
+  if (!qkv || !out) return fail(VITB200_ERR_INVALID, "attention_bf16: null pointer");
+  return launch_attention_bf16(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv),
+                               static_cast<__nv_bfloat16*>(out), batch, T, heads);
+}
+
+int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads) {
+  if (!qkv || !out) return fail(VITB200_ERR_INVALID, "attention_f32: null pointer");
+  return launch_attention_f32(static_cast<cudaStream_t>(stream), qkv, out, batch, T, heads);
+}
+
+int vitb200_patchify(void* stream, const float* images, void* patches, int batch, int H, int W, int C, int ph,
+                     int pw, int Kpad, int out_bf16) {
+  if (!images || !patches) return fail(VITB200_ERR_INVALID, "patchify: null pointer");
+  return launch_patchify(static_cast<cudaStream_t>(stream), images, patches, batch, H, W, C, ph, pw, Kpad, out_bf16 != 0);
+}
+
+int vitb200_cls_rows(void* stream, const float* cls, const float* pos, float* x, int batch, int T, int dim) {
+  if (!cls || !pos || !x) return fail(VITB200_ERR_INVALID, "cls_rows: null pointer");
+  return launch_cls_rows(static_cast<cudaStream_t>(stream), cls, pos, x, batch, T, dim);
+}
+
+int vitb200_pool_layernorm(void* stream, const float* x, const float* scale, const float* bias, void* y,
+                           int batch, int T, int dim, int pool, int out_bf16) {
+  if (!x || !scale || !bias || !y) return fail(VITB200_ERR_INVALID, "pool_layernorm: null pointer");
+  return launch_pool_layernorm(static_cast<cudaStream_t>(stream), x, scale, bias, y, batch, T, dim, pool, out_bf16 != 0);
+}
+
+int vitb200_pack_weight_bf16(void* stream, const float* W, void* Wt, int K, int N, int Kpad) {
+  if (!W || !Wt) return fail(VITB200_ERR_INVALID, "pack_weight_bf16: null pointer");
+  if (Kpad < K) return fail(VITB200_ERR_INVALID, "pack_weight_bf16: Kpad < K");
+  return launch_pack_weight_bf16(static_cast<cudaStream_t>(stream), W, static_cast<__nv_bfloat16*>(Wt), K, N, Kpad);
+}
+
+}  // extern "C"

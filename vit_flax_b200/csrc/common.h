@@ -1,0 +1,73 @@
+// common.h -- shared host-side declarations for libvitb200 (internal; the public
+// surface is include/vitb200.h).
+#pragma once
+#include <cuda.h>            // CUtensorMap type only; the driver is reached via cudart entry points
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/vitb200.h"
+
+namespace vb {
+
+// ---- error plumbing ------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+const std::string& last_error_ref();
+int64_t launch_count();
+
+#define VB_CUDA(expr)                                              \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return ::vb::cuda_fail(_e, #expr);      \
+  } while (0)
+
+#define VB_LAUNCH_CHECK(name)                                      \
+  do {                                                             \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return ::vb::cuda_fail(_e, name);       \
+    ::vb::count_launch();                                          \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+int sm_count();   // SMs of the current device (cached per device)
+
+// ---- TMA descriptors -----------------------------------------------------
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, row pitch = ld
+// elements), box = [box_rows, 64 cols] with 128-byte swizzle.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                      int box_rows);
+
+// ---- kernels (host launchers; all enqueue on `stream`, return 0 / <0) -----
+constexpr int GEMM_BM = 128;   // tcgen05 tile rows (A box rows)
+constexpr int GEMM_BN = 256;   // tcgen05 tile cols (Wt box rows)
+constexpr int GEMM_BK = 64;
+
+int launch_gemm_bf16(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                     const float* bias, void* C, int M, int N, int K, int epilogue,
+                     const float* aux, int tokens_per_image);
+int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const float* bias,
+                    float* C, int M, int N, int K, int epilogue, const float* aux,
+                    int tokens_per_image);
+int launch_layernorm(cudaStream_t stream, const float* x, const float* scale, const float* bias,
+                     void* y, int rows, int dim, bool out_bf16);
+int launch_attention_bf16(cudaStream_t stream, const __nv_bfloat16* qkv, __nv_bfloat16* out,
+                          int batch, int T, int heads);
+int launch_attention_f32(cudaStream_t stream, const float* qkv, float* out, int batch, int T,
+                         int heads);
+int launch_patchify(cudaStream_t stream, const float* images, void* patches, int batch, int H,
+                    int W, int C, int ph, int pw, int Kpad, bool out_bf16);
+int launch_cls_rows(cudaStream_t stream, const float* cls, const float* pos, float* x, int batch,
+                    int T, int dim);
+int launch_pool_layernorm(cudaStream_t stream, const float* x, const float* scale,
+                          const float* bias, void* y, int batch, int T, int dim, int pool,
+                          bool out_bf16);
+int launch_pack_weight_bf16(cudaStream_t stream, const float* W, __nv_bfloat16* Wt, int K, int N,
+                            int Kpad);
+
+}  // namespace vb

@@ -1,0 +1,464 @@
+// simt.cu -- the CUDA-core kernels of the path:
+//   K2  LayerNorm (warp-shuffle, vectorised; fp32 in, bf16 or fp32 out)     vit.py:31,163
+//   K1a patchify + fp32->bf16 cast (im2col folded into the mandatory cast)   vit.py:146
+//   K1b cls rows                                                             vit.py:151-153
+//   K5a pool (cls / mean) + head LayerNorm                                   vit.py:159-163
+//   K7  weight pack (fp32 [K,N] -> bf16 [N,Kpad])
+//   fp32 validation mode: SIMT GEMM with the same fused epilogues and a
+//   straightforward fp32 attention (tolerance 1e-4 against the oracle).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+namespace {
+
+constexpr float LN_EPS = 1e-6f;   // flax nn.LayerNorm default (NOT torch's 1e-5)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------- LayerNorm (K2)
+// One warp per row, the row lives in registers (<= 16 float4 per lane => dim <= 2048).
+template <int NV, bool kBf16>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                      const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * dim);
+  const int nvec = dim >> 2;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      v[i] = __ldcs(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / float(dim);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / float(dim) + LN_EPS);
+  const float4* g4 = reinterpret_cast<const float4*>(scale);
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nvec) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (kBf16) {
+        uint2 p;
+        p.x = pack_bf16x2(o.x, o.y);
+        p.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + int64_t(row) * dim)[c] = p;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + int64_t(row) * dim)[c] = o;
+      }
+    }
+  }
+}
+
+// Any dim: one warp per row, three passes over the (cached) row.
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                         const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float* xr = x + int64_t(row) * dim;
+  float s = 0.f;
+  for (int c = lane; c < dim; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / float(dim);
+  float ss = 0.f;
+  for (int c = lane; c < dim; c += 32) { const float d = xr[c] - mean; ss += d * d; }
+  const float rstd = rsqrtf(warp_sum(ss) / float(dim) + LN_EPS);
+  for (int c = lane; c < dim; c += 32) {
+    const float o = (xr[c] - mean) * rstd * scale[c] + bias[c];
+    if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(y)[int64_t(row) * dim + c] = __float2bfloat16_rn(o);
+    else reinterpret_cast<float*>(y)[int64_t(row) * dim + c] = o;
+  }
+}
+
+template <bool kBf16>
+int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b, void* y, int rows,
+                int dim) {
+  const int grid = ceil_div(rows, 8);
+  const bool vec = (dim % 4 == 0) && dim <= 2048 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                     reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  if (!vec) {
+    layernorm_generic_kernel<kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+  } else {
+    const int nv = ceil_div(dim, 128);
+    if (nv <= 4) layernorm_rows_kernel<4, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else if (nv <= 6) layernorm_rows_kernel<6, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else if (nv <= 8) layernorm_rows_kernel<8, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else if (nv <= 10) layernorm_rows_kernel<10, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else layernorm_rows_kernel<16, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+  }
+  VB_LAUNCH_CHECK("layernorm");
+  return 0;
+}
+
+// -------------------------------------------------------------- patchify (K1a)
+// out[(b*Np + t), f], f = (p1*pw + p2)*C + c  <-  x[b, hh*ph+p1, ww*pw+p2, c]; zero pad f >= K0.
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
+                int C, int ph, int pw, int Kpad) {
+  const int gw = W / pw, gh = H / ph;
+  const int K0 = ph * pw * C;
+  const int64_t pairs_per_row = Kpad >> 1;     // Kpad is even
+  const int64_t total = int64_t(batch) * gh * gw * pairs_per_row;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t prow = i / pairs_per_row;
+    const int f0 = int(i - prow * pairs_per_row) * 2;
+    const int t = int(prow % (gh * gw));
+    const int b = int(prow / (gh * gw));
+    const int hh = t / gw, ww = t - hh * gw;
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int f = f0 + e;
+      if (f < K0) {
+        const int c = f % C, pp = f / C;
+        const int p1 = pp / pw, p2 = pp - p1 * pw;
+        v[e] = __ldg(img + ((int64_t(b) * H + hh * ph + p1) * W + ww * pw + p2) * C + c);
+      } else {
+        v[e] = 0.f;
+      }
+    }
+    if constexpr (kBf16) {
+      reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(v[0], v[1]);
+    } else {
+      reinterpret_cast<float2*>(out)[i] = make_float2(v[0], v[1]);
+    }
+  }
+}
+
+// -------------------------------------------------------------- cls rows (K1b)
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
+                                float* __restrict__ x, int batch, int T, int dim) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= int64_t(batch) * dim) return;
+  const int b = int(i / dim), d = int(i - int64_t(b) * dim);
+  x[int64_t(b) * T * dim + d] = cls[d] + pos[d];
+}
+
+// ------------------------------------------------- pool + head LayerNorm (K5a)
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+pool_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                      const float* __restrict__ bias, void* __restrict__ y, int T, int dim,
+                      int pool) {
+  extern __shared__ float sh[];          // dim floats + 16 reduction slots
+  float* pooled = sh;
+  float* red = sh + dim;
+  const int b = blockIdx.x;
+  const float* xb = x + int64_t(b) * T * dim;
+  float s = 0.f;
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    float v;
+    if (pool == VITB200_POOL_MEAN) {
+      float acc = 0.f;
+      for (int t = 0; t < T; ++t) acc += xb[int64_t(t) * dim + d];
+      v = acc / float(T);
+    } else {
+      v = xb[d];
+    }
+    pooled[d] = v;
+    s += v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float mean = tot / float(dim);
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) { const float c = pooled[d] - mean; ss += c * c; }
+  ss = warp_sum(ss);
+  if (lane == 0) red[8 + warp] = ss;
+  __syncthreads();
+  float tot2 = 0.f;
+  for (int w = 0; w < 8; ++w) tot2 += red[8 + w];
+  const float rstd = rsqrtf(tot2 / float(dim) + LN_EPS);
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    const float o = (pooled[d] - mean) * rstd * scale[d] + bias[d];
+    if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(y)[int64_t(b) * dim + d] = __float2bfloat16_rn(o);
+    else reinterpret_cast<float*>(y)[int64_t(b) * dim + d] = o;
+  }
+}
+
+// ----------------------------------------------------------- weight pack (K7)
+// W fp32 [K, N] (flax kernel) -> Wt bf16 [N, Kpad], zero padded along K.
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    tile[r][tx] = (k < K && n < N) ? W[int64_t(k) * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    if (n < N && k < Kpad) Wt[int64_t(n) * Kpad + k] = __float2bfloat16_rn(tile[tx][r]);
+  }
+}
+
+// ------------------------------------------------------ fp32 SIMT GEMM (mode)
+__device__ __forceinline__ float gelu_tanh_exact(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+
+template <int kEpi>
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
+                const float* __restrict__ aux, int tpi) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;     // 64 rows x 16 k
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;      // 16 k x 64 n
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int m = m0 + a_row, k = k0 + a_k + e;
+      As[a_k + e][a_row] = (m < M && k < K) ? A[int64_t(m) * K + k] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + b_k, n = n0 + b_n + e;
+      Bs[b_k][b_n + e] = (k < K && n < N) ? W[int64_t(k) * N + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    int64_t out_row = m;
+    const float* pos_row = nullptr;
+    if constexpr (kEpi == VITB200_EPI_PATCH_F32) {
+      const int b = m / tpi, t = m - b * tpi;
+      out_row = int64_t(b) * (tpi + 1) + 1 + t;
+      pos_row = aux + int64_t(1 + t) * N;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if constexpr (kEpi != VITB200_EPI_STORE_BF16) v += bias[n];
+      if constexpr (kEpi == VITB200_EPI_BIAS_GELU_BF16) v = gelu_tanh_exact(v);
+      if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32) v += C[out_row * N + n];
+      if constexpr (kEpi == VITB200_EPI_PATCH_F32) v += pos_row[n];
+      C[out_row * N + n] = v;
+    }
+  }
+}
+
+template <int kEpi>
+int launch_gemm_f32_t(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
+                      int M, int N, int K, const float* aux, int tpi) {
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  gemm_f32_kernel<kEpi><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, aux, tpi);
+  VB_LAUNCH_CHECK("gemm_f32_kernel");
+  return 0;
+}
+
+// -------------------------------------------------- fp32 attention (mode)
+// One warp per query row; scores for the row live in shared memory.
+__global__ void __launch_bounds__(256)
+attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int heads) {
+  extern __shared__ float sh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tpad = (T + 31) & ~31;
+  float* sc = sh + warp * (Tpad + 64);
+  float* qs = sc + Tpad;
+  const int bh = blockIdx.x, b = bh / heads, h = bh - b * heads;
+  const int qi = blockIdx.y * 8 + warp;
+  if (qi >= T) return;
+  const int inner = heads * 64, ld = 3 * inner;
+  const float* base = qkv + int64_t(b) * T * ld;
+  const float* qrow = base + int64_t(qi) * ld + h * 64;
+  qs[lane] = qrow[lane];
+  qs[lane + 32] = qrow[lane + 32];
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < T; j += 32) {
+    const float4* kr = reinterpret_cast<const float4*>(base + int64_t(j) * ld + inner + h * 64);
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 kv = __ldg(kr + c);
+      d = fmaf(qs[c * 4 + 0], kv.x, d); d = fmaf(qs[c * 4 + 1], kv.y, d);
+      d = fmaf(qs[c * 4 + 2], kv.z, d); d = fmaf(qs[c * 4 + 3], kv.w, d);
+    }
+    d *= 0.125f;                       // dim_head ** -0.5, dim_head = 64 (vit.py:66)
+    sc[j] = d;
+    mx = fmaxf(mx, d);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+  const float* vbase = base + 2 * inner + h * 64;
+  for (int j = 0; j < T; ++j) {
+    const float p = sc[j];
+    o0 = fmaf(p, __ldg(vbase + int64_t(j) * ld + lane), o0);
+    o1 = fmaf(p, __ldg(vbase + int64_t(j) * ld + lane + 32), o1);
+  }
+  const float inv = 1.f / sum;
+  float* orow = out + (int64_t(b) * T + qi) * inner + h * 64;
+  orow[lane] = o0 * inv;
+  orow[lane + 32] = o1 * inv;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+int launch_layernorm(cudaStream_t st, const float* x, const float* g, const float* b, void* y,
+                     int rows, int dim, bool out_bf16) {
+  if (rows <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "layernorm: empty problem");
+  return out_bf16 ? launch_ln_t<true>(st, x, g, b, y, rows, dim)
+                  : launch_ln_t<false>(st, x, g, b, y, rows, dim);
+}
+
+int launch_patchify(cudaStream_t st, const float* images, void* patches, int batch, int H, int W,
+                    int C, int ph, int pw, int Kpad, bool out_bf16) {
+  if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || ph <= 0 || pw <= 0)
+    return fail(VITB200_ERR_INVALID, "patchify: empty problem");
+  if (H % ph != 0 || W % pw != 0)
+    return fail(VITB200_ERR_INVALID, "patchify: image not divisible by patch (vit.py:133-134)");
+  if (Kpad < ph * pw * C || (Kpad & 1))
+    return fail(VITB200_ERR_INVALID, "patchify: Kpad must be even and >= ph*pw*C");
+  const int64_t total = int64_t(batch) * (H / ph) * (W / pw) * (Kpad / 2);
+  const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
+  if (out_bf16) patchify_kernel<true><<<grid, 256, 0, st>>>(images, patches, batch, H, W, C, ph, pw, Kpad);
+  else patchify_kernel<false><<<grid, 256, 0, st>>>(images, patches, batch, H, W, C, ph, pw, Kpad);
+  VB_LAUNCH_CHECK("patchify_kernel");
+  return 0;
+}
+
+int launch_cls_rows(cudaStream_t st, const float* cls, const float* pos, float* x, int batch, int T,
+                    int dim) {
+  const int64_t total = int64_t(batch) * dim;
+  cls_rows_kernel<<<int((total + 255) / 256), 256, 0, st>>>(cls, pos, x, batch, T, dim);
+  VB_LAUNCH_CHECK("cls_rows_kernel");
+  return 0;
+}
+
+int launch_pool_layernorm(cudaStream_t st, const float* x, const float* g, const float* b, void* y,
+                          int batch, int T, int dim, int pool, bool out_bf16) {
+  if (pool != VITB200_POOL_CLS && pool != VITB200_POOL_MEAN)
+    return fail(VITB200_ERR_INVALID, "pool must be cls or mean (vit.py:137)");
+  const size_t smem = (size_t(dim) + 16) * sizeof(float);
+  if (out_bf16) pool_layernorm_kernel<true><<<batch, 256, smem, st>>>(x, g, b, y, T, dim, pool);
+  else pool_layernorm_kernel<false><<<batch, 256, smem, st>>>(x, g, b, y, T, dim, pool);
+  VB_LAUNCH_CHECK("pool_layernorm_kernel");
+  return 0;
+}
+
+int launch_pack_weight_bf16(cudaStream_t st, const float* W, __nv_bfloat16* Wt, int K, int N,
+                            int Kpad) {
+  dim3 grid(ceil_div(Kpad, 32), ceil_div(N, 32));
+  pack_weight_kernel<<<grid, 256, 0, st>>>(W, Wt, K, N, Kpad);
+  VB_LAUNCH_CHECK("pack_weight_kernel");
+  return 0;
+}
+
+int launch_gemm_f32(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
+                    int M, int N, int K, int epilogue, const float* aux, int tpi) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_f32: empty problem");
+  if (epilogue != VITB200_EPI_STORE_BF16 && bias == nullptr)
+    return fail(VITB200_ERR_INVALID, "gemm_f32: epilogue needs a bias");
+  switch (epilogue) {
+    case VITB200_EPI_STORE_BF16: return launch_gemm_f32_t<VITB200_EPI_STORE_BF16>(st, A, W, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_BIAS_GELU_BF16: return launch_gemm_f32_t<VITB200_EPI_BIAS_GELU_BF16>(st, A, W, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_BIAS_RESID_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_RESID_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_BIAS_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_PATCH_F32:
+      if (aux == nullptr || tpi <= 0) return fail(VITB200_ERR_INVALID, "gemm_f32: PATCH epilogue needs pos_embedding and tokens");
+      return launch_gemm_f32_t<VITB200_EPI_PATCH_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
+    default: return fail(VITB200_ERR_INVALID, "gemm_f32: unknown epilogue");
+  }
+}
+
+int launch_attention_f32(cudaStream_t st, const float* qkv, float* out, int batch, int T, int heads) {
+  if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_f32: empty problem");
+  const int Tpad = (T + 31) & ~31;
+  const size_t smem = size_t(8) * (Tpad + 64) * sizeof(float);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    VB_CUDA(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (smem > 200 * 1024) return fail(VITB200_ERR_UNSUPPORTED, "attention_f32: sequence too long");
+  dim3 grid(batch * heads, ceil_div(T, 8));
+  attention_f32_kernel<<<grid, 256, smem, st>>>(qkv, out, T, heads);
+  VB_LAUNCH_CHECK("attention_f32_kernel");
+  return 0;
+}
+
+}  // namespace vb

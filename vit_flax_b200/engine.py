@@ -1,0 +1,133 @@
+"""Host-side owner of one ``vitb200_model`` handle (one per device / precision).
+
+PyTorch is plumbing here: it provides the device buffers handed to the C ABI
+(``tensor.data_ptr()``) and the stream (``torch.cuda.current_stream()``).  All
+compute happens inside ``libvitb200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .params import flatten_params, geometry, leaf_to_numpy
+
+
+def _stream_ptr(torch, device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """Create -> load_params -> forward.  Not thread-safe (like the C handle)."""
+
+    def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim,
+                 pool="cls", channels=3, precision="bf16", max_batch=256, device=0):
+        import torch  # deferred: plumbing only
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("vit_flax_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._torch = torch
+        self.lib = _lib.load()
+        ih, iw, ph, pw, n = geometry(image_size, patch_size)
+        assert pool in {"cls", "mean"}, "pool type must be either cls (cls token) or mean (mean pooling)"
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.cfg = _lib.Config(
+            image_h=ih, image_w=iw, patch_h=ph, patch_w=pw, channels=channels,
+            num_classes=num_classes, dim=dim, depth=depth, heads=heads, mlp_dim=mlp_dim,
+            pool=_lib.POOL_MEAN if pool == "mean" else _lib.POOL_CLS,
+            precision=_lib.PREC_FP32 if precision == "fp32" else _lib.PREC_BF16,
+            max_batch=max_batch)
+        self.precision = precision
+        self.max_batch = max_batch
+        self.device = torch.device("cuda", device)
+        self.tokens = n + 1
+        self.num_classes = num_classes
+        self.dim = dim
+        self.image_shape = (ih, iw, channels)
+        handle = C.c_void_p()
+        _lib.check(self.lib.vitb200_create(C.byref(self.cfg), device, C.byref(handle)))
+        self.handle = handle
+        self._loaded = False
+
+    # -- params ----------------------------------------------------------------
+    def param_table(self) -> Dict[str, tuple]:
+        out = {}
+        n = _lib.check(self.lib.vitb200_num_params(self.handle))
+        for i in range(n):
+            path = C.c_char_p()
+            shape = (C.c_int64 * 4)()
+            nd = _lib.check(self.lib.vitb200_param_info(self.handle, i, C.byref(path), shape))
+            out[path.value.decode()] = tuple(shape[:nd])
+        return out
+
+    def load_params(self, variables) -> None:
+        """Upload a Flax-style params pytree (dict / FrozenDict / Mapping)."""
+        flat = flatten_params(variables)
+        table = self.param_table()
+        missing = sorted(set(table) - set(flat))
+        extra = sorted(set(flat) - set(table))
+        if missing or extra:
+            raise ValueError(f"params tree does not match the ViT config: missing={missing[:4]} "
+                             f"unexpected={extra[:4]}")
+        for path, leaf in flat.items():
+            a = leaf_to_numpy(leaf)
+            shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+            _lib.check(self.lib.vitb200_set_param(self.handle, path.encode(), a.ctypes.data, shape, a.ndim))
+        _lib.check(self.lib.vitb200_finalize_params(self.handle, _stream_ptr(self._torch, self.device)))
+        self._loaded = True
+
+    # -- forward ---------------------------------------------------------------
+    def _check_images(self, shape):
+        if len(shape) != 4 or tuple(shape[1:]) != self.image_shape:
+            raise ValueError(f"expected images [B, {self.image_shape[0]}, {self.image_shape[1]}, "
+                             f"{self.image_shape[2]}] (NHWC, channels-last), got {tuple(shape)}")
+        if not 1 <= shape[0] <= self.max_batch:
+            raise ValueError(f"batch {shape[0]} outside [1, max_batch={self.max_batch}]")
+
+    def forward(self, images, out=None):
+        """Device path: ``images`` fp32 CUDA tensor [B,H,W,C]; returns fp32 CUDA logits."""
+        torch = self._torch
+        self._check_images(images.shape)
+        if images.dtype != torch.float32 or not images.is_cuda or not images.is_contiguous():
+            raise ValueError("forward expects a contiguous float32 CUDA tensor")
+        b = images.shape[0]
+        if out is None:
+            out = torch.empty((b, self.num_classes), dtype=torch.float32, device=images.device)
+        _lib.check(self.lib.vitb200_forward(self.handle, _stream_ptr(torch, images.device),
+                                            images.data_ptr(), b, out.data_ptr()))
+        return out
+
+    def forward_host(self, images: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """End-to-end path: host fp32 images in, host fp32 logits out (H2D + D2H inside)."""
+        images = np.ascontiguousarray(images, dtype=np.float32)
+        self._check_images(images.shape)
+        b = images.shape[0]
+        if out is None:
+            out = np.empty((b, self.num_classes), np.float32)
+        _lib.check(self.lib.vitb200_forward_host(self.handle, _stream_ptr(self._torch, self.device),
+                                                 images.ctypes.data, b, out.ctypes.data))
+        return out
+
+    def tokens_after_transformer(self, batch: int) -> np.ndarray:
+        out = np.empty((batch, self.tokens, self.dim), np.float32)
+        _lib.check(self.lib.vitb200_debug_tokens(self.handle, _stream_ptr(self._torch, self.device),
+                                                 out.ctypes.data, batch))
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vitb200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def launch_count() -> int:
+    return int(_lib.load().vitb200_launch_count())
