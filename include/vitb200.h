@@ -42,6 +42,13 @@ extern "C" {
 /* cfg.precision */
 #define VITB200_PREC_BF16 0   /* bf16 operands, fp32 accumulate, fp32 residual stream (tcgen05) */
 #define VITB200_PREC_FP32 1   /* fp32 everywhere (SIMT validation mode, tolerance 1e-4)        */
+#define VITB200_PREC_FP16 2   /* fp16 operands, otherwise identical to BF16 (same tcgen05
+                                 kind::f16 rate; 3 more mantissa bits)          */
+
+/* element types of buffers handed to the per-kernel entry points */
+#define VITB200_DT_F32  0
+#define VITB200_DT_BF16 1
+#define VITB200_DT_F16  2
 
 /* cfg.pool -- vit.py:121,159 */
 #define VITB200_POOL_CLS  0
@@ -99,6 +106,22 @@ int vitb200_forward(vitb200_model* m, void* stream, const float* images_dev, int
 /* Same call with HOST buffers (pinned or pageable): H2D, forward, D2H, sync. */
 int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_host, int batch,
                          float* logits_host);
+/* One forward with a CUDA event before every launch: per-category device time (ms) and launch
+ * counts, arrays of VITB200_NUM_CATEGORIES.  Synchronises the stream.  For bench/roofline.  */
+#define VITB200_CAT_PATCHIFY   0
+#define VITB200_CAT_GEMM_PATCH 1
+#define VITB200_CAT_CLS_ROWS   2
+#define VITB200_CAT_LAYERNORM  3
+#define VITB200_CAT_GEMM_QKV   4
+#define VITB200_CAT_ATTENTION  5
+#define VITB200_CAT_GEMM_OUT   6
+#define VITB200_CAT_GEMM_FF1   7
+#define VITB200_CAT_GEMM_FF2   8
+#define VITB200_CAT_POOL_LN    9
+#define VITB200_CAT_GEMM_HEAD  10
+#define VITB200_NUM_CATEGORIES 11
+int vitb200_profile_forward(vitb200_model* m, void* stream, const float* images_dev, int batch,
+                            float* logits_dev, float* ms_by_category, int* launches_by_category);
 /* Copy the token stream after the last block ([batch, T, dim] fp32, device to
  * host) -- parity checks of Transformer.__call__ (vit.py:98-112).            */
 int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int batch);
@@ -106,48 +129,49 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 /* ---- per-kernel entry points (unit parity tests, ncu) -------------------
  * All pointers are DEVICE pointers.                                         */
 
-/* gemm epilogues */
-#define VITB200_EPI_STORE_BF16      0  /* C_bf16 = acc                         (to_qkv, vit.py:68)   */
-#define VITB200_EPI_BIAS_GELU_BF16  1  /* C_bf16 = gelu_tanh(acc + bias)       (vit.py:48-49)        */
+/* gemm epilogues ("16" = the 16-bit operand type of the call, bf16 or fp16) */
+#define VITB200_EPI_STORE_16        0  /* C_16 = acc                           (to_qkv, vit.py:68)   */
+#define VITB200_EPI_BIAS_GELU_16    1  /* C_16 = gelu_tanh(acc + bias)         (vit.py:48-49)        */
 #define VITB200_EPI_BIAS_RESID_F32  2  /* C_f32 += acc + bias  (in place)      (vit.py:51/82 + 39)   */
 #define VITB200_EPI_BIAS_F32        3  /* C_f32 = acc + bias                   (head, vit.py:165)    */
 #define VITB200_EPI_PATCH_F32       4  /* C_f32[b*T+1+t] = acc + bias + pos[1+t]  (vit.py:147-153)   */
 
-/* tcgen05 bf16 GEMM: acc[M,N] = A[M,K] (bf16 row-major) x Wt[N,K]^T (bf16,
- * row-major, i.e. the transposed Flax kernel).  K % 8 == 0, N % 8 == 0.
- * `aux` = pos_embedding [T, N] fp32 and `tokens_per_image` = T-1 for EPI_PATCH. */
-int vitb200_gemm_bf16(void* stream, const void* A, const void* Wt, const float* bias,
-                      void* C, int M, int N, int K, int epilogue,
-                      const float* aux, int tokens_per_image);
+/* tcgen05 GEMM: acc[M,N] = A[M,K] (16-bit row-major) x Wt[N,K]^T (16-bit row-major, i.e. the
+ * transposed Flax kernel), fp32 accumulation in TMEM.  dtype = VITB200_DT_BF16 | _F16.
+ * K % 8 == 0, N % 8 == 0.  `aux` = pos_embedding [T, N] fp32 and `tokens_per_image` = T-1 for
+ * EPI_PATCH.                                                                                  */
+int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bias,
+                    void* C, int M, int N, int K, int epilogue,
+                    const float* aux, int tokens_per_image, int dtype);
 /* SIMT fp32 GEMM (validation mode): acc = A[M,K] x W[K,N] (Flax layout).
- * Epilogues: STORE writes fp32 here; GELU writes fp32.                      */
+ * The two "_16" epilogues write fp32 here.                                  */
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias,
                      float* C, int M, int N, int K, int epilogue,
                      const float* aux, int tokens_per_image);
 
-/* nn.LayerNorm() (vit.py:31,163): x [rows, dim] fp32 -> y (bf16 if out_bf16 else fp32) */
+/* nn.LayerNorm() (vit.py:31,163): x [rows, dim] fp32 -> y of type out_dtype (VITB200_DT_*) */
 int vitb200_layernorm(void* stream, const float* x, const float* scale, const float* bias,
-                      void* y, int rows, int dim, int out_bf16);
+                      void* y, int rows, int dim, int out_dtype);
 
 /* softmax(Q K^T * 64^-0.5) V per (image, head) (vit.py:69-79).  qkv is the
  * to_qkv output [batch*T, 3*heads*64] (q | k | v, head-major inside each),
- * out is [batch*T, heads*64].  bf16 flavour = flash-style tensor-core kernel. */
-int vitb200_attention_bf16(void* stream, const void* qkv, void* out, int batch, int T, int heads);
+ * out is [batch*T, heads*64].  _tc = flash-style tensor-core kernel on 16-bit data. */
+int vitb200_attention_tc(void* stream, const void* qkv, void* out, int batch, int T, int heads,
+                         int dtype);
 int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads);
 
-/* patchify (vit.py:146): images [batch,H,W,C] fp32 -> patches [batch*Np, Kpad]
- * (bf16 if out_bf16 else fp32), feature f = (p1*pw + p2)*C + c, zero padded to Kpad. */
+/* patchify (vit.py:146): images [batch,H,W,C] fp32 -> patches [batch*Np, Kpad] of out_dtype,
+ * feature f = (p1*pw + p2)*C + c, zero padded to Kpad. */
 int vitb200_patchify(void* stream, const float* images, void* patches, int batch,
-                     int H, int W, int C, int ph, int pw, int Kpad, int out_bf16);
+                     int H, int W, int C, int ph, int pw, int Kpad, int out_dtype);
 /* cls rows (vit.py:151-153): x[b*T + 0, :] = cls + pos[0] */
 int vitb200_cls_rows(void* stream, const float* cls, const float* pos, float* x,
                      int batch, int T, int dim);
-/* pool (vit.py:159) + head LayerNorm (vit.py:163): x [batch,T,dim] fp32 ->
- * y [batch, dim] (bf16 if out_bf16 else fp32) */
+/* pool (vit.py:159) + head LayerNorm (vit.py:163): x [batch,T,dim] fp32 -> y [batch, dim] */
 int vitb200_pool_layernorm(void* stream, const float* x, const float* scale, const float* bias,
-                           void* y, int batch, int T, int dim, int pool, int out_bf16);
-/* fp32 [K,N] (Flax kernel) -> bf16 [N,Kpad] transposed pack used by gemm_bf16 */
-int vitb200_pack_weight_bf16(void* stream, const float* W, void* Wt, int K, int N, int Kpad);
+                           void* y, int batch, int T, int dim, int pool, int out_dtype);
+/* fp32 [K,N] (Flax kernel) -> 16-bit [N,Kpad] transposed pack used by gemm_tc */
+int vitb200_pack_weight(void* stream, const float* W, void* Wt, int K, int N, int Kpad, int dtype);
 
 #ifdef __cplusplus
 }

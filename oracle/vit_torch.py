@@ -27,46 +27,60 @@ def tree_to_torch(tree, dtype=torch.float32):
     return _t(tree, dtype)
 
 
+def _r(x, dt):
+    """Round to the 16-bit operand type `dt` and back (no-op when dt is None).  Used to emulate
+    WHERE the tensor-core path rounds (GEMM operands and 16-bit activations), so a bf16/fp16 run
+    can be checked tightly against "the reference computed with the same operand rounding"."""
+    return x if dt is None else x.to(dt).to(x.dtype)
+
+
 def _ln(x, p):
     # nn.LayerNorm(): eps 1e-6, scale+bias (vit.py:31,163)
     return F.layer_norm(x, (x.shape[-1],), p["scale"], p["bias"], eps=1e-6)
 
 
-def _attention(x, p, heads, dim):
+def _attention(x, p, heads, dim, dt=None):
     b, n, _ = x.shape
-    qkv = x @ p["Dense_0"]["kernel"]                                       # vit.py:68
+    qkv = _r(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt), dt)               # vit.py:68
     q, k, v = qkv.chunk(3, dim=-1)                                         # vit.py:69
     q, k, v = (t.view(b, n, heads, DIM_HEAD).transpose(1, 2) for t in (q, k, v))  # vit.py:71
-    # vit.py:73-78; SDPA's default scale is 1/sqrt(dim_head) = dim_head ** -0.5
-    o = F.scaled_dot_product_attention(q, k, v)
-    o = o.transpose(1, 2).reshape(b, n, heads * DIM_HEAD)                  # vit.py:79
+    if dt is None:
+        # vit.py:73-78; SDPA's default scale is 1/sqrt(dim_head) = dim_head ** -0.5
+        o = F.scaled_dot_product_attention(q, k, v)
+    else:   # un-normalised probabilities are what gets rounded before P @ V on the tensor cores
+        s = (q @ k.transpose(-1, -2)) * DIM_HEAD ** -0.5
+        e = torch.exp(s - s.amax(dim=-1, keepdim=True))
+        o = (_r(e, dt) @ v) / e.sum(dim=-1, keepdim=True)
+    o = _r(o.transpose(1, 2).reshape(b, n, heads * DIM_HEAD), dt)          # vit.py:79
     if not (heads == 1 and DIM_HEAD == dim):                               # vit.py:65
-        o = F.linear(o, p["Dense_1"]["kernel"].t(), p["Dense_1"]["bias"])  # vit.py:82
+        o = F.linear(o, _r(p["Dense_1"]["kernel"], dt).t(), p["Dense_1"]["bias"])  # vit.py:82
     return o
 
 
-def _ff(x, p):
-    h = F.gelu(x @ p["Dense_0"]["kernel"] + p["Dense_0"]["bias"], approximate="tanh")  # vit.py:48-49
-    return h @ p["Dense_1"]["kernel"] + p["Dense_1"]["bias"]                           # vit.py:51
+def _ff(x, p, dt=None):
+    h = F.gelu(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt) + p["Dense_0"]["bias"], approximate="tanh")  # vit.py:48-49
+    return _r(h, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"]                           # vit.py:51
 
 
 @torch.no_grad()
 def vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, depth,
-                heads, mlp_dim, pool="cls"):
-    """``params_t``: the ``params`` sub-tree already converted by ``tree_to_torch``."""
+                heads, mlp_dim, pool="cls", operand_dtype=None):
+    """``params_t``: the ``params`` sub-tree already converted by ``tree_to_torch``.
+    ``operand_dtype`` (torch.bfloat16 / torch.float16 / None): emulate 16-bit GEMM operands."""
+    dt = operand_dtype
     p = params_t["params"] if "params" in params_t else params_t
     ph, pw = (patch_size, patch_size) if not isinstance(patch_size, tuple) else patch_size
     x = torch.as_tensor(images).to(p["cls"].dtype)
     b, H, W, c = x.shape
     # vit.py:146 -- unfold-free patchify through view/permute
     x = x.view(b, H // ph, ph, W // pw, pw, c).permute(0, 1, 3, 2, 4, 5).reshape(b, -1, ph * pw * c)
-    x = x @ p["Dense_0"]["kernel"] + p["Dense_0"]["bias"]                  # vit.py:147
+    x = _r(x, dt) @ _r(p["Dense_0"]["kernel"], dt) + p["Dense_0"]["bias"]  # vit.py:147
     x = torch.cat([p["cls"].expand(b, -1, -1), x], dim=1)                  # vit.py:151-152
     x = x + p["pos_embedding"][:, : x.shape[1]]                            # vit.py:153
     tp = p["Transformer_0"]
     for l in range(depth):                                                 # vit.py:108-110
-        x = _attention(_ln(x, tp[f"PreNorm_{2 * l}"]["LayerNorm_0"]), tp[f"Attention_{l}"], heads, dim) + x
-        x = _ff(_ln(x, tp[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"]), tp[f"FeedForward_{l}"]) + x
+        x = _attention(_ln(x, tp[f"PreNorm_{2 * l}"]["LayerNorm_0"]), tp[f"Attention_{l}"], heads, dim, dt) + x
+        x = _ff(_ln(x, tp[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"]), tp[f"FeedForward_{l}"], dt) + x
     x = x.mean(dim=1) if pool == "mean" else x[:, 0]                       # vit.py:159
     x = _ln(x, p["LayerNorm_0"])                                           # vit.py:163
-    return x @ p["Dense_1"]["kernel"] + p["Dense_1"]["bias"]               # vit.py:165
+    return _r(x, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"]   # vit.py:165

@@ -1,7 +1,7 @@
 """Per-kernel parity on a real B200, called through the C ABI (ctypes), checked against the
-CPU oracle (numpy float64 restatement of vit.py).  Tolerances are stated per test:
-bf16-operand kernels are compared on bf16-rounded inputs, so the only error left is fp32
-accumulation order plus the final bf16 rounding where the output is bf16."""
+CPU oracle (numpy float64 restatement of vit.py).  Tolerances are stated per test: 16-bit
+operand kernels (bf16 / fp16) are compared on inputs already rounded to that type, so the only
+error left is fp32 accumulation order plus the final rounding where the output is 16-bit."""
 import ctypes as C
 
 import numpy as np
@@ -28,8 +28,7 @@ def dev(a, dtype=torch.float32):
     return torch.as_tensor(np.asarray(a)).to("cuda", dtype).contiguous()
 
 
-def bf16_round(a):
-    return torch.as_tensor(np.asarray(a, np.float32)).to(torch.bfloat16).float().numpy().astype(np.float64)
+DT16 = {"bf16": (_lib.DT_BF16, torch.bfloat16, 2.0 ** -8), "fp16": (_lib.DT_F16, torch.float16, 2.0 ** -11)}
 
 
 GEMM_SHAPES = [
@@ -43,23 +42,25 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("epi", [_lib.EPI_STORE_BF16, _lib.EPI_BIAS_GELU_BF16,
+@pytest.mark.parametrize("epi", [_lib.EPI_STORE_16, _lib.EPI_BIAS_GELU_16,
                                  _lib.EPI_BIAS_RESID_F32, _lib.EPI_BIAS_F32])
-def test_gemm_bf16_epilogues(lib, M, N, K, epi):
-    if M >= 40000 and epi not in (_lib.EPI_STORE_BF16, _lib.EPI_BIAS_RESID_F32):
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_gemm_tc_epilogues(lib, M, N, K, epi, fmt):
+    if M >= 40000 and epi not in (_lib.EPI_STORE_16, _lib.EPI_BIAS_RESID_F32):
         pytest.skip("large case covers the two memory-heaviest epilogues only")
+    dt, tdt, ulp = DT16[fmt]
     rng = np.random.default_rng(M + N + K + epi)
-    A = dev(rng.standard_normal((M, K)), torch.bfloat16)
+    A = dev(rng.standard_normal((M, K)), tdt)
     W = rng.standard_normal((K, N)).astype(np.float32) / np.sqrt(K)       # flax kernel [in, out]
-    Wt = dev(W.T, torch.bfloat16)                                         # packed [N, K]
+    Wt = dev(W.T, tdt)                                                    # packed [N, K]
     bias = dev(rng.standard_normal(N) * 0.5)
     resid = dev(rng.standard_normal((M, N)))
-    acc = (A.double() @ Wt.double().t())                                  # fp64 on the same bf16 operands
-    if epi == _lib.EPI_STORE_BF16:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    acc = (A.double() @ Wt.double().t())                                  # fp64 on the same 16-bit operands
+    if epi == _lib.EPI_STORE_16:
+        out = torch.empty((M, N), dtype=tdt, device="cuda")
         want = acc
-    elif epi == _lib.EPI_BIAS_GELU_BF16:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    elif epi == _lib.EPI_BIAS_GELU_16:
+        out = torch.empty((M, N), dtype=tdt, device="cuda")
         want = torch.nn.functional.gelu(acc + bias.double(), approximate="tanh")
     elif epi == _lib.EPI_BIAS_RESID_F32:
         out = resid.clone()
@@ -67,19 +68,19 @@ def test_gemm_bf16_epilogues(lib, M, N, K, epi):
     else:
         out = torch.full((M, N), float("nan"), device="cuda")
         want = acc + bias.double()
-    _lib.check(lib.vitb200_gemm_bf16(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(),
-                                     out.data_ptr(), M, N, K, epi, None, 0))
+    _lib.check(lib.vitb200_gemm_tc(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(),
+                                   out.data_ptr(), M, N, K, epi, None, 0, dt))
     torch.cuda.synchronize()
-    err = (out.double() - want).abs().max().item()
-    # fp32 accumulation: ~1e-5; bf16 outputs add one rounding (2^-9 relative, |values| < ~8);
-    # tanh.approx in the GELU epilogue adds < 1e-3 absolute
-    tol = 2e-4 if out.dtype == torch.float32 else 4e-2
-    assert err < tol, f"max abs err {err}"
-    if out.dtype == torch.bfloat16:                                       # and tight in the mean
-        assert (out.double() - want).abs().mean().item() < 3e-3
+    err = (out.double() - want).abs()
+    if out.dtype == torch.float32:
+        assert err.max().item() < 2e-4, f"max abs err {err.max().item()}"      # fp32 accumulation order only
+    else:
+        # one rounding of the output to the 16-bit type (half an ulp of |values| < 8) + tanh.approx (<1e-3)
+        assert err.max().item() < 8 * ulp + 2e-3, f"max abs err {err.max().item()}"
+        assert err.mean().item() < ulp + 2e-4
 
 
-def test_gemm_bf16_patch_epilogue(lib):
+def test_gemm_tc_patch_epilogue(lib):
     # vit.py:147-153: Dense_0 output placed at row b*T+1+t with pos_embedding[1+t] added
     B, Np, K, D = 3, 16, 192, 64
     rng = np.random.default_rng(5)
@@ -88,8 +89,8 @@ def test_gemm_bf16_patch_epilogue(lib):
     bias = dev(rng.standard_normal(D))
     pos = dev(rng.standard_normal((Np + 1, D)))
     x = torch.full((B * (Np + 1), D), 7.0, device="cuda")
-    _lib.check(lib.vitb200_gemm_bf16(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(),
-                                     x.data_ptr(), B * Np, D, K, _lib.EPI_PATCH_F32, pos.data_ptr(), Np))
+    _lib.check(lib.vitb200_gemm_tc(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(),
+                                   x.data_ptr(), B * Np, D, K, _lib.EPI_PATCH_F32, pos.data_ptr(), Np, _lib.DT_BF16))
     torch.cuda.synchronize()
     acc = (A.double() @ Wt.double().t()).view(B, Np, D) + bias.double() + pos.double()[1:]
     got = x.view(B, Np + 1, D)
@@ -97,14 +98,18 @@ def test_gemm_bf16_patch_epilogue(lib):
     assert torch.all(got[:, 0] == 7.0)                                    # cls rows untouched
 
 
-def test_gemm_bf16_rejects_unaligned(lib):
-    a = torch.zeros((8, 12), dtype=torch.bfloat16, device="cuda")
-    rc = lib.vitb200_gemm_bf16(stream(), a.data_ptr(), a.data_ptr(), None, a.data_ptr(), 8, 8, 12, 0, None, 0)
+def test_gemm_tc_rejects_bad_arguments(lib):
+    a = torch.zeros((8, 16), dtype=torch.bfloat16, device="cuda")
+    rc = lib.vitb200_gemm_tc(stream(), a.data_ptr(), a.data_ptr(), None, a.data_ptr(), 8, 8, 12, 0, None, 0, _lib.DT_BF16)
     assert rc == -1 and b"multiples of 8" in lib.vitb200_last_error()
+    rc = lib.vitb200_gemm_tc(stream(), a.data_ptr(), a.data_ptr(), None, a.data_ptr(), 8, 8, 16, 0, None, 0, _lib.DT_F32)
+    assert rc == -1 and b"dtype" in lib.vitb200_last_error()
+    rc = lib.vitb200_gemm_tc(stream(), a.data_ptr(), a.data_ptr(), None, a.data_ptr(), 8, 8, 16, 2, None, 0, _lib.DT_BF16)
+    assert rc == -1 and b"bias" in lib.vitb200_last_error()
 
 
 @pytest.mark.parametrize("M,N,K", [(65, 1024, 3072), (130, 200, 77), (1, 1000, 1024)])
-@pytest.mark.parametrize("epi", [_lib.EPI_STORE_BF16, _lib.EPI_BIAS_GELU_BF16, _lib.EPI_BIAS_RESID_F32, _lib.EPI_BIAS_F32])
+@pytest.mark.parametrize("epi", [_lib.EPI_STORE_16, _lib.EPI_BIAS_GELU_16, _lib.EPI_BIAS_RESID_F32, _lib.EPI_BIAS_F32])
 def test_gemm_f32(lib, M, N, K, epi):
     rng = np.random.default_rng(M * 3 + N + K + epi)
     A = rng.standard_normal((M, K)); W = rng.standard_normal((K, N)) / np.sqrt(K)
@@ -113,34 +118,38 @@ def test_gemm_f32(lib, M, N, K, epi):
     b32 = bias.astype(np.float32).astype(np.float64)
     want = {0: acc, 1: vit_numpy.gelu_tanh(acc + b32), 2: acc + b32 + resid.astype(np.float32), 3: acc + b32}[epi]
     out = dev(resid) if epi == _lib.EPI_BIAS_RESID_F32 else torch.empty((M, N), device="cuda")
-    _lib.check(lib.vitb200_gemm_f32(stream(), dev(A).data_ptr(), dev(W).data_ptr(), dev(bias).data_ptr(),
+    Ad, Wd, bd = dev(A), dev(W), dev(bias)                                # keep the device buffers alive
+    _lib.check(lib.vitb200_gemm_f32(stream(), Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(),
                                     out.data_ptr(), M, N, K, epi, None, 0))
     torch.cuda.synchronize()
     assert np.abs(out.cpu().numpy() - want).max() < 2e-5
 
 
 @pytest.mark.parametrize("rows,dim", [(1000, 768), (197 * 4, 1024), (33, 1280), (64, 64), (9, 100), (5, 2052)])
-@pytest.mark.parametrize("bf16", [0, 1])
-def test_layernorm(lib, rows, dim, bf16):
+@pytest.mark.parametrize("out", ["fp32", "bf16", "fp16"])
+def test_layernorm(lib, rows, dim, out):
     rng = np.random.default_rng(rows + dim)
     x = (rng.standard_normal((rows, dim)) * 2 + 3).astype(np.float32)
     p = {"scale": rng.standard_normal(dim).astype(np.float32), "bias": rng.standard_normal(dim).astype(np.float32)}
     want = vit_numpy.layer_norm(x.astype(np.float64), p)                  # eps 1e-6, vit.py:31
-    y = torch.empty((rows, dim), dtype=torch.bfloat16 if bf16 else torch.float32, device="cuda")
-    _lib.check(lib.vitb200_layernorm(stream(), dev(x).data_ptr(), dev(p["scale"]).data_ptr(),
-                                     dev(p["bias"]).data_ptr(), y.data_ptr(), rows, dim, bf16))
+    dt, tdt, ulp = DT16.get(out, (_lib.DT_F32, torch.float32, 0.0))
+    y = torch.empty((rows, dim), dtype=tdt, device="cuda")
+    xd, gd, bd = dev(x), dev(p["scale"]), dev(p["bias"])
+    _lib.check(lib.vitb200_layernorm(stream(), xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, dim, dt))
     torch.cuda.synchronize()
     err = np.abs(y.float().cpu().numpy() - want).max()
-    assert err < (4e-2 if bf16 else 2e-5)                                 # bf16: one rounding of |y| <~ 8
+    assert err < 2e-5 + 16 * ulp                                          # 16-bit: one rounding of |y| < 16
 
 
 @pytest.mark.parametrize("batch,T,heads", [(2, 65, 16), (3, 197, 12), (2, 257, 16), (1, 1025, 4), (2, 16, 1), (1, 1, 2), (1, 130, 3)])
-def test_attention_bf16(lib, batch, T, heads):
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_attention_tc(lib, batch, T, heads, fmt):
+    dt, tdt, ulp = DT16[fmt]
     rng = np.random.default_rng(T + heads)
     inner = heads * 64
-    qkv = dev(rng.standard_normal((batch * T, 3 * inner)) * 1.5, torch.bfloat16)
-    out = torch.empty((batch * T, inner), dtype=torch.bfloat16, device="cuda")
-    _lib.check(lib.vitb200_attention_bf16(stream(), qkv.data_ptr(), out.data_ptr(), batch, T, heads))
+    qkv = dev(rng.standard_normal((batch * T, 3 * inner)) * 1.5, tdt)
+    out = torch.empty((batch * T, inner), dtype=tdt, device="cuda")
+    _lib.check(lib.vitb200_attention_tc(stream(), qkv.data_ptr(), out.data_ptr(), batch, T, heads, dt))
     torch.cuda.synchronize()
     q, k, v = np.split(qkv.float().cpu().numpy().astype(np.float64).reshape(batch, T, 3 * inner), 3, axis=-1)
     th = lambda t: t.reshape(batch, T, heads, 64).transpose(0, 2, 1, 3)   # vit.py:71
@@ -148,8 +157,8 @@ def test_attention_bf16(lib, batch, T, heads):
     o = np.einsum("bhij,bhjd->bhid", vit_numpy.softmax_last(s), th(v))    # vit.py:75-78
     want = o.transpose(0, 2, 1, 3).reshape(batch * T, inner)              # vit.py:79
     err = np.abs(out.float().cpu().numpy() - want)
-    # P is rounded to bf16 before PV (2^-9 relative) and the output to bf16: |o| <~ 4
-    assert err.max() < 3e-2 and err.mean() < 3e-3, (err.max(), err.mean())
+    # P is rounded to 16 bits before PV and so is the output (|o| <~ 4); ex2.approx adds ~1e-4
+    assert err.max() < 8 * ulp + 1e-3 and err.mean() < ulp + 2e-4, (err.max(), err.mean())
 
 
 @pytest.mark.parametrize("batch,T,heads", [(1, 65, 16), (2, 197, 3), (1, 300, 2)])
@@ -158,7 +167,8 @@ def test_attention_f32(lib, batch, T, heads):
     inner = heads * 64
     qkv = rng.standard_normal((batch * T, 3 * inner)).astype(np.float32)
     out = torch.empty((batch * T, inner), device="cuda")
-    _lib.check(lib.vitb200_attention_f32(stream(), dev(qkv).data_ptr(), out.data_ptr(), batch, T, heads))
+    qd = dev(qkv)
+    _lib.check(lib.vitb200_attention_f32(stream(), qd.data_ptr(), out.data_ptr(), batch, T, heads))
     torch.cuda.synchronize()
     q, k, v = np.split(qkv.astype(np.float64).reshape(batch, T, 3 * inner), 3, axis=-1)
     th = lambda t: t.reshape(batch, T, heads, 64).transpose(0, 2, 1, 3)
@@ -168,19 +178,21 @@ def test_attention_f32(lib, batch, T, heads):
 
 
 @pytest.mark.parametrize("H,W,ph,pw,Cc", [(224, 224, 16, 16, 3), (224, 224, 14, 14, 3), (16, 32, 8, 16, 3), (32, 32, 8, 8, 1)])
-@pytest.mark.parametrize("bf16", [0, 1])
-def test_patchify(lib, H, W, ph, pw, Cc, bf16):
+@pytest.mark.parametrize("out", ["fp32", "bf16", "fp16"])
+def test_patchify(lib, H, W, ph, pw, Cc, out):
     B = 2
+    dt, tdt, _ = DT16.get(out, (_lib.DT_F32, torch.float32, 0.0))
     x = np.random.default_rng(H + pw).standard_normal((B, H, W, Cc)).astype(np.float32)
     K0 = ph * pw * Cc
-    Kpad = (K0 + 63) // 64 * 64 if bf16 else K0 + (K0 & 1)
+    Kpad = (K0 + 63) // 64 * 64 if out != "fp32" else K0 + (K0 & 1)
     Np = (H // ph) * (W // pw)
-    out = torch.full((B * Np, Kpad), 9.0, dtype=torch.bfloat16 if bf16 else torch.float32, device="cuda")
-    _lib.check(lib.vitb200_patchify(stream(), dev(x).data_ptr(), out.data_ptr(), B, H, W, Cc, ph, pw, Kpad, bf16))
+    y = torch.full((B * Np, Kpad), 9.0, dtype=tdt, device="cuda")
+    xd = dev(x)
+    _lib.check(lib.vitb200_patchify(stream(), xd.data_ptr(), y.data_ptr(), B, H, W, Cc, ph, pw, Kpad, dt))
     torch.cuda.synchronize()
     want = vit_numpy.patchify(x, ph, pw).reshape(B * Np, K0)              # vit.py:146
-    got = out.float().cpu().numpy()
-    ref = torch.as_tensor(want).to(torch.bfloat16).float().numpy() if bf16 else want
+    got = y.float().cpu().numpy()
+    ref = torch.as_tensor(want).to(tdt).float().numpy()
     np.testing.assert_array_equal(got[:, :K0], ref)                       # bit-exact (pure data movement + RN cast)
     assert not got[:, K0:].any()                                          # zero padding
 
@@ -190,29 +202,33 @@ def test_cls_rows_and_pool_layernorm(lib):
     rng = np.random.default_rng(1)
     cls, pos = rng.standard_normal(D).astype(np.float32), rng.standard_normal((T, D)).astype(np.float32)
     x = rng.standard_normal((B, T, D)).astype(np.float32)
-    xd = dev(x)
-    _lib.check(lib.vitb200_cls_rows(stream(), dev(cls).data_ptr(), dev(pos).data_ptr(), xd.data_ptr(), B, T, D))
+    xd, cd, pd = dev(x), dev(cls), dev(pos)
+    _lib.check(lib.vitb200_cls_rows(stream(), cd.data_ptr(), pd.data_ptr(), xd.data_ptr(), B, T, D))
     torch.cuda.synchronize()
     got = xd.cpu().numpy()
     np.testing.assert_array_equal(got[:, 0], np.broadcast_to(cls + pos[0], (B, D)))   # vit.py:151-153
     np.testing.assert_array_equal(got[:, 1:], x[:, 1:])
     p = {"scale": rng.standard_normal(D).astype(np.float32), "bias": rng.standard_normal(D).astype(np.float32)}
+    gd, bd = dev(p["scale"]), dev(p["bias"])
     for pool, name in ((0, "cls"), (1, "mean")):
         y = torch.empty((B, D), device="cuda")
-        _lib.check(lib.vitb200_pool_layernorm(stream(), xd.data_ptr(), dev(p["scale"]).data_ptr(),
-                                              dev(p["bias"]).data_ptr(), y.data_ptr(), B, T, D, pool, 0))
+        _lib.check(lib.vitb200_pool_layernorm(stream(), xd.data_ptr(), gd.data_ptr(), bd.data_ptr(),
+                                              y.data_ptr(), B, T, D, pool, _lib.DT_F32))
         torch.cuda.synchronize()
         g = got.astype(np.float64)
         pooled = g.mean(axis=1) if name == "mean" else g[:, 0]            # vit.py:159
         assert np.abs(y.cpu().numpy() - vit_numpy.layer_norm(pooled, p)).max() < 2e-5
 
 
-def test_pack_weight(lib):
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_pack_weight(lib, fmt):
+    dt, tdt, _ = DT16[fmt]
     K, N, Kpad = 588, 1280, 640                                           # ViT-H/14 patch kernel
     W = np.random.default_rng(2).standard_normal((K, N)).astype(np.float32)
-    Wt = torch.full((N, Kpad), 3.0, dtype=torch.bfloat16, device="cuda")
-    _lib.check(lib.vitb200_pack_weight_bf16(stream(), dev(W).data_ptr(), Wt.data_ptr(), K, N, Kpad))
+    Wt = torch.full((N, Kpad), 3.0, dtype=tdt, device="cuda")
+    Wd = dev(W)
+    _lib.check(lib.vitb200_pack_weight(stream(), Wd.data_ptr(), Wt.data_ptr(), K, N, Kpad, dt))
     torch.cuda.synchronize()
     got = Wt.float().cpu().numpy()
-    np.testing.assert_array_equal(got[:, :K], torch.as_tensor(W.T.copy()).to(torch.bfloat16).float().numpy())
+    np.testing.assert_array_equal(got[:, :K], torch.as_tensor(W.T.copy()).to(tdt).float().numpy())
     assert not got[:, K:].any()

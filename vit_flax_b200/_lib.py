@@ -12,9 +12,13 @@ LIB_PATH = Path(__file__).resolve().parent / "libvitb200.so"
 
 # error codes / enums (keep in sync with include/vitb200.h)
 OK = 0
-PREC_BF16, PREC_FP32 = 0, 1
+PREC_BF16, PREC_FP32, PREC_FP16 = 0, 1, 2
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_FP16}
 POOL_CLS, POOL_MEAN = 0, 1
-EPI_STORE_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32 = range(5)
+CATEGORIES = ["patchify", "gemm_patch", "cls_rows", "layernorm", "gemm_qkv", "attention", "gemm_out",
+              "gemm_ff1", "gemm_ff2", "pool_ln", "gemm_head"]
+EPI_STORE_16, EPI_BIAS_GELU_16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32 = range(5)
 
 
 class Config(C.Structure):
@@ -52,16 +56,17 @@ SIGNATURES = {
     "vitb200_finalize_params": (_i, [_vp, _vp]),
     "vitb200_forward": (_i, [_vp, _vp, _fp, _i, _fp]),
     "vitb200_forward_host": (_i, [_vp, _vp, _fp, _i, _fp]),
+    "vitb200_profile_forward": (_i, [_vp, _vp, _fp, _i, _fp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vitb200_debug_tokens": (_i, [_vp, _vp, _fp, _i]),
-    "vitb200_gemm_bf16": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i]),
+    "vitb200_gemm_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i]),
     "vitb200_gemm_f32": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i]),
     "vitb200_layernorm": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i]),
-    "vitb200_attention_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "vitb200_attention_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "vitb200_attention_f32": (_i, [_vp, _fp, _fp, _i, _i, _i]),
     "vitb200_patchify": (_i, [_vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
     "vitb200_cls_rows": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i]),
     "vitb200_pool_layernorm": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i]),
-    "vitb200_pack_weight_bf16": (_i, [_vp, _fp, _vp, _i, _i, _i]),
+    "vitb200_pack_weight": (_i, [_vp, _fp, _vp, _i, _i, _i, _i]),
 }
 
 _lib = None

@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 
 namespace vb {
@@ -29,7 +31,7 @@ struct Leaf {
 struct DenseW {
   int leaf_kernel = -1, leaf_bias = -1;   // indices into leaves
   int K = 0, N = 0, Kpad = 0;
-  __nv_bfloat16* wt = nullptr;            // bf16 [N, Kpad] (bf16 mode)
+  uint16_t* wt = nullptr;                 // bf16/fp16 [N, Kpad] (tensor-core modes)
   CUtensorMap tm{};                       // box 256 x 64 over wt
 };
 
@@ -71,7 +73,8 @@ struct vitb200_model {
   int device = 0;
   int Np = 0, T = 0, K0 = 0, K0pad = 0, inner = 0;
   bool project_out = true;
-  bool bf16 = true;
+  bool tc = true;          // tensor-core (16-bit operand) path, else fp32 SIMT path
+  int dt = VITB200_DT_BF16; // operand type of the tensor-core path
   bool finalized = false;
   bool head_tc = false;
 
@@ -83,10 +86,11 @@ struct vitb200_model {
 
   // activation workspace (bf16 mode uses the bf16 buffers, fp32 mode the f32 ones)
   DevBuf<float> x;                                   // residual stream [B*T, D] fp32 (both modes)
-  DevBuf<__nv_bfloat16> patches_h, xn_h, qkv_h, o_h, hid_h, pooled_h;
+  DevBuf<uint16_t> patches_h, xn_h, qkv_h, o_h, hid_h, pooled_h;
   DevBuf<float> patches_f, xn_f, qkv_f, o_f, hid_f, pooled_f;
   DevBuf<float> img_stage, logit_stage;              // forward_host staging
   std::map<int, ActMaps> act_maps;
+  std::vector<std::pair<int, cudaEvent_t>>* prof = nullptr;   // per-launch marks while profiling
 
   ~vitb200_model() {
     for (auto& l : leaves)
@@ -158,7 +162,7 @@ int alloc_workspace(vitb200_model* m) {
   const size_t R = B * m->T, Rp = B * m->Np;
   int rc;
   if ((rc = m->x.alloc(R * c.dim))) return rc;
-  if (m->bf16) {
+  if (m->tc) {
     if ((rc = m->patches_h.alloc(Rp * m->K0pad))) return rc;
     if ((rc = m->xn_h.alloc(R * c.dim))) return rc;
     if ((rc = m->qkv_h.alloc(R * 3 * m->inner))) return rc;
@@ -199,17 +203,27 @@ int get_act_maps(vitb200_model* m, int batch, const ActMaps** out) {
 int pack_dense(vitb200_model* m, DenseW& d, cudaStream_t st) {
   if (d.leaf_kernel < 0) return 0;
   if (d.wt == nullptr)
-    VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.wt), size_t(d.N) * d.Kpad * sizeof(__nv_bfloat16)));
-  int rc = launch_pack_weight_bf16(st, m->leaves[d.leaf_kernel].dev, d.wt, d.K, d.N, d.Kpad);
+    VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.wt), size_t(d.N) * d.Kpad * sizeof(uint16_t)));
+  int rc = launch_pack_weight(st, m->leaves[d.leaf_kernel].dev, d.wt, d.K, d.N, d.Kpad, m->dt);
   if (rc) return rc;
   return make_tmap_bf16_2d(&d.tm, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN);
 }
 
 inline const float* leaf_ptr(const vitb200_model* m, int idx) { return idx >= 0 ? m->leaves[idx].dev : nullptr; }
 
-__global__ void add_bf16_into_f32_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ x, int64_t n) {
+// profiling marks: one event BEFORE each launch (+ one at the end); launches are back to back
+// on one stream, so the gap between consecutive marks is that launch's duration.
+inline void mark(vitb200_model* m, cudaStream_t st, int cat) {
+  if (!m->prof) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  m->prof->emplace_back(cat, e);
+}
+
+__global__ void add_16_into_f32_kernel(const uint16_t* __restrict__ a, float* __restrict__ x, int64_t n, int dt) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i < n) x[i] += __bfloat162float(a[i]);
+  if (i < n) x[i] += dt == VITB200_DT_F16 ? __half2float(__ushort_as_half(a[i])) : __uint_as_float(uint32_t(a[i]) << 16);
 }
 __global__ void add_f32_into_f32_kernel(const float* __restrict__ a, float* __restrict__ x, int64_t n) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -217,7 +231,7 @@ __global__ void add_f32_into_f32_kernel(const float* __restrict__ a, float* __re
 }
 
 // ---- the forward schedule, bf16 / tcgen05 flavour ---------------------------
-int forward_bf16(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
+int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
   const auto& c = m->cfg;
   const int D = c.dim, I = m->inner, T = m->T, Np = m->Np;
   const int R = batch * T, Rp = batch * Np;
@@ -225,36 +239,52 @@ int forward_bf16(vitb200_model* m, cudaStream_t st, const float* images, int bat
   int rc;
   if ((rc = get_act_maps(m, batch, &am))) return rc;
   // vit.py:146  patchify (+ fp32->bf16 cast, zero pad to K0pad)
+  mark(m, st, VITB200_CAT_PATCHIFY);
   if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
-                            c.patch_h, c.patch_w, m->K0pad, true))) return rc;
+                            c.patch_h, c.patch_w, m->K0pad, m->dt))) return rc;
   // vit.py:147-153  Dense_0 + bias, placed at row b*T+1+t, + pos_embedding[1+t]
-  if ((rc = launch_gemm_bf16(st, am->patches, m->patch.tm, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
-                             Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np))) return rc;
+  mark(m, st, VITB200_CAT_GEMM_PATCH);
+  if ((rc = launch_gemm_tc(st, am->patches, m->patch.tm, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+                             Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt))) return rc;
+  mark(m, st, VITB200_CAT_CLS_ROWS);
   if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
   for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
     Layer& L = m->layers[l];
     // Residual(PreNorm(Attention))  vit.py:31,39,62-87
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, true))) return rc;
-    if ((rc = launch_gemm_bf16(st, am->xn, L.qkv.tm, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_BF16, nullptr, 0))) return rc;
-    if ((rc = launch_attention_bf16(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads))) return rc;
+    mark(m, st, VITB200_CAT_LAYERNORM);
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, m->dt))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_QKV);
+    if ((rc = launch_gemm_tc(st, am->xn, L.qkv.tm, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt))) return rc;
+    mark(m, st, VITB200_CAT_ATTENTION);
+    if ((rc = launch_attention_tc(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads, m->dt))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_OUT);
     if (m->project_out) {
-      if ((rc = launch_gemm_bf16(st, am->o, L.out.tm, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+      if ((rc = launch_gemm_tc(st, am->o, L.out.tm, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt))) return rc;
     } else {   // heads == 1 and dim == 64: to_out is the identity (vit.py:65,85)
       const int64_t n = int64_t(R) * D;
-      add_bf16_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_h.p, m->x.p, n);
-      VB_LAUNCH_CHECK("add_bf16_into_f32_kernel");
+      add_16_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_h.p, m->x.p, n, m->dt);
+      VB_LAUNCH_CHECK("add_16_into_f32_kernel");
     }
     // Residual(PreNorm(FeedForward))  vit.py:31,39,47-53
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, true))) return rc;
-    if ((rc = launch_gemm_bf16(st, am->xn, L.ff1.tm, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_BF16, nullptr, 0))) return rc;
-    if ((rc = launch_gemm_bf16(st, am->h, L.ff2.tm, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+    mark(m, st, VITB200_CAT_LAYERNORM);
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, m->dt))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_FF1);
+    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.tm, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_FF2);
+    if ((rc = launch_gemm_tc(st, am->h, L.ff2.tm, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt))) return rc;
   }
   // vit.py:159-165  pool, LayerNorm_0, Dense_1
   if (m->head_tc) {
-    if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, true))) return rc;
-    if ((rc = launch_gemm_bf16(st, am->pooled, m->head.tm, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
+    mark(m, st, VITB200_CAT_POOL_LN);
+    mark(m, st, VITB200_CAT_POOL_LN);
+  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, m->dt))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_HEAD);
+    if ((rc = launch_gemm_tc(st, am->pooled, m->head.tm, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0, m->dt))) return rc;
   } else {
-    if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, false))) return rc;
+    mark(m, st, VITB200_CAT_POOL_LN);
+    mark(m, st, VITB200_CAT_POOL_LN);
+  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_HEAD);
     if ((rc = launch_gemm_f32(st, m->pooled_f.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
   }
   return 0;
@@ -266,20 +296,24 @@ int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batc
   const int D = c.dim, I = m->inner, T = m->T, Np = m->Np;
   const int R = batch * T, Rp = batch * Np;
   int rc;
+  mark(m, st, VITB200_CAT_PATCHIFY);
   if ((rc = launch_patchify(st, images, m->patches_f.p, batch, c.image_h, c.image_w, c.channels,
-                            c.patch_h, c.patch_w, m->K0pad, false))) return rc;
-  // K = K0pad with zero-padded A columns; W rows beyond K0 are never read (A there is 0,
-  // and the kernel guards k < K with K = K0): use the true K0 and the padded lda via a copy-free trick:
-  // the SIMT kernel takes a dense [M,K] A, so run it on K0pad only when K0pad == K0.
-  if (m->K0pad != m->K0) return fail(VITB200_ERR_UNSUPPORTED, "internal: fp32 path expects K0pad == K0");
+                            c.patch_h, c.patch_w, m->K0pad, VITB200_DT_F32))) return rc;
+  // fp32 mode keeps K0pad == K0 (checked at create), so the patch matrix is a dense [Rp, K0].
+  mark(m, st, VITB200_CAT_GEMM_PATCH);
   if ((rc = launch_gemm_f32(st, m->patches_f.p, leaf_ptr(m, m->patch.leaf_kernel), leaf_ptr(m, m->patch.leaf_bias), m->x.p,
                             Rp, D, m->K0, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np))) return rc;
+  mark(m, st, VITB200_CAT_CLS_ROWS);
   if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
   for (int l = 0; l < c.depth; ++l) {
     Layer& L = m->layers[l];
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_f.p, R, D, false))) return rc;
-    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.qkv.leaf_kernel), nullptr, m->qkv_f.p, R, 3 * I, D, VITB200_EPI_STORE_BF16, nullptr, 0))) return rc;
+    mark(m, st, VITB200_CAT_LAYERNORM);
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_f.p, R, D, VITB200_DT_F32))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_QKV);
+    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.qkv.leaf_kernel), nullptr, m->qkv_f.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0))) return rc;
+    mark(m, st, VITB200_CAT_ATTENTION);
     if ((rc = launch_attention_f32(st, m->qkv_f.p, m->o_f.p, batch, T, c.heads))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_OUT);
     if (m->project_out) {
       if ((rc = launch_gemm_f32(st, m->o_f.p, leaf_ptr(m, L.out.leaf_kernel), leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
     } else {
@@ -287,11 +321,16 @@ int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batc
       add_f32_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_f.p, m->x.p, n);
       VB_LAUNCH_CHECK("add_f32_into_f32_kernel");
     }
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_f.p, R, D, false))) return rc;
-    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.ff1.leaf_kernel), leaf_ptr(m, L.ff1.leaf_bias), m->hid_f.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_BF16, nullptr, 0))) return rc;
+    mark(m, st, VITB200_CAT_LAYERNORM);
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_f.p, R, D, VITB200_DT_F32))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_FF1);
+    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.ff1.leaf_kernel), leaf_ptr(m, L.ff1.leaf_bias), m->hid_f.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_FF2);
     if ((rc = launch_gemm_f32(st, m->hid_f.p, leaf_ptr(m, L.ff2.leaf_kernel), leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
   }
-  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, false))) return rc;
+  mark(m, st, VITB200_CAT_POOL_LN);
+  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32))) return rc;
+  mark(m, st, VITB200_CAT_GEMM_HEAD);
   return launch_gemm_f32(st, m->pooled_f.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0);
 }
 
@@ -338,7 +377,7 @@ int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out) {
     return fail(VITB200_ERR_INVALID, "create: image dimensions must be divisible by the patch size");
   if (c.pool != VITB200_POOL_CLS && c.pool != VITB200_POOL_MEAN)     // vit.py:137
     return fail(VITB200_ERR_INVALID, "create: pool must be cls or mean");
-  if (c.precision != VITB200_PREC_BF16 && c.precision != VITB200_PREC_FP32)
+  if (c.precision != VITB200_PREC_BF16 && c.precision != VITB200_PREC_FP32 && c.precision != VITB200_PREC_FP16)
     return fail(VITB200_ERR_INVALID, "create: unknown precision");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -358,14 +397,15 @@ int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out) {
   m->Np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
   m->T = m->Np + 1;
   m->K0 = c.patch_h * c.patch_w * c.channels;
-  m->bf16 = c.precision == VITB200_PREC_BF16;
-  m->K0pad = m->bf16 ? int(round_up(m->K0, GEMM_BK)) : m->K0 + (m->K0 & 1);
+  m->tc = c.precision != VITB200_PREC_FP32;
+  m->dt = c.precision == VITB200_PREC_FP16 ? VITB200_DT_F16 : VITB200_DT_BF16;
+  m->K0pad = m->tc ? int(round_up(m->K0, GEMM_BK)) : m->K0 + (m->K0 & 1);
   m->inner = DIM_HEAD * c.heads;
   m->project_out = !(c.heads == 1 && DIM_HEAD == c.dim);             // vit.py:65
-  m->head_tc = m->bf16 && (c.num_classes % 8 == 0);
-  if (m->bf16 && (c.dim % 8 != 0 || c.mlp_dim % 8 != 0))
-    return fail(VITB200_ERR_UNSUPPORTED, "create: bf16 mode needs dim and mlp_dim to be multiples of 8");
-  if (!m->bf16 && m->K0pad != m->K0)
+  m->head_tc = m->tc && (c.num_classes % 8 == 0);
+  if (m->tc && (c.dim % 8 != 0 || c.mlp_dim % 8 != 0))
+    return fail(VITB200_ERR_UNSUPPORTED, "create: bf16/fp16 modes need dim and mlp_dim to be multiples of 8");
+  if (!m->tc && m->K0pad != m->K0)
     return fail(VITB200_ERR_UNSUPPORTED, "create: fp32 mode needs an even patch feature count");
   build_registry(m.get());
   int rc = alloc_workspace(m.get());
@@ -421,7 +461,7 @@ int vitb200_finalize_params(vitb200_model* m, void* stream) {
     if (!l.set) return fail(VITB200_ERR_PARAM_MISSING, "finalize_params: parameter '" + l.path + "' was never set");
   DeviceGuard guard(m->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (m->bf16) {
+  if (m->tc) {
     int rc;
     if ((rc = pack_dense(m, m->patch, st))) return rc;
     for (auto& L : m->layers) {
@@ -443,7 +483,7 @@ int vitb200_forward(vitb200_model* m, void* stream, const float* images_dev, int
   if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "forward: batch must be in [1, max_batch]");
   DeviceGuard guard(m->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return m->bf16 ? forward_bf16(m, st, images_dev, batch, logits_dev) : forward_f32(m, st, images_dev, batch, logits_dev);
+  return m->tc ? forward_tc(m, st, images_dev, batch, logits_dev) : forward_f32(m, st, images_dev, batch, logits_dev);
 }
 
 int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_host, int batch, float* logits_host) {
@@ -465,6 +505,33 @@ int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_hos
   return 0;
 }
 
+int vitb200_profile_forward(vitb200_model* m, void* stream, const float* images_dev, int batch, float* logits_dev,
+                            float* ms_by_category, int* launches_by_category) {
+  if (!m || !ms_by_category || !launches_by_category) return fail(VITB200_ERR_INVALID, "profile_forward: null argument");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<std::pair<int, cudaEvent_t>> marks;
+  marks.reserve(512);
+  m->prof = &marks;
+  int rc = vitb200_forward(m, stream, images_dev, batch, logits_dev);
+  mark(m, st, -1);
+  m->prof = nullptr;
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (int c = 0; c < VITB200_NUM_CATEGORIES; ++c) { ms_by_category[c] = 0.f; launches_by_category[c] = 0; }
+  if (rc == 0 && e == cudaSuccess) {
+    for (size_t i = 0; i + 1 < marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[i].second, marks[i + 1].second);
+      const int c = marks[i].first;
+      if (c >= 0 && c < VITB200_NUM_CATEGORIES) { ms_by_category[c] += ms; launches_by_category[c] += 1; }
+    }
+  }
+  for (auto& mk : marks) cudaEventDestroy(mk.second);
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "profile_forward: cudaStreamSynchronize");
+  return 0;
+}
+
 int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int batch) {
   if (!m || !tokens_host) return fail(VITB200_ERR_INVALID, "debug_tokens: null argument");
   if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "debug_tokens: bad batch");
@@ -476,14 +543,17 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 }
 
 // ---- per-kernel entry points ------------------------------------------------
-int vitb200_gemm_bf16(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
-                      int K, int epilogue, const float* aux, int tokens_per_image) {
-  if (!A || !Wt || !C) return fail(VITB200_ERR_INVALID, "gemm_bf16: null pointer");
+int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
+                    int K, int epilogue, const float* aux, int tokens_per_image, int dtype) {
+  if (!A || !Wt || !C) return fail(VITB200_ERR_INVALID, "gemm_tc: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
+  if ((N % 8) != 0 || (K % 8) != 0)
+    return fail(VITB200_ERR_INVALID, "gemm_tc: N and K must be multiples of 8");
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap_bf16_2d(&ta, A, M, K, K, GEMM_BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tb, Wt, N, K, K, GEMM_BN))) return rc;
-  return launch_gemm_bf16(static_cast<cudaStream_t>(stream), ta, tb, bias, C, M, N, K, epilogue, aux, tokens_per_image);
+  return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, bias, C, M, N, K, epilogue, aux, tokens_per_image, dtype);
 }
 
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias, float* C, int M, int N,
@@ -493,15 +563,14 @@ int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* 
 }
 
 int vitb200_layernorm(void* stream, const float* x, const float* scale, const float* bias, void* y, int rows,
-                      int dim, int out_bf16) {
+                      int dim, int out_dtype) {
   if (!x || !scale || !bias || !y) return fail(VITB200_ERR_INVALID, "layernorm: null pointer");
-  return launch_layernorm(static_cast<cudaStream_t>(stream), x, scale, bias, y, rows, dim, out_bf16 != 0);
+  return launch_layernorm(static_cast<cudaStream_t>(stream), x, scale, bias, y, rows, dim, out_dtype);
 }
 
-int vitb200_attention_bf16(void* stream, const void* qkv, void* out, int batch, int T, int heads) {
-  if (!qkv || !out) return fail(VITB200_ERR_INVALID, "attention_bf16: null pointer");
-  return launch_attention_bf16(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(qkv),
-                               static_cast<__nv_bfloat16*>(out), batch, T, heads);
+int vitb200_attention_tc(void* stream, const void* qkv, void* out, int batch, int T, int heads, int dtype) {
+  if (!qkv || !out) return fail(VITB200_ERR_INVALID, "attention_tc: null pointer");
+  return launch_attention_tc(static_cast<cudaStream_t>(stream), qkv, out, batch, T, heads, dtype);
 }
 
 int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads) {
@@ -510,9 +579,9 @@ int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch,
 }
 
 int vitb200_patchify(void* stream, const float* images, void* patches, int batch, int H, int W, int C, int ph,
-                     int pw, int Kpad, int out_bf16) {
+                     int pw, int Kpad, int out_dtype) {
   if (!images || !patches) return fail(VITB200_ERR_INVALID, "patchify: null pointer");
-  return launch_patchify(static_cast<cudaStream_t>(stream), images, patches, batch, H, W, C, ph, pw, Kpad, out_bf16 != 0);
+  return launch_patchify(static_cast<cudaStream_t>(stream), images, patches, batch, H, W, C, ph, pw, Kpad, out_dtype);
 }
 
 int vitb200_cls_rows(void* stream, const float* cls, const float* pos, float* x, int batch, int T, int dim) {
@@ -521,15 +590,15 @@ int vitb200_cls_rows(void* stream, const float* cls, const float* pos, float* x,
 }
 
 int vitb200_pool_layernorm(void* stream, const float* x, const float* scale, const float* bias, void* y,
-                           int batch, int T, int dim, int pool, int out_bf16) {
+                           int batch, int T, int dim, int pool, int out_dtype) {
   if (!x || !scale || !bias || !y) return fail(VITB200_ERR_INVALID, "pool_layernorm: null pointer");
-  return launch_pool_layernorm(static_cast<cudaStream_t>(stream), x, scale, bias, y, batch, T, dim, pool, out_bf16 != 0);
+  return launch_pool_layernorm(static_cast<cudaStream_t>(stream), x, scale, bias, y, batch, T, dim, pool, out_dtype);
 }
 
-int vitb200_pack_weight_bf16(void* stream, const float* W, void* Wt, int K, int N, int Kpad) {
-  if (!W || !Wt) return fail(VITB200_ERR_INVALID, "pack_weight_bf16: null pointer");
-  if (Kpad < K) return fail(VITB200_ERR_INVALID, "pack_weight_bf16: Kpad < K");
-  return launch_pack_weight_bf16(static_cast<cudaStream_t>(stream), W, static_cast<__nv_bfloat16*>(Wt), K, N, Kpad);
+int vitb200_pack_weight(void* stream, const float* W, void* Wt, int K, int N, int Kpad, int dtype) {
+  if (!W || !Wt) return fail(VITB200_ERR_INVALID, "pack_weight: null pointer");
+  if (Kpad < K) return fail(VITB200_ERR_INVALID, "pack_weight: Kpad < K");
+  return launch_pack_weight(static_cast<cudaStream_t>(stream), W, Wt, K, N, Kpad, dtype);
 }
 
 }  // extern "C"

@@ -27,20 +27,21 @@ __device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
 }
 
 // rows [row0, row0+nrows) of a [*, ld] bf16 matrix (64 columns starting at col0) -> smem
-__device__ __forceinline__ void load_rows_async(uint32_t sbase, const __nv_bfloat16* g, int64_t ld,
+__device__ __forceinline__ void load_rows_async(uint32_t sbase, const uint16_t* g, int64_t ld,
                                                 int row0, int nrows, int row_limit, int tid,
                                                 int nthreads) {
   for (int i = tid; i < nrows * 8; i += nthreads) {
     const int r = i >> 3, c = i & 7;
     const int grow = row0 + r;
     const bool ok = grow < row_limit;
-    const __nv_bfloat16* src = g + int64_t(ok ? grow : 0) * ld + c * 8;
+    const uint16_t* src = g + int64_t(ok ? grow : 0) * ld + c * 8;
     cp_async16(swz(sbase, r, c), src, ok);
   }
 }
 
+template <int kDT>
 __global__ void __launch_bounds__(MAX_WARPS * 32, 1)
-attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+attention_tc_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out,
                       int T, int heads) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nwarps = blockDim.x >> 5;
@@ -49,9 +50,9 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
   const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads;
   const int inner = heads * DH;
   const int64_t ld = 3 * int64_t(inner);
-  const __nv_bfloat16* qbase = qkv + int64_t(b) * T * ld + h * DH;
-  const __nv_bfloat16* kbase = qbase + inner;
-  const __nv_bfloat16* vbase = qbase + 2 * inner;
+  const uint16_t* qbase = qkv + int64_t(b) * T * ld + h * DH;
+  const uint16_t* kbase = qbase + inner;
+  const uint16_t* vbase = qbase + 2 * inner;
 
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK = sQ + uint32_t(nwarps) * 16 * ROW_BYTES;
@@ -117,8 +118,8 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
             const int key = p * 16 + (mi >> 1) * 8 + r;
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4(swz(kS, key, ks * 2 + (mi & 1)), b0, b1, b2, b3);
-            mma_bf16_16816(s[2 * p], qf[ks], b0, b1);
-            mma_bf16_16816(s[2 * p + 1], qf[ks], b2, b3);
+            mma_16816<kDT>(s[2 * p], qf[ks], b0, b1);
+            mma_16816<kDT>(s[2 * p + 1], qf[ks], b2, b3);
           }
         }
       }
@@ -153,8 +154,8 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
         l_run[0] += p0 + p1;
         l_run[1] += p2 + p3;
         const int j = nt >> 1;
-        if ((nt & 1) == 0) { pf[j][0] = pack_bf16x2(p0, p1); pf[j][1] = pack_bf16x2(p2, p3); }
-        else               { pf[j][2] = pack_bf16x2(p0, p1); pf[j][3] = pack_bf16x2(p2, p3); }
+        if ((nt & 1) == 0) { pf[j][0] = pack2<kDT>(p0, p1); pf[j][1] = pack2<kDT>(p2, p3); }
+        else               { pf[j][2] = pack2<kDT>(p0, p1); pf[j][3] = pack2<kDT>(p2, p3); }
       }
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt) {
@@ -171,8 +172,8 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
             const int key = j * 16 + (mi & 1) * 8 + r;
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4_trans(swz(vS, key, dp * 2 + (mi >> 1)), b0, b1, b2, b3);
-            mma_bf16_16816(o[2 * dp], pf[j], b0, b1);
-            mma_bf16_16816(o[2 * dp + 1], pf[j], b2, b3);
+            mma_16816<kDT>(o[2 * dp], pf[j], b0, b1);
+            mma_16816<kDT>(o[2 * dp + 1], pf[j], b2, b3);
           }
         }
       }
@@ -195,9 +196,9 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
       const int row_a = warp * 16 + g, row_b = row_a + 8;
       const uint32_t off = uint32_t(tg) * 4;      // 2 bf16 = 4 bytes inside the 16 B chunk
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(swz(sQ, row_a, dt) + off),
-                   "r"(pack_bf16x2(o[dt][0] * inv[0], o[dt][1] * inv[0])) : "memory");
+                   "r"(pack2<kDT>(o[dt][0] * inv[0], o[dt][1] * inv[0])) : "memory");
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(swz(sQ, row_b, dt) + off),
-                   "r"(pack_bf16x2(o[dt][2] * inv[1], o[dt][3] * inv[1])) : "memory");
+                   "r"(pack2<kDT>(o[dt][2] * inv[1], o[dt][3] * inv[1])) : "memory");
     }
     __syncwarp();
 #pragma unroll
@@ -218,26 +219,36 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 
 }  // namespace
 
-int launch_attention_bf16(cudaStream_t stream, const __nv_bfloat16* qkv, __nv_bfloat16* out,
-                          int batch, int T, int heads) {
-  if (batch <= 0 || T <= 0 || heads <= 0)
-    return fail(VITB200_ERR_INVALID, "attention_bf16: empty problem");
-  if (int64_t(batch) * heads > 65535)
-    return fail(VITB200_ERR_INVALID, "attention_bf16: batch*heads exceeds grid.y limit; chunk the batch");
+template <int kDT>
+static int launch_attention_t(cudaStream_t stream, const uint16_t* qkv, uint16_t* out, int batch,
+                              int T, int heads) {
   const int nq16 = ceil_div(T, 16);
   const int ctas = ceil_div(nq16, MAX_WARPS);
   const int nwarps = ceil_div(nq16, ctas);
   const size_t smem = size_t(nwarps) * 16 * ROW_BYTES + 4 * size_t(KV_BLOCK) * ROW_BYTES;
   static bool configured = false;
   if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(attention_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<kDT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  MAX_WARPS * 16 * ROW_BYTES + 4 * KV_BLOCK * ROW_BYTES));
     configured = true;
   }
   dim3 grid(ctas, batch * heads);
-  attention_bf16_kernel<<<grid, nwarps * 32, smem, stream>>>(qkv, out, T, heads);
-  VB_LAUNCH_CHECK("attention_bf16_kernel");
+  attention_tc_kernel<kDT><<<grid, nwarps * 32, smem, stream>>>(qkv, out, T, heads);
+  VB_LAUNCH_CHECK("attention_tc_kernel");
   return 0;
+}
+
+int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads,
+                        int dtype) {
+  if (batch <= 0 || T <= 0 || heads <= 0)
+    return fail(VITB200_ERR_INVALID, "attention_tc: empty problem");
+  if (int64_t(batch) * heads > 65535)
+    return fail(VITB200_ERR_INVALID, "attention_tc: batch*heads exceeds grid.y limit; chunk the batch");
+  if (dtype == DT_BF16)
+    return launch_attention_t<DT_BF16>(stream, static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), batch, T, heads);
+  if (dtype == DT_F16)
+    return launch_attention_t<DT_F16>(stream, static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), batch, T, heads);
+  return fail(VITB200_ERR_INVALID, "attention_tc: dtype must be bf16 or fp16");
 }
 
 }  // namespace vb

@@ -38,7 +38,7 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 int sm_count();   // SMs of the current device (cached per device)
 
 // ---- TMA descriptors -----------------------------------------------------
-// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, row pitch = ld
+// 2-D 16-bit (bf16/fp16) row-major tensor [rows, cols] (cols contiguous, row pitch = ld
 // elements), box = [box_rows, 64 cols] with 128-byte swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                       int box_rows);
@@ -48,26 +48,27 @@ constexpr int GEMM_BM = 128;   // tcgen05 tile rows (A box rows)
 constexpr int GEMM_BN = 256;   // tcgen05 tile cols (Wt box rows)
 constexpr int GEMM_BK = 64;
 
-int launch_gemm_bf16(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                     const float* bias, void* C, int M, int N, int K, int epilogue,
-                     const float* aux, int tokens_per_image);
+// `dtype` / `out_dtype` are VITB200_DT_* values.
+int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                   const float* bias, void* C, int M, int N, int K, int epilogue,
+                   const float* aux, int tokens_per_image, int dtype);
 int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const float* bias,
                     float* C, int M, int N, int K, int epilogue, const float* aux,
                     int tokens_per_image);
 int launch_layernorm(cudaStream_t stream, const float* x, const float* scale, const float* bias,
-                     void* y, int rows, int dim, bool out_bf16);
-int launch_attention_bf16(cudaStream_t stream, const __nv_bfloat16* qkv, __nv_bfloat16* out,
-                          int batch, int T, int heads);
+                     void* y, int rows, int dim, int out_dtype);
+int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
+                        int heads, int dtype);
 int launch_attention_f32(cudaStream_t stream, const float* qkv, float* out, int batch, int T,
                          int heads);
 int launch_patchify(cudaStream_t stream, const float* images, void* patches, int batch, int H,
-                    int W, int C, int ph, int pw, int Kpad, bool out_bf16);
+                    int W, int C, int ph, int pw, int Kpad, int out_dtype);
 int launch_cls_rows(cudaStream_t stream, const float* cls, const float* pos, float* x, int batch,
                     int T, int dim);
 int launch_pool_layernorm(cudaStream_t stream, const float* x, const float* scale,
                           const float* bias, void* y, int batch, int T, int dim, int pool,
-                          bool out_bf16);
-int launch_pack_weight_bf16(cudaStream_t stream, const float* W, __nv_bfloat16* Wt, int K, int N,
-                            int Kpad);
+                          int out_dtype);
+int launch_pack_weight(cudaStream_t stream, const float* W, void* Wt, int K, int N, int Kpad,
+                       int dtype);
 
 }  // namespace vb

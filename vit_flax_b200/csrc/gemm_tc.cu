@@ -1,4 +1,4 @@
-// gemm_tc.cu -- K3: persistent, warp-specialised tcgen05 bf16 GEMM with fused
+// gemm_tc.cu -- K3: persistent, warp-specialised tcgen05 16-bit (bf16 or fp16 operands) GEMM with fused
 // epilogues.  acc[M,N] = A[M,K] x Wt[N,K]^T, fp32 accumulation in TMEM.
 //
 // Replaces every flax `nn.Dense` on the hot path (vit.py:48,51,68,82,147,165)
@@ -39,9 +39,9 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.0f + tanh_approx(u));
 }
 
-template <int kEpi>
+template <int kEpi, int kDT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ bias, void* __restrict__ Cout,
                     int M, int N, int K, const float* __restrict__ aux, int tpi) {
@@ -108,7 +108,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = umma_idesc_16(BM, BN, kDT == DT_F16 ? 0 : 1);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -165,15 +165,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
         tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
         tmem_ld_wait();
         if (row_ok) {
-          if constexpr (kEpi == VITB200_EPI_STORE_BF16 || kEpi == VITB200_EPI_BIAS_GELU_BF16) {
-            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(Cout) + out_row * N + n0;
+          if constexpr (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16) {
+            uint16_t* crow = reinterpret_cast<uint16_t*>(Cout) + out_row * N + n0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (n0 + j * 8 < N) {
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]);
-                if constexpr (kEpi == VITB200_EPI_BIAS_GELU_BF16) {
+                if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16) {
                   const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j * 8));
                   const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j * 8 + 4));
                   v[0] = gelu_tanh_fast(v[0] + b0.x); v[1] = gelu_tanh_fast(v[1] + b0.y);
@@ -182,8 +182,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                   v[6] = gelu_tanh_fast(v[6] + b1.z); v[7] = gelu_tanh_fast(v[7] + b1.w);
                 }
                 uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                o.x = pack2<kDT>(v[0], v[1]); o.y = pack2<kDT>(v[2], v[3]);
+                o.z = pack2<kDT>(v[4], v[5]); o.w = pack2<kDT>(v[6], v[7]);
                 *reinterpret_cast<uint4*>(crow + j * 8) = o;
               }
             }
@@ -228,49 +228,60 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   }
 }
 
-template <int kEpi>
+template <int kEpi, int kDT>
 int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                const float* bias, void* C, int M, int N, int K, const float* aux, int tpi) {
   static bool configured = false;   // per-process; attribute is per-function, device-agnostic
   if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<kEpi>,
+    VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<kEpi><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, bias, C, M, N, K,
-                                                                      aux, tpi);
-  VB_LAUNCH_CHECK("gemm_bf16_tc_kernel");
+  gemm_tc_kernel<kEpi, kDT><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, bias, C, M, N, K,
+                                                                       aux, tpi);
+  VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
+}
+
+template <int kDT>
+int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                 const float* bias, void* C, int M, int N, int K, int epilogue, const float* aux,
+                 int tpi) {
+  switch (epilogue) {
+    case VITB200_EPI_STORE_16:
+      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_BIAS_GELU_16:
+      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_BIAS_RESID_F32:
+      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_BIAS_F32:
+      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_PATCH_F32:
+      if (aux == nullptr || tpi <= 0)
+        return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
+      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+    default:
+      return fail(VITB200_ERR_INVALID, "gemm_tc: unknown epilogue");
+  }
 }
 
 }  // namespace
 
-int launch_gemm_bf16(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                     const float* bias, void* C, int M, int N, int K, int epilogue,
-                     const float* aux, int tpi) {
-  if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_bf16: empty problem");
+int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                   const float* bias, void* C, int M, int N, int K, int epilogue,
+                   const float* aux, int tpi, int dtype) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
-    return fail(VITB200_ERR_INVALID, "gemm_bf16: N and K must be multiples of 8");
-  if (epilogue != VITB200_EPI_STORE_BF16 && bias == nullptr)
-    return fail(VITB200_ERR_INVALID, "gemm_bf16: epilogue needs a bias");
-  switch (epilogue) {
-    case VITB200_EPI_STORE_BF16:
-      return launch_one<VITB200_EPI_STORE_BF16>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_BIAS_GELU_BF16:
-      return launch_one<VITB200_EPI_BIAS_GELU_BF16>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_BIAS_RESID_F32:
-      return launch_one<VITB200_EPI_BIAS_RESID_F32>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_BIAS_F32:
-      return launch_one<VITB200_EPI_BIAS_F32>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_PATCH_F32:
-      if (aux == nullptr || tpi <= 0)
-        return fail(VITB200_ERR_INVALID, "gemm_bf16: PATCH epilogue needs pos_embedding and tokens");
-      return launch_one<VITB200_EPI_PATCH_F32>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
-    default:
-      return fail(VITB200_ERR_INVALID, "gemm_bf16: unknown epilogue");
-  }
+    return fail(VITB200_ERR_INVALID, "gemm_tc: N and K must be multiples of 8");
+  if (epilogue != VITB200_EPI_STORE_16 && bias == nullptr)
+    return fail(VITB200_ERR_INVALID, "gemm_tc: epilogue needs a bias");
+  if (dtype == DT_BF16)
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, bias, C, M, N, K, epilogue, aux, tpi);
+  if (dtype == DT_F16)
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, bias, C, M, N, K, epilogue, aux, tpi);
+  return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 
 }  // namespace vb

@@ -3,7 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace vb {
 
@@ -46,8 +48,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// Spin with a watchdog: a protocol bug traps (launch fails with an error) instead of
+// hanging the GPU.  ~4e9 cycles is seconds, far beyond any legitimate wait here.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("vitb200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+             int(blockIdx.x), int(threadIdx.x), bar, parity);
+      __trap();
+    }
+  }
 }
 // cluster-scope acquire wait (barrier completed by a remote CTA's arrive)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -194,11 +206,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t addr) {
   return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) |
          (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, K-major A; B major selectable.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_major = 0) {
+// kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32, K-major A; B major selectable.
+// `fmt`: 0 = F16, 1 = BF16 (UMMA F16F32Format).
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fmt, int b_mn_major = 0) {
   return (1u << 4)                       // D format  : F32
-         | (1u << 7)                     // A format  : BF16
-         | (1u << 10)                    // B format  : BF16
+         | (uint32_t(fmt) << 7)          // A format
+         | (uint32_t(fmt) << 10)         // B format
          | (uint32_t(b_mn_major) << 16)  // B major   : 0 = K, 1 = MN
          | (uint32_t(N >> 3) << 17)      // N >> 3
          | (uint32_t(M >> 4) << 24);     // M >> 4
@@ -236,19 +249,47 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4],
-                                               uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
-      "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// 16-bit storage formats of the tensor-core path (values of VITB200_DT_*)
+constexpr int DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2;
+
+// D(16x8,f32) += A(16x16,row) * B(16x8,col), operands bf16 or fp16
+template <int kDT>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                          uint32_t b1) {
+  if constexpr (kDT == DT_F16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 "
+        "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
+        "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
-  return *reinterpret_cast<uint32_t*>(&v);
+// two fp32 -> packed 16-bit pair (lo in bits [0,16)); fp16 saturates to +-65504 instead of inf
+template <int kDT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  if constexpr (kDT == DT_F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+template <int kDT>
+__device__ __forceinline__ uint16_t cvt16(float v) {
+  return static_cast<uint16_t>(pack2<kDT>(v, 0.f) & 0xFFFFu);
+}
+template <int kDT>
+__device__ __forceinline__ float to_f32(uint16_t h) {
+  if constexpr (kDT == DT_F16) return __half2float(__ushort_as_half(h));
+  else return __uint_as_float(uint32_t(h) << 16);
 }
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;

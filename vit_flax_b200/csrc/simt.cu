@@ -28,7 +28,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ------------------------------------------------------------- LayerNorm (K2)
 // One warp per row, the row lives in registers (<= 16 float4 per lane => dim <= 2048).
-template <int NV, bool kBf16>
+template <int NV, int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                       const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
@@ -72,11 +72,11 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ sca
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if constexpr (kBf16) {
+      if constexpr (kDT != DT_F32) {
         uint2 p;
-        p.x = pack_bf16x2(o.x, o.y);
-        p.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + int64_t(row) * dim)[c] = p;
+        p.x = pack2<kDT>(o.x, o.y);
+        p.y = pack2<kDT>(o.z, o.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + int64_t(row) * dim)[c] = p;
       } else {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + int64_t(row) * dim)[c] = o;
       }
@@ -85,7 +85,7 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ sca
 }
 
 // Any dim: one warp per row, three passes over the (cached) row.
-template <bool kBf16>
+template <int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                          const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
@@ -101,12 +101,12 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
   const float rstd = rsqrtf(warp_sum(ss) / float(dim) + LN_EPS);
   for (int c = lane; c < dim; c += 32) {
     const float o = (xr[c] - mean) * rstd * scale[c] + bias[c];
-    if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(y)[int64_t(row) * dim + c] = __float2bfloat16_rn(o);
+    if constexpr (kDT != DT_F32) reinterpret_cast<uint16_t*>(y)[int64_t(row) * dim + c] = cvt16<kDT>(o);
     else reinterpret_cast<float*>(y)[int64_t(row) * dim + c] = o;
   }
 }
 
-template <bool kBf16>
+template <int kDT>
 int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b, void* y, int rows,
                 int dim) {
   const int grid = ceil_div(rows, 8);
@@ -114,14 +114,14 @@ int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b,
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                      reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
   if (!vec) {
-    layernorm_generic_kernel<kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    layernorm_generic_kernel<kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
   } else {
     const int nv = ceil_div(dim, 128);
-    if (nv <= 4) layernorm_rows_kernel<4, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else if (nv <= 6) layernorm_rows_kernel<6, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else if (nv <= 8) layernorm_rows_kernel<8, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else if (nv <= 10) layernorm_rows_kernel<10, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else layernorm_rows_kernel<16, kBf16><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    if (nv <= 4) layernorm_rows_kernel<4, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else if (nv <= 6) layernorm_rows_kernel<6, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else if (nv <= 8) layernorm_rows_kernel<8, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else if (nv <= 10) layernorm_rows_kernel<10, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    else layernorm_rows_kernel<16, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
   }
   VB_LAUNCH_CHECK("layernorm");
   return 0;
@@ -129,7 +129,7 @@ int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b,
 
 // -------------------------------------------------------------- patchify (K1a)
 // out[(b*Np + t), f], f = (p1*pw + p2)*C + c  <-  x[b, hh*ph+p1, ww*pw+p2, c]; zero pad f >= K0.
-template <bool kBf16>
+template <int kDT>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
                 int C, int ph, int pw, int Kpad) {
@@ -156,8 +156,8 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
         v[e] = 0.f;
       }
     }
-    if constexpr (kBf16) {
-      reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(v[0], v[1]);
+    if constexpr (kDT != DT_F32) {
+      reinterpret_cast<uint32_t*>(out)[i] = pack2<kDT>(v[0], v[1]);
     } else {
       reinterpret_cast<float2*>(out)[i] = make_float2(v[0], v[1]);
     }
@@ -174,7 +174,7 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
 }
 
 // ------------------------------------------------- pool + head LayerNorm (K5a)
-template <bool kBf16>
+template <int kDT>
 __global__ void __launch_bounds__(256)
 pool_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                       const float* __restrict__ bias, void* __restrict__ y, int T, int dim,
@@ -214,15 +214,16 @@ pool_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ sca
   const float rstd = rsqrtf(tot2 / float(dim) + LN_EPS);
   for (int d = threadIdx.x; d < dim; d += blockDim.x) {
     const float o = (pooled[d] - mean) * rstd * scale[d] + bias[d];
-    if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(y)[int64_t(b) * dim + d] = __float2bfloat16_rn(o);
+    if constexpr (kDT != DT_F32) reinterpret_cast<uint16_t*>(y)[int64_t(b) * dim + d] = cvt16<kDT>(o);
     else reinterpret_cast<float*>(y)[int64_t(b) * dim + d] = o;
   }
 }
 
 // ----------------------------------------------------------- weight pack (K7)
 // W fp32 [K, N] (flax kernel) -> Wt bf16 [N, Kpad], zero padded along K.
+template <int kDT>
 __global__ void __launch_bounds__(256)
-pack_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int Kpad) {
+pack_weight_kernel(const float* __restrict__ W, uint16_t* __restrict__ Wt, int K, int N, int Kpad) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -233,7 +234,7 @@ pack_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, 
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     const int n = n0 + r, k = k0 + tx;
-    if (n < N && k < Kpad) Wt[int64_t(n) * Kpad + k] = __float2bfloat16_rn(tile[tx][r]);
+    if (n < N && k < Kpad) Wt[int64_t(n) * Kpad + k] = cvt16<kDT>(tile[tx][r]);
   }
 }
 
@@ -303,8 +304,8 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = acc[i][j];
-      if constexpr (kEpi != VITB200_EPI_STORE_BF16) v += bias[n];
-      if constexpr (kEpi == VITB200_EPI_BIAS_GELU_BF16) v = gelu_tanh_exact(v);
+      if constexpr (kEpi != VITB200_EPI_STORE_16) v += bias[n];
+      if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16) v = gelu_tanh_exact(v);
       if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32) v += C[out_row * N + n];
       if constexpr (kEpi == VITB200_EPI_PATCH_F32) v += pos_row[n];
       C[out_row * N + n] = v;
@@ -378,15 +379,23 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
+#define VB_DT_DISPATCH(dt, CALL)                                                        \
+  switch (dt) {                                                                        \
+    case DT_F32: { constexpr int kDT = DT_F32; CALL; break; }                          \
+    case DT_BF16: { constexpr int kDT = DT_BF16; CALL; break; }                        \
+    case DT_F16: { constexpr int kDT = DT_F16; CALL; break; }                          \
+    default: return fail(VITB200_ERR_INVALID, "dtype must be VITB200_DT_F32/BF16/F16"); \
+  }
+
 int launch_layernorm(cudaStream_t st, const float* x, const float* g, const float* b, void* y,
-                     int rows, int dim, bool out_bf16) {
+                     int rows, int dim, int out_dtype) {
   if (rows <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "layernorm: empty problem");
-  return out_bf16 ? launch_ln_t<true>(st, x, g, b, y, rows, dim)
-                  : launch_ln_t<false>(st, x, g, b, y, rows, dim);
+  VB_DT_DISPATCH(out_dtype, return launch_ln_t<kDT>(st, x, g, b, y, rows, dim));
+  return 0;
 }
 
 int launch_patchify(cudaStream_t st, const float* images, void* patches, int batch, int H, int W,
-                    int C, int ph, int pw, int Kpad, bool out_bf16) {
+                    int C, int ph, int pw, int Kpad, int out_dtype) {
   if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || ph <= 0 || pw <= 0)
     return fail(VITB200_ERR_INVALID, "patchify: empty problem");
   if (H % ph != 0 || W % pw != 0)
@@ -395,8 +404,7 @@ int launch_patchify(cudaStream_t st, const float* images, void* patches, int bat
     return fail(VITB200_ERR_INVALID, "patchify: Kpad must be even and >= ph*pw*C");
   const int64_t total = int64_t(batch) * (H / ph) * (W / pw) * (Kpad / 2);
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
-  if (out_bf16) patchify_kernel<true><<<grid, 256, 0, st>>>(images, patches, batch, H, W, C, ph, pw, Kpad);
-  else patchify_kernel<false><<<grid, 256, 0, st>>>(images, patches, batch, H, W, C, ph, pw, Kpad);
+  VB_DT_DISPATCH(out_dtype, (patchify_kernel<kDT><<<grid, 256, 0, st>>>(images, patches, batch, H, W, C, ph, pw, Kpad)));
   VB_LAUNCH_CHECK("patchify_kernel");
   return 0;
 }
@@ -410,20 +418,20 @@ int launch_cls_rows(cudaStream_t st, const float* cls, const float* pos, float* 
 }
 
 int launch_pool_layernorm(cudaStream_t st, const float* x, const float* g, const float* b, void* y,
-                          int batch, int T, int dim, int pool, bool out_bf16) {
+                          int batch, int T, int dim, int pool, int out_dtype) {
   if (pool != VITB200_POOL_CLS && pool != VITB200_POOL_MEAN)
     return fail(VITB200_ERR_INVALID, "pool must be cls or mean (vit.py:137)");
   const size_t smem = (size_t(dim) + 16) * sizeof(float);
-  if (out_bf16) pool_layernorm_kernel<true><<<batch, 256, smem, st>>>(x, g, b, y, T, dim, pool);
-  else pool_layernorm_kernel<false><<<batch, 256, smem, st>>>(x, g, b, y, T, dim, pool);
+  VB_DT_DISPATCH(out_dtype, (pool_layernorm_kernel<kDT><<<batch, 256, smem, st>>>(x, g, b, y, T, dim, pool)));
   VB_LAUNCH_CHECK("pool_layernorm_kernel");
   return 0;
 }
 
-int launch_pack_weight_bf16(cudaStream_t st, const float* W, __nv_bfloat16* Wt, int K, int N,
-                            int Kpad) {
+int launch_pack_weight(cudaStream_t st, const float* W, void* Wt, int K, int N, int Kpad, int dtype) {
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(VITB200_ERR_INVALID, "pack_weight: dtype must be bf16 or fp16");
   dim3 grid(ceil_div(Kpad, 32), ceil_div(N, 32));
-  pack_weight_kernel<<<grid, 256, 0, st>>>(W, Wt, K, N, Kpad);
+  if (dtype == DT_BF16) pack_weight_kernel<DT_BF16><<<grid, 256, 0, st>>>(W, static_cast<uint16_t*>(Wt), K, N, Kpad);
+  else pack_weight_kernel<DT_F16><<<grid, 256, 0, st>>>(W, static_cast<uint16_t*>(Wt), K, N, Kpad);
   VB_LAUNCH_CHECK("pack_weight_kernel");
   return 0;
 }
@@ -431,11 +439,11 @@ int launch_pack_weight_bf16(cudaStream_t st, const float* W, __nv_bfloat16* Wt, 
 int launch_gemm_f32(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
                     int M, int N, int K, int epilogue, const float* aux, int tpi) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_f32: empty problem");
-  if (epilogue != VITB200_EPI_STORE_BF16 && bias == nullptr)
+  if (epilogue != VITB200_EPI_STORE_16 && bias == nullptr)
     return fail(VITB200_ERR_INVALID, "gemm_f32: epilogue needs a bias");
   switch (epilogue) {
-    case VITB200_EPI_STORE_BF16: return launch_gemm_f32_t<VITB200_EPI_STORE_BF16>(st, A, W, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_BIAS_GELU_BF16: return launch_gemm_f32_t<VITB200_EPI_BIAS_GELU_BF16>(st, A, W, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_STORE_16: return launch_gemm_f32_t<VITB200_EPI_STORE_16>(st, A, W, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_BIAS_GELU_16: return launch_gemm_f32_t<VITB200_EPI_BIAS_GELU_16>(st, A, W, bias, C, M, N, K, aux, tpi);
     case VITB200_EPI_BIAS_RESID_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_RESID_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
     case VITB200_EPI_BIAS_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
     case VITB200_EPI_PATCH_F32:

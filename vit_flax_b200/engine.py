@@ -23,7 +23,7 @@ class Engine:
     """Create -> load_params -> forward.  Not thread-safe (like the C handle)."""
 
     def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim,
-                 pool="cls", channels=3, precision="bf16", max_batch=256, device=0):
+                 pool="cls", channels=3, precision="fp16", max_batch=256, device=0):
         import torch  # deferred: plumbing only
 
         if not torch.cuda.is_available():
@@ -32,13 +32,13 @@ class Engine:
         self.lib = _lib.load()
         ih, iw, ph, pw, n = geometry(image_size, patch_size)
         assert pool in {"cls", "mean"}, "pool type must be either cls (cls token) or mean (mean pooling)"
-        if precision not in ("bf16", "fp32"):
-            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
         self.cfg = _lib.Config(
             image_h=ih, image_w=iw, patch_h=ph, patch_w=pw, channels=channels,
             num_classes=num_classes, dim=dim, depth=depth, heads=heads, mlp_dim=mlp_dim,
             pool=_lib.POOL_MEAN if pool == "mean" else _lib.POOL_CLS,
-            precision=_lib.PREC_FP32 if precision == "fp32" else _lib.PREC_BF16,
+            precision=_lib.PRECISIONS[precision],
             max_batch=max_batch)
         self.precision = precision
         self.max_batch = max_batch
@@ -110,6 +110,20 @@ class Engine:
         _lib.check(self.lib.vitb200_forward_host(self.handle, _stream_ptr(self._torch, self.device),
                                                  images.ctypes.data, b, out.ctypes.data))
         return out
+
+    def profile_forward(self, images, out=None):
+        """One forward with per-launch CUDA events -> {category: (ms, launches)}."""
+        torch = self._torch
+        self._check_images(images.shape)
+        b = images.shape[0]
+        if out is None:
+            out = torch.empty((b, self.num_classes), dtype=torch.float32, device=images.device)
+        n = len(_lib.CATEGORIES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        _lib.check(self.lib.vitb200_profile_forward(self.handle, _stream_ptr(torch, images.device),
+                                                    images.data_ptr(), b, out.data_ptr(), ms, cnt))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.CATEGORIES)}
 
     def tokens_after_transformer(self, batch: int) -> np.ndarray:
         out = np.empty((batch, self.tokens, self.dim), np.float32)

@@ -21,7 +21,9 @@ import numpy as np
 
 from .params import count_params, flatten_params, geometry, init_params
 
-_DEFAULT_PRECISION = os.environ.get("VITB200_PRECISION", "bf16")
+# 16-bit tensor-core operand format used when `precision` is not given: "fp16" (default; same
+# tcgen05 rate as bf16, 8x smaller logit error -- DESIGN.md "Operand format"), "bf16", or "fp32".
+_DEFAULT_PRECISION = os.environ.get("VITB200_PRECISION", "fp16")
 
 
 def _seed_from_key(key: Any) -> int:
@@ -97,7 +99,7 @@ class ViT:
         back as a numpy array; a CUDA ``torch.Tensor`` stays on the device and
         a CUDA tensor is returned.  ``rngs`` is accepted and ignored at dropout
         rate 0 (Flax draws nothing there).  Keyword-only extras are ours:
-        ``precision`` ('bf16' tcgen05 path, 'fp32' validation path)."""
+        ``precision`` ('fp16' / 'bf16' tcgen05 paths, 'fp32' validation path)."""
         if self.dropout != 0.0 or self.emb_dropout != 0.0:
             raise NotImplementedError(
                 "dropout > 0 is not built (SURVEY.md section 8f); the reference has no eval switch, "
