@@ -60,7 +60,8 @@ struct DevBuf {
 };
 
 struct ActMaps {   // TMA descriptors over the activation workspace for one batch size
-  CUtensorMap patches, xn, o, h, pooled;
+  CUtensorMap patches, xn, o, h, pooled;   // A operands
+  CUtensorMap c_qkv, c_hid, c_x;           // GEMM outputs (TMA store / reduce-add)
 };
 
 }  // namespace
@@ -188,12 +189,16 @@ int get_act_maps(vitb200_model* m, int batch, const ActMaps** out) {
     const int64_t R = int64_t(batch) * m->T, Rp = int64_t(batch) * m->Np;
     ActMaps am;
     int rc;
-    if ((rc = make_tmap_bf16_2d(&am.patches, m->patches_h.p, Rp, m->K0pad, m->K0pad, GEMM_BM))) return rc;
-    if ((rc = make_tmap_bf16_2d(&am.xn, m->xn_h.p, R, c.dim, c.dim, GEMM_BM))) return rc;
-    if ((rc = make_tmap_bf16_2d(&am.o, m->o_h.p, R, m->inner, m->inner, GEMM_BM))) return rc;
-    if ((rc = make_tmap_bf16_2d(&am.h, m->hid_h.p, R, c.mlp_dim, c.mlp_dim, GEMM_BM))) return rc;
+    const int dt = m->dt;
+    if ((rc = make_tmap_2d(&am.patches, m->patches_h.p, Rp, m->K0pad, m->K0pad, GEMM_BM, dt))) return rc;
+    if ((rc = make_tmap_2d(&am.xn, m->xn_h.p, R, c.dim, c.dim, GEMM_BM, dt))) return rc;
+    if ((rc = make_tmap_2d(&am.o, m->o_h.p, R, m->inner, m->inner, GEMM_BM, dt))) return rc;
+    if ((rc = make_tmap_2d(&am.h, m->hid_h.p, R, c.mlp_dim, c.mlp_dim, GEMM_BM, dt))) return rc;
     if (m->head_tc)
-      if ((rc = make_tmap_bf16_2d(&am.pooled, m->pooled_h.p, batch, c.dim, c.dim, GEMM_BM))) return rc;
+      if ((rc = make_tmap_2d(&am.pooled, m->pooled_h.p, batch, c.dim, c.dim, GEMM_BM, dt))) return rc;
+    if ((rc = make_tmap_2d(&am.c_qkv, m->qkv_h.p, R, 3 * m->inner, 3 * m->inner, GEMM_BM, dt))) return rc;
+    if ((rc = make_tmap_2d(&am.c_hid, m->hid_h.p, R, c.mlp_dim, c.mlp_dim, GEMM_BM, dt))) return rc;
+    if ((rc = make_tmap_2d(&am.c_x, m->x.p, R, c.dim, c.dim, GEMM_BM, VITB200_DT_F32))) return rc;
     it = m->act_maps.emplace(batch, am).first;
   }
   *out = &it->second;
@@ -206,7 +211,7 @@ int pack_dense(vitb200_model* m, DenseW& d, cudaStream_t st) {
     VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.wt), size_t(d.N) * d.Kpad * sizeof(uint16_t)));
   int rc = launch_pack_weight(st, m->leaves[d.leaf_kernel].dev, d.wt, d.K, d.N, d.Kpad, m->dt);
   if (rc) return rc;
-  return make_tmap_bf16_2d(&d.tm, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN);
+  return make_tmap_2d(&d.tm, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN, m->dt);
 }
 
 inline const float* leaf_ptr(const vitb200_model* m, int idx) { return idx >= 0 ? m->leaves[idx].dev : nullptr; }
@@ -244,7 +249,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
                             c.patch_h, c.patch_w, m->K0pad, m->dt))) return rc;
   // vit.py:147-153  Dense_0 + bias, placed at row b*T+1+t, + pos_embedding[1+t]
   mark(m, st, VITB200_CAT_GEMM_PATCH);
-  if ((rc = launch_gemm_tc(st, am->patches, m->patch.tm, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+  if ((rc = launch_gemm_tc(st, am->patches, m->patch.tm, nullptr, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
                              Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt))) return rc;
   mark(m, st, VITB200_CAT_CLS_ROWS);
   if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
@@ -254,12 +259,12 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_QKV);
-    if ((rc = launch_gemm_tc(st, am->xn, L.qkv.tm, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt))) return rc;
+    if ((rc = launch_gemm_tc(st, am->xn, L.qkv.tm, &am->c_qkv, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt))) return rc;
     mark(m, st, VITB200_CAT_ATTENTION);
     if ((rc = launch_attention_tc(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_OUT);
     if (m->project_out) {
-      if ((rc = launch_gemm_tc(st, am->o, L.out.tm, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt))) return rc;
+      if ((rc = launch_gemm_tc(st, am->o, L.out.tm, &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt))) return rc;
     } else {   // heads == 1 and dim == 64: to_out is the identity (vit.py:65,85)
       const int64_t n = int64_t(R) * D;
       add_16_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_h.p, m->x.p, n, m->dt);
@@ -269,9 +274,9 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF1);
-    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.tm, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt))) return rc;
+    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.tm, &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF2);
-    if ((rc = launch_gemm_tc(st, am->h, L.ff2.tm, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt))) return rc;
+    if ((rc = launch_gemm_tc(st, am->h, L.ff2.tm, &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt))) return rc;
   }
   // vit.py:159-165  pool, LayerNorm_0, Dense_1
   if (m->head_tc) {
@@ -279,7 +284,9 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_POOL_LN);
   if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_HEAD);
-    if ((rc = launch_gemm_tc(st, am->pooled, m->head.tm, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0, m->dt))) return rc;
+    CUtensorMap c_logits;   // the caller's buffer: encoded per call (host-side, ~1 us)
+    if ((rc = make_tmap_2d(&c_logits, logits, batch, c.num_classes, c.num_classes, GEMM_BM, VITB200_DT_F32))) return rc;
+    if ((rc = launch_gemm_tc(st, am->pooled, m->head.tm, &c_logits, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0, m->dt))) return rc;
   } else {
     mark(m, st, VITB200_CAT_POOL_LN);
     mark(m, st, VITB200_CAT_POOL_LN);
@@ -549,11 +556,17 @@ int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bi
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
     return fail(VITB200_ERR_INVALID, "gemm_tc: N and K must be multiples of 8");
-  CUtensorMap ta, tb;
+  if (dtype != VITB200_DT_BF16 && dtype != VITB200_DT_F16)
+    return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
+  CUtensorMap ta, tb, tc;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&ta, A, M, K, K, GEMM_BM))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tb, Wt, N, K, K, GEMM_BN))) return rc;
-  return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, bias, C, M, N, K, epilogue, aux, tokens_per_image, dtype);
+  if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, dtype))) return rc;
+  if ((rc = make_tmap_2d(&tb, Wt, N, K, K, GEMM_BN, dtype))) return rc;
+  const bool out16 = epilogue == VITB200_EPI_STORE_16 || epilogue == VITB200_EPI_BIAS_GELU_16;
+  const bool direct = epilogue == VITB200_EPI_PATCH_F32;
+  if (!direct && (rc = make_tmap_2d(&tc, C, M, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
+  return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, direct ? nullptr : &tc, bias, C, M, N, K, epilogue,
+                        aux, tokens_per_image, dtype);
 }
 
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias, float* C, int M, int N,

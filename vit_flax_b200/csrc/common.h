@@ -38,10 +38,13 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 int sm_count();   // SMs of the current device (cached per device)
 
 // ---- TMA descriptors -----------------------------------------------------
-// 2-D 16-bit (bf16/fp16) row-major tensor [rows, cols] (cols contiguous, row pitch = ld
-// elements), box = [box_rows, 64 cols] with 128-byte swizzle.
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
-                      int box_rows);
+// 2-D row-major tensor [rows, cols] (cols contiguous, row pitch = ld elements) of element type
+// `dt` (VITB200_DT_*); box = [box_rows, 128 bytes of columns] with 128-byte swizzle.
+int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                 int box_rows, int dt);
+// 3-D [batch, rows, cols] 16-bit tensor, box = [1, box_rows, 64 cols].
+int make_tmap_3d_16(CUtensorMap* out, const void* base, int64_t batch, int64_t rows, int64_t cols,
+                    int64_t ld, int box_rows, int dt);
 
 // ---- kernels (host launchers; all enqueue on `stream`, return 0 / <0) -----
 constexpr int GEMM_BM = 128;   // tcgen05 tile rows (A box rows)
@@ -49,9 +52,11 @@ constexpr int GEMM_BN = 256;   // tcgen05 tile cols (Wt box rows)
 constexpr int GEMM_BK = 64;
 
 // `dtype` / `out_dtype` are VITB200_DT_* values.
+// tmC: output map (16-bit [M,N] box 64 cols for the *_16 epilogues, fp32 [M,N] box 32 cols for
+// BIAS_RESID_F32 / BIAS_F32); may be null for PATCH_F32, which stores through `C` directly.
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                   const float* bias, void* C, int M, int N, int K, int epilogue,
-                   const float* aux, int tokens_per_image, int dtype);
+                   const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
+                   int epilogue, const float* aux, int tokens_per_image, int dtype);
 int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const float* bias,
                     float* C, int M, int N, int K, int epilogue, const float* aux,
                     int tokens_per_image);

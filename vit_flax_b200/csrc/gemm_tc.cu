@@ -1,19 +1,22 @@
-// gemm_tc.cu -- K3: persistent, warp-specialised tcgen05 16-bit (bf16 or fp16 operands) GEMM with fused
-// epilogues.  acc[M,N] = A[M,K] x Wt[N,K]^T, fp32 accumulation in TMEM.
+// gemm_tc.cu -- K3: persistent, warp-specialised tcgen05 GEMM (bf16 or fp16 operands) with
+// fused epilogues.  acc[M,N] = A[M,K] x Wt[N,K]^T, fp32 accumulation in TMEM.
 //
-// Replaces every flax `nn.Dense` on the hot path (vit.py:48,51,68,82,147,165)
-// together with what follows it in the reference: bias add, tanh-GELU
-// (vit.py:49), the Residual add (vit.py:39), cls/pos-embedding placement
-// (vit.py:151-153).
+// Replaces every flax `nn.Dense` on the hot path (vit.py:48,51,68,82,147,165) together with what
+// follows it in the reference: bias add, tanh-GELU (vit.py:49), the Residual add (vit.py:39),
+// cls/pos-embedding placement (vit.py:151-153).
 //
 // Structure (one CTA per SM, 12 warps):
 //   warp 0  lane 0 : TMA producer  (A box 128x64, Wt box 256x64, SWIZZLE_128B)
-//   warp 1  lane 0 : tcgen05.mma issuer, M=128 N=256 K=16 x4 per smem stage
+//   warp 1  lane 0 : tcgen05.mma issuer, M=128 N=256 K=16, 4 per smem stage
 //   warp 2         : TMEM allocator (512 columns = 2 accumulator stages)
-//   warps 4..11    : epilogue: tcgen05.ld 32x32b -> regs -> fused math -> global
-// Pipelines: smem ring (4 stages, full/empty mbarriers) between TMA and MMA;
-// TMEM double buffer (tfull/tempty mbarriers) between MMA and epilogue, so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 4..11    : epilogue, two groups of 4 warps (one warp per TMEM lane quarter);
+//                    group g owns the 128-byte-wide column slabs s = g, g+2, ... of the tile:
+//                    tcgen05.ld -> fused math -> swizzled smem slab -> TMA store
+//                    (16-bit outputs, fp32 head) or TMA reduce-add into the fp32 residual
+//                    stream (x += acc + bias happens in L2; the SM never reads x).
+// Pipelines: smem ring (3 stages, full/empty mbarriers) between TMA and MMA; TMEM double buffer
+// (tfull/tempty mbarriers) between MMA and epilogue, so the epilogue of tile i overlaps the MMAs
+// of tile i+1; two slab buffers per epilogue group so a slab drains while the next is filled.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -22,7 +25,7 @@ namespace vb {
 namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES = BN * BK * 2;            // 32 KB
@@ -30,7 +33,9 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;   // 384
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SLAB_BYTES = BM * 128;            // 128 rows x 128 B = 16 KB
+constexpr int NUM_SLABS = 4;                    // 2 per epilogue group
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_SLABS * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  -- nn.gelu default (vit.py:49)
@@ -42,21 +47,27 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 template <int kEpi, int kDT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                    const __grid_constant__ CUtensorMap tmB,
-                    const float* __restrict__ bias, void* __restrict__ Cout,
-                    int M, int N, int K, const float* __restrict__ aux, int tpi) {
+               const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC,
+               const float* __restrict__ bias, void* __restrict__ Cout,
+               int M, int N, int K, const float* __restrict__ aux, int tpi) {
+  constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16);
+  constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
+  constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
+  constexpr int SLABS_PER_TILE = BN / SLAB_COLS;
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * A_BYTES;
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-  // barrier layout: full[4] empty[4] tfull[2] tempty[2] | tmem ptr
+  const uint32_t sSlab = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bars = sSlab + NUM_SLABS * SLAB_BYTES;
+  // barrier layout: full[STAGES] empty[STAGES] tfull[2] tempty[2] | tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
-  // generic pointer to the tmem slot for reading it back
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -70,6 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if constexpr (!kDirect) prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -140,76 +152,114 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     // ===================== epilogue =====================
     const int ew = warp - 4;
     const int q = ew & 3;        // TMEM lane quarter this warp may access (== warp % 4)
-    const int hf = ew >> 2;      // which 128-column half of the 256-column accumulator
+    const int grp = ew >> 2;     // epilogue group: owns slabs grp, grp+2, ...
+    const bool leader = (q == 0 && lane == 0);   // issues / waits the group's TMA stores
+    const int lrow = q * 32 + lane;              // row inside the tile == TMEM lane
     int acc = 0;
     uint32_t acc_phase = 0;
+    int buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      int64_t out_row = row;
-      const float* pos_row = nullptr;
-      if constexpr (kEpi == VITB200_EPI_PATCH_F32) {
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+
+      if constexpr (kDirect) {
+        // ---- PATCH: row b*Np+t -> output row b*T+1+t, + bias + pos_embedding[1+t] ----
+        const int row = m_blk * BM + lrow;
+        const bool row_ok = row < M;
         const int b = row / tpi, t = row - b * tpi;
-        out_row = int64_t(b) * (tpi + 1) + 1 + t;
-        pos_row = aux + int64_t(1 + t) * N;
-      }
+        float* crow_base = reinterpret_cast<float*>(Cout) + (int64_t(b) * (tpi + 1) + 1 + t) * N;
+        const float* pos_row = aux + int64_t(1 + t) * N;
 #pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        const int col0 = hf * 128 + chunk * 32;
-        const int n0 = n_blk * BN + col0;
-        if (n0 >= N) break;                         // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), r);
-        tmem_ld_wait();
-        if (row_ok) {
-          if constexpr (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16) {
-            uint16_t* crow = reinterpret_cast<uint16_t*>(Cout) + out_row * N + n0;
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          const int n0 = n_blk * BN + grp * 128 + chunk * 32;
+          if (n0 >= N) break;                         // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + uint32_t(grp * 128 + chunk * 32), r);
+          tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n0 + j * 8 < N) {
+            for (int j = 0; j < 8; ++j) {
+              if (n0 + j * 4 < N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j * 4));
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j * 4));
+                float4 o;
+                o.x = __uint_as_float(r[j * 4 + 0]) + b4.x + p4.x;
+                o.y = __uint_as_float(r[j * 4 + 1]) + b4.y + p4.y;
+                o.z = __uint_as_float(r[j * 4 + 2]) + b4.z + p4.z;
+                o.w = __uint_as_float(r[j * 4 + 3]) + b4.w + p4.w;
+                *reinterpret_cast<float4*>(crow_base + n0 + j * 4) = o;
+              }
+            }
+          }
+        }
+      } else {
+        // ---- slab epilogue: regs -> swizzled smem slab -> TMA store / reduce-add ----
+#pragma unroll 1
+        for (int s = grp; s < SLABS_PER_TILE; s += 2) {
+          const int n0 = n_blk * BN + s * SLAB_COLS;
+          if (n0 >= N) break;                          // uniform over the group
+          const uint32_t slab = sSlab + uint32_t(grp * 2 + buf) * SLAB_BYTES;
+          // the slab buffer used two slabs ago must have been read out by its TMA store
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1 + grp, 128);
+          const uint32_t srow = slab + uint32_t(lrow) * 128u;
+          const int sw = lrow & 7;
+          if constexpr (kOut16) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(t_row + uint32_t(s * SLAB_COLS + half * 32), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {            // 8 columns -> one 16-byte chunk
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]);
                 if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j * 8));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j * 8 + 4));
+                  const int nb = n0 + half * 32 + j * 8;
+                  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                  if (nb < N) {
+                    b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
+                    b1 = __ldg(reinterpret_cast<const float4*>(bias + nb + 4));
+                  }
                   v[0] = gelu_tanh_fast(v[0] + b0.x); v[1] = gelu_tanh_fast(v[1] + b0.y);
                   v[2] = gelu_tanh_fast(v[2] + b0.z); v[3] = gelu_tanh_fast(v[3] + b0.w);
                   v[4] = gelu_tanh_fast(v[4] + b1.x); v[5] = gelu_tanh_fast(v[5] + b1.y);
                   v[6] = gelu_tanh_fast(v[6] + b1.z); v[7] = gelu_tanh_fast(v[7] + b1.w);
                 }
-                uint4 o;
-                o.x = pack2<kDT>(v[0], v[1]); o.y = pack2<kDT>(v[2], v[3]);
-                o.z = pack2<kDT>(v[4], v[5]); o.w = pack2<kDT>(v[6], v[7]);
-                *reinterpret_cast<uint4*>(crow + j * 8) = o;
+                const int chunk = half * 4 + j;
+                st_shared_v4(srow + (uint32_t(chunk ^ sw) << 4), pack2<kDT>(v[0], v[1]),
+                             pack2<kDT>(v[2], v[3]), pack2<kDT>(v[4], v[5]), pack2<kDT>(v[6], v[7]));
               }
             }
           } else {
-            float* crow = reinterpret_cast<float*>(Cout) + out_row * N + n0;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + uint32_t(s * SLAB_COLS), r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (n0 + j * 4 < N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j * 4));
-                float4 o;
-                o.x = __uint_as_float(r[j * 4 + 0]) + b4.x;
-                o.y = __uint_as_float(r[j * 4 + 1]) + b4.y;
-                o.z = __uint_as_float(r[j * 4 + 2]) + b4.z;
-                o.w = __uint_as_float(r[j * 4 + 3]) + b4.w;
-                if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32) {
-                  const float4 x4 = *reinterpret_cast<const float4*>(crow + j * 4);
-                  o.x += x4.x; o.y += x4.y; o.z += x4.z; o.w += x4.w;
-                }
-                if constexpr (kEpi == VITB200_EPI_PATCH_F32) {
-                  const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j * 4));
-                  o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
-                }
-                *reinterpret_cast<float4*>(crow + j * 4) = o;
-              }
+            for (int j = 0; j < 8; ++j) {              // 4 fp32 columns -> one 16-byte chunk
+              const int nb = n0 + j * 4;
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (nb < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + nb));
+              st_shared_v4(srow + (uint32_t(j ^ sw) << 4),
+                           __float_as_uint(__uint_as_float(r[j * 4 + 0]) + b4.x),
+                           __float_as_uint(__uint_as_float(r[j * 4 + 1]) + b4.y),
+                           __float_as_uint(__uint_as_float(r[j * 4 + 2]) + b4.z),
+                           __float_as_uint(__uint_as_float(r[j * 4 + 3]) + b4.w));
             }
           }
+          fence_proxy_async_smem();                    // generic-proxy smem writes -> async proxy
+          named_bar_sync(1 + grp, 128);
+          if (leader) {
+            if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32)
+              tma_reduce_add_2d(&tmC, slab, n0, m_blk * BM);      // x += acc + bias
+            else
+              tma_store_2d(&tmC, slab, n0, m_blk * BM);
+            tma_store_commit();
+          }
+          buf ^= 1;
         }
       }
       tc_fence_before();
@@ -218,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (!kDirect && leader) tma_store_wait<0>();       // smem must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -230,7 +281,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
 
 template <int kEpi, int kDT>
 int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
-               const float* bias, void* C, int M, int N, int K, const float* aux, int tpi) {
+               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
+               const float* aux, int tpi) {
   static bool configured = false;   // per-process; attribute is per-function, device-agnostic
   if (!configured) {
     VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT>,
@@ -239,29 +291,29 @@ int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& t
   }
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<kEpi, kDT><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, bias, C, M, N, K,
-                                                                       aux, tpi);
+  gemm_tc_kernel<kEpi, kDT><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, bias, C, M, N,
+                                                                       K, aux, tpi);
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
 
 template <int kDT>
 int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                 const float* bias, void* C, int M, int N, int K, int epilogue, const float* aux,
-                 int tpi) {
+                 const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
+                 int epilogue, const float* aux, int tpi) {
   switch (epilogue) {
     case VITB200_EPI_STORE_16:
-      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
     case VITB200_EPI_BIAS_GELU_16:
-      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
     case VITB200_EPI_BIAS_RESID_F32:
-      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
     case VITB200_EPI_BIAS_F32:
-      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
     case VITB200_EPI_PATCH_F32:
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
-      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
     default:
       return fail(VITB200_ERR_INVALID, "gemm_tc: unknown epilogue");
   }
@@ -270,17 +322,20 @@ int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap&
 }  // namespace
 
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                   const float* bias, void* C, int M, int N, int K, int epilogue,
-                   const float* aux, int tpi, int dtype) {
+                   const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
+                   int epilogue, const float* aux, int tpi, int dtype) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
     return fail(VITB200_ERR_INVALID, "gemm_tc: N and K must be multiples of 8");
   if (epilogue != VITB200_EPI_STORE_16 && bias == nullptr)
     return fail(VITB200_ERR_INVALID, "gemm_tc: epilogue needs a bias");
+  if (epilogue != VITB200_EPI_PATCH_F32 && tmC == nullptr)
+    return fail(VITB200_ERR_INVALID, "gemm_tc: output tensor map missing");
+  const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
   if (dtype == DT_BF16)
-    return dispatch_epi<DT_BF16>(stream, tmA, tmB, bias, C, M, N, K, epilogue, aux, tpi);
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi);
   if (dtype == DT_F16)
-    return dispatch_epi<DT_F16>(stream, tmA, tmB, bias, C, M, N, K, epilogue, aux, tpi);
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi);
   return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 

@@ -47,8 +47,7 @@ int sm_count() {
   return cached[dev];
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
-                      int box_rows) {
+static bool load_encoder() {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -56,20 +55,51 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
             cudaSuccess && q == cudaDriverEntryPointSuccess)
       g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   });
-  if (!g_encode) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+  return g_encode != nullptr;
+}
+
+static CUtensorMapDataType tmap_type(int dt) {
+  return dt == VITB200_DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+         : dt == VITB200_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                 int box_rows, int dt) {
+  if (!load_encoder()) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const int esz = dt == VITB200_DT_F32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * esz) % 16 != 0)
     return fail(VITB200_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte row pitch");
   if (box_rows < 1 || box_rows > 256) return fail(VITB200_ERR_INVALID, "TMA box rows out of range");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
-                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(out, tmap_type(dt), 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  return 0;
+}
+
+// [batch, rows, cols] 16-bit tensor (cols contiguous): box = [1, box_rows, 64 cols], 128-byte swizzle.
+// Rows >= `rows` of an image are out of bounds for that image: zero-filled on load, clipped on store.
+int make_tmap_3d_16(CUtensorMap* out, const void* base, int64_t batch, int64_t rows, int64_t cols,
+                    int64_t ld, int box_rows, int dt) {
+  if (!load_encoder()) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(VITB200_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte row pitch");
+  if (box_rows < 1 || box_rows > 256) return fail(VITB200_ERR_INVALID, "TMA box rows out of range");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * static_cast<cuuint64_t>(rows)};
+  cuuint32_t box[3] = {64u, static_cast<cuuint32_t>(box_rows), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = g_encode(out, tmap_type(dt), 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult " + std::to_string(int(r)));
   return 0;
 }
 
