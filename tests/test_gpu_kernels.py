@@ -141,9 +141,17 @@ def test_layernorm(lib, rows, dim, out):
     assert err < 2e-5 + 16 * ulp                                          # 16-bit: one rounding of |y| < 16
 
 
-@pytest.mark.parametrize("batch,T,heads", [(2, 65, 16), (3, 197, 12), (2, 257, 16), (1, 1025, 4), (2, 16, 1), (1, 1, 2), (1, 130, 3)])
+@pytest.mark.parametrize("batch,T,heads", [(2, 65, 16), (3, 197, 12), (2, 257, 16), (1, 1025, 4), (2, 16, 1), (1, 1, 2), (1, 130, 3),
+                                               (40, 197, 12), (1, 208, 1), (2, 128, 2), (3, 64, 5)])
 @pytest.mark.parametrize("fmt", ["bf16", "fp16"])
-def test_attention_tc(lib, batch, T, heads, fmt):
+@pytest.mark.parametrize("impl", ["auto", "hmma"])
+def test_attention_tc(lib, batch, T, heads, fmt, impl, monkeypatch):
+    """auto = tcgen05/TMEM kernel when T <= 208 else the streamed-KV mma.sync kernel; hmma forces
+    the latter (both generations stay covered at every shape)."""
+    if impl == "hmma":
+        monkeypatch.setenv("VITB200_ATTENTION", "hmma")
+    else:
+        monkeypatch.delenv("VITB200_ATTENTION", raising=False)
     dt, tdt, ulp = DT16[fmt]
     rng = np.random.default_rng(T + heads)
     inner = heads * 64

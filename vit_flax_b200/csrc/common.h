@@ -64,6 +64,9 @@ int launch_layernorm(cudaStream_t stream, const float* x, const float* scale, co
                      void* y, int rows, int dim, int out_dtype);
 int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
                         int heads, int dtype);
+bool attention_tc5_supports(int T);
+int launch_attention_tc5(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
+                         int heads, int dtype);
 int launch_attention_f32(cudaStream_t stream, const float* qkv, float* out, int batch, int T,
                          int heads);
 int launch_patchify(cudaStream_t stream, const float* images, void* patches, int batch, int H,
