@@ -45,9 +45,12 @@ GEMM_SHAPES = [
 @pytest.mark.parametrize("epi", [_lib.EPI_STORE_16, _lib.EPI_BIAS_GELU_16,
                                  _lib.EPI_BIAS_RESID_F32, _lib.EPI_BIAS_F32])
 @pytest.mark.parametrize("fmt", ["bf16", "fp16"])
-def test_gemm_tc_epilogues(lib, M, N, K, epi, fmt):
+@pytest.mark.parametrize("cta_group", ["1", "2"])
+def test_gemm_tc_epilogues(lib, M, N, K, epi, fmt, cta_group, monkeypatch):
+    """cta_group 1: one CTA per 128x256 tile; 2: CTA pair (cluster of 2, cta_group::2) per 256x256 tile."""
     if M >= 40000 and epi not in (_lib.EPI_STORE_16, _lib.EPI_BIAS_RESID_F32):
         pytest.skip("large case covers the two memory-heaviest epilogues only")
+    monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
     dt, tdt, ulp = DT16[fmt]
     rng = np.random.default_rng(M + N + K + epi)
     A = dev(rng.standard_normal((M, K)), tdt)
@@ -80,9 +83,11 @@ def test_gemm_tc_epilogues(lib, M, N, K, epi, fmt):
         assert err.mean().item() < ulp + 2e-4
 
 
-def test_gemm_tc_patch_epilogue(lib):
+@pytest.mark.parametrize("cta_group", ["1", "2"])
+@pytest.mark.parametrize("B,Np,K,D", [(3, 16, 192, 64), (4, 196, 768, 768)])
+def test_gemm_tc_patch_epilogue(lib, cta_group, B, Np, K, D, monkeypatch):
     # vit.py:147-153: Dense_0 output placed at row b*T+1+t with pos_embedding[1+t] added
-    B, Np, K, D = 3, 16, 192, 64
+    monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
     rng = np.random.default_rng(5)
     A = dev(rng.standard_normal((B * Np, K)), torch.bfloat16)
     Wt = dev(rng.standard_normal((D, K)) / np.sqrt(K), torch.bfloat16)

@@ -56,7 +56,10 @@ constexpr int GEMM_BK = 64;
 // BIAS_RESID_F32 / BIAS_F32); may be null for PATCH_F32, which stores through `C` directly.
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
-                   int epilogue, const float* aux, int tokens_per_image, int dtype);
+                   int epilogue, const float* aux, int tokens_per_image, int dtype, int cta_group);
+// 1 = one CTA per 128x256 tile (Wt box 256 rows), 2 = CTA pair per 256x256 tile (Wt box 128 rows).
+// The Wt tensor map must be encoded with GEMM_BN / cta_group box rows.
+int gemm_tc_cta_group(int M);
 int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const float* bias,
                     float* C, int M, int N, int K, int epilogue, const float* aux,
                     int tokens_per_image);

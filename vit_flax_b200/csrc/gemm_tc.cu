@@ -14,9 +14,15 @@
 //                    tcgen05.ld -> fused math -> swizzled smem slab -> TMA store
 //                    (16-bit outputs, fp32 head) or TMA reduce-add into the fp32 residual
 //                    stream (x += acc + bias happens in L2; the SM never reads x).
-// Pipelines: smem ring (3 stages, full/empty mbarriers) between TMA and MMA; TMEM double buffer
+// kCG = 2 pairs two CTAs (cluster of 2, `cta_group::2`): the pair computes a 256x256 tile, each
+// CTA loading its 128 rows of A and its 128-row half of Wt; only the leader CTA issues MMAs, smem
+// traffic per SM drops from 192 to 128 B/clk (the 1-CTA form is smem-bandwidth bound at ~62 %
+// tensor-pipe activity, profiles/r01_gemm_ncu.md).
+// Pipelines: smem ring (3 stages (5 in pair mode), full/empty mbarriers) between TMA and MMA; TMEM double buffer
 // (tfull/tempty mbarriers) between MMA and epilogue, so the epilogue of tile i overlaps the MMAs
 // of tile i+1; two slab buffers per epilogue group so a slab drains while the next is filled.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -25,17 +31,23 @@ namespace vb {
 namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int STAGES = 3;
 constexpr int UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2;            // 16 KB
-constexpr int B_BYTES = BN * BK * 2;            // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
+constexpr int A_BYTES = BM * BK * 2;            // 16 KB: 128 rows of A per CTA
+template <int kCG> struct Cfg {
+  static constexpr int STAGES = kCG == 2 ? 5 : 3;
+  static constexpr int B_ROWS = BN / kCG;                       // rows of Wt this CTA loads
+  static constexpr int B_BYTES = B_ROWS * BK * 2;               // 32 KB / 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;         // 48 KB / 32 KB
+  static constexpr int TILE_M = BM * kCG;                       // 128 / 256
+};
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;   // 384
 constexpr int TMEM_COLS = 512;
 constexpr int SLAB_BYTES = BM * 128;            // 128 rows x 128 B = 16 KB
 constexpr int NUM_SLABS = 4;                    // 2 per epilogue group
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_SLABS * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+template <int kCG> constexpr int smem_bytes() {
+  return Cfg<kCG>::STAGES * Cfg<kCG>::STAGE_BYTES + NUM_SLABS * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+}
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  -- nn.gelu default (vit.py:49)
@@ -44,7 +56,7 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.0f + tanh_approx(u));
 }
 
-template <int kEpi, int kDT>
+template <int kEpi, int kDT, int kCG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmB,
@@ -55,6 +67,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
   constexpr int SLABS_PER_TILE = BN / SLAB_COLS;
+  constexpr int STAGES = Cfg<kCG>::STAGES, B_BYTES = Cfg<kCG>::B_BYTES;
+  constexpr int STAGE_BYTES = Cfg<kCG>::STAGE_BYTES, TILE_M = Cfg<kCG>::TILE_M;
+  // pair mode: rank of this CTA in its cluster of 2 (0 = leader, issues the MMAs)
+  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0u;
+  const int tile0 = kCG == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = kCG == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -73,7 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + BM - 1) / BM;
+  const int m_tiles = (M + TILE_M - 1) / TILE_M;
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
@@ -85,18 +103,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 1);                       // pair: only the leader arrives (arms both CTAs' bytes)
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+      mbar_init(tempty_bar(s), NUM_EPI_WARPS * kCG);   // pair: epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_slot, TMEM_COLS);
+  if (warp == 2) tmem_alloc<kCG>(tmem_slot, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -105,28 +123,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int a_row = m_blk * TILE_M + int(rank) * BM;
+        const int b_row = n_blk * BN + int(rank) * Cfg<kCG>::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(sA + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(sB + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, n_blk * BN);
+          if constexpr (kCG == 1) {
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sA + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, a_row);
+            tma_load_2d(sB + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, b_row);
+          } else {
+            // Both CTAs' loads complete on the LEADER's full barrier (the MMA issuer waits there).
+            // Only the leader arrives, arming the bytes of both CTAs: the peer's complete_tx may
+            // land first (tx-count goes transiently negative) but the phase cannot complete
+            // before the leader's arrival.  A remote arrive from the peer is not needed and its
+            // cluster-scope release costs >1000 cycles per stage (profiles/r01_gemm_pair.md).
+            const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            tma_load_2d_cg2(sA + stage * A_BYTES, &tmA, lead_full, kb * BK, a_row);
+            tma_load_2d_cg2(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_16(BM, BN, kDT == DT_F16 ? 0 : 1);
+    // ===================== MMA issuer (leader CTA only in pair mode) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(TILE_M, BN, kDT == DT_F16 ? 0 : 1);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        if constexpr (kCG == 2) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -135,14 +168,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           const uint32_t a0 = sA + stage * A_BYTES, b0 = sB + stage * B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16_ss<1>(d_tmem, umma_desc_k_sw128(a0 + k * UMMA_K * 2),
-                            umma_desc_k_sw128(b0 + k * UMMA_K * 2), idesc,
-                            (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss<kCG>(d_tmem, umma_desc_k_sw128(a0 + k * UMMA_K * 2),
+                              umma_desc_k_sw128(b0 + k * UMMA_K * 2), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));          // smem slot free once these MMAs retire
+          // smem slot free (in both CTAs) once these MMAs retire
+          if constexpr (kCG == 2) umma_commit_cg2_mc(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));              // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs)
+        if constexpr (kCG == 2) umma_commit_cg2_mc(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -158,15 +195,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m_row0 = m_blk * TILE_M + int(rank) * BM;      // first output row of this CTA
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
 
       if constexpr (kDirect) {
         // ---- PATCH: row b*Np+t -> output row b*T+1+t, + bias + pos_embedding[1+t] ----
-        const int row = m_blk * BM + lrow;
+        const int row = m_row0 + lrow;
         const bool row_ok = row < M;
         const int b = row / tpi, t = row - b * tpi;
         float* crow_base = reinterpret_cast<float*>(Cout) + (int64_t(b) * (tpi + 1) + 1 + t) * N;
@@ -254,9 +292,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           named_bar_sync(1 + grp, 128);
           if (leader) {
             if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32)
-              tma_reduce_add_2d(&tmC, slab, n0, m_blk * BM);      // x += acc + bias
+              tma_reduce_add_2d(&tmC, slab, n0, m_row0);          // x += acc + bias
             else
-              tma_store_2d(&tmC, slab, n0, m_blk * BM);
+              tma_store_2d(&tmC, slab, n0, m_row0);
             tma_store_commit();
           }
           buf ^= 1;
@@ -264,7 +302,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (kCG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's barrier
+        else mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -272,48 +313,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();   // peer smem/TMEM stay live until here
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, TMEM_COLS);
+    tmem_dealloc<kCG>(tmem_base, TMEM_COLS);
   }
+}
+
+template <int kEpi, int kDT, int kCG>
+int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+              const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
+              const float* aux, int tpi) {
+  static bool configured = false;   // per-process; attribute is per-function, device-agnostic
+  if (!configured) {
+    VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG>()));
+    configured = true;
+  }
+  const int tiles = ceil_div(M, Cfg<kCG>::TILE_M) * ceil_div(N, BN);
+  const int max_units = sm_count() / kCG;
+  const int units = tiles < max_units ? tiles : max_units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * kCG);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes<kCG>();
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kEpi, kDT, kCG>, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi));
+  VB_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
 }
 
 template <int kEpi, int kDT>
 int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-               const float* aux, int tpi) {
-  static bool configured = false;   // per-process; attribute is per-function, device-agnostic
-  if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
-  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<kEpi, kDT><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, bias, C, M, N,
-                                                                       K, aux, tpi);
-  VB_LAUNCH_CHECK("gemm_tc_kernel");
-  return 0;
+               const float* aux, int tpi, int cta_group) {
+  if (cta_group == 2) return launch_cg<kEpi, kDT, 2>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
+  return launch_cg<kEpi, kDT, 1>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
 }
 
 template <int kDT>
 int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-                 int epilogue, const float* aux, int tpi) {
+                 int epilogue, const float* aux, int tpi, int cta_group) {
   switch (epilogue) {
     case VITB200_EPI_STORE_16:
-      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
     case VITB200_EPI_BIAS_GELU_16:
-      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
     case VITB200_EPI_BIAS_RESID_F32:
-      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
     case VITB200_EPI_BIAS_F32:
-      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
     case VITB200_EPI_PATCH_F32:
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
-      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
+      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
     default:
       return fail(VITB200_ERR_INVALID, "gemm_tc: unknown epilogue");
   }
@@ -321,9 +382,17 @@ int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap&
 
 }  // namespace
 
+int gemm_tc_cta_group(int M) {
+  // VITB200_GEMM_CTA_GROUP=1|2 overrides (A/B tests); pairs only pay off with >= 2 row blocks
+  const char* e = getenv("VITB200_GEMM_CTA_GROUP");
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return M > GEMM_BM ? 2 : 1;
+}
+
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
-                   int epilogue, const float* aux, int tpi, int dtype) {
+                   int epilogue, const float* aux, int tpi, int dtype, int cta_group) {
+  if (cta_group != 1 && cta_group != 2) return fail(VITB200_ERR_INVALID, "gemm_tc: cta_group must be 1 or 2");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
     return fail(VITB200_ERR_INVALID, "gemm_tc: N and K must be multiples of 8");
@@ -333,9 +402,9 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
     return fail(VITB200_ERR_INVALID, "gemm_tc: output tensor map missing");
   const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
   if (dtype == DT_BF16)
-    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi);
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group);
   if (dtype == DT_F16)
-    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi);
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group);
   return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 

@@ -31,13 +31,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+// Arrive on the barrier at the same smem offset in CTA `cta` of the cluster.  RELAXED: callers
+// order their own side first (tcgen05.wait::ld + tcgen05.fence::before_thread_sync); a
+// cluster-scope release here stalls the warp for >1000 cycles.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+// arrive on a barrier given by its shared::cluster address
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -64,12 +76,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // cluster-scope acquire wait (barrier completed by a remote CTA's arrive)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+  const long long t0 = clock64();
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && clock64() - t0 > 4000000000LL) {
+      printf("vitb200: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+             int(blockIdx.x), int(threadIdx.x), bar, parity);
+      __trap();
+    }
   }
 }
 
