@@ -21,7 +21,10 @@ from _util import C1, C2, C3, C4, C5, TINY, TINY_MEAN, images_for, load_golden
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 5e-2}   # bf16: operand-format noise floor, see docstring
-TOL_VS_EMULATED = 1e-2                              # 16-bit run vs oracle with the same operand rounding
+# 16-bit run vs the oracle with the SAME operand rounding: what is left is accumulation order and
+# one-ulp rounding flips, so it scales with the format's ulp (bf16's is 8x fp16's; measured on
+# ViT-B/16 depth 12: fp16 2.3e-3, bf16 1.8e-2).
+TOL_VS_EMULATED = {"fp16": 1e-2, "bf16": 4e-2}
 TORCH_DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
 
 
@@ -94,7 +97,7 @@ def _check_16bit(cfg, batch, depth=None, pool="cls", seed=0, precision="fp16", t
     print(f"[parity] {precision} depth={cfg['depth']} batch={batch}: max abs logit error {err:.5f} "
           f"(vs same-rounding oracle {err_emu:.5f})")
     assert err < tol, f"{precision}: max abs logit error {err}"
-    assert err_emu < TOL_VS_EMULATED, f"{precision}: {err_emu} away from the same-rounding oracle"
+    assert err_emu < TOL_VS_EMULATED[precision], f"{precision}: {err_emu} away from the same-rounding oracle"
     srt = np.sort(want, axis=1)
     confident = (srt[:, -1] - srt[:, -2]) > 2 * tol
     assert np.array_equal(got.argmax(1)[confident], want.argmax(1)[confident])

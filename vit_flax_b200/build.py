@@ -29,7 +29,7 @@ FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + (["-DVITB200_TRACE"] if os.environ.get("VITB200_TRACE") else [])   # debug timelines (profiles/trace_attention.py)
 
 
 def _digest() -> str:

@@ -1,103 +1,165 @@
-// attention_tc5.cu -- K4 (second generation): fused attention on tcgen05 / TMEM for sequences
-// that fit one key block (T <= 208 tokens: every 224-px /16 config, i.e. ViT-B/16 and ViT-L/16).
+// attention_tc5.cu -- K4: fused attention on tcgen05 / TMEM for sequences that fit one key block
+// (T <= 208 tokens: every 224-px /16 config, i.e. ViT-B/16 and ViT-L/16).
 //
 //   out = softmax(Q K^T * 64^-0.5) V   per (image, head)                        vit.py:69-79
 //
-// One work item = (image, head, 128-query tile).  Persistent CTAs, 12 warps:
-//   warp 0  lane 0 : TMA producer: Q tile, K, V boxes cut straight out of the to_qkv output viewed
-//                    as [B, T, 3I] (the split / head rearranges of vit.py:69-71 are coordinates);
-//                    rows >= T are out of bounds of the image and arrive as zeros.
-//   warp 1  lane 0 : tcgen05.mma issuer:  S = Q K^T  (M=128, N=KP, K=64; SS operands)
-//                                         O = P V    (M=128, N=64,  K=KP; P from TMEM, V MN-major)
-//   warp 2         : TMEM allocator: two 256-column slots; S occupies [0,KP), P (16-bit, two keys
-//                    per column) overwrites [0,KP/2), O lives at [128,192) of the same slot.
-//   warps 4..11    : softmax + epilogue, thread = (row, column half).  The half-row of S is read
-//                    ONCE into registers; row max / row sum are exchanged between the two halves
-//                    through shared memory; P goes back to TMEM with tcgen05.st; the epilogue of
-//                    item i-1 (O / rowsum -> 16-bit -> smem -> TMA store, rows >= T clipped) runs
-//                    between the max exchange and the exponentials of item i, which frees the
-//                    TMEM slot early enough for S(i+1) to be computed under softmax(i).
+// One work item = (image, head, 128-query tile).  Persistent CTAs, 16 warps:
+//   warp 0  lane 0 : TMA producer.  Q tile, K, V boxes are cut straight out of the to_qkv output
+//                    viewed as [B, T, 3I] (the split / head rearranges of vit.py:69-71 are
+//                    coordinates); rows >= T are out of bounds of the image and arrive as zeros.
+//                    K and V of an (image, head) are loaded once and shared by its q tiles (2-deep
+//                    ring); Q has a 4-deep ring, so loads run one to two items ahead of the MMAs.
+//   warps 1, 3     : tcgen05.mma issuers, one per TMEM slot (lane 0 each, blocking mbarrier waits):
+//                      S = Q K^T  (M=128, N=KP, K=64; SS operands)
+//                      O = P V    (M=128, N=64,  K=KP; P from TMEM, V MN-major)
+//                    S(i+2) is queued right behind PV(i): MMAs of one thread execute in order.
+//   warp 2         : TMEM allocator: two slots of KP columns (S fp32, then P as 16-bit pairs over
+//                    the first KP/2 columns) + one 64-column O accumulator shared by both slots.
+//   warps 4..7     : softmax group 0 -- items 0, 2, 4, ... of this CTA (slot 0)
+//   warps 8..11    : softmax group 1 -- items 1, 3, 5, ... of this CTA (slot 1)
+//   warps 12..15   : epilogue: O -> registers (frees the accumulator for the next PV), x 1/rowsum,
+//                    16-bit, swizzled smem staging (2 buffers) -> TMA store, rows >= T clipped.
+// A softmax thread owns one query row (= one TMEM lane): row max and row sum need no exchange.
+// Pass 1 streams the score row out of TMEM for the max, pass 2 streams it again (TMEM reads are
+// cheap), exponentiates, sums in fp32 and writes P back over S with tcgen05.st; 1/rowsum goes to
+// the epilogue warps through shared memory.
+// Bound (measured, profiles/r01_attention.md): the XU pipe -- ex2 (8 cycles per warp instruction and
+// SMSP) AND the fp32 -> 16-bit pack F2FP (4 cycles) share it: 20 cycles per pair of scores.  The
+// exponential phases of consecutive items take turns (mbarrier hand-off): left alone the two
+// groups fall into step -- both exponentiate, then both wait for their MMAs -- which idles the XU
+// for the length of everything else.  A polynomial ex2 on the FMA pipe (kPoly quarters of the
+// pairs; Cody-Waite + degree-3 minimax, rel. error 7.5e-5) is built in but off by default: on
+// B200 FFMA2 issues at 2.25 cycles per warp instruction, so the 5 FFMA2 + 3 FADD2 + 2 IMAD it
+// costs per pair outweigh the 16 XU cycles it saves.
+// Warps whose 32 query rows are all >= T (the last quarter of the 69-row tail tile at T = 197)
+// skip their softmax: rows of an MMA are independent and those rows are never stored.
 // The [B,h,T,T] score tensor of vit.py:73-75 never reaches HBM.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
 namespace vb {
 
+#ifdef VITB200_TRACE
+// debug timeline of CTA 0: g_trace[event][item] = clock64 at the event (profiles/trace_attention.py)
+__device__ long long g_trace[12][64];
+#define TRACE(ev, i) do { if (blockIdx.x == 0 && (i) < 64) g_trace[ev][i] = clock64(); } while (0)
+#else
+#define TRACE(ev, i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int DH = 64;
 constexpr int QT = 128;                 // queries per work item (UMMA M)
-constexpr int NT = 384;                 // threads per CTA
+constexpr int NT = 512;                 // threads per CTA: 4 service warps, 2 x 4 softmax, 4 epilogue
 constexpr int Q_BYTES = QT * 128;       // 16 KB
-constexpr int O_BYTES = QT * 128;       // 16 KB staging for the TMA store
+constexpr int O_BYTES = QT * 128;       // 16 KB staging for the TMA store (one per softmax group)
 
-template <int OFF, int REM>
-__device__ __forceinline__ void ld_row(uint32_t taddr, uint32_t* r) {
-  if constexpr (REM >= 32) {
-    tmem_ld_32x32b_x32p(taddr + OFF, r + OFF);
-    ld_row<OFF + 32, REM - 32>(taddr, r);
-  } else if constexpr (REM >= 16) {
-    tmem_ld_32x32b_x16(taddr + OFF, r + OFF);
-    ld_row<OFF + 16, REM - 16>(taddr, r);
-  } else if constexpr (REM >= 8) {
-    tmem_ld_32x32b_x8(taddr + OFF, r + OFF);
-    ld_row<OFF + 8, REM - 8>(taddr, r);
-  }
-}
-template <int OFF, int REM>
-__device__ __forceinline__ void st_row(uint32_t taddr, const uint32_t* r) {
-  if constexpr (REM >= 16) {
-    tmem_st_32x32b_x16(taddr + OFF, r + OFF);
-    st_row<OFF + 16, REM - 16>(taddr, r);
-  } else if constexpr (REM >= 8) {
-    tmem_st_32x32b_x8(taddr + OFF, r + OFF);
-    st_row<OFF + 8, REM - 8>(taddr, r);
-  } else if constexpr (REM >= 4) {
-    tmem_st_32x32b_x4(taddr + OFF, r + OFF);
-    st_row<OFF + 4, REM - 4>(taddr, r);
-  }
-}
+constexpr int QS = 4;                   // Q ring depth (one tile per item)
+constexpr int KS = 2;                   // K/V ring depth (one entry per (image, head), shared by its q tiles)
 
 template <int KP>
 struct Smem {
   static constexpr int KV_BYTES = KP * 128;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-  static constexpr int OFF_O = OFF_V + 2 * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_O + O_BYTES;          // 16 mbarriers + tmem slot
-  static constexpr int OFF_XMAX = OFF_BAR + 256;               // float [2 slots][2][128]
-  static constexpr int OFF_XSUM = OFF_XMAX + 2 * 2 * 128 * 4;  // float [2 slots][2][128]
-  static constexpr int TOTAL = OFF_XSUM + 2 * 2 * 128 * 4 + 1024 /*align slack*/;
+  static constexpr int OFF_K = OFF_Q + QS * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KS * KV_BYTES;
+  static constexpr int OFF_O = OFF_V + KS * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_O + 2 * O_BYTES;        // 2 staging buffers; then 32 mbarrier slots
+  static constexpr int OFF_INV = OFF_BAR + 256;              // float [4][128]: 1/rowsum, by item parity mod 4
+  static constexpr int TOTAL = OFF_INV + 4 * 128 * 4 + 1024 /*align slack*/;
   static_assert(KV_BYTES % 1024 == 0, "K/V stage must keep 1024-byte alignment");
+  static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int kDT, int KP>
+// 2^x for x <= 0 on the FMA/ALU pipes, two lanes at a time.  x = n + f, n = round(x), f in
+// [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial; 2^n is added into the exponent field.
+__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, float& p1) {
+  const float MAGIC = 12582912.f;   // 1.5 * 2^23: (x + MAGIC) holds round(x) in its low mantissa bits
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  const unsigned long long xc = pack_f32x2(x0, x1);
+  const unsigned long long t2 = add_f32x2(xc, pack_f32x2(MAGIC, MAGIC));
+  const unsigned long long n2 = add_f32x2(t2, pack_f32x2(-MAGIC, -MAGIC));
+  const unsigned long long f2 = fma_f32x2(n2, pack_f32x2(-1.f, -1.f), xc);
+  unsigned long long p2 = fma_f32x2(pack_f32x2(0.0551716648f, 0.0551716648f), f2,
+                                    pack_f32x2(0.2426111251f, 0.2426111251f));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677f, 0.6932609677f));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float t0, t1, q0, q1;
+  unpack_f32x2(t2, t0, t1);
+  unpack_f32x2(p2, q0, q1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
+// NN (32 or 16) score columns of this thread's row, already in registers:
+// p = exp2(s*sl2 + mneg) -> fp32 partial sums (la/lb) -> 16-bit P pairs.  kPoly of every 4 pairs
+// go through the polynomial; kMask: the chunk may reach past T (keys >= T are zero-filled K rows:
+// score 0, not -inf, so they are forced to -inf here).
+template <int kDT, int NN, int kPoly, bool kMask>
+__device__ __forceinline__ void softmax_chunk(uint32_t* r, uint32_t* pp, int c0, int T,
+                                              unsigned long long sl2x2, unsigned long long mnegx2,
+                                              unsigned long long& la, unsigned long long& lb) {
+  if constexpr (kMask) {
+#pragma unroll
+    for (int j = 0; j < NN; ++j)
+      if (c0 + j >= T) r[j] = __float_as_uint(-INFINITY);
+  }
+#pragma unroll
+  for (int j = 0; j < NN / 2; ++j) {
+    const unsigned long long a2 =
+        fma_f32x2(pack_f32x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), sl2x2, mnegx2);
+    float p0, p1;
+    if ((j & 3) < kPoly) {
+      exp2_poly2(a2, p0, p1);
+    } else {
+      float a0, a1;
+      unpack_f32x2(a2, a0, a1);
+      p0 = ex2_approx(a0);
+      p1 = ex2_approx(a1);
+    }
+    if (j & 1) lb = add_f32x2(lb, pack_f32x2(p0, p1));
+    else la = add_f32x2(la, pack_f32x2(p0, p1));
+    pp[j] = pack2<kDT>(p0, p1);
+  }
+}
+
+template <int kDT, int KP, int kPoly>
 __global__ void __launch_bounds__(NT, 1)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I], box 128 rows
                      const __grid_constant__ CUtensorMap tmKV,   // qkv [B,T,3I], box KP rows
                      const __grid_constant__ CUtensorMap tmO,    // out [B,T,I],  box 128 rows
-                     int T, int heads, int nqt, int items) {
+                     int T, int heads, int nqt, int items, int turns) {
   using L = Smem<KP>;
-  constexpr int CH = KP / 2;            // S columns per thread (one half of the row)
-  constexpr int PH = CH / 2;            // packed P columns per thread
+  // TMEM columns: slot s holds S (fp32, KP columns) then P (16-bit pairs, KP/2 columns) of the
+  // item in flight on it; one O accumulator (64 columns) is shared by both slots.
+  constexpr uint32_t SLOT_COLS = KP <= 128 ? 128 : 208;
+  constexpr uint32_t O_COL = 2 * SLOT_COLS;
+  static_assert(O_COL + DH <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base + L::OFF_Q, sK = base + L::OFF_K, sV = base + L::OFF_V, sO = base + L::OFF_O;
   const uint32_t bars = base + L::OFF_BAR;
-  auto qk_full = [&](int s) { return bars + 8u * (0 + s); };
-  auto v_full = [&](int s) { return bars + 8u * (2 + s); };
-  auto qk_empty = [&](int s) { return bars + 8u * (4 + s); };
-  auto v_empty = [&](int s) { return bars + 8u * (6 + s); };
-  auto s_ready = [&](int s) { return bars + 8u * (8 + s); };
-  auto p_ready = [&](int s) { return bars + 8u * (10 + s); };
-  auto o_ready = [&](int s) { return bars + 8u * (12 + s); };
-  auto slot_free = [&](int s) { return bars + 8u * (14 + s); };
-  const uint32_t tmem_slot = bars + 8u * 16;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_BAR + 8 * 16);
-  float* xmax = reinterpret_cast<float*>(gbase + L::OFF_XMAX);
-  float* xsum = reinterpret_cast<float*>(gbase + L::OFF_XSUM);
+  auto q_full = [&](int s) { return bars + 8u * (0 + s); };    // [QS]
+  auto q_empty = [&](int s) { return bars + 8u * (4 + s); };   // [QS]
+  auto k_full = [&](int s) { return bars + 8u * (8 + s); };    // [KS]
+  auto v_full = [&](int s) { return bars + 8u * (10 + s); };
+  auto k_empty = [&](int s) { return bars + 8u * (12 + s); };
+  auto v_empty = [&](int s) { return bars + 8u * (14 + s); };
+  auto s_ready = [&](int s) { return bars + 8u * (16 + s); };  // [2 TMEM slots]
+  auto p_ready = [&](int s) { return bars + 8u * (18 + s); };
+  auto o_ready = [&](int s) { return bars + 8u * (20 + s); };
+  const uint32_t o_free = bars + 8u * 22;
+  const uint32_t xu_done = bars + 8u * 23;                     // exponential phases take turns (see below)
+  const uint32_t tmem_slot = bars + 8u * 24;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_BAR + 8 * 24);
+  float* inv_sh = reinterpret_cast<float*>(gbase + L::OFF_INV);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = heads * DH;
@@ -111,16 +173,21 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
     prefetch_tmap(&tmO);
   }
   if (warp == 1 && lane == 0) {
+    for (int s = 0; s < QS; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(qk_full(s), 1);
+      mbar_init(k_full(s), 1);
       mbar_init(v_full(s), 1);
-      mbar_init(qk_empty(s), 1);
+      mbar_init(k_empty(s), 1);
       mbar_init(v_empty(s), 1);
       mbar_init(s_ready(s), 1);
-      mbar_init(p_ready(s), 8);
+      mbar_init(p_ready(s), 4);
       mbar_init(o_ready(s), 1);
-      mbar_init(slot_free(s), 8);
     }
+    mbar_init(o_free, 4);
+    mbar_init(xu_done, 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
@@ -129,172 +196,248 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // K and V of one (image, head) are loaded once and shared by its q tiles: entry e of the K/V ring
+  // belongs to the e-th distinct (image, head) this CTA touches.
+  const int bh0 = int(first / nqt);
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // Loads are issued in the order they are needed (K, Q, V of an item); every ring slot it
+    // waits for was released at least one item ago, so the producer runs well ahead.
     if (lane == 0) {
       for (int i = 0; i < n; ++i) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
         const int64_t item = first + i;
         const int bh = int(item / nqt), qt = int(item - int64_t(bh) * nqt);
         const int b = bh / heads, h = bh - b * heads;
-        mbar_wait(qk_empty(s), ph ^ 1u);
-        mbar_arrive_expect_tx(qk_full(s), Q_BYTES + L::KV_BYTES);
-        tma_load_3d(sQ + s * Q_BYTES, &tmQ, qk_full(s), h * DH, qt * QT, b);
-        tma_load_3d(sK + s * L::KV_BYTES, &tmKV, qk_full(s), inner + h * DH, 0, b);
-        mbar_wait(v_empty(s), ph ^ 1u);
-        mbar_arrive_expect_tx(v_full(s), L::KV_BYTES);
-        tma_load_3d(sV + s * L::KV_BYTES, &tmKV, v_full(s), 2 * inner + h * DH, 0, b);
+        const int e = bh - bh0, es = e & 1;
+        const uint32_t eph = (e >> 1) & 1;
+        const bool first_of_bh = (i == 0) || (qt == 0);
+        if (first_of_bh) {
+          mbar_wait(k_empty(es), eph ^ 1u);
+          mbar_arrive_expect_tx(k_full(es), L::KV_BYTES);
+          tma_load_3d(sK + es * L::KV_BYTES, &tmKV, k_full(es), inner + h * DH, 0, b);
+        }
+        const int qs = i & (QS - 1);
+        mbar_wait(q_empty(qs), ((i / QS) & 1) ^ 1u);
+        TRACE(0, i);
+        mbar_arrive_expect_tx(q_full(qs), Q_BYTES);
+        tma_load_3d(sQ + qs * Q_BYTES, &tmQ, q_full(qs), h * DH, qt * QT, b);
+        if (first_of_bh) {
+          mbar_wait(v_empty(es), eph ^ 1u);
+          TRACE(1, i);
+          mbar_arrive_expect_tx(v_full(es), L::KV_BYTES);
+          tma_load_3d(sV + es * L::KV_BYTES, &tmKV, v_full(es), 2 * inner + h * DH, 0, b);
+        }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers: warp 1 drives TMEM slot 0, warp 3 slot 1 =====================
+    // A slot runs S(i) -> PV(i) -> S(i+2) -> ...  S(i+2) may follow PV(i) at once: one thread's MMAs
+    // execute in order, so PV(i) has consumed P(i) before S(i+2) overwrites it, and O has its own
+    // columns.  The O accumulator is shared by both slots: PV(i) waits until the epilogue of item
+    // i-1 has pulled its O into registers (o_free), which also orders the two issuers' products.
+    // Every wait is a blocking mbarrier wait (hardware suspend): no polling next to the softmax warps.
     if (lane == 0) {
       constexpr int fmt = kDT == DT_F16 ? 0 : 1;
       constexpr uint32_t idesc_s = umma_idesc_16(QT, KP, fmt, 0);   // B = K, K-major
       constexpr uint32_t idesc_o = umma_idesc_16(QT, DH, fmt, 1);   // B = V, MN-major
+      const int s = warp == 1 ? 0 : 1;
+      const uint32_t d_s = tmem_base + s * SLOT_COLS, d_o = tmem_base + O_COL;
+      const int first_lo = int(first % nqt);             // q tile of item 0
+      auto meta = [&](int i, int& es, uint32_t& eph, bool& last_of_bh) {
+        const int t = first_lo + i;                      // tiles since the start of (image, head) bh0
+        const int e = t / nqt, qt = t - e * nqt;
+        es = e & 1;
+        eph = (e >> 1) & 1;
+        last_of_bh = (i == n - 1) || (qt == nqt - 1);
+      };
       auto issue_s = [&](int i) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(slot_free(s), ph ^ 1u);
-        mbar_wait(qk_full(s), ph);
+        int es; uint32_t eph; bool last_of_bh;
+        meta(i, es, eph, last_of_bh);
+        const int qs = i & (QS - 1);
+        mbar_wait(q_full(qs), (i / QS) & 1);
+        mbar_wait(k_full(es), eph);
+        TRACE(2, i);
         tc_fence_after();
-        const uint32_t q0 = sQ + s * Q_BYTES, k0 = sK + s * L::KV_BYTES;
+        const uint32_t q0 = sQ + qs * Q_BYTES, k0 = sK + es * L::KV_BYTES;
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_bf16_ss<1>(tmem_base + s * 256, umma_desc_k_sw128(q0 + k * 32),
-                          umma_desc_k_sw128(k0 + k * 32), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(qk_empty(s));
+          umma_bf16_ss<1>(d_s, umma_desc_k_sw128(q0 + k * 32), umma_desc_k_sw128(k0 + k * 32), idesc_s,
+                          k != 0 ? 1u : 0u);
+        umma_commit(q_empty(qs));
+        if (last_of_bh) umma_commit(k_empty(es));
         umma_commit(s_ready(s));
       };
-      auto issue_pv = [&](int i) {
-        const int s = i & 1;
+      if (s < n) issue_s(s);
+      for (int i = s; i < n; i += 2) {
+        int es; uint32_t eph; bool last_of_bh;
+        meta(i, es, eph, last_of_bh);
         const uint32_t ph = (i >> 1) & 1;
         mbar_wait(p_ready(s), ph);
-        mbar_wait(v_full(s), ph);
+        mbar_wait(v_full(es), eph);
+        mbar_wait(o_free, uint32_t(i & 1) ^ 1u);
+        TRACE(3, i);
         tc_fence_after();
-        const uint32_t v0 = sV + s * L::KV_BYTES;
+        const uint32_t v0 = sV + es * L::KV_BYTES;
 #pragma unroll
         for (int kk = 0; kk < KP / 16; ++kk)
-          umma_bf16_ts(tmem_base + s * 256 + 128, tmem_base + s * 256 + kk * 8,
-                       umma_desc_mn_sw128(v0 + kk * 2048), idesc_o, kk != 0 ? 1u : 0u);
-        umma_commit(v_empty(s));
+          umma_bf16_ts(d_o, d_s + kk * 8, umma_desc_mn_sw128(v0 + kk * 2048), idesc_o, kk != 0 ? 1u : 0u);
+        if (last_of_bh) umma_commit(v_empty(es));
         umma_commit(o_ready(s));
-      };
-      if (n > 0) issue_s(0);
-      for (int i = 0; i < n; ++i) {
-        if (i + 1 < n) issue_s(i + 1);
-        issue_pv(i);
+        if (i + 2 < n) issue_s(i + 2);
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ===================== softmax + epilogue =====================
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== softmax (two independent groups) =====================
     const int w = warp - 4;
     const int q = w & 3;                  // TMEM lane quarter (== warp % 4)
-    const int hf = w >> 2;                // column half of the score row
+    const int grp = w >> 2;               // group == TMEM slot == smem stage parity
     const int row = q * 32 + lane;        // query row in the tile == TMEM lane
-    const bool leader = (w == 0 && lane == 0);
-    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t t_slot = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(grp * SLOT_COLS);
     const float sl2 = 0.125f * 1.4426950408889634f;   // dim_head^-0.5 * log2(e)   (vit.py:66)
+    // score row = NFULL chunks of 32 columns (+ one of 16); chunks past KMIN may hold keys >= T
+    constexpr int NFULL = KP / 32, TAIL = KP % 32;
+    constexpr int KMIN = KP == 208 ? 128 : (KP == 128 ? 64 : 0);   // launch_poly: T > KMIN
+    static_assert(TAIL == 0 || TAIL == 16, "key block = n*32 (+16)");
+    constexpr int HANDOFF = NFULL >= 3 ? NFULL - 2 : NFULL - 1;   // chunk after which the next item may start its exponentials
 
-    // epilogue of item j: O / rowsum -> 16-bit -> swizzled smem -> TMA store.  Called by all 256
-    // threads right after a group barrier (which also orders the xsum / staging-buffer hazards).
-    auto epilogue = [&](int j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      const int64_t item = first + j;
+    for (int i = grp; i < n; i += 2) {
+      const uint32_t ph = (i >> 1) & 1;
+      const int64_t item = first + i;
       const int bh = int(item / nqt), qt = int(item - int64_t(bh) * nqt);
       const int b = bh / heads, h = bh - b * heads;
-      mbar_wait(o_ready(s), ph);
+      const bool active = qt * QT + q * 32 < T;          // warp-uniform: any valid query row here?
+      if (q == 0 && lane == 0) TRACE(4, i);
+      mbar_wait(s_ready(grp), ph);
+      if (q == 0 && lane == 0) TRACE(5, i);
       tc_fence_after();
-      const float inv = 1.0f / (xsum[(s * 2 + 0) * 128 + row] + xsum[(s * 2 + 1) * 128 + row]);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {        // 2 x 16 columns of this thread's 32
-        uint32_t o[16];
-        tmem_ld_32x32b_x16(t_lane + uint32_t(s * 256 + 128 + hf * 32 + c * 16), o);
+      if (active) {
+        // Both passes stream the row through two register buffers: the tcgen05.ld of chunk c+1
+        // is in flight while chunk c is processed (tcgen05.wait::ld covers all outstanding loads).
+        uint32_t r[2][32];
+        // ---- pass 1: row max ----
+        float mx = -INFINITY;
+        tmem_ld_32x32b_x32p(t_slot, r[0]);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {      // 8 columns -> one 16-byte chunk
-          const int chunk = hf * 4 + c * 2 + g;
-          st_shared_v4(sO + uint32_t(row) * 128u + (uint32_t(chunk ^ (row & 7)) << 4),
+        for (int c = 0; c < NFULL; ++c) {
+          if (c + 1 < NFULL) tmem_ld_32x32b_x32p(t_slot + (c + 1) * 32, r[(c + 1) & 1]);
+          else if (TAIL) tmem_ld_32x32b_x16(t_slot + (c + 1) * 32, r[(c + 1) & 1]);
+          uint32_t* rc = r[c & 1];
+          if (c * 32 + 32 > KMIN && c * 32 + 32 > T) {   // warp-uniform: only the chunk(s) past T pay
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j >= T) rc[j] = __float_as_uint(-INFINITY);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            mx = fmaxf(mx, fmaxf(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1])));
+          if (c + 1 < NFULL || TAIL) tmem_ld_wait();
+        }
+        if constexpr (TAIL != 0) {
+          uint32_t* rc = r[NFULL & 1];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (NFULL * 32 + j >= T) rc[j] = __float_as_uint(-INFINITY);
+#pragma unroll
+          for (int j = 0; j < 16; j += 2)
+            mx = fmaxf(mx, fmaxf(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1])));
+        }
+        if (q == 0 && lane == 0) TRACE(6, i);
+        // The exponential phases of consecutive items take turns on the MUFU: left alone the two
+        // groups fall into step (both exponentiate, then both wait), which idles the pipe that
+        // bounds this kernel for the length of everything else.
+        if (turns) mbar_wait(xu_done, uint32_t(i & 1) ^ 1u);
+        // ---- pass 2: p = exp2((s - max) * scale * log2e), un-normalised; row sum in fp32; P -> TMEM
+        // P chunk c (16 columns of 16-bit pairs) lands on S columns [16c, 16c+16), all read already.
+        const float mneg = -mx * sl2;
+        const unsigned long long sl2x2 = pack_f32x2(sl2, sl2), mnegx2 = pack_f32x2(mneg, mneg);
+        unsigned long long la = pack_f32x2(0.f, 0.f), lb = la;
+        tmem_ld_32x32b_x32p(t_slot, r[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NFULL; ++c) {
+          if (c + 1 < NFULL) tmem_ld_32x32b_x32p(t_slot + (c + 1) * 32, r[(c + 1) & 1]);
+          else if (TAIL) tmem_ld_32x32b_x16(t_slot + (c + 1) * 32, r[(c + 1) & 1]);
+          uint32_t pp[16];
+          if (c * 32 + 32 > KMIN && c * 32 + 32 > T) softmax_chunk<kDT, 32, 0, true>(r[c & 1], pp, c * 32, T, sl2x2, mnegx2, la, lb);
+          else softmax_chunk<kDT, 32, kPoly, false>(r[c & 1], pp, c * 32, T, sl2x2, mnegx2, la, lb);
+          if (c + 1 < NFULL || TAIL) tmem_ld_wait();    // chunk c+1 is in registers: its S columns may go
+          tmem_st_32x32b_x16(t_slot + c * 16, pp);
+          if (c == HANDOFF && turns == 2) { __syncwarp(); if (lane == 0) mbar_arrive(xu_done); }
+        }
+        if constexpr (TAIL != 0) {
+          uint32_t pp[8];
+          softmax_chunk<kDT, 16, 0, true>(r[NFULL & 1], pp, NFULL * 32, T, sl2x2, mnegx2, la, lb);
+          tmem_st_32x32b_x8(t_slot + NFULL * 16, pp);
+        }
+        float l0, l1;
+        unpack_f32x2(add_f32x2(la, lb), l0, l1);
+        inv_sh[(i & 3) * 128 + row] = 1.0f / (l0 + l1);   // for the epilogue warps (ordered by p_ready)
+        tmem_st_wait();
+        if (turns == 1 && lane == 0) mbar_arrive(xu_done);
+      } else if (turns) {
+        mbar_wait(xu_done, uint32_t(i & 1) ^ 1u);
+        if (lane == 0) mbar_arrive(xu_done);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready(grp));
+      if (q == 0 && lane == 0) TRACE(7, i);
+
+    }
+  } else if (warp >= 12) {
+    // ===================== epilogue: O / rowsum -> 16-bit -> swizzled smem -> TMA store ==========
+    const int q = warp & 3;               // TMEM lane quarter (== warp % 4)
+    const int row = q * 32 + lane;
+    const bool leader = (q == 0 && lane == 0);
+    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
+    for (int i = 0; i < n; ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int64_t item = first + i;
+      const int bh = int(item / nqt), qt = int(item - int64_t(bh) * nqt);
+      const int b = bh / heads, h = bh - b * heads;
+      const bool active = qt * QT + q * 32 < T;
+      const uint32_t sOi = sO + uint32_t(i & 1) * O_BYTES;
+      if (leader) TRACE(8, i);
+      mbar_wait(o_ready(s), ph);                         // PV(i) done; it was issued after p_ready(i),
+                                                         // which ordered the group's 1/rowsum writes
+      tc_fence_after();
+      uint32_t o[64];
+      float inv = 0.f;
+      if (active) {
+        tmem_ld_32x32b_x32p(t_lane + O_COL, o);
+        tmem_ld_32x32b_x32p(t_lane + O_COL + 32, o + 32);
+        inv = inv_sh[(i & 3) * 128 + row];
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);                // O is in registers: PV(i+1) may overwrite it
+      if (active) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {        // 8 columns -> one 16-byte chunk
+          st_shared_v4(sOi + uint32_t(row) * 128u + (uint32_t(g ^ (row & 7)) << 4),
                        pack2<kDT>(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv),
                        pack2<kDT>(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv),
                        pack2<kDT>(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv),
                        pack2<kDT>(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv));
         }
       }
-      tc_fence_before();
       fence_proxy_async_smem();
-      named_bar_sync(4, 256);
-      if (lane == 0) mbar_arrive(slot_free(s));          // TMEM slot (S/P/O of item j) reusable
-      if (leader) {
-        tma_store_3d(&tmO, sO, h * DH, qt * QT, b);      // rows >= T are clipped by the tensor map
-        tma_store_commit();
-      }
-    };
-
-    for (int i = 0; i < n; ++i) {
-      const int s = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
-      mbar_wait(s_ready(s), ph);
-      tc_fence_after();
-      uint32_t sr[CH];
-      ld_row<0, CH>(t_lane + uint32_t(s * 256 + hf * CH), sr);
-      tmem_ld_wait();
-      // half-row max.  Keys >= T come from zero-filled K rows (score 0, not -inf): they are masked,
-      // but only in the 8-column groups that reach past T (warp-uniform test), so the common path
-      // is one 3-input max per two scores and nothing else.
-      const int nvalid = T - hf * CH;       // valid columns of this half (may be <= 0 or >= CH)
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c8 = 0; c8 < CH / 8; ++c8) {
-        if ((c8 + 1) * 8 > nvalid) {
-#pragma unroll
-          for (int j = c8 * 8; j < c8 * 8 + 8; ++j)
-            if (j >= nvalid) sr[j] = __float_as_uint(-INFINITY);
-        }
-#pragma unroll
-        for (int j = c8 * 8; j < c8 * 8 + 8; j += 2)
-          mx = fmaxf(mx, fmaxf(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])));
-      }
-      xmax[(s * 2 + hf) * 128 + row] = mx;       // slot-indexed: no WAR race with a slow partner
-      if (leader) tma_store_wait_read<0>();              // staging buffer of epilogue(i-2) drained
-      tc_fence_before();
-      named_bar_sync(3, 256);                            // all S reads done; maxima + staging visible
-      mx = fmaxf(mx, xmax[(s * 2 + (hf ^ 1)) * 128 + row]);
-      if (i > 0) epilogue(i - 1);
-      // p = exp2((s - max) * scale * log2e); un-normalised, row sum kept in fp32
-      const float mneg = -mx * sl2;
-      const unsigned long long sl2x2 = pack_f32x2(sl2, sl2), mnegx2 = pack_f32x2(mneg, mneg);
-      unsigned long long lx2 = pack_f32x2(0.f, 0.f);
-      uint32_t pp[PH];
-#pragma unroll
-      for (int j = 0; j < PH; ++j) {
-        float a0, a1;
-        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * j]), __uint_as_float(sr[2 * j + 1])),
-                               sl2x2, mnegx2), a0, a1);
-        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-        lx2 = add_f32x2(lx2, pack_f32x2(p0, p1));
-        pp[j] = pack2<kDT>(p0, p1);
-      }
-      float l0, l1;
-      unpack_f32x2(lx2, l0, l1);
-      const float l = l0 + l1;
-      xsum[(s * 2 + hf) * 128 + row] = l;
-      st_row<0, PH>(t_lane + uint32_t(s * 256 + hf * PH), pp);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready(s));
-    }
-    if (n > 0) {
+      // the store of item i-1 (other staging buffer) has been read out: after the barrier every
+      // epilogue thread may write that buffer for item i+1
       if (leader) tma_store_wait_read<0>();
-      named_bar_sync(3, 256);
-      epilogue(n - 1);
-      if (leader) tma_store_wait<0>();
+      named_bar_sync(1, 128);
+      if (leader) {
+        tma_store_3d(&tmO, sOi, h * DH, qt * QT, b);     // rows >= T are clipped by the tensor map
+        tma_store_commit();
+        TRACE(10, i);
+      }
     }
+    if (leader) tma_store_wait<0>();                     // smem must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -305,12 +448,23 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
   }
 }
 
-template <int kDT, int KP>
+// how the two softmax groups share the MUFU: 0 = free-running, 1 = exponential phases strictly
+// alternate, 2 = alternate with the hand-off two chunks before the end (VITB200_ATTN_TURNS)
+int attn_turns() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITB200_ATTN_TURNS");
+    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return v;
+}
+
+template <int kDT, int KP, int kPoly>
 int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
   using L = Smem<KP>;
   static bool configured = false;
   if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<kDT, KP>,
+    VB_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<kDT, KP, kPoly>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
@@ -325,19 +479,46 @@ int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
   if (items64 > 0x7fffffff) return fail(VITB200_ERR_INVALID, "attention: too many work items");
   const int items = int(items64);
   const int grid = items < sm_count() ? items : sm_count();
-  attention_tc5_kernel<kDT, KP><<<grid, NT, L::TOTAL, stream>>>(tq, tkv, to, T, heads, nqt, items);
+  attention_tc5_kernel<kDT, KP, kPoly><<<grid, NT, L::TOTAL, stream>>>(tq, tkv, to, T, heads, nqt, items, attn_turns());
   VB_LAUNCH_CHECK("attention_tc5_kernel");
   return 0;
 }
 
+// share of the ex2 evaluated on the FMA pipe, in quarters (0..2); VITB200_ATTN_POLY overrides
+int poly_quarters() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITB200_ATTN_POLY");
+    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+  }
+  return v;
+}
+
+template <int kDT, int kPoly>
+int launch_poly(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
+  if (T <= 64) return launch_kp<kDT, 64, kPoly>(stream, qkv, out, batch, T, heads);
+  if (T <= 128) return launch_kp<kDT, 128, kPoly>(stream, qkv, out, batch, T, heads);
+  return launch_kp<kDT, 208, kPoly>(stream, qkv, out, batch, T, heads);
+}
+
 template <int kDT>
 int launch_dt(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
-  if (T <= 64) return launch_kp<kDT, 64>(stream, qkv, out, batch, T, heads);
-  if (T <= 128) return launch_kp<kDT, 128>(stream, qkv, out, batch, T, heads);
-  return launch_kp<kDT, 208>(stream, qkv, out, batch, T, heads);
+  switch (poly_quarters()) {
+    case 0: return launch_poly<kDT, 0>(stream, qkv, out, batch, T, heads);
+    case 2: return launch_poly<kDT, 2>(stream, qkv, out, batch, T, heads);
+    default: return launch_poly<kDT, 1>(stream, qkv, out, batch, T, heads);
+  }
 }
 
 }  // namespace
+
+#ifdef VITB200_TRACE
+}  // namespace vb
+extern "C" int vitb200_debug_attention_trace(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, vb::g_trace, sizeof(long long) * (n < 12 * 64 ? n : 12 * 64)) == cudaSuccess ? 0 : -2;
+}
+namespace vb {
+#endif
 
 bool attention_tc5_supports(int T) { return T >= 1 && T <= 208; }
 

@@ -60,6 +60,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking probe (no hardware suspend): for a thread that polls several barriers
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // Spin with a watchdog: a protocol bug traps (launch fails with an error) instead of
 // hanging the GPU.  ~4e9 cycles is seconds, far beyond any legitimate wait here.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
