@@ -174,6 +174,31 @@ def test_attention_tc(lib, batch, T, heads, fmt, impl, monkeypatch):
     assert err.max() < 8 * ulp + 1e-3 and err.mean() < ulp + 2e-4, (err.max(), err.mean())
 
 
+@pytest.mark.parametrize("batch,T,heads", [(256, 197, 12), (300, 197, 5), (97, 128, 3)])
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_attention_tc_every_image_of_a_full_batch(lib, batch, T, heads, fmt, monkeypatch):
+    """BASELINE-size batch: EVERY (image, head) is checked (torch fp32 reference on the GPU, in
+    chunks), several launches back to back.  Regression test for a K-ring release race that
+    corrupted a handful of (image, head) tiles only when all 148 persistent CTAs were busy."""
+    monkeypatch.delenv("VITB200_ATTENTION", raising=False)
+    dt, tdt, ulp = DT16[fmt]
+    inner = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(batch + T)
+    qkv = (torch.randn((batch * T, 3 * inner), device="cuda", generator=g) * 1.5).to(tdt)
+    for rep in range(3):
+        out = torch.full((batch * T, inner), float("nan"), dtype=tdt, device="cuda")
+        _lib.check(lib.vitb200_attention_tc(stream(), qkv.data_ptr(), out.data_ptr(), batch, T, heads, dt))
+        torch.cuda.synchronize()
+        worst = 0.0
+        for b0 in range(0, batch, 32):
+            nb = min(32, batch - b0)
+            rows = slice(b0 * T, (b0 + nb) * T)
+            q, k, v = (t.reshape(nb, T, heads, 64).permute(0, 2, 1, 3).float() for t in qkv[rows].split(inner, dim=1))
+            want = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).permute(0, 2, 1, 3).reshape(nb * T, inner)
+            worst = max(worst, float((out[rows].float() - want).abs().max()))
+        assert worst < 8 * ulp + 1e-3, (rep, worst)
+
+
 @pytest.mark.parametrize("batch,T,heads", [(1, 65, 16), (2, 197, 3), (1, 300, 2)])
 def test_attention_f32(lib, batch, T, heads):
     rng = np.random.default_rng(T)

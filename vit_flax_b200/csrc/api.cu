@@ -34,6 +34,8 @@ struct DenseW {
   uint16_t* wt = nullptr;                 // bf16/fp16 [N, Kpad] (tensor-core modes)
   CUtensorMap tm{};                       // box 256 x 64 over wt (one CTA per tile)
   CUtensorMap tm2{};                      // box 128 x 64 over wt (CTA pair per tile)
+  CUtensorMap tm4{};                      // box 64 x 64 over wt (cluster of two pairs, multicast)
+  const CUtensorMap& map(int cg) const { return cg == 4 ? tm4 : (cg == 2 ? tm2 : tm); }
 };
 
 struct Layer {
@@ -213,7 +215,8 @@ int pack_dense(vitb200_model* m, DenseW& d, cudaStream_t st) {
   int rc = launch_pack_weight(st, m->leaves[d.leaf_kernel].dev, d.wt, d.K, d.N, d.Kpad, m->dt);
   if (rc) return rc;
   if ((rc = make_tmap_2d(&d.tm, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN, m->dt))) return rc;
-  return make_tmap_2d(&d.tm2, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN / 2, m->dt);
+  if ((rc = make_tmap_2d(&d.tm2, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN / 2, m->dt))) return rc;
+  return make_tmap_2d(&d.tm4, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN / 4, m->dt);
 }
 
 inline const float* leaf_ptr(const vitb200_model* m, int idx) { return idx >= 0 ? m->leaves[idx].dev : nullptr; }
@@ -252,7 +255,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
                             c.patch_h, c.patch_w, m->K0pad, m->dt))) return rc;
   // vit.py:147-153  Dense_0 + bias, placed at row b*T+1+t, + pos_embedding[1+t]
   mark(m, st, VITB200_CAT_GEMM_PATCH);
-  if ((rc = launch_gemm_tc(st, am->patches, cgp == 2 ? m->patch.tm2 : m->patch.tm, nullptr, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+  if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), nullptr, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
                              Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt, cgp))) return rc;
   mark(m, st, VITB200_CAT_CLS_ROWS);
   if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
@@ -262,12 +265,12 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_QKV);
-    if ((rc = launch_gemm_tc(st, am->xn, cg == 2 ? L.qkv.tm2 : L.qkv.tm, &am->c_qkv, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt, cg))) return rc;
+    if ((rc = launch_gemm_tc(st, am->xn, L.qkv.map(cg), &am->c_qkv, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt, cg))) return rc;
     mark(m, st, VITB200_CAT_ATTENTION);
     if ((rc = launch_attention_tc(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_OUT);
     if (m->project_out) {
-      if ((rc = launch_gemm_tc(st, am->o, cg == 2 ? L.out.tm2 : L.out.tm, &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg))) return rc;
+      if ((rc = launch_gemm_tc(st, am->o, L.out.map(cg), &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg))) return rc;
     } else {   // heads == 1 and dim == 64: to_out is the identity (vit.py:65,85)
       const int64_t n = int64_t(R) * D;
       add_16_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_h.p, m->x.p, n, m->dt);
@@ -277,9 +280,9 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF1);
-    if ((rc = launch_gemm_tc(st, am->xn, cg == 2 ? L.ff1.tm2 : L.ff1.tm, &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt, cg))) return rc;
+    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.map(cg), &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt, cg))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF2);
-    if ((rc = launch_gemm_tc(st, am->h, cg == 2 ? L.ff2.tm2 : L.ff2.tm, &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg))) return rc;
+    if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg))) return rc;
   }
   // vit.py:159-165  pool, LayerNorm_0, Dense_1
   if (m->head_tc) {
@@ -289,7 +292,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_GEMM_HEAD);
     CUtensorMap c_logits;   // the caller's buffer: encoded per call (host-side, ~1 us)
     if ((rc = make_tmap_2d(&c_logits, logits, batch, c.num_classes, c.num_classes, GEMM_BM, VITB200_DT_F32))) return rc;
-    if ((rc = launch_gemm_tc(st, am->pooled, cgh == 2 ? m->head.tm2 : m->head.tm, &c_logits, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0, m->dt, cgh))) return rc;
+    if ((rc = launch_gemm_tc(st, am->pooled, m->head.map(cgh), &c_logits, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0, m->dt, cgh))) return rc;
   } else {
     mark(m, st, VITB200_CAT_POOL_LN);
     mark(m, st, VITB200_CAT_POOL_LN);

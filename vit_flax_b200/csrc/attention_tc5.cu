@@ -180,8 +180,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(v_full(s), 1);
-      mbar_init(k_empty(s), 1);
-      mbar_init(v_empty(s), 1);
+      mbar_init(k_empty(s), nqt);                      // one arrival per q tile of the (image, head): the
+      mbar_init(v_empty(s), nqt);                      // two issuers release a K/V entry independently
       mbar_init(s_ready(s), 1);
       mbar_init(p_ready(s), 4);
       mbar_init(o_ready(s), 1);
@@ -195,6 +195,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();                // the to_qkv GEMM has completed
 
   // K and V of one (image, head) are loaded once and shared by its q tiles: entry e of the K/V ring
   // belongs to the e-th distinct (image, head) this CTA touches.
@@ -244,16 +246,19 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
       const int s = warp == 1 ? 0 : 1;
       const uint32_t d_s = tmem_base + s * SLOT_COLS, d_o = tmem_base + O_COL;
       const int first_lo = int(first % nqt);             // q tile of item 0
-      auto meta = [&](int i, int& es, uint32_t& eph, bool& last_of_bh) {
+      // K/V ring entry of item i.  Every item arrives once on k_empty / v_empty of its entry (the
+      // entry is free when all nqt tiles of the (image, head) have); `missing` = tiles of the first
+      // (image, head) that belong to the previous CTA, whose arrivals item 0 supplies.
+      auto meta = [&](int i, int& es, uint32_t& eph, int& missing) {
         const int t = first_lo + i;                      // tiles since the start of (image, head) bh0
-        const int e = t / nqt, qt = t - e * nqt;
+        const int e = t / nqt;
         es = e & 1;
         eph = (e >> 1) & 1;
-        last_of_bh = (i == n - 1) || (qt == nqt - 1);
+        missing = i == 0 ? first_lo : 0;
       };
       auto issue_s = [&](int i) {
-        int es; uint32_t eph; bool last_of_bh;
-        meta(i, es, eph, last_of_bh);
+        int es, missing; uint32_t eph;
+        meta(i, es, eph, missing);
         const int qs = i & (QS - 1);
         mbar_wait(q_full(qs), (i / QS) & 1);
         mbar_wait(k_full(es), eph);
@@ -265,13 +270,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
           umma_bf16_ss<1>(d_s, umma_desc_k_sw128(q0 + k * 32), umma_desc_k_sw128(k0 + k * 32), idesc_s,
                           k != 0 ? 1u : 0u);
         umma_commit(q_empty(qs));
-        if (last_of_bh) umma_commit(k_empty(es));
+        umma_commit(k_empty(es));
+        for (int j = 0; j < missing; ++j) mbar_arrive(k_empty(es));
         umma_commit(s_ready(s));
       };
       if (s < n) issue_s(s);
       for (int i = s; i < n; i += 2) {
-        int es; uint32_t eph; bool last_of_bh;
-        meta(i, es, eph, last_of_bh);
+        int es, missing; uint32_t eph;
+        meta(i, es, eph, missing);
         const uint32_t ph = (i >> 1) & 1;
         mbar_wait(p_ready(s), ph);
         mbar_wait(v_full(es), eph);
@@ -282,7 +288,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
 #pragma unroll
         for (int kk = 0; kk < KP / 16; ++kk)
           umma_bf16_ts(d_o, d_s + kk * 8, umma_desc_mn_sw128(v0 + kk * 2048), idesc_o, kk != 0 ? 1u : 0u);
-        if (last_of_bh) umma_commit(v_empty(es));
+        umma_commit(v_empty(es));
+        for (int j = 0; j < missing; ++j) mbar_arrive(v_empty(es));
         umma_commit(o_ready(s));
         if (i + 2 < n) issue_s(i + 2);
       }
@@ -479,7 +486,8 @@ int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
   if (items64 > 0x7fffffff) return fail(VITB200_ERR_INVALID, "attention: too many work items");
   const int items = int(items64);
   const int grid = items < sm_count() ? items : sm_count();
-  attention_tc5_kernel<kDT, KP, kPoly><<<grid, NT, L::TOTAL, stream>>>(tq, tkv, to, T, heads, nqt, items, attn_turns());
+  VB_CUDA(launch_kernel(attention_tc5_kernel<kDT, KP, kPoly>, dim3(grid), dim3(NT), L::TOTAL, stream, 1,
+                        tq, tkv, to, T, heads, nqt, items, attn_turns()));
   VB_LAUNCH_CHECK("attention_tc5_kernel");
   return 0;
 }

@@ -36,6 +36,37 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 int sm_count();   // SMs of the current device (cached per device)
+bool pdl_enabled();   // VITB200_PDL=0 turns programmatic dependent launch off (A/B tests)
+
+// cudaLaunchKernelEx with the attributes every kernel of the path uses: programmatic stream
+// serialization (the kernel calls pdl_wait() before touching global memory) and, for the tcgen05
+// GEMM, a thread-block cluster.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = unsigned(cluster);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = unsigned(na);
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- TMA descriptors -----------------------------------------------------
 // 2-D row-major tensor [rows, cols] (cols contiguous, row pitch = ld elements) of element type
@@ -57,7 +88,8 @@ constexpr int GEMM_BK = 64;
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tokens_per_image, int dtype, int cta_group);
-// 1 = one CTA per 128x256 tile (Wt box 256 rows), 2 = CTA pair per 256x256 tile (Wt box 128 rows).
+// 1 = one CTA per 128x256 tile (Wt box 256 rows), 2 = CTA pair per 256x256 tile (Wt box 128 rows),
+// 4 = cluster of two pairs sharing a multicast weight tile (Wt box 64 rows).
 // The Wt tensor map must be encoded with GEMM_BN / cta_group box rows.
 int gemm_tc_cta_group(int M);
 int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const float* bias,

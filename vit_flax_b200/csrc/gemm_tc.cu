@@ -33,12 +33,18 @@ namespace {
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB: 128 rows of A per CTA
+// kCG: 1 = one CTA per 128x256 tile; 2 = CTA pair (cta_group::2) per 256x256 tile; 4 = cluster of two
+// pairs working on two vertically adjacent 256x256 tiles that share their weight tile: each CTA
+// fetches a quarter of it and TMA-multicasts it to its opposite number in the other pair.
 template <int kCG> struct Cfg {
-  static constexpr int STAGES = kCG == 2 ? 5 : 3;
-  static constexpr int B_ROWS = BN / kCG;                       // rows of Wt this CTA loads
+  static constexpr int MMA_CG = kCG == 1 ? 1 : 2;               // tcgen05 cta_group
+  static constexpr int STAGES = kCG == 1 ? 3 : 5;
+  static constexpr int B_ROWS = BN / MMA_CG;                    // rows of Wt in this CTA's smem
+  static constexpr int B_LOAD_ROWS = BN / kCG;                  // rows of Wt this CTA fetches
   static constexpr int B_BYTES = B_ROWS * BK * 2;               // 32 KB / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;         // 48 KB / 32 KB
-  static constexpr int TILE_M = BM * kCG;                       // 128 / 256
+  static constexpr int TILE_M = BM * MMA_CG;                    // 128 / 256
+  static constexpr int PAIRS = kCG == 4 ? 2 : 1;                // tiles per cluster step
 };
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;   // 384
@@ -62,17 +68,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, void* __restrict__ Cout,
-               int M, int N, int K, const float* __restrict__ aux, int tpi) {
+               int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg) {
   constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16);
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
   constexpr int SLABS_PER_TILE = BN / SLAB_COLS;
   constexpr int STAGES = Cfg<kCG>::STAGES, B_BYTES = Cfg<kCG>::B_BYTES;
   constexpr int STAGE_BYTES = Cfg<kCG>::STAGE_BYTES, TILE_M = Cfg<kCG>::TILE_M;
-  // pair mode: rank of this CTA in its cluster of 2 (0 = leader, issues the MMAs)
-  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0u;
-  const int tile0 = kCG == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
-  const int tile_step = kCG == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
+  constexpr int MMA_CG = Cfg<kCG>::MMA_CG, PAIRS = Cfg<kCG>::PAIRS;
+  // crank: rank in the cluster; rank: 0 = leader of its CTA pair (issues the MMAs), 1 = peer;
+  // pair: which of the cluster's tiles this CTA works on
+  const uint32_t crank = kCG == 1 ? 0u : cluster_ctarank();
+  const uint32_t rank = crank & 1u, pair = crank >> 1;
+  const uint32_t lead = crank & ~1u;                 // cluster rank of this pair's leader
+  const int tile0 = int(blockIdx.x) / kCG;           // cluster index
+  const int tile_step = int(gridDim.x) / kCG;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -91,7 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + TILE_M - 1) / TILE_M;
+  const int m_tiles = ((M + TILE_M - 1) / TILE_M + PAIRS - 1) / PAIRS;   // cluster steps along M
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
@@ -104,19 +114,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);                       // pair: only the leader arrives (arms both CTAs' bytes)
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), PAIRS);                  // cluster of 4: both pairs must have consumed the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), NUM_EPI_WARPS * kCG);   // pair: epilogue warps of both CTAs
+      mbar_init(tempty_bar(s), NUM_EPI_WARPS * MMA_CG);   // pair: epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kCG>(tmem_slot, TMEM_COLS);
+  if (warp == 2) tmem_alloc<MMA_CG>(tmem_slot, TMEM_COLS);
   tc_fence_before();
-  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (kCG != 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();   // the next kernel's CTAs may take this SM as soon as this one leaves it
+  pdl_wait();                // previous kernel complete: A, bias, the residual stream are final
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -125,24 +137,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int a_row = m_blk * TILE_M + int(rank) * BM;
-        const int b_row = n_blk * BN + int(rank) * Cfg<kCG>::B_ROWS;
+        const int a_row = (m_blk * PAIRS + int(pair)) * TILE_M + int(rank) * BM;
+        const int b_row = n_blk * BN + int(rank) * Cfg<kCG>::B_ROWS + int(pair) * Cfg<kCG>::B_LOAD_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if constexpr (kCG == 1) {
+          if (dbg & 1) {   // timing experiment: no loads, the MMAs chew on stale smem
+            if (rank == 0) mbar_arrive(full_bar(stage));
+          } else if constexpr (kCG == 1) {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d(sA + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, a_row);
             tma_load_2d(sB + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, b_row);
           } else {
-            // Both CTAs' loads complete on the LEADER's full barrier (the MMA issuer waits there).
+            // Both CTAs' loads complete on the pair LEADER's full barrier (the MMA issuer waits there).
             // Only the leader arrives, arming the bytes of both CTAs: the peer's complete_tx may
             // land first (tx-count goes transiently negative) but the phase cannot complete
             // before the leader's arrival.  A remote arrive from the peer is not needed and its
             // cluster-scope release costs >1000 cycles per stage (profiles/r01_gemm_pair.md).
-            const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+            const uint32_t lead_full = mapa_shared(full_bar(stage), lead);
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             tma_load_2d_cg2(sA + stage * A_BYTES, &tmA, lead_full, kb * BK, a_row);
-            tma_load_2d_cg2(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, b_row);
+            if constexpr (kCG == 2) {
+              tma_load_2d_cg2(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, b_row);
+            } else {
+              // 64 of this CTA's 128 weight rows, delivered to the same smem offset here and in the
+              // CTA of equal rank in the other pair; each destination signals its own pair leader.
+              tma_load_2d_cg2_mc(sB + stage * B_BYTES + pair * (Cfg<kCG>::B_LOAD_ROWS * BK * 2), &tmB,
+                                 lead_full, kb * BK, b_row, uint16_t(0x5u << rank));
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -153,12 +174,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     // ===================== MMA issuer (leader CTA only in pair mode) =====================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_16(TILE_M, BN, kDT == DT_F16 ? 0 : 1);
+      const uint16_t pair_mask = uint16_t(0x3u << lead);               // both CTAs of this pair
+      const uint16_t all_mask = uint16_t((1u << kCG) - 1u);             // every CTA whose smem the stage's loads touch
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        if constexpr (kCG == 2) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        if constexpr (kCG != 1) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -168,17 +191,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           const uint32_t a0 = sA + stage * A_BYTES, b0 = sB + stage * B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16_ss<kCG>(d_tmem, umma_desc_k_sw128(a0 + k * UMMA_K * 2),
+            umma_bf16_ss<MMA_CG>(d_tmem, umma_desc_k_sw128(a0 + k * UMMA_K * 2),
                               umma_desc_k_sw128(b0 + k * UMMA_K * 2), idesc,
                               (kb | k) != 0 ? 1u : 0u);
           }
           // smem slot free (in both CTAs) once these MMAs retire
-          if constexpr (kCG == 2) umma_commit_cg2_mc(empty_bar(stage), 3);
+          if constexpr (kCG != 1) umma_commit_cg2_mc(empty_bar(stage), all_mask);
           else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         // accumulator ready for the epilogue (of both CTAs)
-        if constexpr (kCG == 2) umma_commit_cg2_mc(tfull_bar(acc), 3);
+        if constexpr (kCG != 1) umma_commit_cg2_mc(tfull_bar(acc), pair_mask);
         else umma_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -197,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     int buf = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int m_row0 = m_blk * TILE_M + int(rank) * BM;      // first output row of this CTA
+      const int m_row0 = (m_blk * PAIRS + int(pair)) * TILE_M + int(rank) * BM;   // first output row of this CTA
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
@@ -237,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll 1
         for (int s = grp; s < SLABS_PER_TILE; s += 2) {
           const int n0 = n_blk * BN + s * SLAB_COLS;
-          if (n0 >= N) break;                          // uniform over the group
+          if (n0 >= N || (dbg & 4)) break;             // uniform over the group
           const uint32_t slab = sSlab + uint32_t(grp * 2 + buf) * SLAB_BYTES;
           // the slab buffer used two slabs ago must have been read out by its TMA store
           if (leader) tma_store_wait_read<1>();
@@ -290,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           }
           fence_proxy_async_smem();                    // generic-proxy smem writes -> async proxy
           named_bar_sync(1 + grp, 128);
-          if (leader) {
+          if (leader && !(dbg & 2)) {
             if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32)
               tma_reduce_add_2d(&tmC, slab, n0, m_row0);          // x += acc + bias
             else
@@ -303,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kCG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's barrier
+        if constexpr (kCG != 1) mbar_arrive_cluster(tempty_bar(acc), lead);   // the pair leader's barrier
         else mbar_arrive(tempty_bar(acc));
       }
       acc ^= 1;
@@ -313,11 +336,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   }
 
   tc_fence_before();
-  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();   // peer smem/TMEM stay live until here
+  if constexpr (kCG != 1) cluster_sync_all(); else __syncthreads();   // peer smem/TMEM stay live until here
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kCG>(tmem_base, TMEM_COLS);
+    tmem_dealloc<MMA_CG>(tmem_base, TMEM_COLS);
   }
+}
+
+int gemm_dbg() {   // VITB200_GEMM_DBG bit 0: no TMA loads, bit 1: no output stores, bit 2: no epilogue at all
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VITB200_GEMM_DBG"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 template <int kEpi, int kDT, int kCG>
@@ -325,27 +354,35 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
               const float* aux, int tpi) {
   static bool configured = false;   // per-process; attribute is per-function, device-agnostic
+  static int max_units = 0;         // clusters (CTAs for kCG == 1) that can be resident at once
   if (!configured) {
     VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG>()));
+    max_units = sm_count() / kCG;
+    if (kCG > 2) {   // clusters of 4 do not tile every GPC: ask how many fit (33 on a 148-SM B200)
+      int n = 0;
+      cudaLaunchConfig_t cfg{};
+      cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = smem_bytes<kCG>();
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kCG;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3(sm_count() / kCG * kCG);
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<kEpi, kDT, kCG>, &cfg) == cudaSuccess && n > 0)
+        max_units = n < max_units ? n : max_units;
+      else
+        cudaGetLastError();
+    }
     configured = true;
   }
-  const int tiles = ceil_div(M, Cfg<kCG>::TILE_M) * ceil_div(N, BN);
-  const int max_units = sm_count() / kCG;
+  const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, BN);
   const int units = tiles < max_units ? tiles : max_units;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(units * kCG);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = smem_bytes<kCG>();
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kEpi, kDT, kCG>, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi));
+  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG>, dim3(units * kCG), dim3(NUM_THREADS), smem_bytes<kCG>(),
+                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg()));
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -354,6 +391,7 @@ template <int kEpi, int kDT>
 int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
                const float* aux, int tpi, int cta_group) {
+  if (cta_group == 4) return launch_cg<kEpi, kDT, 4>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
   if (cta_group == 2) return launch_cg<kEpi, kDT, 2>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
   return launch_cg<kEpi, kDT, 1>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
 }
@@ -383,16 +421,19 @@ int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap&
 }  // namespace
 
 int gemm_tc_cta_group(int M) {
-  // VITB200_GEMM_CTA_GROUP=1|2 overrides (A/B tests); pairs only pay off with >= 2 row blocks
+  // VITB200_GEMM_CTA_GROUP=1|2|4 overrides (A/B tests).  Pairs pay off with >= 2 row blocks.  The
+  // weight-multicast cluster of two pairs (4) cuts the L2 reads per flop by a quarter but measured
+  // no faster per SM and only 33 such clusters fit a 148-SM B200 ("What bounds the GEMM"):
+  // it stays opt-in.
   const char* e = getenv("VITB200_GEMM_CTA_GROUP");
-  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) return e[0] - '0';
   return M > GEMM_BM ? 2 : 1;
 }
 
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tpi, int dtype, int cta_group) {
-  if (cta_group != 1 && cta_group != 2) return fail(VITB200_ERR_INVALID, "gemm_tc: cta_group must be 1 or 2");
+  if (cta_group != 1 && cta_group != 2 && cta_group != 4) return fail(VITB200_ERR_INVALID, "gemm_tc: cta_group must be 1, 2 or 4");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
     return fail(VITB200_ERR_INVALID, "gemm_tc: N and K must be multiples of 8");

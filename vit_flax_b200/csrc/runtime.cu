@@ -2,6 +2,7 @@
 // descriptor encoding (driver entry point fetched through cudart, so the
 // library has no link-time dependency on libcuda and loads on a CPU-only box).
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -33,6 +34,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITB200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int sm_count() {
   static int cached[64] = {0};

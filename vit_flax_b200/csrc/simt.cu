@@ -32,6 +32,8 @@ template <int NV, int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                       const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -89,6 +91,8 @@ template <int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                          const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -114,14 +118,14 @@ int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b,
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                      reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
   if (!vec) {
-    layernorm_generic_kernel<kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    VB_CUDA(launch_kernel(layernorm_generic_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
   } else {
     const int nv = ceil_div(dim, 128);
-    if (nv <= 4) layernorm_rows_kernel<4, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else if (nv <= 6) layernorm_rows_kernel<6, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else if (nv <= 8) layernorm_rows_kernel<8, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else if (nv <= 10) layernorm_rows_kernel<10, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
-    else layernorm_rows_kernel<16, kDT><<<grid, 256, 0, st>>>(x, g, b, y, rows, dim);
+    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
+    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
+    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
+    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
+    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
   }
   VB_LAUNCH_CHECK("layernorm");
   return 0;
@@ -133,6 +137,8 @@ template <int kDT>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
                 int C, int ph, int pw, int Kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int gw = W / pw, gh = H / ph;
   const int K0 = ph * pw * C;
   const int64_t pairs_per_row = Kpad >> 1;     // Kpad is even
@@ -167,6 +173,8 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
 // -------------------------------------------------------------- cls rows (K1b)
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
                                 float* __restrict__ x, int batch, int T, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= int64_t(batch) * dim) return;
   const int b = int(i / dim), d = int(i - int64_t(b) * dim);
@@ -179,6 +187,8 @@ __global__ void __launch_bounds__(256)
 pool_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                       const float* __restrict__ bias, void* __restrict__ y, int T, int dim,
                       int pool) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];          // dim floats + 16 reduction slots
   float* pooled = sh;
   float* red = sh + dim;
@@ -404,7 +414,7 @@ int launch_patchify(cudaStream_t st, const float* images, void* patches, int bat
     return fail(VITB200_ERR_INVALID, "patchify: Kpad must be even and >= ph*pw*C");
   const int64_t total = int64_t(batch) * (H / ph) * (W / pw) * (Kpad / 2);
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
-  VB_DT_DISPATCH(out_dtype, (patchify_kernel<kDT><<<grid, 256, 0, st>>>(images, patches, batch, H, W, C, ph, pw, Kpad)));
+  VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad)));
   VB_LAUNCH_CHECK("patchify_kernel");
   return 0;
 }
@@ -412,7 +422,7 @@ int launch_patchify(cudaStream_t st, const float* images, void* patches, int bat
 int launch_cls_rows(cudaStream_t st, const float* cls, const float* pos, float* x, int batch, int T,
                     int dim) {
   const int64_t total = int64_t(batch) * dim;
-  cls_rows_kernel<<<int((total + 255) / 256), 256, 0, st>>>(cls, pos, x, batch, T, dim);
+  VB_CUDA(launch_kernel(cls_rows_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, 1, cls, pos, x, batch, T, dim));
   VB_LAUNCH_CHECK("cls_rows_kernel");
   return 0;
 }
@@ -422,7 +432,7 @@ int launch_pool_layernorm(cudaStream_t st, const float* x, const float* g, const
   if (pool != VITB200_POOL_CLS && pool != VITB200_POOL_MEAN)
     return fail(VITB200_ERR_INVALID, "pool must be cls or mean (vit.py:137)");
   const size_t smem = (size_t(dim) + 16) * sizeof(float);
-  VB_DT_DISPATCH(out_dtype, (pool_layernorm_kernel<kDT><<<batch, 256, smem, st>>>(x, g, b, y, T, dim, pool)));
+  VB_DT_DISPATCH(out_dtype, (launch_kernel(pool_layernorm_kernel<kDT>, dim3(batch), dim3(256), smem, st, 1, x, g, b, y, T, dim, pool)));
   VB_LAUNCH_CHECK("pool_layernorm_kernel");
   return 0;
 }
