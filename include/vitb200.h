@@ -106,6 +106,14 @@ int vitb200_forward(vitb200_model* m, void* stream, const float* images_dev, int
 /* Same call with HOST buffers (pinned or pageable): H2D, forward, D2H, sync. */
 int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_host, int batch,
                          float* logits_host);
+/* Pipelined end-to-end variant for a stream of batches: submit enqueues H2D (own copy stream),
+ * forward (caller's stream) and D2H (own copy stream) of one batch and returns at once; at most
+ * two jobs may be in flight, so the H2D copy of batch k+1 overlaps the forward of batch k.
+ * wait_host blocks until the OLDEST submitted job's logits are in `logits_host`.  Host buffers
+ * should be pinned and must stay valid until the job has been waited for.                     */
+int vitb200_submit_host(vitb200_model* m, void* stream, const float* images_host, int batch,
+                        float* logits_host);
+int vitb200_wait_host(vitb200_model* m);
 /* One forward with a CUDA event before every launch: per-category device time (ms) and launch
  * counts, arrays of VITB200_NUM_CATEGORIES.  Synchronises the stream.  For bench/roofline.  */
 #define VITB200_CAT_PATCHIFY   0

@@ -166,6 +166,20 @@ def test_device_path_equals_host_path_and_is_batch_independent():
     assert np.abs(y_host[:8] - want).max() < TOL["fp16"]
 
 
+def test_apply_stream_matches_apply():
+    """Pipelined host path (two batches in flight, H2D overlapping the forward) == blocking path."""
+    cfg = dict(C2, depth=2)
+    variables = perturb_params(init_params(seed=5, **cfg), seed=6)
+    v = ViT(**cfg)
+    batches = [images_for(cfg, n, seed=s) for s, n in enumerate([16, 7, 16, 1, 12])]
+    want = [v.apply(variables, b, max_batch=16).copy() for b in batches]
+    got = [y.copy() for y in v.apply_stream(variables, iter(batches), max_batch=16)]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    assert list(v.apply_stream(variables, iter([]), max_batch=16)) == []
+
+
 def test_error_behaviour():
     eng = Engine(precision="fp16", max_batch=2, **TINY)
     variables = perturb_params(init_params(seed=0, **TINY))

@@ -56,6 +56,8 @@ SIGNATURES = {
     "vitb200_finalize_params": (_i, [_vp, _vp]),
     "vitb200_forward": (_i, [_vp, _vp, _fp, _i, _fp]),
     "vitb200_forward_host": (_i, [_vp, _vp, _fp, _i, _fp]),
+    "vitb200_submit_host": (_i, [_vp, _vp, _fp, _i, _fp]),
+    "vitb200_wait_host": (_i, [_vp]),
     "vitb200_profile_forward": (_i, [_vp, _vp, _fp, _i, _fp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vitb200_debug_tokens": (_i, [_vp, _vp, _fp, _i]),
     "vitb200_gemm_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i]),

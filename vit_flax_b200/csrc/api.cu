@@ -93,6 +93,15 @@ struct vitb200_model {
   DevBuf<uint16_t> patches_h, xn_h, qkv_h, o_h, hid_h, pooled_h;
   DevBuf<float> patches_f, xn_f, qkv_f, o_f, hid_f, pooled_f;
   DevBuf<float> img_stage, logit_stage;              // forward_host staging
+  // submit_host / wait_host: two jobs in flight (H2D of job k+1 overlaps the forward of job k)
+  struct HostJob {
+    DevBuf<float> img, logit;
+    cudaEvent_t h2d_done = nullptr, fwd_done = nullptr, d2h_done = nullptr;
+    bool pending = false;       // submitted, not yet waited for
+    bool used = false;          // events have been recorded at least once
+  } job[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  int64_t jobs_submitted = 0, jobs_waited = 0;
   std::map<int, ActMaps> act_maps;
   std::vector<std::pair<int, cudaEvent_t>>* prof = nullptr;   // per-launch marks while profiling
 
@@ -107,6 +116,14 @@ struct vitb200_model {
     patches_h.release(); xn_h.release(); qkv_h.release(); o_h.release(); hid_h.release(); pooled_h.release();
     patches_f.release(); xn_f.release(); qkv_f.release(); o_f.release(); hid_f.release(); pooled_f.release();
     img_stage.release(); logit_stage.release();
+    for (auto& j : job) {
+      j.img.release(); j.logit.release();
+      if (j.h2d_done) cudaEventDestroy(j.h2d_done);
+      if (j.fwd_done) cudaEventDestroy(j.fwd_done);
+      if (j.d2h_done) cudaEventDestroy(j.d2h_done);
+    }
+    if (h2d_stream) cudaStreamDestroy(h2d_stream);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
   }
 };
 
@@ -515,6 +532,59 @@ int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_hos
   if ((rc = vitb200_forward(m, stream, m->img_stage.p, batch, m->logit_stage.p))) return rc;
   VB_CUDA(cudaMemcpyAsync(logits_host, m->logit_stage.p, out_bytes, cudaMemcpyDeviceToHost, st));
   VB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int vitb200_submit_host(vitb200_model* m, void* stream, const float* images_host, int batch, float* logits_host) {
+  if (!m || !images_host || !logits_host) return fail(VITB200_ERR_INVALID, "submit_host: null argument");
+  if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "submit_host: batch must be in [1, max_batch]");
+  if (m->jobs_submitted - m->jobs_waited >= 2) return fail(VITB200_ERR_INVALID, "submit_host: two jobs already in flight, call wait_host first");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto& c = m->cfg;
+  int rc;
+  if (!m->h2d_stream) {
+    VB_CUDA(cudaStreamCreateWithFlags(&m->h2d_stream, cudaStreamNonBlocking));
+    VB_CUDA(cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
+  }
+  vitb200_model::HostJob& j = m->job[m->jobs_submitted & 1];
+  const size_t img_elems = size_t(c.max_batch) * c.image_h * c.image_w * c.channels;
+  if (j.img.n < img_elems && (rc = j.img.alloc(img_elems))) return rc;
+  if (j.logit.n < size_t(c.max_batch) * c.num_classes && (rc = j.logit.alloc(size_t(c.max_batch) * c.num_classes))) return rc;
+  if (!j.h2d_done) {
+    VB_CUDA(cudaEventCreateWithFlags(&j.h2d_done, cudaEventDisableTiming));
+    VB_CUDA(cudaEventCreateWithFlags(&j.fwd_done, cudaEventDisableTiming));
+    VB_CUDA(cudaEventCreateWithFlags(&j.d2h_done, cudaEventDisableTiming));
+  }
+  const size_t in_bytes = size_t(batch) * c.image_h * c.image_w * c.channels * sizeof(float);
+  const size_t out_bytes = size_t(batch) * c.num_classes * sizeof(float);
+  // H2D on its own stream: the slot's previous forward (two jobs ago) has read its images
+  if (j.used) VB_CUDA(cudaStreamWaitEvent(m->h2d_stream, j.fwd_done, 0));
+  VB_CUDA(cudaMemcpyAsync(j.img.p, images_host, in_bytes, cudaMemcpyHostToDevice, m->h2d_stream));
+  VB_CUDA(cudaEventRecord(j.h2d_done, m->h2d_stream));
+  // forward on the caller's stream: images have landed, the slot's previous logits have left
+  VB_CUDA(cudaStreamWaitEvent(st, j.h2d_done, 0));
+  if (j.used) VB_CUDA(cudaStreamWaitEvent(st, j.d2h_done, 0));
+  if ((rc = vitb200_forward(m, stream, j.img.p, batch, j.logit.p))) return rc;
+  VB_CUDA(cudaEventRecord(j.fwd_done, st));
+  // D2H on its own stream
+  VB_CUDA(cudaStreamWaitEvent(m->d2h_stream, j.fwd_done, 0));
+  VB_CUDA(cudaMemcpyAsync(logits_host, j.logit.p, out_bytes, cudaMemcpyDeviceToHost, m->d2h_stream));
+  VB_CUDA(cudaEventRecord(j.d2h_done, m->d2h_stream));
+  j.used = true;
+  j.pending = true;
+  ++m->jobs_submitted;
+  return 0;
+}
+
+int vitb200_wait_host(vitb200_model* m) {
+  if (!m) return fail(VITB200_ERR_INVALID, "wait_host: null model");
+  if (m->jobs_waited >= m->jobs_submitted) return fail(VITB200_ERR_INVALID, "wait_host: nothing in flight");
+  DeviceGuard guard(m->device);
+  vitb200_model::HostJob& j = m->job[m->jobs_waited & 1];
+  VB_CUDA(cudaEventSynchronize(j.d2h_done));
+  j.pending = false;
+  ++m->jobs_waited;
   return 0;
 }
 

@@ -111,6 +111,45 @@ class Engine:
                                                  images.ctypes.data, b, out.ctypes.data))
         return out
 
+    def submit_host(self, images: np.ndarray, out: np.ndarray) -> None:
+        """Pipelined end-to-end path: enqueue H2D + forward + D2H of one batch and return at once
+        (at most two jobs in flight; ``wait_host`` completes the oldest).  ``images`` / ``out``
+        must be C-contiguous float32 (pinned for real overlap) and stay alive until waited for."""
+        if images.dtype != np.float32 or not images.flags.c_contiguous:
+            raise ValueError("submit_host expects a C-contiguous float32 array")
+        self._check_images(images.shape)
+        b = images.shape[0]
+        if out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (b, self.num_classes):
+            raise ValueError(f"submit_host expects a C-contiguous float32 out of shape ({b}, {self.num_classes})")
+        _lib.check(self.lib.vitb200_submit_host(self.handle, _stream_ptr(self._torch, self.device),
+                                                images.ctypes.data, b, out.ctypes.data))
+
+    def wait_host(self) -> None:
+        _lib.check(self.lib.vitb200_wait_host(self.handle))
+
+    def forward_host_stream(self, batches):
+        """Generator over host batches -> host logits, in order, two batches in flight: the H2D
+        copy of batch k+1 overlaps the forward of batch k.  Logits are written into pinned
+        staging arrays that are re-used two batches later: copy them if they must outlive that."""
+        torch = self._torch
+        outs = [torch.empty((self.max_batch, self.num_classes), dtype=torch.float32).pin_memory().numpy()
+                for _ in range(2)]
+        pending = []
+        k = 0
+        for images in batches:
+            images = np.ascontiguousarray(images, dtype=np.float32)
+            if len(pending) == 2:
+                self.wait_host()
+                yield pending.pop(0)
+            out = outs[k & 1][: images.shape[0]]
+            self.submit_host(images, out)
+            pending.append(out)
+            self._keepalive = images            # the host buffer must outlive the async copy
+            k += 1
+        while pending:
+            self.wait_host()
+            yield pending.pop(0)
+
     def profile_forward(self, images, out=None):
         """One forward with per-launch CUDA events -> {category: (ms, launches)}."""
         torch = self._torch

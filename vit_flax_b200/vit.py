@@ -119,6 +119,33 @@ class ViT:
             return eng.forward(xin)
         return eng.forward_host(np.asarray(x, dtype=np.float32))
 
+    def apply_stream(self, variables: Any, batches, *, precision: Optional[str] = None,
+                     device: Optional[int] = None, max_batch: int = 256):
+        """Serving-style extension of ``apply`` (ours, not in the reference): iterate host batches
+        ``[B, H, W, C]`` float32 and yield their logits in order, keeping two batches in flight so the
+        host->device copy of the next batch overlaps the forward of the current one.  Yielded arrays
+        are staging buffers re-used two batches later."""
+        if self.dropout != 0.0 or self.emb_dropout != 0.0:
+            raise NotImplementedError("dropout > 0 is not built; construct ViT with the default rates 0.0")
+        from .runtime import get_engine
+
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        channels = self._validate(np.shape(first))
+        if device is None:
+            device = _current_device()
+        eng = get_engine(self, channels, precision or _DEFAULT_PRECISION, device, max_batch, variables, False)
+
+        def chain():
+            yield first
+            for b in it:
+                self._validate(np.shape(b))
+                yield b
+        yield from eng.forward_host_stream(chain())
+
     def __call__(self, *a, **k):  # flax modules are called through init/apply
         raise TypeError("call ViT through .init(rngs, x) / .apply(variables, x), like the flax module")
 
