@@ -13,7 +13,8 @@ rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 lib = _lib.load()
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 shapes = [(256, 197, 12), (1, 197, 12), (3, 197, 1), (37, 197, 5), (8, 65, 16), (5, 128, 3), (2, 208, 2),
-          (9, 129, 4), (4, 1, 2), (64, 17, 7), (300, 197, 12), (2, 64, 1)]
+          (9, 129, 4), (4, 1, 2), (64, 17, 7), (300, 197, 12), (2, 64, 1),
+          (40, 257, 16), (3, 209, 2), (5, 288, 3), (2, 289, 2), (6, 1025, 4), (1, 2000, 1), (33, 385, 3)]
 worst = 0.0
 n = 0
 for r in range(rounds):

@@ -244,12 +244,13 @@ int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int bat
                         int dtype) {
   if (batch <= 0 || T <= 0 || heads <= 0)
     return fail(VITB200_ERR_INVALID, "attention_tc: empty problem");
-  // VITB200_ATTENTION=hmma forces the mma.sync generation (A/B tests); default: tcgen05 when the
-  // sequence fits one key block, streamed-KV mma.sync kernel otherwise.
+  // VITB200_ATTENTION=hmma forces the mma.sync generation (A/B tests); default: the tcgen05
+  // kernels -- one key block when T <= 208, streamed key blocks with an online softmax beyond.
   const char* force = getenv("VITB200_ATTENTION");
   const bool want_hmma = force && force[0] == 'h';
   if (!want_hmma && attention_tc5_supports(T))
     return launch_attention_tc5(stream, qkv, out, batch, T, heads, dtype);
+  if (!want_hmma) return launch_attention_tc5m(stream, qkv, out, batch, T, heads, dtype);
   if (int64_t(batch) * heads > 65535)
     return fail(VITB200_ERR_INVALID, "attention_tc: batch*heads exceeds grid.y limit; chunk the batch");
   if (dtype == DT_BF16)

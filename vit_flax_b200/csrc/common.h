@@ -102,6 +102,9 @@ int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int bat
 bool attention_tc5_supports(int T);
 int launch_attention_tc5(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
                          int heads, int dtype);
+// tcgen05 kernel for T > 208: streamed key blocks, online softmax (attention_tc5m.cu)
+int launch_attention_tc5m(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
+                          int heads, int dtype);
 int launch_attention_f32(cudaStream_t stream, const float* qkv, float* out, int batch, int T,
                          int heads);
 int launch_patchify(cudaStream_t stream, const float* images, void* patches, int batch, int H,
