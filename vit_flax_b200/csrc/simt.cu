@@ -170,6 +170,47 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
   }
 }
 
+// Fast path (pw*C even, which covers every config of the path): walk the IMAGE ROWS.  Row (b, y) is
+// W*C contiguous floats and is made of gw patch-row segments of pw*C floats; segment ww lands at
+// out[(b, hh, ww), p1*pw*C ...] with y = hh*ph + p1.  One float2 per thread: coalesced reads, writes
+// in runs of pw*C 16-bit values (96 B at P = 16).  The pad columns K0..Kpad are zeroed by a second
+// grid-stride loop, so the buffer needs no memset.
+template <int kDT>
+__global__ void __launch_bounds__(256)
+patchify_rows_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
+                     int C, int ph, int pw, int Kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int gw = W / pw, gh = H / ph;
+  const int seg = pw * C;                 // floats per patch-row segment (even)
+  const int pairs_per_row = (W * C) >> 1;
+  const int K0 = ph * seg;
+  const int pad_pairs = (Kpad - K0) >> 1;
+  const int64_t total = int64_t(batch) * H * pairs_per_row;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / pairs_per_row;                 // image row (b, y)
+    const int t = int(i - r * pairs_per_row);
+    const int b = int(r / H), y = int(r - int64_t(b) * H);
+    const int hh = y / ph, p1 = y - hh * ph;
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(img) + i);
+    const int x = t * 2;
+    const int ww = x / seg, rem = x - ww * seg;
+    const int64_t o = ((int64_t(b) * gh + hh) * gw + ww) * Kpad + p1 * seg + rem;   // even
+    if constexpr (kDT != DT_F32) reinterpret_cast<uint32_t*>(out)[o >> 1] = pack2<kDT>(v.x, v.y);
+    else reinterpret_cast<float2*>(out)[o >> 1] = v;
+  }
+  if (pad_pairs > 0) {
+    const int64_t npad = int64_t(batch) * gh * gw * pad_pairs;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < npad; i += int64_t(gridDim.x) * blockDim.x) {
+      const int64_t patch = i / pad_pairs;
+      const int k = int(i - patch * pad_pairs);
+      const int64_t o = patch * Kpad + K0 + 2 * k;
+      if constexpr (kDT != DT_F32) reinterpret_cast<uint32_t*>(out)[o >> 1] = 0u;
+      else reinterpret_cast<float2*>(out)[o >> 1] = make_float2(0.f, 0.f);
+    }
+  }
+}
+
 // -------------------------------------------------------------- cls rows (K1b)
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
                                 float* __restrict__ x, int batch, int T, int dim) {
@@ -412,6 +453,13 @@ int launch_patchify(cudaStream_t st, const float* images, void* patches, int bat
     return fail(VITB200_ERR_INVALID, "patchify: image not divisible by patch (vit.py:133-134)");
   if (Kpad < ph * pw * C || (Kpad & 1))
     return fail(VITB200_ERR_INVALID, "patchify: Kpad must be even and >= ph*pw*C");
+  if (((pw * C) & 1) == 0 && (reinterpret_cast<uintptr_t>(images) & 7) == 0) {
+    const int64_t total = int64_t(batch) * H * ((W * C) >> 1);
+    const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
+    VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_rows_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad)));
+    VB_LAUNCH_CHECK("patchify_rows_kernel");
+    return 0;
+  }
   const int64_t total = int64_t(batch) * (H / ph) * (W / pw) * (Kpad / 2);
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
   VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad)));
