@@ -4,6 +4,7 @@ Public surface = the reference's: ``ViT(...)``, ``.init(rngs, x)``, ``.apply(var
 Importing this package does not need a GPU; computing anything does (no CPU fallback).
 """
 from .params import count_params, flatten_params, init_params, perturb_params  # noqa: F401
+from .checkpoint import load_params, save_params  # noqa: F401
 from .vit import ViT  # noqa: F401
 
-__all__ = ["ViT", "init_params", "perturb_params", "flatten_params", "count_params"]
+__all__ = ["ViT", "init_params", "perturb_params", "flatten_params", "count_params", "load_params", "save_params"]
