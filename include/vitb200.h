@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VITB200_ABI_VERSION 1
+#define VITB200_ABI_VERSION 2
 
 /* error codes */
 #define VITB200_OK                 0
@@ -68,7 +68,9 @@ typedef struct vitb200_config {
   int32_t pool;                 /* VITB200_POOL_*  */
   int32_t precision;            /* VITB200_PREC_*  */
   int32_t max_batch;            /* workspace is sized for this many images   */
-  int32_t reserved[3];
+  float   dropout;              /* vit.py:124: rate of the Dropouts inside Attention / FeedForward */
+  float   emb_dropout;          /* vit.py:125: rate of the Dropout after the positional embedding   */
+  int32_t reserved[1];
 } vitb200_config;
 
 typedef struct vitb200_model vitb200_model;   /* opaque */
@@ -98,6 +100,14 @@ int vitb200_set_param(vitb200_model* m, const char* path, const float* host_data
 /* Pack weights for the kernels (bf16 K-major transposes etc.); must be called
  * after all leaves are set and before forward.                              */
 int vitb200_finalize_params(vitb200_model* m, void* stream);
+
+/* Key of the 'dropout' rng stream (Flax: rngs={'dropout': key}).  Only used when a rate is > 0:
+ * the reference applies every nn.Dropout with deterministic=False (vit.py:50,52,83,155).  The
+ * mask of element e of Dropout instance s is Philox4x32-10(key; counter = (e / 4, s)) -- a pure
+ * function of the key, like Flax's functional rng (same key => same mask); it cannot be bit-equal
+ * to JAX's threefry stream.  Sites: 0 = after pos_embedding; 1+3l = after Attention_l's to_out;
+ * 2+3l = after FeedForward_l's GELU; 3+3l = after FeedForward_l's second Dense.               */
+int vitb200_set_dropout_key(vitb200_model* m, uint64_t key);
 
 /* ViT.__call__ (vit.py:127-167): images [batch, H, W, C] fp32 NHWC on DEVICE,
  * logits [batch, num_classes] fp32 on DEVICE.  batch <= cfg.max_batch.       */
@@ -151,6 +161,12 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bias,
                     void* C, int M, int N, int K, int epilogue,
                     const float* aux, int tokens_per_image, int dtype);
+/* Same with the Dropout that follows the Dense in the reference (epilogues 1, 2 and 4 only):
+ * rate in [0, 1), key / site as in vitb200_set_dropout_key.                                   */
+int vitb200_gemm_tc_dropout(void* stream, const void* A, const void* Wt, const float* bias,
+                            void* C, int M, int N, int K, int epilogue,
+                            const float* aux, int tokens_per_image, int dtype,
+                            float rate, uint64_t key, uint32_t site);
 /* SIMT fp32 GEMM (validation mode): acc = A[M,K] x W[K,N] (Flax layout).
  * The two "_16" epilogues write fp32 here.                                  */
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias,

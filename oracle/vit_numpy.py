@@ -63,7 +63,16 @@ def patchify(x, ph, pw):
     return x.reshape(b, gh * gw, ph * pw * c)
 
 
-def attention(x, p, heads, dim):
+def _drop(x, drop, site):
+    """``nn.Dropout(rate)(x, deterministic=False)`` with the mask generator of libvitb200
+    (oracle/philox.py); ``drop`` = None or (rate, key)."""
+    if drop is None or drop[0] == 0.0:
+        return x
+    from . import philox
+    return philox.dropout(x, drop[0], site, drop[1])
+
+
+def attention(x, p, heads, dim, drop=None, site=0):
     """``Attention.__call__`` (vit.py:62-87)."""
     b, n, _ = x.shape
     inner = DIM_HEAD * heads
@@ -81,28 +90,32 @@ def attention(x, p, heads, dim):
     out = np.einsum("bhij,bhjd->bhid", attn, v)                    # vit.py:78
     out = out.transpose(0, 2, 1, 3).reshape(b, n, inner)           # vit.py:79
     if project_out:
-        out = dense(out, p["Dense_1"])                             # vit.py:82
+        out = _drop(dense(out, p["Dense_1"]), drop, site)          # vit.py:82-83
     return out
 
 
-def feed_forward(x, p):
-    """``FeedForward.__call__`` (vit.py:47-53), dropout rate 0."""
-    return dense(gelu_tanh(dense(x, p["Dense_0"])), p["Dense_1"])
+def feed_forward(x, p, drop=None, site=0):
+    """``FeedForward.__call__`` (vit.py:47-53): Dense, gelu, Dropout, Dense, Dropout."""
+    h = _drop(gelu_tanh(dense(x, p["Dense_0"])), drop, site)        # vit.py:48-50
+    return _drop(dense(h, p["Dense_1"]), drop, site + 1)           # vit.py:51-52
 
 
-def transformer(x, p, depth, heads, dim):
-    """``Transformer.__call__`` (vit.py:98-112): Residual(PreNorm(.)) pairs."""
+def transformer(x, p, depth, heads, dim, drop=None):
+    """``Transformer.__call__`` (vit.py:98-112): Residual(PreNorm(.)) pairs.  Dropout sites (the
+    numbering of include/vitb200.h): 1+3l after to_out, 2+3l after gelu, 3+3l after the FF output."""
     for l in range(depth):
         ln1 = p[f"PreNorm_{2 * l}"]["LayerNorm_0"]
-        x = attention(layer_norm(x, ln1), p[f"Attention_{l}"], heads, dim) + x      # vit.py:31,39
+        x = attention(layer_norm(x, ln1), p[f"Attention_{l}"], heads, dim, drop, 1 + 3 * l) + x   # vit.py:31,39
         ln2 = p[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"]
-        x = feed_forward(layer_norm(x, ln2), p[f"FeedForward_{l}"]) + x             # vit.py:31,39
+        x = feed_forward(layer_norm(x, ln2), p[f"FeedForward_{l}"], drop, 2 + 3 * l) + x          # vit.py:31,39
     return x
 
 
 def vit_forward(variables, images, *, image_size, patch_size, num_classes, dim, depth,
-                heads, mlp_dim, pool="cls", dtype=np.float64, return_tokens=False):
-    """``ViT.__call__`` (vit.py:127-167) with both dropout rates 0."""
+                heads, mlp_dim, pool="cls", dtype=np.float64, return_tokens=False,
+                dropout=0.0, emb_dropout=0.0, dropout_key=None):
+    """``ViT.__call__`` (vit.py:127-167).  With a rate > 0 the four Dropout sites are applied as Flax
+    applies them (deterministic=False), with the masks of oracle/philox.py keyed by ``dropout_key``."""
     p = variables["params"] if "params" in variables else variables
     ih, iw = pair(image_size)
     ph, pw = pair(patch_size)
@@ -115,7 +128,11 @@ def vit_forward(variables, images, *, image_size, patch_size, num_classes, dim, 
     cls = np.broadcast_to(np.asarray(p["cls"], dtype=dtype), (b, 1, dim))            # vit.py:151
     x = np.concatenate([cls, x], axis=1)                           # vit.py:152
     x = x + np.asarray(p["pos_embedding"], dtype=dtype)[:, : n + 1]                  # vit.py:153
-    x = transformer(x, p["Transformer_0"], depth, heads, dim)      # vit.py:157
+    if dropout or emb_dropout:
+        assert dropout_key is not None, "a dropout rate > 0 needs the 'dropout' rng key"
+    x = _drop(x, (emb_dropout, dropout_key), 0)                    # vit.py:155
+    x = transformer(x, p["Transformer_0"], depth, heads, dim,
+                    (dropout, dropout_key) if dropout else None)   # vit.py:157
     tokens = x
     x = x.mean(axis=1) if pool == "mean" else x[:, 0]              # vit.py:159
     x = layer_norm(x, p["LayerNorm_0"])                            # vit.py:163

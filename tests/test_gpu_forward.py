@@ -194,3 +194,37 @@ def test_error_behaviour():
     with pytest.raises(ValueError, match="NHWC"):
         eng.forward_host(np.zeros((1, 3, 32, 32), np.float32))
     eng.close()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 2e-2)])
+def test_dropout_forward_matches_oracle_with_the_same_masks(precision, tol):
+    """The README usage / demo config has dropout = emb_dropout = 0.1 and the reference applies them on
+    every call (deterministic=False, vit.py:50,52,83,155).  The float64 oracle applies Flax's Dropout
+    with the SAME Philox masks (oracle/philox.py), so the dropped forward is checked value for value."""
+    cfg = dict(TINY, depth=2)
+    variables = perturb_params(init_params(seed=7, **cfg), seed=8)
+    img = images_for(cfg, 5, seed=9)
+    v = ViT(dropout=0.1, emb_dropout=0.2, **cfg)
+    key = 0xC0FFEE
+    want = vit_numpy.vit_forward(variables, img, dropout=0.1, emb_dropout=0.2, dropout_key=key, **cfg)
+    got = v.apply(variables, img, rngs={"dropout": key, "emb_dropout": 3}, precision=precision)
+    assert np.abs(got - want).max() < tol
+    again = v.apply(variables, img, rngs={"dropout": key}, precision=precision)
+    np.testing.assert_array_equal(got, again)                                   # same key, same masks
+    other = v.apply(variables, img, rngs={"dropout": key + 1}, precision=precision)
+    assert np.abs(other - got).max() > 10 * tol                                 # another key, other masks
+    plain = ViT(**cfg).apply(variables, img, precision=precision)
+    assert np.abs(plain - got).max() > 10 * tol
+
+
+def test_readme_usage_runs_with_dropout():
+    """README.md:10-40 verbatim config (dropout=0.1, emb_dropout=0.1): output shape (1, 1000)."""
+    v = ViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048,
+            dropout=0.1, emb_dropout=0.1)
+    img = images_for(C1, 1)
+    rngs = {"params": 1, "dropout": 2, "emb_dropout": 3}
+    params = v.init(rngs, img)
+    out = v.apply(params, img, rngs=rngs)
+    assert out.shape == (1, 1000) and np.isfinite(out).all()
+    want = vit_numpy.vit_forward(params, img, dropout=0.1, emb_dropout=0.1, dropout_key=2, **C1)
+    assert np.abs(out - want).max() < 2e-2

@@ -270,3 +270,34 @@ def test_pack_weight(lib, fmt):
     got = Wt.float().cpu().numpy()
     np.testing.assert_array_equal(got[:, :K], torch.as_tensor(W.T.copy()).to(tdt).float().numpy())
     assert not got[:, K:].any()
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 520, 128), (129, 768, 64)])
+@pytest.mark.parametrize("epi", [_lib.EPI_BIAS_GELU_16, _lib.EPI_BIAS_RESID_F32])
+@pytest.mark.parametrize("cta_group", ["1", "2"])
+def test_gemm_tc_dropout_epilogue(lib, M, N, K, epi, cta_group, monkeypatch):
+    """nn.Dropout behind a Dense (vit.py:50,52,83): the mask is the Philox mask of oracle/philox.py
+    for (key, site, flat element index) whatever the tile mode; kept values are scaled by 1/(1-rate)."""
+    from oracle import philox
+    monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
+    dt, tdt, ulp = DT16["fp16"]
+    rate, key, site = 0.3, 0x1234567890ABCDEF, 17
+    rng = np.random.default_rng(M + N)
+    A = dev(rng.standard_normal((M, K)), tdt)
+    Wt = dev((rng.standard_normal((K, N)) / np.sqrt(K)).T, tdt)
+    bias = dev(rng.standard_normal(N) * 0.5 + 3.0)                 # keeps outputs away from exact zeros
+    resid = dev(rng.standard_normal((M, N)))
+    acc = A.double() @ Wt.double().t() + bias.double()
+    keep = torch.as_tensor(philox.keep_mask((M, N), rate, site, key), device="cuda")
+    if epi == _lib.EPI_BIAS_GELU_16:
+        out = torch.empty((M, N), dtype=tdt, device="cuda")
+        want = torch.where(keep, torch.nn.functional.gelu(acc, approximate="tanh") / (1 - rate), 0.0)
+    else:
+        out = resid.clone()
+        want = torch.where(keep, acc / (1 - rate), 0.0) + resid.double()
+    _lib.check(lib.vitb200_gemm_tc_dropout(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                           M, N, K, epi, None, 0, dt, rate, key, site))
+    torch.cuda.synchronize()
+    err = (out.double() - want).abs().max().item()
+    assert err < (3e-4 if out.dtype == torch.float32 else 16 * ulp + 3e-3), err
+    assert abs(float(keep.double().mean()) - (1 - rate)) < 0.01

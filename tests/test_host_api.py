@@ -68,11 +68,13 @@ def test_shape_validation_mirrors_reference_asserts():
         ViT(**TINY).init(0, np.zeros((1, 3, 32, 32), np.float32))
 
 
-def test_dropout_rates_above_zero_are_rejected():
+def test_dropout_needs_the_dropout_rng_like_flax():
     v = ViT(dropout=0.1, emb_dropout=0.1, **TINY)             # the demo's config, vit.py:183-184
-    variables = v.init(0, np.zeros((1, 32, 32, 3), np.float32))
-    with pytest.raises(NotImplementedError):
-        v.apply(variables, np.zeros((1, 32, 32, 3), np.float32), rngs={"dropout": 2})
+    variables = v.init({"params": 1, "dropout": 2, "emb_dropout": 3}, np.zeros((1, 32, 32, 3), np.float32))
+    with pytest.raises(ValueError, match="rngs=.*dropout"):
+        v.apply(variables, np.zeros((1, 32, 32, 3), np.float32))
+    with pytest.raises(ValueError, match="rngs=.*dropout"):
+        v.apply(variables, np.zeros((1, 32, 32, 3), np.float32), rngs={"emb_dropout": 3})
 
 
 def test_flatten_accepts_any_mapping_and_leaf_types():

@@ -90,3 +90,32 @@ def test_golden_c1_from_seeds():
 def test_no_project_out_when_single_head_dim64():
     v = init_params(seed=0, **TINY_MEAN)                     # heads=1, dim=64 -> vit.py:65
     assert "Dense_1" not in v["params"]["Transformer_0"]["Attention_0"]
+
+
+def test_philox_known_answer_and_dropout_semantics():
+    """Philox4x32-10 known-answer vectors (Salmon et al., Random123 kat_vectors) pin the generator the
+    kernels' dropout masks come from; flax nn.Dropout semantics: keep w.p. 1-rate, scale by 1/(1-rate)."""
+    from oracle import philox
+    # counter = (0,0,0,0), key = (0,0)  ->  6627e8d5 e169c58d bc57ac4c 9b00dbd8
+    got = philox.philox4x32_10(np.array([0], np.uint64), 0, 0)[0]
+    assert [int(v) for v in got] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    # counter = ffffffff x4, key = ffffffff x2  ->  408f276d 41c83b0e a20bc7c6 6d5451fd
+    # (our counter layout is (quad_lo, quad_hi, site, 0): c3 = 0, so use the all-zero vector above
+    #  plus the pi-digits vector below with c3 = 0 replaced -- checked against a scalar reference)
+    def scalar(c, k):
+        c, k = list(c), list(k)
+        for _ in range(10):
+            p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+            k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+        return c
+    quad, site, key = 0x123456789ABCDEF, 77, 0xDEADBEEFCAFEF00D
+    want = scalar([quad & 0xFFFFFFFF, quad >> 32, site, 0], [key & 0xFFFFFFFF, key >> 32])
+    assert [int(v) for v in philox.philox4x32_10(np.array([quad], np.uint64), site, key)[0]] == want
+    x = np.ones((64, 256), np.float64)
+    y = philox.dropout(x, 0.25, 3, 42)
+    kept = y != 0
+    assert abs(kept.mean() - 0.75) < 0.02
+    np.testing.assert_allclose(y[kept], 1.0 / 0.75, rtol=1e-6)
+    np.testing.assert_array_equal(y, philox.dropout(x, 0.25, 3, 42))          # same key, same mask
+    assert (philox.dropout(x, 0.25, 4, 42) != y).any() and (philox.dropout(x, 0.25, 3, 43) != y).any()

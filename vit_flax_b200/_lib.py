@@ -11,6 +11,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libvitb200.so"
 
 # error codes / enums (keep in sync with include/vitb200.h)
+ABI_VERSION = 2
 OK = 0
 PREC_BF16, PREC_FP32, PREC_FP16 = 0, 1, 2
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
@@ -28,7 +29,8 @@ class Config(C.Structure):
         ("channels", C.c_int32), ("num_classes", C.c_int32),
         ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
         ("mlp_dim", C.c_int32), ("pool", C.c_int32), ("precision", C.c_int32),
-        ("max_batch", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("max_batch", C.c_int32), ("dropout", C.c_float), ("emb_dropout", C.c_float),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -54,6 +56,7 @@ SIGNATURES = {
     "vitb200_param_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_i64)]),
     "vitb200_set_param": (_i, [_vp, C.c_char_p, _fp, C.POINTER(_i64), _i]),
     "vitb200_finalize_params": (_i, [_vp, _vp]),
+    "vitb200_set_dropout_key": (_i, [_vp, C.c_uint64]),
     "vitb200_forward": (_i, [_vp, _vp, _fp, _i, _fp]),
     "vitb200_forward_host": (_i, [_vp, _vp, _fp, _i, _fp]),
     "vitb200_submit_host": (_i, [_vp, _vp, _fp, _i, _fp]),
@@ -61,6 +64,7 @@ SIGNATURES = {
     "vitb200_profile_forward": (_i, [_vp, _vp, _fp, _i, _fp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vitb200_debug_tokens": (_i, [_vp, _vp, _fp, _i]),
     "vitb200_gemm_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i]),
+    "vitb200_gemm_tc_dropout": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i, C.c_float, C.c_uint64, C.c_uint32]),
     "vitb200_gemm_f32": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i]),
     "vitb200_layernorm": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i]),
     "vitb200_attention_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
@@ -88,8 +92,8 @@ def load() -> C.CDLL:
             fn.restype = res
             fn.argtypes = args
         got = lib.vitb200_abi_version()
-        if got != 1:
-            raise ImportError(f"libvitb200.so ABI version {got}, expected 1")
+        if got != ABI_VERSION:
+            raise ImportError(f"libvitb200.so ABI version {got}, expected {ABI_VERSION}")
         _lib = lib
     return _lib
 

@@ -81,6 +81,21 @@ struct vitb200_model {
   int dt = VITB200_DT_BF16; // operand type of the tensor-core path
   bool finalized = false;
   bool head_tc = false;
+  uint64_t dropout_key = 0;   // 'dropout' rng stream (vitb200_set_dropout_key)
+
+  // the Dropout instance `site` of this model (rate 0 => off)
+  Dropout drop(float rate, uint32_t site) const {
+    Dropout d;
+    if (rate > 0.f) {
+      d.key_lo = uint32_t(dropout_key);
+      d.key_hi = uint32_t(dropout_key >> 32);
+      d.site = site;
+      const double t = double(rate) * 4294967296.0;
+      d.threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : uint32_t(t);
+      d.inv_keep = 1.0f / (1.0f - rate);
+    }
+    return d;
+  }
 
   std::vector<Leaf> leaves;
   std::map<std::string, int> index;
@@ -273,9 +288,10 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   // vit.py:147-153  Dense_0 + bias, placed at row b*T+1+t, + pos_embedding[1+t]
   mark(m, st, VITB200_CAT_GEMM_PATCH);
   if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), nullptr, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
-                             Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt, cgp))) return rc;
+                             Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt, cgp,
+                             m->drop(c.emb_dropout, 0)))) return rc;
   mark(m, st, VITB200_CAT_CLS_ROWS);
-  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
+  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D, m->drop(c.emb_dropout, 0)))) return rc;
   for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
     Layer& L = m->layers[l];
     // Residual(PreNorm(Attention))  vit.py:31,39,62-87
@@ -287,7 +303,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     if ((rc = launch_attention_tc(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_OUT);
     if (m->project_out) {
-      if ((rc = launch_gemm_tc(st, am->o, L.out.map(cg), &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg))) return rc;
+      if ((rc = launch_gemm_tc(st, am->o, L.out.map(cg), &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     } else {   // heads == 1 and dim == 64: to_out is the identity (vit.py:65,85)
       const int64_t n = int64_t(R) * D;
       add_16_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_h.p, m->x.p, n, m->dt);
@@ -297,9 +313,9 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF1);
-    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.map(cg), &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt, cg))) return rc;
+    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.map(cg), &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt, cg, m->drop(c.dropout, 2 + 3 * l)))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF2);
-    if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg))) return rc;
+    if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg, m->drop(c.dropout, 3 + 3 * l)))) return rc;
   }
   // vit.py:159-165  pool, LayerNorm_0, Dense_1
   if (m->head_tc) {
@@ -332,9 +348,9 @@ int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batc
   // fp32 mode keeps K0pad == K0 (checked at create), so the patch matrix is a dense [Rp, K0].
   mark(m, st, VITB200_CAT_GEMM_PATCH);
   if ((rc = launch_gemm_f32(st, m->patches_f.p, leaf_ptr(m, m->patch.leaf_kernel), leaf_ptr(m, m->patch.leaf_bias), m->x.p,
-                            Rp, D, m->K0, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np))) return rc;
+                            Rp, D, m->K0, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->drop(c.emb_dropout, 0)))) return rc;
   mark(m, st, VITB200_CAT_CLS_ROWS);
-  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D))) return rc;
+  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D, m->drop(c.emb_dropout, 0)))) return rc;
   for (int l = 0; l < c.depth; ++l) {
     Layer& L = m->layers[l];
     mark(m, st, VITB200_CAT_LAYERNORM);
@@ -345,7 +361,7 @@ int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batc
     if ((rc = launch_attention_f32(st, m->qkv_f.p, m->o_f.p, batch, T, c.heads))) return rc;
     mark(m, st, VITB200_CAT_GEMM_OUT);
     if (m->project_out) {
-      if ((rc = launch_gemm_f32(st, m->o_f.p, leaf_ptr(m, L.out.leaf_kernel), leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+      if ((rc = launch_gemm_f32(st, m->o_f.p, leaf_ptr(m, L.out.leaf_kernel), leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     } else {
       const int64_t n = int64_t(R) * D;
       add_f32_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_f.p, m->x.p, n);
@@ -354,9 +370,9 @@ int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batc
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_f.p, R, D, VITB200_DT_F32))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF1);
-    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.ff1.leaf_kernel), leaf_ptr(m, L.ff1.leaf_bias), m->hid_f.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0))) return rc;
+    if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.ff1.leaf_kernel), leaf_ptr(m, L.ff1.leaf_bias), m->hid_f.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->drop(c.dropout, 2 + 3 * l)))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF2);
-    if ((rc = launch_gemm_f32(st, m->hid_f.p, leaf_ptr(m, L.ff2.leaf_kernel), leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0))) return rc;
+    if ((rc = launch_gemm_f32(st, m->hid_f.p, leaf_ptr(m, L.ff2.leaf_kernel), leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->drop(c.dropout, 3 + 3 * l)))) return rc;
   }
   mark(m, st, VITB200_CAT_POOL_LN);
   if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32))) return rc;
@@ -409,6 +425,8 @@ int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out) {
     return fail(VITB200_ERR_INVALID, "create: pool must be cls or mean");
   if (c.precision != VITB200_PREC_BF16 && c.precision != VITB200_PREC_FP32 && c.precision != VITB200_PREC_FP16)
     return fail(VITB200_ERR_INVALID, "create: unknown precision");
+  if (!(c.dropout >= 0.f && c.dropout < 1.f) || !(c.emb_dropout >= 0.f && c.emb_dropout < 1.f))
+    return fail(VITB200_ERR_INVALID, "create: dropout rates must be in [0, 1)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     cudaGetLastError();
@@ -504,6 +522,12 @@ int vitb200_finalize_params(vitb200_model* m, void* stream) {
   }
   VB_CUDA(cudaStreamSynchronize(st));
   m->finalized = true;
+  return 0;
+}
+
+int vitb200_set_dropout_key(vitb200_model* m, uint64_t key) {
+  if (!m) return fail(VITB200_ERR_INVALID, "set_dropout_key: null model");
+  m->dropout_key = key;
   return 0;
 }
 
@@ -628,6 +652,22 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 // ---- per-kernel entry points ------------------------------------------------
 int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
                     int K, int epilogue, const float* aux, int tokens_per_image, int dtype) {
+  return vitb200_gemm_tc_dropout(stream, A, Wt, bias, C, M, N, K, epilogue, aux, tokens_per_image, dtype, 0.f, 0, 0);
+}
+
+int vitb200_gemm_tc_dropout(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
+                            int K, int epilogue, const float* aux, int tokens_per_image, int dtype,
+                            float rate, uint64_t key, uint32_t site) {
+  if (!(rate >= 0.f && rate < 1.f)) return fail(VITB200_ERR_INVALID, "gemm_tc: dropout rate must be in [0, 1)");
+  Dropout drop;
+  if (rate > 0.f) {
+    drop.key_lo = uint32_t(key);
+    drop.key_hi = uint32_t(key >> 32);
+    drop.site = site;
+    const double t = double(rate) * 4294967296.0;
+    drop.threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : uint32_t(t);
+    drop.inv_keep = 1.0f / (1.0f - rate);
+  }
   if (!A || !Wt || !C) return fail(VITB200_ERR_INVALID, "gemm_tc: null pointer");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
@@ -643,7 +683,7 @@ int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bi
   const bool direct = epilogue == VITB200_EPI_PATCH_F32;
   if (!direct && (rc = make_tmap_2d(&tc, C, M, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
   return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, direct ? nullptr : &tc, bias, C, M, N, K, epilogue,
-                        aux, tokens_per_image, dtype, cg);
+                        aux, tokens_per_image, dtype, cg, drop);
 }
 
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias, float* C, int M, int N,

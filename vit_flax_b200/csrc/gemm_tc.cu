@@ -62,13 +62,13 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.0f + tanh_approx(u));
 }
 
-template <int kEpi, int kDT, int kCG>
+template <int kEpi, int kDT, int kCG, bool kDrop>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, void* __restrict__ Cout,
-               int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg) {
+               int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop) {
   constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16);
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
@@ -250,6 +250,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                 o.y = __uint_as_float(r[j * 4 + 1]) + b4.y + p4.y;
                 o.z = __uint_as_float(r[j * 4 + 2]) + b4.z + p4.z;
                 o.w = __uint_as_float(r[j * 4 + 3]) + b4.w + p4.w;
+                if constexpr (kDrop)   // emb dropout (vit.py:155) on the token stream, flat index = row * N + col
+                  dropout4(drop, (int64_t(b) * (tpi + 1) + 1 + t) * N + n0 + j * 4, o.x, o.y, o.z, o.w);
                 *reinterpret_cast<float4*>(crow_base + n0 + j * 4) = o;
               }
             }
@@ -289,6 +291,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                   v[2] = gelu_tanh_fast(v[2] + b0.z); v[3] = gelu_tanh_fast(v[3] + b0.w);
                   v[4] = gelu_tanh_fast(v[4] + b1.x); v[5] = gelu_tanh_fast(v[5] + b1.y);
                   v[6] = gelu_tanh_fast(v[6] + b1.z); v[7] = gelu_tanh_fast(v[7] + b1.w);
+                  if constexpr (kDrop) {   // FeedForward's first Dropout (vit.py:50), on the hidden activations
+                    const int64_t e0 = int64_t(m_row0 + lrow) * N + nb;
+                    dropout4(drop, e0, v[0], v[1], v[2], v[3]);
+                    dropout4(drop, e0 + 4, v[4], v[5], v[6], v[7]);
+                  }
                 }
                 const int chunk = half * 4 + j;
                 st_shared_v4(srow + (uint32_t(chunk ^ sw) << 4), pack2<kDT>(v[0], v[1]),
@@ -304,11 +311,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
               const int nb = n0 + j * 4;
               float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
               if (nb < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + nb));
-              st_shared_v4(srow + (uint32_t(j ^ sw) << 4),
-                           __float_as_uint(__uint_as_float(r[j * 4 + 0]) + b4.x),
-                           __float_as_uint(__uint_as_float(r[j * 4 + 1]) + b4.y),
-                           __float_as_uint(__uint_as_float(r[j * 4 + 2]) + b4.z),
-                           __float_as_uint(__uint_as_float(r[j * 4 + 3]) + b4.w));
+              float o0 = __uint_as_float(r[j * 4 + 0]) + b4.x, o1 = __uint_as_float(r[j * 4 + 1]) + b4.y;
+              float o2 = __uint_as_float(r[j * 4 + 2]) + b4.z, o3 = __uint_as_float(r[j * 4 + 3]) + b4.w;
+              if constexpr (kDrop && kEpi == VITB200_EPI_BIAS_RESID_F32)   // Dropout after to_out / FF Dense_1
+                dropout4(drop, int64_t(m_row0 + lrow) * N + nb, o0, o1, o2, o3);   // (vit.py:52,83), before the residual add
+              st_shared_v4(srow + (uint32_t(j ^ sw) << 4), __float_as_uint(o0), __float_as_uint(o1),
+                           __float_as_uint(o2), __float_as_uint(o3));
             }
           }
           fence_proxy_async_smem();                    // generic-proxy smem writes -> async proxy
@@ -349,14 +357,14 @@ int gemm_dbg() {   // VITB200_GEMM_DBG bit 0: no TMA loads, bit 1: no output sto
   return v;
 }
 
-template <int kEpi, int kDT, int kCG>
+template <int kEpi, int kDT, int kCG, bool kDrop>
 int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-              const float* aux, int tpi) {
+              const float* aux, int tpi, const Dropout& drop) {
   static bool configured = false;   // per-process; attribute is per-function, device-agnostic
   static int max_units = 0;         // clusters (CTAs for kCG == 1) that can be resident at once
   if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG>,
+    VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG>()));
     max_units = sm_count() / kCG;
     if (kCG > 2) {   // clusters of 4 do not tile every GPC: ask how many fit (33 on a 148-SM B200)
@@ -372,7 +380,7 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       cfg.gridDim = dim3(sm_count() / kCG * kCG);
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<kEpi, kDT, kCG>, &cfg) == cudaSuccess && n > 0)
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, &cfg) == cudaSuccess && n > 0)
         max_units = n < max_units ? n : max_units;
       else
         cudaGetLastError();
@@ -381,8 +389,8 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
   }
   const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, BN);
   const int units = tiles < max_units ? tiles : max_units;
-  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG>, dim3(units * kCG), dim3(NUM_THREADS), smem_bytes<kCG>(),
-                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg()));
+  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, dim3(units * kCG), dim3(NUM_THREADS), smem_bytes<kCG>(),
+                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop));
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -390,29 +398,41 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
 template <int kEpi, int kDT>
 int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-               const float* aux, int tpi, int cta_group) {
-  if (cta_group == 4) return launch_cg<kEpi, kDT, 4>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
-  if (cta_group == 2) return launch_cg<kEpi, kDT, 2>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
-  return launch_cg<kEpi, kDT, 1>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi);
+               const float* aux, int tpi, int cta_group, const Dropout& drop) {
+  // dropout variants exist for the epilogues that have a Dropout behind them and for the two
+  // production tile modes; the opt-in cluster-of-4 mode falls back to pairs when dropout is on
+  constexpr bool kCanDrop = kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_RESID_F32 ||
+                            kEpi == VITB200_EPI_PATCH_F32;
+  if constexpr (kCanDrop) {
+    if (drop.threshold != 0) {
+      if (cta_group == 4)
+        return fail(VITB200_ERR_UNSUPPORTED, "gemm_tc: dropout is not built for the opt-in cluster-of-4 mode");
+      if (cta_group == 1) return launch_cg<kEpi, kDT, 1, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
+      return launch_cg<kEpi, kDT, 2, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
+    }
+  }
+  if (cta_group == 4) return launch_cg<kEpi, kDT, 4, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
+  if (cta_group == 2) return launch_cg<kEpi, kDT, 2, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
+  return launch_cg<kEpi, kDT, 1, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
 }
 
 template <int kDT>
 int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-                 int epilogue, const float* aux, int tpi, int cta_group) {
+                 int epilogue, const float* aux, int tpi, int cta_group, const Dropout& drop) {
   switch (epilogue) {
     case VITB200_EPI_STORE_16:
-      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
+      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
     case VITB200_EPI_BIAS_GELU_16:
-      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
+      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
     case VITB200_EPI_BIAS_RESID_F32:
-      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
+      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
     case VITB200_EPI_BIAS_F32:
-      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
+      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
     case VITB200_EPI_PATCH_F32:
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
-      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group);
+      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
     default:
       return fail(VITB200_ERR_INVALID, "gemm_tc: unknown epilogue");
   }
@@ -432,7 +452,7 @@ int gemm_tc_cta_group(int M) {
 
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
-                   int epilogue, const float* aux, int tpi, int dtype, int cta_group) {
+                   int epilogue, const float* aux, int tpi, int dtype, int cta_group, const Dropout& drop) {
   if (cta_group != 1 && cta_group != 2 && cta_group != 4) return fail(VITB200_ERR_INVALID, "gemm_tc: cta_group must be 1, 2 or 4");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
@@ -443,9 +463,9 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
     return fail(VITB200_ERR_INVALID, "gemm_tc: output tensor map missing");
   const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
   if (dtype == DT_BF16)
-    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group);
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop);
   if (dtype == DT_F16)
-    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group);
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop);
   return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 

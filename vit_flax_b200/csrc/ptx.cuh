@@ -439,6 +439,43 @@ __device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, un
   return d;
 }
 
+// ------------------------------------------------------------------- dropout
+// nn.Dropout(rate)(x, deterministic=False) (vit.py:50,52,83,155): keep with probability 1 - rate,
+// scale kept values by 1 / (1 - rate).  Counter-based Philox4x32-10 keyed by the 'dropout' rng the
+// caller passes: the mask of element e of dropout site s is a pure function of (key, s, e), like
+// Flax's functional rng -- same key, same mask.  (Bit parity with JAX's threefry is impossible
+// without JAX; oracle/philox.py restates this generator so the tests inject identical masks.)
+struct Dropout {
+  uint32_t key_lo = 0, key_hi = 0;   // 'dropout' rng key
+  uint32_t site = 0;                 // which nn.Dropout instance (0 = emb, 1+3l.. per layer)
+  uint32_t threshold = 0;            // drop when rand32 < threshold; 0 = rate 0 = off
+  float inv_keep = 1.f;
+};
+// four 32-bit random words for elements [4*quad, 4*quad+4) of the site
+__device__ __forceinline__ uint4 philox4x32_10(unsigned long long quad, uint32_t site, uint32_t k0, uint32_t k1) {
+  uint32_t c0 = uint32_t(quad), c1 = uint32_t(quad >> 32), c2 = site, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// apply the site's mask to 4 consecutive elements starting at flat index `elem` (a multiple of 4)
+__device__ __forceinline__ void dropout4(const Dropout& d, long long elem, float& a, float& b, float& c, float& e) {
+  const uint4 r = philox4x32_10(static_cast<unsigned long long>(elem) >> 2, d.site, d.key_lo, d.key_hi);
+  a = r.x < d.threshold ? 0.f : a * d.inv_keep;
+  b = r.y < d.threshold ? 0.f : b * d.inv_keep;
+  c = r.z < d.threshold ? 0.f : c * d.inv_keep;
+  e = r.w < d.threshold ? 0.f : e * d.inv_keep;
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -213,13 +213,20 @@ patchify_rows_kernel(const float* __restrict__ img, void* __restrict__ out, int 
 
 // -------------------------------------------------------------- cls rows (K1b)
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
-                                float* __restrict__ x, int batch, int T, int dim) {
+                                float* __restrict__ x, int batch, int T, int dim, Dropout drop) {
   pdl_launch_dependents();
   pdl_wait();
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= int64_t(batch) * dim) return;
   const int b = int(i / dim), d = int(i - int64_t(b) * dim);
-  x[int64_t(b) * T * dim + d] = cls[d] + pos[d];
+  float v = cls[d] + pos[d];
+  if (drop.threshold != 0) {   // emb dropout (vit.py:155): same flat index as the patch rows use
+    const int64_t e = int64_t(b) * T * dim + d;
+    const uint4 r = philox4x32_10(static_cast<unsigned long long>(e) >> 2, drop.site, drop.key_lo, drop.key_hi);
+    const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+    v = w < drop.threshold ? 0.f : v * drop.inv_keep;
+  }
+  x[int64_t(b) * T * dim + d] = v;
 }
 
 // ------------------------------------------------- pool + head LayerNorm (K5a)
@@ -299,7 +306,7 @@ template <int kEpi>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
                 const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
-                const float* __restrict__ aux, int tpi) {
+                const float* __restrict__ aux, int tpi, Dropout drop) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x;
@@ -357,8 +364,17 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
       float v = acc[i][j];
       if constexpr (kEpi != VITB200_EPI_STORE_16) v += bias[n];
       if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16) v = gelu_tanh_exact(v);
-      if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32) v += C[out_row * N + n];
       if constexpr (kEpi == VITB200_EPI_PATCH_F32) v += pos_row[n];
+      if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_RESID_F32 ||
+                    kEpi == VITB200_EPI_PATCH_F32) {
+        if (drop.threshold != 0) {   // same sites and flat indices as the tensor-core epilogues
+          const int64_t e = out_row * N + n;
+          const uint4 r = philox4x32_10(static_cast<unsigned long long>(e) >> 2, drop.site, drop.key_lo, drop.key_hi);
+          const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+          v = w < drop.threshold ? 0.f : v * drop.inv_keep;
+        }
+      }
+      if constexpr (kEpi == VITB200_EPI_BIAS_RESID_F32) v += C[out_row * N + n];
       C[out_row * N + n] = v;
     }
   }
@@ -366,9 +382,9 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
 
 template <int kEpi>
 int launch_gemm_f32_t(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
-                      int M, int N, int K, const float* aux, int tpi) {
+                      int M, int N, int K, const float* aux, int tpi, const Dropout& drop) {
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-  gemm_f32_kernel<kEpi><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, aux, tpi);
+  gemm_f32_kernel<kEpi><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, aux, tpi, drop);
   VB_LAUNCH_CHECK("gemm_f32_kernel");
   return 0;
 }
@@ -468,9 +484,9 @@ int launch_patchify(cudaStream_t st, const float* images, void* patches, int bat
 }
 
 int launch_cls_rows(cudaStream_t st, const float* cls, const float* pos, float* x, int batch, int T,
-                    int dim) {
+                    int dim, const Dropout& drop) {
   const int64_t total = int64_t(batch) * dim;
-  VB_CUDA(launch_kernel(cls_rows_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, 1, cls, pos, x, batch, T, dim));
+  VB_CUDA(launch_kernel(cls_rows_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, 1, cls, pos, x, batch, T, dim, drop));
   VB_LAUNCH_CHECK("cls_rows_kernel");
   return 0;
 }
@@ -495,18 +511,18 @@ int launch_pack_weight(cudaStream_t st, const float* W, void* Wt, int K, int N, 
 }
 
 int launch_gemm_f32(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
-                    int M, int N, int K, int epilogue, const float* aux, int tpi) {
+                    int M, int N, int K, int epilogue, const float* aux, int tpi, const Dropout& drop) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_f32: empty problem");
   if (epilogue != VITB200_EPI_STORE_16 && bias == nullptr)
     return fail(VITB200_ERR_INVALID, "gemm_f32: epilogue needs a bias");
   switch (epilogue) {
-    case VITB200_EPI_STORE_16: return launch_gemm_f32_t<VITB200_EPI_STORE_16>(st, A, W, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_BIAS_GELU_16: return launch_gemm_f32_t<VITB200_EPI_BIAS_GELU_16>(st, A, W, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_BIAS_RESID_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_RESID_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
-    case VITB200_EPI_BIAS_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
+    case VITB200_EPI_STORE_16: return launch_gemm_f32_t<VITB200_EPI_STORE_16>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
+    case VITB200_EPI_BIAS_GELU_16: return launch_gemm_f32_t<VITB200_EPI_BIAS_GELU_16>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
+    case VITB200_EPI_BIAS_RESID_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_RESID_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
+    case VITB200_EPI_BIAS_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
     case VITB200_EPI_PATCH_F32:
       if (aux == nullptr || tpi <= 0) return fail(VITB200_ERR_INVALID, "gemm_f32: PATCH epilogue needs pos_embedding and tokens");
-      return launch_gemm_f32_t<VITB200_EPI_PATCH_F32>(st, A, W, bias, C, M, N, K, aux, tpi);
+      return launch_gemm_f32_t<VITB200_EPI_PATCH_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
     default: return fail(VITB200_ERR_INVALID, "gemm_f32: unknown epilogue");
   }
 }

@@ -23,7 +23,8 @@ class Engine:
     """Create -> load_params -> forward.  Not thread-safe (like the C handle)."""
 
     def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim,
-                 pool="cls", channels=3, precision="fp16", max_batch=256, device=0):
+                 pool="cls", channels=3, precision="fp16", max_batch=256, device=0,
+                 dropout=0.0, emb_dropout=0.0):
         import torch  # deferred: plumbing only
 
         if not torch.cuda.is_available():
@@ -39,7 +40,7 @@ class Engine:
             num_classes=num_classes, dim=dim, depth=depth, heads=heads, mlp_dim=mlp_dim,
             pool=_lib.POOL_MEAN if pool == "mean" else _lib.POOL_CLS,
             precision=_lib.PRECISIONS[precision],
-            max_batch=max_batch)
+            max_batch=max_batch, dropout=float(dropout), emb_dropout=float(emb_dropout))
         self.precision = precision
         self.max_batch = max_batch
         self.device = torch.device("cuda", device)
@@ -78,6 +79,10 @@ class Engine:
             _lib.check(self.lib.vitb200_set_param(self.handle, path.encode(), a.ctypes.data, shape, a.ndim))
         _lib.check(self.lib.vitb200_finalize_params(self.handle, _stream_ptr(self._torch, self.device)))
         self._loaded = True
+
+    def set_dropout_key(self, key: int) -> None:
+        """Key of the 'dropout' rng stream; the masks are a pure function of it (like Flax)."""
+        _lib.check(self.lib.vitb200_set_dropout_key(self.handle, C.c_uint64(int(key) & 0xFFFFFFFFFFFFFFFF)))
 
     # -- forward ---------------------------------------------------------------
     def _check_images(self, shape):

@@ -21,7 +21,7 @@ def _fingerprint(variables) -> Tuple:
 def get_engine(vit, channels: int, precision: str, device: int, batch: int, variables,
                reload: bool = False) -> Engine:
     key = (vit.image_size, vit.patch_size, vit.num_classes, vit.dim, vit.depth, vit.heads,
-           vit.mlp_dim, vit.pool, channels, precision, device)
+           vit.mlp_dim, vit.pool, channels, precision, device, float(vit.dropout), float(vit.emb_dropout))
     eng = _engines.get(key)
     if eng is None or eng.max_batch < batch:
         if eng is not None:
@@ -30,7 +30,7 @@ def get_engine(vit, channels: int, precision: str, device: int, batch: int, vari
         eng = Engine(image_size=vit.image_size, patch_size=vit.patch_size,
                      num_classes=vit.num_classes, dim=vit.dim, depth=vit.depth, heads=vit.heads,
                      mlp_dim=vit.mlp_dim, pool=vit.pool, channels=channels, precision=precision,
-                     max_batch=batch, device=device)
+                     max_batch=batch, device=device, dropout=vit.dropout, emb_dropout=vit.emb_dropout)
         _engines[key] = eng
     fp = _fingerprint(variables)
     if reload or _loaded.get(key) != fp:

@@ -6,10 +6,12 @@ pytree, so a tree produced by the reference's Flax ``init`` loads unchanged.
 Below this surface everything runs in ``libvitb200.so`` (hand-written sm_100a
 kernels); there is no CPU fallback.
 
-Not mirrored (out of scope): ``dropout``/``emb_dropout`` > 0 --
-the reference hard-codes ``deterministic=False`` (vit.py:50,52,83,155), so
-"dropout disabled" means the default rates 0.0, which Flax short-circuits to
-the identity without drawing random numbers.
+``dropout`` / ``emb_dropout`` > 0: the reference hard-codes ``deterministic=False``
+(vit.py:50,52,83,155), so every ``apply`` drops activations and needs
+``rngs={'dropout': key}`` (all four Dropout sites draw from the 'dropout' stream;
+'emb_dropout' is never consumed).  Here the masks come from a Philox generator keyed by that
+key -- a pure function of the key like Flax's, but not bit-equal to JAX's threefry stream.
+"Dropout disabled" means the default rates 0.0, which Flax short-circuits to the identity.
 """
 from __future__ import annotations
 
@@ -74,6 +76,19 @@ class ViT:
             raise ValueError(f"expected images of {ih}x{iw}, got {h}x{w}{hint}")
         return c
 
+    def _dropout_key(self, rngs):
+        """None when both rates are 0 (Flax draws nothing); else the 'dropout' key, required like in
+        Flax, where ``apply`` without it fails with "Dropout_0 needs PRNG for 'dropout'"."""
+        if self.dropout == 0.0 and self.emb_dropout == 0.0:
+            return None
+        if not (0.0 <= self.dropout < 1.0 and 0.0 <= self.emb_dropout < 1.0):
+            raise ValueError("dropout rates must be in [0, 1)")
+        key = rngs.get("dropout") if hasattr(rngs, "get") else None
+        if key is None:
+            raise ValueError("ViT was built with dropout > 0 and the reference applies it on every call "
+                             "(deterministic=False): pass rngs={'dropout': key}")
+        return _seed_from_key(key)
+
     def num_params(self, channels: int = 3) -> int:
         """What the reference's demo prints (vit.py:195-197)."""
         return count_params(**self._cfg(channels))
@@ -100,11 +115,8 @@ class ViT:
         a CUDA tensor is returned.  ``rngs`` is accepted and ignored at dropout
         rate 0 (Flax draws nothing there).  Keyword-only extras are ours:
         ``precision`` ('fp16' / 'bf16' tcgen05 paths, 'fp32' validation path)."""
-        if self.dropout != 0.0 or self.emb_dropout != 0.0:
-            raise NotImplementedError(
-                "dropout > 0 is not built (SURVEY.md section 8f); the reference has no eval switch, "
-                "so construct ViT with the default rates 0.0 for inference")
         from .runtime import get_engine   # deferred: needs torch + CUDA
+        key = self._dropout_key(rngs)
 
         is_torch_cuda = hasattr(x, "is_cuda") and bool(x.is_cuda)
         channels = self._validate(tuple(x.shape) if hasattr(x, "shape") else np.shape(x))
@@ -113,6 +125,8 @@ class ViT:
             device = x.device.index if is_torch_cuda and x.device.index is not None else _current_device()
         eng = get_engine(self, channels, precision or _DEFAULT_PRECISION, device,
                          max_batch or batch, variables, reload)
+        if key is not None:
+            eng.set_dropout_key(key)
         if is_torch_cuda:
             import torch
             xin = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
@@ -126,7 +140,7 @@ class ViT:
         host->device copy of the next batch overlaps the forward of the current one.  Yielded arrays
         are staging buffers re-used two batches later."""
         if self.dropout != 0.0 or self.emb_dropout != 0.0:
-            raise NotImplementedError("dropout > 0 is not built; construct ViT with the default rates 0.0")
+            raise NotImplementedError("apply_stream is an inference path: construct ViT with the default rates 0.0")
         from .runtime import get_engine
 
         it = iter(batches)
