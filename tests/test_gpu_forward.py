@@ -228,3 +228,25 @@ def test_readme_usage_runs_with_dropout():
     assert out.shape == (1, 1000) and np.isfinite(out).all()
     want = vit_numpy.vit_forward(params, img, dropout=0.1, emb_dropout=0.1, dropout_key=2, **C1)
     assert np.abs(out - want).max() < 2e-2
+
+
+def test_vit_l16_full_batch_2048_rows_do_not_overflow():
+    """BASELINE configs[2] at its full single-GPU batch: 2048 images = 403,456 token rows, 6.6 GB of
+    activations (row*ld offsets pass 2^31 elements and 2^32 bytes).  Size-independent property: an
+    image's logits do not depend on where it sits in the batch -- first, middle and last images
+    equal the same images run as a batch of 12; the last ones are also checked against the oracle."""
+    cfg = dict(C3, depth=2)
+    variables = perturb_params(init_params(seed=11, **cfg), seed=12)
+    eng = Engine(precision="fp16", max_batch=2048, **cfg)
+    eng.load_params(variables)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((2048, 224, 224, 3), device="cuda", generator=g)
+    y = eng.forward(x)
+    pick = [0, 1, 2, 3, 1022, 1023, 1024, 1025, 2044, 2045, 2046, 2047]
+    y_small = eng.forward(x[pick].contiguous())
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert (y[pick] - y_small).abs().max().item() < 1e-4
+    want = oracle_logits(variables, x[2044:].cpu().numpy(), cfg)
+    assert np.abs(y[2044:].cpu().numpy() - want).max() < TOL["fp16"]
+    eng.close()

@@ -6,6 +6,8 @@
 //   K7  weight pack (fp32 [K,N] -> bf16 [N,Kpad])
 //   fp32 validation mode: SIMT GEMM with the same fused epilogues and a
 //   straightforward fp32 attention (tolerance 1e-4 against the oracle).
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -31,12 +33,15 @@ __device__ __forceinline__ float warp_max(float v) {
 template <int NV, int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                      const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
+                      const float* __restrict__ bias, void* __restrict__ y, int rows, int dim, int reverse) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= rows) return;
+  // Rows are walked from the END of the residual stream: the GEMM that just updated x wrote its
+  // last row blocks last, so they are what the 126 MB L2 still holds of the 155 MB stream, and the
+  // GEMM that follows starts with the row blocks this kernel wrote last (VITB200_LN_REVERSE=0: off).
+  const int row = reverse ? rows - 1 - (blockIdx.x * 8 + warp) : blockIdx.x * 8 + warp;
+  if (row < 0 || row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + int64_t(row) * dim);
   const int nvec = dim >> 2;
   float4 v[NV];
@@ -110,6 +115,15 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
+int ln_reverse() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITB200_LN_REVERSE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
 template <int kDT>
 int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b, void* y, int rows,
                 int dim) {
@@ -121,11 +135,11 @@ int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b,
     VB_CUDA(launch_kernel(layernorm_generic_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
   } else {
     const int nv = ceil_div(dim, 128);
-    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
-    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
-    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
-    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
-    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
+    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
+    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
+    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
+    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
+    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
   }
   VB_LAUNCH_CHECK("layernorm");
   return 0;
