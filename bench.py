@@ -150,7 +150,9 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    # every step is a bounded sample (args.cpu_images images, ~0.75 s on 24 cores); the step count is
+    # capped so that the whole run stays within a couple of minutes whatever K the caller passes
+    steps, warmup = max(1, min(args.steps, 30)), max(1, min(args.warmup, 3))
     cb = cpu_reference(steps, warmup, args.cpu_images)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s",
@@ -334,7 +336,7 @@ def run_b200(args) -> None:
             other_line["note"] = ("bf16 operands: weight rounding alone moves these logits by 1.9e-2 (DESIGN.md, "
                                   "Operand format)" if other == "bf16" else "fp16 operands")
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference(steps=2, warmup=1, sample_images=args.cpu_images)
+            cpu = cpu_reference(steps=12, warmup=1, sample_images=args.cpu_images)   # ~10 s of CPU work
 
     if rank == 0:
         total_tflops = fl["total"] * value / 1e12
@@ -396,7 +398,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("VITB200_PRECISION", "fp16"), choices=["fp16", "bf16"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--cpu-images", type=int, default=16, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-images", type=int, default=64, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
