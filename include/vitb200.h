@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VITB200_ABI_VERSION 2
+#define VITB200_ABI_VERSION 3
 
 /* error codes */
 #define VITB200_OK                 0
@@ -49,6 +49,10 @@ extern "C" {
 #define VITB200_DT_F32  0
 #define VITB200_DT_BF16 1
 #define VITB200_DT_F16  2
+
+/* cfg.flags: the variations simple_vit.py needs on the same path */
+#define VITB200_FLAG_NCHW   1   /* images are [B, C, H, W] (simple_vit.py:125), not [B, H, W, C]     */
+#define VITB200_FLAG_NO_CLS 2   /* no class token: T = num_patches, pos_embedding is [1, Np, dim]   */
 
 /* cfg.pool -- vit.py:121,159 */
 #define VITB200_POOL_CLS  0
@@ -70,6 +74,8 @@ typedef struct vitb200_config {
   int32_t max_batch;            /* workspace is sized for this many images   */
   float   dropout;              /* vit.py:124: rate of the Dropouts inside Attention / FeedForward */
   float   emb_dropout;          /* vit.py:125: rate of the Dropout after the positional embedding   */
+  int32_t flags;                /* VITB200_FLAG_*; 0 = vit.py                                        */
+  float   ln_eps;               /* LayerNorm epsilon; 0 = flax default 1e-6 (vit.py:31,163)          */
   int32_t reserved[1];
 } vitb200_config;
 

@@ -27,11 +27,11 @@ def test_every_declared_symbol_is_exported(lib_built):
     raw = C.CDLL(str(_lib.LIB_PATH))
     for s in declared_symbols():
         assert hasattr(raw, s), f"{s} declared in include/vitb200.h but not exported"
-    assert lib_built.vitb200_abi_version() == _lib.ABI_VERSION == 2
+    assert lib_built.vitb200_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_config_struct_layout():
-    assert C.sizeof(_lib.Config) == 16 * 4
+    assert C.sizeof(_lib.Config) == 18 * 4
 
 
 def test_create_without_gpu_is_an_error_not_a_fallback(lib_built):

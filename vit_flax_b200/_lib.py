@@ -11,7 +11,8 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libvitb200.so"
 
 # error codes / enums (keep in sync with include/vitb200.h)
-ABI_VERSION = 2
+ABI_VERSION = 3
+FLAG_NCHW, FLAG_NO_CLS = 1, 2
 OK = 0
 PREC_BF16, PREC_FP32, PREC_FP16 = 0, 1, 2
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
@@ -30,7 +31,7 @@ class Config(C.Structure):
         ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
         ("mlp_dim", C.c_int32), ("pool", C.c_int32), ("precision", C.c_int32),
         ("max_batch", C.c_int32), ("dropout", C.c_float), ("emb_dropout", C.c_float),
-        ("reserved", C.c_int32 * 1),
+        ("flags", C.c_int32), ("ln_eps", C.c_float), ("reserved", C.c_int32 * 1),
     ]
 
 

@@ -76,6 +76,9 @@ struct vitb200_model {
   vitb200_config cfg{};
   int device = 0;
   int Np = 0, T = 0, K0 = 0, K0pad = 0, inner = 0;
+  int cls_off = 1;         // 1: class token in front of every image (vit.py:151-152); 0: SimpleViT
+  int nchw = 0;
+  float eps = 1e-6f;
   bool project_out = true;
   bool tc = true;          // tensor-core (16-bit operand) path, else fp32 SIMT path
   int dt = VITB200_DT_BF16; // operand type of the tensor-core path
@@ -284,19 +287,19 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   // vit.py:146  patchify (+ fp32->bf16 cast, zero pad to K0pad)
   mark(m, st, VITB200_CAT_PATCHIFY);
   if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
-                            c.patch_h, c.patch_w, m->K0pad, m->dt))) return rc;
+                            c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw))) return rc;
   // vit.py:147-153  Dense_0 + bias, placed at row b*T+1+t, + pos_embedding[1+t]
   mark(m, st, VITB200_CAT_GEMM_PATCH);
   if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), nullptr, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
                              Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt, cgp,
-                             m->drop(c.emb_dropout, 0)))) return rc;
+                             m->drop(c.emb_dropout, 0), m->cls_off))) return rc;
   mark(m, st, VITB200_CAT_CLS_ROWS);
-  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D, m->drop(c.emb_dropout, 0)))) return rc;
+  if (m->cls_off && (rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D, m->drop(c.emb_dropout, 0)))) return rc;
   for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
     Layer& L = m->layers[l];
     // Residual(PreNorm(Attention))  vit.py:31,39,62-87
     mark(m, st, VITB200_CAT_LAYERNORM);
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, m->dt))) return rc;
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, m->dt, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_QKV);
     if ((rc = launch_gemm_tc(st, am->xn, L.qkv.map(cg), &am->c_qkv, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt, cg))) return rc;
     mark(m, st, VITB200_CAT_ATTENTION);
@@ -311,7 +314,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     }
     // Residual(PreNorm(FeedForward))  vit.py:31,39,47-53
     mark(m, st, VITB200_CAT_LAYERNORM);
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, m->dt))) return rc;
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, m->dt, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF1);
     if ((rc = launch_gemm_tc(st, am->xn, L.ff1.map(cg), &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt, cg, m->drop(c.dropout, 2 + 3 * l)))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF2);
@@ -321,7 +324,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   if (m->head_tc) {
     mark(m, st, VITB200_CAT_POOL_LN);
     mark(m, st, VITB200_CAT_POOL_LN);
-  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, m->dt))) return rc;
+  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, m->dt, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_HEAD);
     CUtensorMap c_logits;   // the caller's buffer: encoded per call (host-side, ~1 us)
     if ((rc = make_tmap_2d(&c_logits, logits, batch, c.num_classes, c.num_classes, GEMM_BM, VITB200_DT_F32))) return rc;
@@ -329,7 +332,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   } else {
     mark(m, st, VITB200_CAT_POOL_LN);
     mark(m, st, VITB200_CAT_POOL_LN);
-  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32))) return rc;
+  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_HEAD);
     if ((rc = launch_gemm_f32(st, m->pooled_f.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
   }
@@ -344,17 +347,17 @@ int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batc
   int rc;
   mark(m, st, VITB200_CAT_PATCHIFY);
   if ((rc = launch_patchify(st, images, m->patches_f.p, batch, c.image_h, c.image_w, c.channels,
-                            c.patch_h, c.patch_w, m->K0pad, VITB200_DT_F32))) return rc;
+                            c.patch_h, c.patch_w, m->K0pad, VITB200_DT_F32, m->nchw))) return rc;
   // fp32 mode keeps K0pad == K0 (checked at create), so the patch matrix is a dense [Rp, K0].
   mark(m, st, VITB200_CAT_GEMM_PATCH);
   if ((rc = launch_gemm_f32(st, m->patches_f.p, leaf_ptr(m, m->patch.leaf_kernel), leaf_ptr(m, m->patch.leaf_bias), m->x.p,
-                            Rp, D, m->K0, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->drop(c.emb_dropout, 0)))) return rc;
+                            Rp, D, m->K0, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->drop(c.emb_dropout, 0), m->cls_off))) return rc;
   mark(m, st, VITB200_CAT_CLS_ROWS);
-  if ((rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D, m->drop(c.emb_dropout, 0)))) return rc;
+  if (m->cls_off && (rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D, m->drop(c.emb_dropout, 0)))) return rc;
   for (int l = 0; l < c.depth; ++l) {
     Layer& L = m->layers[l];
     mark(m, st, VITB200_CAT_LAYERNORM);
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_f.p, R, D, VITB200_DT_F32))) return rc;
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_f.p, R, D, VITB200_DT_F32, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_QKV);
     if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.qkv.leaf_kernel), nullptr, m->qkv_f.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0))) return rc;
     mark(m, st, VITB200_CAT_ATTENTION);
@@ -368,14 +371,14 @@ int forward_f32(vitb200_model* m, cudaStream_t st, const float* images, int batc
       VB_LAUNCH_CHECK("add_f32_into_f32_kernel");
     }
     mark(m, st, VITB200_CAT_LAYERNORM);
-    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_f.p, R, D, VITB200_DT_F32))) return rc;
+    if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_f.p, R, D, VITB200_DT_F32, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF1);
     if ((rc = launch_gemm_f32(st, m->xn_f.p, leaf_ptr(m, L.ff1.leaf_kernel), leaf_ptr(m, L.ff1.leaf_bias), m->hid_f.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->drop(c.dropout, 2 + 3 * l)))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF2);
     if ((rc = launch_gemm_f32(st, m->hid_f.p, leaf_ptr(m, L.ff2.leaf_kernel), leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->drop(c.dropout, 3 + 3 * l)))) return rc;
   }
   mark(m, st, VITB200_CAT_POOL_LN);
-  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32))) return rc;
+  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32, m->eps))) return rc;
   mark(m, st, VITB200_CAT_GEMM_HEAD);
   return launch_gemm_f32(st, m->pooled_f.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0);
 }
@@ -443,7 +446,10 @@ int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out) {
   m->cfg = c;
   m->device = device;
   m->Np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
-  m->T = m->Np + 1;
+  m->cls_off = (c.flags & VITB200_FLAG_NO_CLS) ? 0 : 1;
+  m->nchw = (c.flags & VITB200_FLAG_NCHW) ? 1 : 0;
+  m->eps = c.ln_eps > 0.f ? c.ln_eps : 1e-6f;
+  m->T = m->Np + m->cls_off;
   m->K0 = c.patch_h * c.patch_w * c.channels;
   m->tc = c.precision != VITB200_PREC_FP32;
   m->dt = c.precision == VITB200_PREC_FP16 ? VITB200_DT_F16 : VITB200_DT_BF16;

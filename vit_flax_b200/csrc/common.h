@@ -89,16 +89,16 @@ constexpr int GEMM_BK = 64;
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tokens_per_image, int dtype, int cta_group,
-                   const Dropout& drop = Dropout());
+                   const Dropout& drop = Dropout(), int cls_off = 1);
 // 1 = one CTA per 128x256 tile (Wt box 256 rows), 2 = CTA pair per 256x256 tile (Wt box 128 rows),
 // 4 = cluster of two pairs sharing a multicast weight tile (Wt box 64 rows).
 // The Wt tensor map must be encoded with GEMM_BN / cta_group box rows.
 int gemm_tc_cta_group(int M);
 int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const float* bias,
                     float* C, int M, int N, int K, int epilogue, const float* aux,
-                    int tokens_per_image, const Dropout& drop = Dropout());
+                    int tokens_per_image, const Dropout& drop = Dropout(), int cls_off = 1);
 int launch_layernorm(cudaStream_t stream, const float* x, const float* scale, const float* bias,
-                     void* y, int rows, int dim, int out_dtype);
+                     void* y, int rows, int dim, int out_dtype, float eps = 1e-6f);
 int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
                         int heads, int dtype);
 bool attention_tc5_supports(int T);
@@ -110,12 +110,12 @@ int launch_attention_tc5m(cudaStream_t stream, const void* qkv, void* out, int b
 int launch_attention_f32(cudaStream_t stream, const float* qkv, float* out, int batch, int T,
                          int heads);
 int launch_patchify(cudaStream_t stream, const float* images, void* patches, int batch, int H,
-                    int W, int C, int ph, int pw, int Kpad, int out_dtype);
+                    int W, int C, int ph, int pw, int Kpad, int out_dtype, int nchw = 0);
 int launch_cls_rows(cudaStream_t stream, const float* cls, const float* pos, float* x, int batch,
                     int T, int dim, const Dropout& drop = Dropout());
 int launch_pool_layernorm(cudaStream_t stream, const float* x, const float* scale,
                           const float* bias, void* y, int batch, int T, int dim, int pool,
-                          int out_dtype);
+                          int out_dtype, float eps = 1e-6f);
 int launch_pack_weight(cudaStream_t stream, const float* W, void* Wt, int K, int N, int Kpad,
                        int dtype);
 

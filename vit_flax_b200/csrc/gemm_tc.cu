@@ -68,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, void* __restrict__ Cout,
-               int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop) {
+               int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop, int cls_off) {
   constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16);
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
@@ -226,12 +226,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
 
       if constexpr (kDirect) {
-        // ---- PATCH: row b*Np+t -> output row b*T+1+t, + bias + pos_embedding[1+t] ----
+        // ---- PATCH: row b*Np+t -> output row b*T+cls+t, + bias + pos_embedding[cls+t]; cls = 1 with a
+        // class token in front of every image (ViT, vit.py:151-153), 0 without (SimpleViT) ----
         const int row = m_row0 + lrow;
         const bool row_ok = row < M;
         const int b = row / tpi, t = row - b * tpi;
-        float* crow_base = reinterpret_cast<float*>(Cout) + (int64_t(b) * (tpi + 1) + 1 + t) * N;
-        const float* pos_row = aux + int64_t(1 + t) * N;
+        float* crow_base = reinterpret_cast<float*>(Cout) + (int64_t(b) * (tpi + cls_off) + cls_off + t) * N;
+        const float* pos_row = aux + int64_t(cls_off + t) * N;
 #pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int n0 = n_blk * BN + grp * 128 + chunk * 32;
@@ -251,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                 o.z = __uint_as_float(r[j * 4 + 2]) + b4.z + p4.z;
                 o.w = __uint_as_float(r[j * 4 + 3]) + b4.w + p4.w;
                 if constexpr (kDrop)   // emb dropout (vit.py:155) on the token stream, flat index = row * N + col
-                  dropout4(drop, (int64_t(b) * (tpi + 1) + 1 + t) * N + n0 + j * 4, o.x, o.y, o.z, o.w);
+                  dropout4(drop, (int64_t(b) * (tpi + cls_off) + cls_off + t) * N + n0 + j * 4, o.x, o.y, o.z, o.w);
                 *reinterpret_cast<float4*>(crow_base + n0 + j * 4) = o;
               }
             }
@@ -360,7 +361,7 @@ int gemm_dbg() {   // VITB200_GEMM_DBG bit 0: no TMA loads, bit 1: no output sto
 template <int kEpi, int kDT, int kCG, bool kDrop>
 int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-              const float* aux, int tpi, const Dropout& drop) {
+              const float* aux, int tpi, const Dropout& drop, int cls_off) {
   static bool configured = false;   // per-process; attribute is per-function, device-agnostic
   static int max_units = 0;         // clusters (CTAs for kCG == 1) that can be resident at once
   if (!configured) {
@@ -390,7 +391,7 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
   const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, BN);
   const int units = tiles < max_units ? tiles : max_units;
   VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, dim3(units * kCG), dim3(NUM_THREADS), smem_bytes<kCG>(),
-                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop));
+                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off));
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -398,7 +399,7 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
 template <int kEpi, int kDT>
 int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-               const float* aux, int tpi, int cta_group, const Dropout& drop) {
+               const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off) {
   // dropout variants exist for the epilogues that have a Dropout behind them and for the two
   // production tile modes; the opt-in cluster-of-4 mode falls back to pairs when dropout is on
   constexpr bool kCanDrop = kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_RESID_F32 ||
@@ -407,32 +408,32 @@ int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& t
     if (drop.threshold != 0) {
       if (cta_group == 4)
         return fail(VITB200_ERR_UNSUPPORTED, "gemm_tc: dropout is not built for the opt-in cluster-of-4 mode");
-      if (cta_group == 1) return launch_cg<kEpi, kDT, 1, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
-      return launch_cg<kEpi, kDT, 2, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
+      if (cta_group == 1) return launch_cg<kEpi, kDT, 1, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
+      return launch_cg<kEpi, kDT, 2, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
     }
   }
-  if (cta_group == 4) return launch_cg<kEpi, kDT, 4, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
-  if (cta_group == 2) return launch_cg<kEpi, kDT, 2, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
-  return launch_cg<kEpi, kDT, 1, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop);
+  if (cta_group == 4) return launch_cg<kEpi, kDT, 4, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
+  if (cta_group == 2) return launch_cg<kEpi, kDT, 2, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
+  return launch_cg<kEpi, kDT, 1, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
 }
 
 template <int kDT>
 int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-                 int epilogue, const float* aux, int tpi, int cta_group, const Dropout& drop) {
+                 int epilogue, const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off) {
   switch (epilogue) {
     case VITB200_EPI_STORE_16:
-      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
+      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
     case VITB200_EPI_BIAS_GELU_16:
-      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
+      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
     case VITB200_EPI_BIAS_RESID_F32:
-      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
+      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
     case VITB200_EPI_BIAS_F32:
-      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
+      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
     case VITB200_EPI_PATCH_F32:
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
-      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop);
+      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
     default:
       return fail(VITB200_ERR_INVALID, "gemm_tc: unknown epilogue");
   }
@@ -452,7 +453,8 @@ int gemm_tc_cta_group(int M) {
 
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
-                   int epilogue, const float* aux, int tpi, int dtype, int cta_group, const Dropout& drop) {
+                   int epilogue, const float* aux, int tpi, int dtype, int cta_group, const Dropout& drop,
+                   int cls_off) {
   if (cta_group != 1 && cta_group != 2 && cta_group != 4) return fail(VITB200_ERR_INVALID, "gemm_tc: cta_group must be 1, 2 or 4");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
@@ -463,9 +465,9 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
     return fail(VITB200_ERR_INVALID, "gemm_tc: output tensor map missing");
   const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
   if (dtype == DT_BF16)
-    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop);
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off);
   if (dtype == DT_F16)
-    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop);
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off);
   return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 

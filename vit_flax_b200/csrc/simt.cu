@@ -15,7 +15,8 @@ namespace vb {
 
 namespace {
 
-constexpr float LN_EPS = 1e-6f;   // flax nn.LayerNorm default (NOT torch's 1e-5)
+// eps is a kernel argument: 1e-6 = flax nn.LayerNorm default (vit.py:31,163; NOT torch's 1e-5),
+// 1e-5 for SimpleViT's LayerNorm(epsilon = 1e-5) (simple_vit.py:41,58,118)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -33,7 +34,7 @@ __device__ __forceinline__ float warp_max(float v) {
 template <int NV, int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                      const float* __restrict__ bias, void* __restrict__ y, int rows, int dim, int reverse) {
+                      const float* __restrict__ bias, void* __restrict__ y, int rows, int dim, int reverse, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,7 +67,7 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ sca
       ss += (a * a + b * b) + (cc * cc + d * d);
     }
   }
-  const float rstd = rsqrtf(warp_sum(ss) / float(dim) + LN_EPS);
+  const float rstd = rsqrtf(warp_sum(ss) / float(dim) + eps);
   const float4* g4 = reinterpret_cast<const float4*>(scale);
   const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
@@ -95,7 +96,7 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ sca
 template <int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                         const float* __restrict__ bias, void* __restrict__ y, int rows, int dim) {
+                         const float* __restrict__ bias, void* __restrict__ y, int rows, int dim, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,7 +108,7 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
   const float mean = warp_sum(s) / float(dim);
   float ss = 0.f;
   for (int c = lane; c < dim; c += 32) { const float d = xr[c] - mean; ss += d * d; }
-  const float rstd = rsqrtf(warp_sum(ss) / float(dim) + LN_EPS);
+  const float rstd = rsqrtf(warp_sum(ss) / float(dim) + eps);
   for (int c = lane; c < dim; c += 32) {
     const float o = (xr[c] - mean) * rstd * scale[c] + bias[c];
     if constexpr (kDT != DT_F32) reinterpret_cast<uint16_t*>(y)[int64_t(row) * dim + c] = cvt16<kDT>(o);
@@ -126,20 +127,20 @@ int ln_reverse() {
 
 template <int kDT>
 int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b, void* y, int rows,
-                int dim) {
+                int dim, float eps) {
   const int grid = ceil_div(rows, 8);
   const bool vec = (dim % 4 == 0) && dim <= 2048 &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                      reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
   if (!vec) {
-    VB_CUDA(launch_kernel(layernorm_generic_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim));
+    VB_CUDA(launch_kernel(layernorm_generic_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, eps));
   } else {
     const int nv = ceil_div(dim, 128);
-    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
-    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
-    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
-    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
-    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse()));
+    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
+    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
+    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
+    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
+    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
   }
   VB_LAUNCH_CHECK("layernorm");
   return 0;
@@ -150,7 +151,7 @@ int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b,
 template <int kDT>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
-                int C, int ph, int pw, int Kpad) {
+                int C, int ph, int pw, int Kpad, int nchw) {
   pdl_launch_dependents();
   pdl_wait();
   const int gw = W / pw, gh = H / ph;
@@ -171,7 +172,9 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
       if (f < K0) {
         const int c = f % C, pp = f / C;
         const int p1 = pp / pw, p2 = pp - p1 * pw;
-        v[e] = __ldg(img + ((int64_t(b) * H + hh * ph + p1) * W + ww * pw + p2) * C + c);
+        // NHWC (vit.py:146) or NCHW (simple_vit.py:125: 'b c (h p1) (w p2) -> b h w (p1 p2 c)')
+        v[e] = nchw ? __ldg(img + ((int64_t(b) * C + c) * H + hh * ph + p1) * W + ww * pw + p2)
+                    : __ldg(img + ((int64_t(b) * H + hh * ph + p1) * W + ww * pw + p2) * C + c);
       } else {
         v[e] = 0.f;
       }
@@ -192,7 +195,7 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
 template <int kDT>
 __global__ void __launch_bounds__(256)
 patchify_rows_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
-                     int C, int ph, int pw, int Kpad) {
+                     int C, int ph, int pw, int Kpad) {   // NHWC only; NCHW goes through patchify_kernel
   pdl_launch_dependents();
   pdl_wait();
   const int gw = W / pw, gh = H / ph;
@@ -248,7 +251,7 @@ template <int kDT>
 __global__ void __launch_bounds__(256)
 pool_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                       const float* __restrict__ bias, void* __restrict__ y, int T, int dim,
-                      int pool) {
+                      int pool, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sh[];          // dim floats + 16 reduction slots
@@ -283,7 +286,7 @@ pool_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ sca
   __syncthreads();
   float tot2 = 0.f;
   for (int w = 0; w < 8; ++w) tot2 += red[8 + w];
-  const float rstd = rsqrtf(tot2 / float(dim) + LN_EPS);
+  const float rstd = rsqrtf(tot2 / float(dim) + eps);
   for (int d = threadIdx.x; d < dim; d += blockDim.x) {
     const float o = (pooled[d] - mean) * rstd * scale[d] + bias[d];
     if constexpr (kDT != DT_F32) reinterpret_cast<uint16_t*>(y)[int64_t(b) * dim + d] = cvt16<kDT>(o);
@@ -320,7 +323,7 @@ template <int kEpi>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
                 const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
-                const float* __restrict__ aux, int tpi, Dropout drop) {
+                const float* __restrict__ aux, int tpi, Dropout drop, int cls_off) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x;
@@ -368,8 +371,8 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
     const float* pos_row = nullptr;
     if constexpr (kEpi == VITB200_EPI_PATCH_F32) {
       const int b = m / tpi, t = m - b * tpi;
-      out_row = int64_t(b) * (tpi + 1) + 1 + t;
-      pos_row = aux + int64_t(1 + t) * N;
+      out_row = int64_t(b) * (tpi + cls_off) + cls_off + t;
+      pos_row = aux + int64_t(cls_off + t) * N;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -396,9 +399,9 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W,
 
 template <int kEpi>
 int launch_gemm_f32_t(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
-                      int M, int N, int K, const float* aux, int tpi, const Dropout& drop) {
+                      int M, int N, int K, const float* aux, int tpi, const Dropout& drop, int cls_off) {
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-  gemm_f32_kernel<kEpi><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, aux, tpi, drop);
+  gemm_f32_kernel<kEpi><<<grid, 256, 0, st>>>(A, W, bias, C, M, N, K, aux, tpi, drop, cls_off);
   VB_LAUNCH_CHECK("gemm_f32_kernel");
   return 0;
 }
@@ -469,21 +472,21 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   }
 
 int launch_layernorm(cudaStream_t st, const float* x, const float* g, const float* b, void* y,
-                     int rows, int dim, int out_dtype) {
+                     int rows, int dim, int out_dtype, float eps) {
   if (rows <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "layernorm: empty problem");
-  VB_DT_DISPATCH(out_dtype, return launch_ln_t<kDT>(st, x, g, b, y, rows, dim));
+  VB_DT_DISPATCH(out_dtype, return launch_ln_t<kDT>(st, x, g, b, y, rows, dim, eps));
   return 0;
 }
 
 int launch_patchify(cudaStream_t st, const float* images, void* patches, int batch, int H, int W,
-                    int C, int ph, int pw, int Kpad, int out_dtype) {
+                    int C, int ph, int pw, int Kpad, int out_dtype, int nchw) {
   if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || ph <= 0 || pw <= 0)
     return fail(VITB200_ERR_INVALID, "patchify: empty problem");
   if (H % ph != 0 || W % pw != 0)
     return fail(VITB200_ERR_INVALID, "patchify: image not divisible by patch (vit.py:133-134)");
   if (Kpad < ph * pw * C || (Kpad & 1))
     return fail(VITB200_ERR_INVALID, "patchify: Kpad must be even and >= ph*pw*C");
-  if (((pw * C) & 1) == 0 && (reinterpret_cast<uintptr_t>(images) & 7) == 0) {
+  if (!nchw && ((pw * C) & 1) == 0 && (reinterpret_cast<uintptr_t>(images) & 7) == 0) {
     const int64_t total = int64_t(batch) * H * ((W * C) >> 1);
     const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
     VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_rows_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad)));
@@ -492,7 +495,7 @@ int launch_patchify(cudaStream_t st, const float* images, void* patches, int bat
   }
   const int64_t total = int64_t(batch) * (H / ph) * (W / pw) * (Kpad / 2);
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
-  VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad)));
+  VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad, nchw)));
   VB_LAUNCH_CHECK("patchify_kernel");
   return 0;
 }
@@ -506,11 +509,11 @@ int launch_cls_rows(cudaStream_t st, const float* cls, const float* pos, float* 
 }
 
 int launch_pool_layernorm(cudaStream_t st, const float* x, const float* g, const float* b, void* y,
-                          int batch, int T, int dim, int pool, int out_dtype) {
+                          int batch, int T, int dim, int pool, int out_dtype, float eps) {
   if (pool != VITB200_POOL_CLS && pool != VITB200_POOL_MEAN)
     return fail(VITB200_ERR_INVALID, "pool must be cls or mean (vit.py:137)");
   const size_t smem = (size_t(dim) + 16) * sizeof(float);
-  VB_DT_DISPATCH(out_dtype, (launch_kernel(pool_layernorm_kernel<kDT>, dim3(batch), dim3(256), smem, st, 1, x, g, b, y, T, dim, pool)));
+  VB_DT_DISPATCH(out_dtype, (launch_kernel(pool_layernorm_kernel<kDT>, dim3(batch), dim3(256), smem, st, 1, x, g, b, y, T, dim, pool, eps)));
   VB_LAUNCH_CHECK("pool_layernorm_kernel");
   return 0;
 }
@@ -525,18 +528,19 @@ int launch_pack_weight(cudaStream_t st, const float* W, void* Wt, int K, int N, 
 }
 
 int launch_gemm_f32(cudaStream_t st, const float* A, const float* W, const float* bias, float* C,
-                    int M, int N, int K, int epilogue, const float* aux, int tpi, const Dropout& drop) {
+                    int M, int N, int K, int epilogue, const float* aux, int tpi, const Dropout& drop,
+                    int cls_off) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_f32: empty problem");
   if (epilogue != VITB200_EPI_STORE_16 && bias == nullptr)
     return fail(VITB200_ERR_INVALID, "gemm_f32: epilogue needs a bias");
   switch (epilogue) {
-    case VITB200_EPI_STORE_16: return launch_gemm_f32_t<VITB200_EPI_STORE_16>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
-    case VITB200_EPI_BIAS_GELU_16: return launch_gemm_f32_t<VITB200_EPI_BIAS_GELU_16>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
-    case VITB200_EPI_BIAS_RESID_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_RESID_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
-    case VITB200_EPI_BIAS_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
+    case VITB200_EPI_STORE_16: return launch_gemm_f32_t<VITB200_EPI_STORE_16>(st, A, W, bias, C, M, N, K, aux, tpi, drop, cls_off);
+    case VITB200_EPI_BIAS_GELU_16: return launch_gemm_f32_t<VITB200_EPI_BIAS_GELU_16>(st, A, W, bias, C, M, N, K, aux, tpi, drop, cls_off);
+    case VITB200_EPI_BIAS_RESID_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_RESID_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop, cls_off);
+    case VITB200_EPI_BIAS_F32: return launch_gemm_f32_t<VITB200_EPI_BIAS_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop, cls_off);
     case VITB200_EPI_PATCH_F32:
       if (aux == nullptr || tpi <= 0) return fail(VITB200_ERR_INVALID, "gemm_f32: PATCH epilogue needs pos_embedding and tokens");
-      return launch_gemm_f32_t<VITB200_EPI_PATCH_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop);
+      return launch_gemm_f32_t<VITB200_EPI_PATCH_F32>(st, A, W, bias, C, M, N, K, aux, tpi, drop, cls_off);
     default: return fail(VITB200_ERR_INVALID, "gemm_f32: unknown epilogue");
   }
 }

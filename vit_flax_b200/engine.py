@@ -24,7 +24,7 @@ class Engine:
 
     def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim,
                  pool="cls", channels=3, precision="fp16", max_batch=256, device=0,
-                 dropout=0.0, emb_dropout=0.0):
+                 dropout=0.0, emb_dropout=0.0, nchw=False, cls_token=True, ln_eps=0.0):
         import torch  # deferred: plumbing only
 
         if not torch.cuda.is_available():
@@ -40,14 +40,16 @@ class Engine:
             num_classes=num_classes, dim=dim, depth=depth, heads=heads, mlp_dim=mlp_dim,
             pool=_lib.POOL_MEAN if pool == "mean" else _lib.POOL_CLS,
             precision=_lib.PRECISIONS[precision],
-            max_batch=max_batch, dropout=float(dropout), emb_dropout=float(emb_dropout))
+            max_batch=max_batch, dropout=float(dropout), emb_dropout=float(emb_dropout),
+            flags=(_lib.FLAG_NCHW if nchw else 0) | (0 if cls_token else _lib.FLAG_NO_CLS), ln_eps=float(ln_eps))
         self.precision = precision
         self.max_batch = max_batch
         self.device = torch.device("cuda", device)
-        self.tokens = n + 1
+        self.tokens = n + (1 if cls_token else 0)
+        self.nchw = bool(nchw)
         self.num_classes = num_classes
         self.dim = dim
-        self.image_shape = (ih, iw, channels)
+        self.image_shape = (channels, ih, iw) if nchw else (ih, iw, channels)
         handle = C.c_void_p()
         _lib.check(self.lib.vitb200_create(C.byref(self.cfg), device, C.byref(handle)))
         self.handle = handle
@@ -88,7 +90,8 @@ class Engine:
     def _check_images(self, shape):
         if len(shape) != 4 or tuple(shape[1:]) != self.image_shape:
             raise ValueError(f"expected images [B, {self.image_shape[0]}, {self.image_shape[1]}, "
-                             f"{self.image_shape[2]}] (NHWC, channels-last), got {tuple(shape)}")
+                             f"{self.image_shape[2]}] ({'NCHW' if self.nchw else 'NHWC, channels-last'}), "
+                             f"got {tuple(shape)}")
         if not 1 <= shape[0] <= self.max_batch:
             raise ValueError(f"batch {shape[0]} outside [1, max_batch={self.max_batch}]")
 

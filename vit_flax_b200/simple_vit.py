@@ -1,0 +1,151 @@
+"""``SimpleViT`` (vit_flax/simple_vit.py:99-134) on the same kernels.
+
+Differences from ``ViT`` that the engine takes as configuration: NCHW images
+(simple_vit.py:125), no class token, a fixed 2-D sin/cos positional table instead of a learned one
+(simple_vit.py:14-25, 127-128), ``LayerNorm(epsilon=1e-5, use_bias=False)`` inside Attention /
+FeedForward and in the head (simple_vit.py:41, 58, 118), a bias-free ``to_out`` (simple_vit.py:61),
+mean pooling (simple_vit.py:131).  ``dim_head`` is a field here (default 64); the kernels are
+built for 64.  The params pytree is the one Flax's compact naming gives that file.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Any, Dict, Optional, Tuple, Union
+
+import numpy as np
+
+from .params import _lecun_normal as lecun_normal, geometry, leaf_to_numpy
+from .vit import _current_device, _seed_from_key
+
+
+def posemb_sincos_2d(h: int, w: int, dim: int, temperature: float = 10000.0) -> np.ndarray:
+    """simple_vit.py:14-25 -> [h*w, dim] float32."""
+    assert dim % 4 == 0, "feature dimension must be multiple of 4 for sincos emb"
+    y, x = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    omega = np.arange(dim // 4, dtype=np.float32) / np.float32(dim // 4 - 1)
+    omega = (1.0 / (np.float32(temperature) ** omega)).astype(np.float32)
+    y = y.reshape(-1, 1).astype(np.float32) * omega[None, :]
+    x = x.reshape(-1, 1).astype(np.float32) * omega[None, :]
+    return np.concatenate((np.sin(x), np.cos(x), np.sin(y), np.cos(y)), axis=1).astype(np.float32)
+
+
+@dataclasses.dataclass(frozen=True)
+class SimpleViT:
+    """Same fields, order and defaults as simple_vit.py:99-108."""
+    image_size: Union[int, Tuple[int, int]]
+    patch_size: Union[int, Tuple[int, int]]
+    num_classes: int
+    dim: int
+    depth: int
+    heads: int
+    mlp_dim: int
+    channels: int = 3
+    dim_head: int = 64
+
+    def _geometry(self):
+        ih, iw, ph, pw, n = geometry(self.image_size, self.patch_size)     # simple_vit.py:113-116
+        if self.dim_head != 64:
+            raise NotImplementedError("the attention kernels are built for dim_head = 64")
+        return ih, iw, ph, pw, n
+
+    def _validate(self, shape):
+        ih, iw, _, _, _ = self._geometry()
+        if len(shape) != 4 or tuple(int(s) for s in shape[1:]) != (self.channels, ih, iw):
+            raise ValueError(f"expected images [B, {self.channels}, {ih}, {iw}] (NCHW, simple_vit.py:125), "
+                             f"got {tuple(shape)}")
+
+    # ------------------------------------------------------------------ params
+    def init(self, rngs: Any, x: Any) -> Dict[str, Dict]:
+        """``{'params': tree}`` with Flax's names for simple_vit.py: Dense_0 (patch embedding),
+        Transformer_0/{Attention_l/{LayerNorm_0/scale, Dense_0/kernel, Dense_1/kernel},
+        FeedForward_l/{LayerNorm_0/scale, Dense_0, Dense_1}}, Sequential_0/{layers_0/scale, layers_1}."""
+        self._validate(np.shape(x))
+        _, _, ph, pw, _ = self._geometry()
+        key = rngs.get("params") if hasattr(rngs, "get") else rngs
+        rng = np.random.default_rng(_seed_from_key(key))
+        inner = self.dim_head * self.heads
+        k0 = ph * pw * self.channels
+
+        def dense(i, o, bias=True):
+            d = {"kernel": lecun_normal(rng, (i, o))}
+            if bias:
+                d["bias"] = np.zeros((o,), np.float32)
+            return d
+
+        t = {}
+        for l in range(self.depth):
+            t[f"Attention_{l}"] = {"LayerNorm_0": {"scale": np.ones((self.dim,), np.float32)},
+                                   "Dense_0": dense(self.dim, 3 * inner, False),
+                                   "Dense_1": dense(inner, self.dim, False)}
+            t[f"FeedForward_{l}"] = {"LayerNorm_0": {"scale": np.ones((self.dim,), np.float32)},
+                                     "Dense_0": dense(self.dim, self.mlp_dim), "Dense_1": dense(self.mlp_dim, self.dim)}
+        return {"params": {"Dense_0": dense(k0, self.dim), "Transformer_0": t,
+                           "Sequential_0": {"layers_0": {"scale": np.ones((self.dim,), np.float32)},
+                                            "layers_1": dense(self.dim, self.num_classes)}}}
+
+    def _engine_tree(self, variables) -> Dict[str, Any]:
+        """Re-express the SimpleViT pytree in the leaf names the engine registers (those of vit.py):
+        absent biases become zeros, the sin/cos table takes the place of pos_embedding."""
+        ih, iw, ph, pw, n = self._geometry()
+        p = variables["params"] if "params" in variables else variables
+        z = lambda k: np.zeros((k,), np.float32)
+        f = leaf_to_numpy
+        tp = p["Transformer_0"]
+        t = {}
+        for l in range(self.depth):
+            a, ff = tp[f"Attention_{l}"], tp[f"FeedForward_{l}"]
+            t[f"PreNorm_{2 * l}"] = {"LayerNorm_0": {"scale": f(a["LayerNorm_0"]["scale"]), "bias": z(self.dim)}}
+            t[f"Attention_{l}"] = {"Dense_0": {"kernel": f(a["Dense_0"]["kernel"])},
+                                   "Dense_1": {"kernel": f(a["Dense_1"]["kernel"]), "bias": z(self.dim)}}
+            t[f"PreNorm_{2 * l + 1}"] = {"LayerNorm_0": {"scale": f(ff["LayerNorm_0"]["scale"]), "bias": z(self.dim)}}
+            t[f"FeedForward_{l}"] = {"Dense_0": {k: f(v) for k, v in ff["Dense_0"].items()},
+                                     "Dense_1": {k: f(v) for k, v in ff["Dense_1"].items()}}
+        head = p["Sequential_0"]
+        return {"params": {
+            "pos_embedding": posemb_sincos_2d(ih // ph, iw // pw, self.dim)[None],
+            "cls": np.zeros((1, 1, self.dim), np.float32),
+            "Dense_0": {k: f(v) for k, v in p["Dense_0"].items()},
+            "Transformer_0": t,
+            "LayerNorm_0": {"scale": f(head["layers_0"]["scale"]), "bias": z(self.dim)},
+            "Dense_1": {k: f(v) for k, v in head["layers_1"].items()}}}
+
+    # ------------------------------------------------------------------- apply
+    def apply(self, variables: Any, img: Any, rngs: Any = None, *, precision: Optional[str] = None,
+              device: Optional[int] = None, max_batch: Optional[int] = None):
+        """``v.apply(params, img)`` -> logits ``[B, num_classes]`` float32; ``img`` is NCHW."""
+        from . import vit as _vit
+        from .engine import Engine
+        is_cuda = hasattr(img, "is_cuda") and bool(img.is_cuda)
+        self._validate(tuple(img.shape) if hasattr(img, "shape") else np.shape(img))
+        batch = int(img.shape[0])
+        if device is None:
+            device = img.device.index if is_cuda and img.device.index is not None else _current_device()
+        key = (self, precision or _vit._DEFAULT_PRECISION, device)
+        eng, loaded = _ENGINES.get(key, (None, None))
+        if eng is None or eng.max_batch < (max_batch or batch):
+            if eng is not None:
+                eng.close()
+            ih, iw, ph, pw, _ = self._geometry()
+            eng = Engine(image_size=(ih, iw), patch_size=(ph, pw), num_classes=self.num_classes, dim=self.dim,
+                         depth=self.depth, heads=self.heads, mlp_dim=self.mlp_dim, pool="mean",
+                         channels=self.channels, precision=precision or _vit._DEFAULT_PRECISION,
+                         max_batch=max_batch or batch, device=device, nchw=True, cls_token=False, ln_eps=1e-5)
+            loaded = None
+        if loaded != id(variables):
+            eng.load_params(self._engine_tree(variables))
+            loaded = id(variables)
+        _ENGINES[key] = (eng, loaded)
+        if is_cuda:
+            import torch
+            x = img if (img.dtype == torch.float32 and img.is_contiguous()) else img.float().contiguous()
+            return eng.forward(x)
+        return eng.forward_host(np.asarray(img, dtype=np.float32))
+
+
+_ENGINES: Dict[Any, Any] = {}
+
+
+def clear_cache() -> None:
+    for eng, _ in _ENGINES.values():
+        eng.close()
+    _ENGINES.clear()
