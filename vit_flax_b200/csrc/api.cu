@@ -292,9 +292,8 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   mark(m, st, VITB200_CAT_GEMM_PATCH);
   if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), nullptr, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
                              Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt, cgp,
-                             m->drop(c.emb_dropout, 0), m->cls_off))) return rc;
-  mark(m, st, VITB200_CAT_CLS_ROWS);
-  if (m->cls_off && (rc = launch_cls_rows(st, leaf_ptr(m, m->leaf_cls), leaf_ptr(m, m->leaf_pos), m->x.p, batch, T, D, m->drop(c.emb_dropout, 0)))) return rc;
+                             m->drop(c.emb_dropout, 0), m->cls_off, leaf_ptr(m, m->leaf_cls)))) return rc;
+  // (the class-token rows b*T = cls + pos[0] are written by the same epilogue: vit.py:151-153)
   for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
     Layer& L = m->layers[l];
     // Residual(PreNorm(Attention))  vit.py:31,39,62-87

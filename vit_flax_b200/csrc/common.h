@@ -89,7 +89,8 @@ constexpr int GEMM_BK = 64;
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tokens_per_image, int dtype, int cta_group,
-                   const Dropout& drop = Dropout(), int cls_off = 1);
+                   const Dropout& drop = Dropout(), int cls_off = 1, const float* cls = nullptr);
+// `cls` (PATCH epilogue, cls_off == 1): also write the class-token rows b*T = cls + pos[0]
 // 1 = one CTA per 128x256 tile (Wt box 256 rows), 2 = CTA pair per 256x256 tile (Wt box 128 rows),
 // 4 = cluster of two pairs sharing a multicast weight tile (Wt box 64 rows).
 // The Wt tensor map must be encoded with GEMM_BN / cta_group box rows.

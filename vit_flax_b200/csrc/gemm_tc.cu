@@ -68,7 +68,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, void* __restrict__ Cout,
-               int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop, int cls_off) {
+               int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop, int cls_off,
+               const float* __restrict__ cls) {
   constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16);
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
@@ -254,6 +255,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                 if constexpr (kDrop)   // emb dropout (vit.py:155) on the token stream, flat index = row * N + col
                   dropout4(drop, (int64_t(b) * (tpi + cls_off) + cls_off + t) * N + n0 + j * 4, o.x, o.y, o.z, o.w);
                 *reinterpret_cast<float4*>(crow_base + n0 + j * 4) = o;
+                if (cls != nullptr && t == 0) {
+                  // the class token in front of image b (vit.py:151-153): row b*T = cls + pos_embedding[0],
+                  // written by the thread that owns the image's first patch row
+                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(cls + n0 + j * 4));
+                  const float4 q4 = __ldg(reinterpret_cast<const float4*>(aux + n0 + j * 4));
+                  float4 z = make_float4(c4.x + q4.x, c4.y + q4.y, c4.z + q4.z, c4.w + q4.w);
+                  const int64_t e0 = int64_t(b) * (tpi + 1) * N + n0 + j * 4;
+                  if constexpr (kDrop) dropout4(drop, e0, z.x, z.y, z.z, z.w);
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(Cout) + e0) = z;
+                }
               }
             }
           }
@@ -361,7 +372,7 @@ int gemm_dbg() {   // VITB200_GEMM_DBG bit 0: no TMA loads, bit 1: no output sto
 template <int kEpi, int kDT, int kCG, bool kDrop>
 int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-              const float* aux, int tpi, const Dropout& drop, int cls_off) {
+              const float* aux, int tpi, const Dropout& drop, int cls_off, const float* cls) {
   static bool configured = false;   // per-process; attribute is per-function, device-agnostic
   static int max_units = 0;         // clusters (CTAs for kCG == 1) that can be resident at once
   if (!configured) {
@@ -391,7 +402,7 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
   const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, BN);
   const int units = tiles < max_units ? tiles : max_units;
   VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, dim3(units * kCG), dim3(NUM_THREADS), smem_bytes<kCG>(),
-                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off));
+                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off, cls));
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -399,7 +410,7 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
 template <int kEpi, int kDT>
 int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-               const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off) {
+               const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off, const float* cls) {
   // dropout variants exist for the epilogues that have a Dropout behind them and for the two
   // production tile modes; the opt-in cluster-of-4 mode falls back to pairs when dropout is on
   constexpr bool kCanDrop = kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_RESID_F32 ||
@@ -408,32 +419,33 @@ int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& t
     if (drop.threshold != 0) {
       if (cta_group == 4)
         return fail(VITB200_ERR_UNSUPPORTED, "gemm_tc: dropout is not built for the opt-in cluster-of-4 mode");
-      if (cta_group == 1) return launch_cg<kEpi, kDT, 1, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
-      return launch_cg<kEpi, kDT, 2, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
+      if (cta_group == 1) return launch_cg<kEpi, kDT, 1, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
+      return launch_cg<kEpi, kDT, 2, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
     }
   }
-  if (cta_group == 4) return launch_cg<kEpi, kDT, 4, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
-  if (cta_group == 2) return launch_cg<kEpi, kDT, 2, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
-  return launch_cg<kEpi, kDT, 1, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off);
+  if (cta_group == 4) return launch_cg<kEpi, kDT, 4, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
+  if (cta_group == 2) return launch_cg<kEpi, kDT, 2, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
+  return launch_cg<kEpi, kDT, 1, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
 }
 
 template <int kDT>
 int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-                 int epilogue, const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off) {
+                 int epilogue, const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off,
+                 const float* cls) {
   switch (epilogue) {
     case VITB200_EPI_STORE_16:
-      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
+      return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     case VITB200_EPI_BIAS_GELU_16:
-      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
+      return launch_one<VITB200_EPI_BIAS_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     case VITB200_EPI_BIAS_RESID_F32:
-      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
+      return launch_one<VITB200_EPI_BIAS_RESID_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     case VITB200_EPI_BIAS_F32:
-      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
+      return launch_one<VITB200_EPI_BIAS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     case VITB200_EPI_PATCH_F32:
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
-      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off);
+      return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     default:
       return fail(VITB200_ERR_INVALID, "gemm_tc: unknown epilogue");
   }
@@ -454,7 +466,7 @@ int gemm_tc_cta_group(int M) {
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tpi, int dtype, int cta_group, const Dropout& drop,
-                   int cls_off) {
+                   int cls_off, const float* cls) {
   if (cta_group != 1 && cta_group != 2 && cta_group != 4) return fail(VITB200_ERR_INVALID, "gemm_tc: cta_group must be 1, 2 or 4");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
@@ -465,9 +477,11 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
     return fail(VITB200_ERR_INVALID, "gemm_tc: output tensor map missing");
   const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
   if (dtype == DT_BF16)
-    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off);
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off,
+                                 cls_off == 1 && epilogue == VITB200_EPI_PATCH_F32 ? cls : nullptr);
   if (dtype == DT_F16)
-    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off);
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off,
+                                 cls_off == 1 && epilogue == VITB200_EPI_PATCH_F32 ? cls : nullptr);
   return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 
