@@ -388,6 +388,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
         mbar_wait(xu_done, uint32_t(i & 1) ^ 1u);
         if (lane == 0) mbar_arrive(xu_done);
       }
+      // A parity wait tells "phase t-1 done" from "not done" only if phase t-2 is known to be done.
+      // Phase i (this group's turn) is complete once all four warps of the group have arrived:
+      // the group barrier below makes that true before any of them tests for the partner's turn
+      // i+1 -- otherwise a fast warp would take the still-open phase i for it and run ahead.
+      if (turns) named_bar_sync(2 + grp, 128);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready(grp));

@@ -70,12 +70,26 @@ __device__ __forceinline__ void exp_chunk(uint32_t* r, uint32_t* pp, int c0, int
   }
 }
 
+// Wait for turn `turn` on the hand-off barrier: phases complete in turn order, one per turn, when
+// the 4 warps of the acting group arrive.  A parity wait tells "phase turn-1 done" from "not done"
+// only if phase turn-2 (this group's previous turn) is known to be complete: every arrive is
+// therefore followed by a group barrier (pass_turn), so that no warp tests for the partner's turn
+// while its own group's phase is still open.
+__device__ __forceinline__ void wait_turn(uint32_t bar, uint32_t turn) {
+  mbar_wait(bar, (turn & 1u) ^ 1u);
+}
+__device__ __forceinline__ void pass_turn(uint32_t bar, int grp, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+  named_bar_sync(2 + grp, 128);
+}
+
 template <int kDT, int KP>
 __global__ void __launch_bounds__(NT, 1)
 attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I], box 128 rows
                       const __grid_constant__ CUtensorMap tmKV,   // qkv [B,T,3I], box KP rows
                       const __grid_constant__ CUtensorMap tmO,    // out [B,T,I],  box 128 rows
-                      int T, int heads, int nqt, int nkb, int items) {
+                      int T, int heads, int nqt, int nkb, int items, int turns) {
   using L = SmemM<KP>;
   constexpr uint32_t O_COL = 2 * KP;
   extern __shared__ uint8_t smem_raw[];
@@ -94,8 +108,9 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
   auto pv_done = [&](int s) { return bars + 8u * (20 + s); };
   auto o_ready = [&](int s) { return bars + 8u * (22 + s); };
   auto o_free = [&](int s) { return bars + 8u * (24 + s); };
-  const uint32_t tmem_slot = bars + 8u * 26;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_BAR + 8 * 26);
+  const uint32_t xu_done = bars + 8u * 26;                     // exponential phases take turns
+  const uint32_t tmem_slot = bars + 8u * 27;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_BAR + 8 * 27);
   float* inv_sh = reinterpret_cast<float*>(gbase + L::OFF_INV);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,6 +146,7 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
       mbar_init(v_full(s), 1);
       mbar_init(v_empty(s), 1);
     }
+    mbar_init(xu_done, 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
@@ -235,6 +251,7 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < nkb; ++j) {
         const uint32_t u = uint32_t((i >> 1) * nkb + j);
+        const uint32_t turn = 2u * u + uint32_t(grp);      // position in the alternating order
         const int nvalid = T - j * KP;                    // valid keys of this block (>= KP: all)
         mbar_wait(s_ready(grp), u & 1u);
         tc_fence_after();
@@ -289,6 +306,9 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
             }
           }
           m = m_new;
+          // The exponential phases of the two groups take turns, block by block (see attention_tc5.cu:
+          // free-running groups fall into step and idle the XU pipe while both wait for their MMAs).
+          if (turns) wait_turn(xu_done, turn);
           // ---- pass 2: p = exp2((s - m) * scale * log2e); l += sum(p); P -> TMEM over S ----
           const float mneg = -m * sl2;
           const unsigned long long sl2x2 = pack_f32x2(sl2, sl2), mnegx2 = pack_f32x2(mneg, mneg);
@@ -315,10 +335,21 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
           l += l0 + l1;
           if (j == nkb - 1) inv_sh[(i & 3) * 128 + row] = 1.0f / l;   // for the epilogue warps
           tmem_st_wait();
+        } else if (turns) {
+          wait_turn(xu_done, turn);
         }
+        if (turns) pass_turn(xu_done, grp, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready(grp));
+      }
+    }
+    if (turns && grp == 1 && (n & 1)) {
+      // the last item has no partner: group 1 passes its turns on so group 0 is never left waiting
+      for (int j = 0; j < nkb; ++j) {
+        const uint32_t turn = 2u * uint32_t((n >> 1) * nkb + j) + 1u;
+        wait_turn(xu_done, turn);
+        pass_turn(xu_done, grp, lane);
       }
     }
   } else if (warp >= 12) {
@@ -377,6 +408,15 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
   }
 }
 
+int attn_m_turns() {   // VITB200_ATTN_TURNS=0: free-running groups (A/B tests)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VITB200_ATTN_TURNS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+
 template <int kDT, int KP>
 int launch_m(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
   using L = SmemM<KP>;
@@ -398,7 +438,7 @@ int launch_m(cudaStream_t stream, const void* qkv, void* out, int batch, int T, 
   const int items = int(items64);
   const int grid = items < sm_count() ? items : sm_count();
   VB_CUDA(launch_kernel(attention_tc5m_kernel<kDT, KP>, dim3(grid), dim3(NT), L::TOTAL, stream, 1,
-                        tq, tkv, to, T, heads, nqt, nkb, items));
+                        tq, tkv, to, T, heads, nqt, nkb, items, attn_m_turns()));
   VB_LAUNCH_CHECK("attention_tc5m_kernel");
   return 0;
 }

@@ -86,8 +86,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      printf("vitb200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
-             int(blockIdx.x), int(threadIdx.x), bar, parity);
+      if ((threadIdx.x & 31) == 0)   // one line per warp: the set of stuck waits is the diagnosis
+        printf("vitb200: mbarrier wait timed out (block %d warp %d bar 0x%x parity %u)\n",
+               int(blockIdx.x), int(threadIdx.x >> 5), bar, parity);
       __trap();
     }
   }
