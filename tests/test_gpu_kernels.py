@@ -301,3 +301,36 @@ def test_gemm_tc_dropout_epilogue(lib, M, N, K, epi, cta_group, monkeypatch):
     err = (out.double() - want).abs().max().item()
     assert err < (3e-4 if out.dtype == torch.float32 else 16 * ulp + 3e-3), err
     assert abs(float(keep.double().mean()) - (1 - rate)) < 0.01
+
+
+def test_gemm_tc_random_shapes(lib, monkeypatch):
+    """Shape fuzz: 40 random (M, N, K, epilogue, tile mode) with ragged edges in every dimension
+    (N, K multiples of 8 only), checked against fp64 on the same 16-bit operands."""
+    rng = np.random.default_rng(2024)
+    dt, tdt, ulp = DT16["fp16"]
+    for case in range(40):
+        M = int(rng.choice([1, 7, 127, 129, 255, 257, 300, 511, 513, 1000, 3000, int(rng.integers(1, 5000))]))
+        N = 8 * int(rng.integers(1, 160))
+        K = 8 * int(rng.integers(1, 100))
+        epi = int(rng.choice([_lib.EPI_STORE_16, _lib.EPI_BIAS_GELU_16, _lib.EPI_BIAS_RESID_F32, _lib.EPI_BIAS_F32]))
+        monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", str(rng.choice(["1", "2", "4"])))
+        A = dev(rng.standard_normal((M, K)), tdt)
+        Wt = dev((rng.standard_normal((K, N)) / np.sqrt(K)).T, tdt)
+        bias = dev(rng.standard_normal(N) * 0.5)
+        resid = dev(rng.standard_normal((M, N)))
+        acc = A.double() @ Wt.double().t()
+        if epi == _lib.EPI_STORE_16:
+            out, want = torch.empty((M, N), dtype=tdt, device="cuda"), acc
+        elif epi == _lib.EPI_BIAS_GELU_16:
+            out = torch.empty((M, N), dtype=tdt, device="cuda")
+            want = torch.nn.functional.gelu(acc + bias.double(), approximate="tanh")
+        elif epi == _lib.EPI_BIAS_RESID_F32:
+            out, want = resid.clone(), acc + bias.double() + resid.double()
+        else:
+            out, want = torch.full((M, N), float("nan"), device="cuda"), acc + bias.double()
+        _lib.check(lib.vitb200_gemm_tc(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                       M, N, K, epi, None, 0, dt))
+        torch.cuda.synchronize()
+        err = (out.double() - want).abs().max().item()
+        tol = 3e-4 if out.dtype == torch.float32 else 8 * ulp + 2e-3
+        assert err < tol, (case, M, N, K, epi, err)
