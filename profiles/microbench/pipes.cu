@@ -28,6 +28,9 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float seed)
       if (OP == 6) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(a[(i + 1) & 7])); a[i] = __uint_as_float(r & 0x3fffffffu); }
       if (OP == 7) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
       if (OP == 8) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
+      if (OP == 10) { uint32_t u = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
+      if (OP == 11) { uint32_t u = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
+      if (OP == 12) { uint32_t u = __float_as_uint(a[i]); float f; asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(f) : "r"(u)); a[i] = f + 1.0f; }
       if (OP == 9) { uint32_t u = __float_as_uint(a[i]); asm volatile("shl.b32 %0, %0, 3;" : "+r"(u)); asm volatile("add.u32 %0, %0, %1;" : "+r"(u) : "r"(__float_as_uint(seed))); a[i] = __uint_as_float(u); }
     }
   }
@@ -63,5 +66,8 @@ int main() {
   run<5>("max.f32 (3-input)", 1);
   run<8>("max.f32 (2-input)", 1);
   run<9>("shl+add (u32)", 1);
+  run<10>("ex2.approx.ftz.f16x2", 2);
+  run<11>("ex2.approx.ftz.bf16x2", 2);
+  run<12>("cvt.f32.f16 + add", 1);
   return 0;
 }
