@@ -45,7 +45,7 @@ GEMM_SHAPES = [
 @pytest.mark.parametrize("epi", [_lib.EPI_STORE_16, _lib.EPI_BIAS_GELU_16,
                                  _lib.EPI_BIAS_RESID_F32, _lib.EPI_BIAS_F32])
 @pytest.mark.parametrize("fmt", ["bf16", "fp16"])
-@pytest.mark.parametrize("cta_group", ["1", "2"])
+@pytest.mark.parametrize("cta_group", ["1", "2", "64"])
 def test_gemm_tc_epilogues(lib, M, N, K, epi, fmt, cta_group, monkeypatch):
     """cta_group 1: one CTA per 128x256 tile; 2: CTA pair (cluster of 2, cta_group::2) per 256x256 tile."""
     if M >= 40000 and epi not in (_lib.EPI_STORE_16, _lib.EPI_BIAS_RESID_F32):
@@ -83,7 +83,7 @@ def test_gemm_tc_epilogues(lib, M, N, K, epi, fmt, cta_group, monkeypatch):
         assert err.mean().item() < ulp + 2e-4
 
 
-@pytest.mark.parametrize("cta_group", ["1", "2"])
+@pytest.mark.parametrize("cta_group", ["1", "2", "64"])
 @pytest.mark.parametrize("B,Np,K,D", [(3, 16, 192, 64), (4, 196, 768, 768)])
 def test_gemm_tc_patch_epilogue(lib, cta_group, B, Np, K, D, monkeypatch):
     # vit.py:147-153: Dense_0 output placed at row b*T+1+t with pos_embedding[1+t] added
@@ -274,7 +274,7 @@ def test_pack_weight(lib, fmt):
 
 @pytest.mark.parametrize("M,N,K", [(300, 520, 128), (129, 768, 64)])
 @pytest.mark.parametrize("epi", [_lib.EPI_BIAS_GELU_16, _lib.EPI_BIAS_RESID_F32])
-@pytest.mark.parametrize("cta_group", ["1", "2"])
+@pytest.mark.parametrize("cta_group", ["1", "2", "64"])
 def test_gemm_tc_dropout_epilogue(lib, M, N, K, epi, cta_group, monkeypatch):
     """nn.Dropout behind a Dense (vit.py:50,52,83): the mask is the Philox mask of oracle/philox.py
     for (key, site, flat element index) whatever the tile mode; kept values are scaled by 1/(1-rate)."""
@@ -313,7 +313,7 @@ def test_gemm_tc_random_shapes(lib, monkeypatch):
         N = 8 * int(rng.integers(1, 160))
         K = 8 * int(rng.integers(1, 100))
         epi = int(rng.choice([_lib.EPI_STORE_16, _lib.EPI_BIAS_GELU_16, _lib.EPI_BIAS_RESID_F32, _lib.EPI_BIAS_F32]))
-        monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", str(rng.choice(["1", "2", "4"])))
+        monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", str(rng.choice(["1", "2", "4", "64"])))
         A = dev(rng.standard_normal((M, K)), tdt)
         Wt = dev((rng.standard_normal((K, N)) / np.sqrt(K)).T, tdt)
         bias = dev(rng.standard_normal(N) * 0.5)

@@ -35,7 +35,7 @@ struct DenseW {
   CUtensorMap tm{};                       // box 256 x 64 over wt (one CTA per tile)
   CUtensorMap tm2{};                      // box 128 x 64 over wt (CTA pair per tile)
   CUtensorMap tm4{};                      // box 64 x 64 over wt (cluster of two pairs, multicast)
-  const CUtensorMap& map(int cg) const { return cg == 4 ? tm4 : (cg == 2 ? tm2 : tm); }
+  const CUtensorMap& map(int mode) const { return (mode == 4 || mode == 64) ? tm4 : (mode == 2 ? tm2 : tm); }
 };
 
 struct Layer {
@@ -283,7 +283,9 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   const ActMaps* am;
   int rc;
   if ((rc = get_act_maps(m, batch, &am))) return rc;
-  const int cg = gemm_tc_cta_group(R), cgp = gemm_tc_cta_group(Rp), cgh = gemm_tc_cta_group(batch);
+  // tile mode per GEMM shape (pairs for anything that fills the machine, small tiles otherwise)
+  const int cgp = gemm_tc_tile_mode(Rp, D), cgh = gemm_tc_tile_mode(batch, c.num_classes);
+  const int cg_qkv = gemm_tc_tile_mode(R, 3 * I), cg_d = gemm_tc_tile_mode(R, D), cg_ff1 = gemm_tc_tile_mode(R, c.mlp_dim);
   // vit.py:146  patchify (+ fp32->bf16 cast, zero pad to K0pad)
   mark(m, st, VITB200_CAT_PATCHIFY);
   if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
@@ -300,12 +302,12 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), m->xn_h.p, R, D, m->dt, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_QKV);
-    if ((rc = launch_gemm_tc(st, am->xn, L.qkv.map(cg), &am->c_qkv, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt, cg))) return rc;
+    if ((rc = launch_gemm_tc(st, am->xn, L.qkv.map(cg_qkv), &am->c_qkv, nullptr, m->qkv_h.p, R, 3 * I, D, VITB200_EPI_STORE_16, nullptr, 0, m->dt, cg_qkv))) return rc;
     mark(m, st, VITB200_CAT_ATTENTION);
     if ((rc = launch_attention_tc(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads, m->dt))) return rc;
     mark(m, st, VITB200_CAT_GEMM_OUT);
     if (m->project_out) {
-      if ((rc = launch_gemm_tc(st, am->o, L.out.map(cg), &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg, m->drop(c.dropout, 1 + 3 * l)))) return rc;
+      if ((rc = launch_gemm_tc(st, am->o, L.out.map(cg_d), &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg_d, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     } else {   // heads == 1 and dim == 64: to_out is the identity (vit.py:65,85)
       const int64_t n = int64_t(R) * D;
       add_16_into_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(m->o_h.p, m->x.p, n, m->dt);
@@ -315,9 +317,9 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_LAYERNORM);
     if ((rc = launch_layernorm(st, m->x.p, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), m->xn_h.p, R, D, m->dt, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF1);
-    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.map(cg), &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt, cg, m->drop(c.dropout, 2 + 3 * l)))) return rc;
+    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.map(cg_ff1), &am->c_hid, leaf_ptr(m, L.ff1.leaf_bias), m->hid_h.p, R, c.mlp_dim, D, VITB200_EPI_BIAS_GELU_16, nullptr, 0, m->dt, cg_ff1, m->drop(c.dropout, 2 + 3 * l)))) return rc;
     mark(m, st, VITB200_CAT_GEMM_FF2);
-    if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg, m->drop(c.dropout, 3 + 3 * l)))) return rc;
+    if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg_d), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg_d, m->drop(c.dropout, 3 + 3 * l)))) return rc;
   }
   // vit.py:159-165  pool, LayerNorm_0, Dense_1
   if (m->head_tc) {
@@ -682,8 +684,8 @@ int vitb200_gemm_tc_dropout(void* stream, const void* A, const void* Wt, const f
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, dtype))) return rc;
-  const int cg = gemm_tc_cta_group(M);
-  if ((rc = make_tmap_2d(&tb, Wt, N, K, K, GEMM_BN / cg, dtype))) return rc;
+  const int cg = gemm_tc_tile_mode(M, N);
+  if ((rc = make_tmap_2d(&tb, Wt, N, K, K, cg == 64 ? 64 : GEMM_BN / cg, dtype))) return rc;
   const bool out16 = epilogue == VITB200_EPI_STORE_16 || epilogue == VITB200_EPI_BIAS_GELU_16;
   const bool direct = epilogue == VITB200_EPI_PATCH_F32;
   if (!direct && (rc = make_tmap_2d(&tc, C, M, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;

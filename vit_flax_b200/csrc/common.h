@@ -95,6 +95,8 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
 // 4 = cluster of two pairs sharing a multicast weight tile (Wt box 64 rows).
 // The Wt tensor map must be encoded with GEMM_BN / cta_group box rows.
 int gemm_tc_cta_group(int M);
+// tile mode for an [M, N] output: 1, 2, (4) as above or 64 = one CTA per 128x64 tile (Wt box 64 rows)
+int gemm_tc_tile_mode(int M, int N);
 int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const float* bias,
                     float* C, int M, int N, int K, int epilogue, const float* aux,
                     int tokens_per_image, const Dropout& drop = Dropout(), int cls_off = 1);

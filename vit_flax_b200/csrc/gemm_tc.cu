@@ -36,19 +36,24 @@ constexpr int A_BYTES = BM * BK * 2;            // 16 KB: 128 rows of A per CTA
 // kCG: 1 = one CTA per 128x256 tile; 2 = CTA pair (cta_group::2) per 256x256 tile; 4 = cluster of two
 // pairs working on two vertically adjacent 256x256 tiles that share their weight tile: each CTA
 // fetches a quarter of it and TMA-multicasts it to its opposite number in the other pair.
+// kCG (tile mode): 1 = one CTA per 128x256 tile; 2 = CTA pair (cta_group::2) per 256x256 tile; 4 =
+// cluster of two pairs sharing a multicast weight tile; 64 = one CTA per 128x64 tile (small problems:
+// four times as many tiles, so a forward at batch 1..32 spreads over the SMs instead of 3..12 CTAs).
 template <int kCG> struct Cfg {
-  static constexpr int MMA_CG = kCG == 1 ? 1 : 2;               // tcgen05 cta_group
-  static constexpr int STAGES = kCG == 1 ? 3 : 5;
-  static constexpr int B_ROWS = BN / MMA_CG;                    // rows of Wt in this CTA's smem
-  static constexpr int B_LOAD_ROWS = BN / kCG;                  // rows of Wt this CTA fetches
-  static constexpr int B_BYTES = B_ROWS * BK * 2;               // 32 KB / 16 KB
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;         // 48 KB / 32 KB
+  static constexpr int CL = kCG == 64 ? 1 : kCG;                // CTAs per cluster
+  static constexpr int BN_ = kCG == 64 ? 64 : BN;               // tile columns
+  static constexpr int MMA_CG = CL == 1 ? 1 : 2;                // tcgen05 cta_group
+  static constexpr int STAGES = kCG == 64 ? 6 : (CL == 1 ? 3 : 5);
+  static constexpr int B_ROWS = BN_ / MMA_CG;                   // rows of Wt in this CTA's smem
+  static constexpr int B_LOAD_ROWS = BN_ / CL;                  // rows of Wt this CTA fetches
+  static constexpr int B_BYTES = B_ROWS * BK * 2;               // 32 KB / 16 KB / 8 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;         // 48 KB / 32 KB / 24 KB
   static constexpr int TILE_M = BM * MMA_CG;                    // 128 / 256
   static constexpr int PAIRS = kCG == 4 ? 2 : 1;                // tiles per cluster step
+  static constexpr int TMEM_COLS = BN_ == 64 ? 128 : 512;       // two accumulator stages
 };
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;   // 384
-constexpr int TMEM_COLS = 512;
 constexpr int SLAB_BYTES = BM * 128;            // 128 rows x 128 B = 16 KB
 constexpr int NUM_SLABS = 4;                    // 2 per epilogue group
 template <int kCG> constexpr int smem_bytes() {
@@ -73,17 +78,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16);
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
-  constexpr int SLABS_PER_TILE = BN / SLAB_COLS;
+  constexpr int SLABS_PER_TILE = Cfg<kCG>::BN_ / SLAB_COLS;
   constexpr int STAGES = Cfg<kCG>::STAGES, B_BYTES = Cfg<kCG>::B_BYTES;
   constexpr int STAGE_BYTES = Cfg<kCG>::STAGE_BYTES, TILE_M = Cfg<kCG>::TILE_M;
-  constexpr int MMA_CG = Cfg<kCG>::MMA_CG, PAIRS = Cfg<kCG>::PAIRS;
+  constexpr int MMA_CG = Cfg<kCG>::MMA_CG, PAIRS = Cfg<kCG>::PAIRS, CL = Cfg<kCG>::CL;
+  constexpr int BN = Cfg<kCG>::BN_, TMEM_COLS = Cfg<kCG>::TMEM_COLS;   // shadow the 256-column default
   // crank: rank in the cluster; rank: 0 = leader of its CTA pair (issues the MMAs), 1 = peer;
   // pair: which of the cluster's tiles this CTA works on
-  const uint32_t crank = kCG == 1 ? 0u : cluster_ctarank();
+  const uint32_t crank = CL == 1 ? 0u : cluster_ctarank();
   const uint32_t rank = crank & 1u, pair = crank >> 1;
   const uint32_t lead = crank & ~1u;                 // cluster rank of this pair's leader
-  const int tile0 = int(blockIdx.x) / kCG;           // cluster index
-  const int tile_step = int(gridDim.x) / kCG;
+  const int tile0 = int(blockIdx.x) / CL;            // cluster index
+  const int tile_step = int(gridDim.x) / CL;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -125,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   }
   if (warp == 2) tmem_alloc<MMA_CG>(tmem_slot, TMEM_COLS);
   tc_fence_before();
-  if constexpr (kCG != 1) cluster_sync_all(); else __syncthreads();
+  if constexpr (CL != 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_launch_dependents();   // the next kernel's CTAs may take this SM as soon as this one leaves it
@@ -144,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (dbg & 1) {   // timing experiment: no loads, the MMAs chew on stale smem
             if (rank == 0) mbar_arrive(full_bar(stage));
-          } else if constexpr (kCG == 1) {
+          } else if constexpr (CL == 1) {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
             tma_load_2d(sA + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, a_row);
             tma_load_2d(sB + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, b_row);
@@ -157,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             const uint32_t lead_full = mapa_shared(full_bar(stage), lead);
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
             tma_load_2d_cg2(sA + stage * A_BYTES, &tmA, lead_full, kb * BK, a_row);
-            if constexpr (kCG == 2) {
+            if constexpr (CL == 2) {
               tma_load_2d_cg2(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, b_row);
             } else {
               // 64 of this CTA's 128 weight rows, delivered to the same smem offset here and in the
@@ -176,13 +182,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_16(TILE_M, BN, kDT == DT_F16 ? 0 : 1);
       const uint16_t pair_mask = uint16_t(0x3u << lead);               // both CTAs of this pair
-      const uint16_t all_mask = uint16_t((1u << kCG) - 1u);             // every CTA whose smem the stage's loads touch
+      const uint16_t all_mask = uint16_t((1u << CL) - 1u);             // every CTA whose smem the stage's loads touch
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        if constexpr (kCG != 1) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        if constexpr (CL != 1) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -197,12 +203,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                               (kb | k) != 0 ? 1u : 0u);
           }
           // smem slot free (in both CTAs) once these MMAs retire
-          if constexpr (kCG != 1) umma_commit_cg2_mc(empty_bar(stage), all_mask);
+          if constexpr (CL != 1) umma_commit_cg2_mc(empty_bar(stage), all_mask);
           else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         // accumulator ready for the epilogue (of both CTAs)
-        if constexpr (kCG != 1) umma_commit_cg2_mc(tfull_bar(acc), pair_mask);
+        if constexpr (CL != 1) umma_commit_cg2_mc(tfull_bar(acc), pair_mask);
         else umma_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -235,11 +241,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
         float* crow_base = reinterpret_cast<float*>(Cout) + (int64_t(b) * (tpi + cls_off) + cls_off + t) * N;
         const float* pos_row = aux + int64_t(cls_off + t) * N;
 #pragma unroll 1
-        for (int chunk = 0; chunk < 4; ++chunk) {
-          const int n0 = n_blk * BN + grp * 128 + chunk * 32;
+        for (int chunk = 0; chunk < BN / 64; ++chunk) {   // each group owns half of the tile's columns
+          const int n0 = n_blk * BN + grp * (BN / 2) + chunk * 32;
           if (n0 >= N) break;                         // warp-uniform
           uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + uint32_t(grp * 128 + chunk * 32), r);
+          tmem_ld_32x32b_x32(t_row + uint32_t(grp * (BN / 2) + chunk * 32), r);
           tmem_ld_wait();
           if (row_ok) {
 #pragma unroll
@@ -346,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kCG != 1) mbar_arrive_cluster(tempty_bar(acc), lead);   // the pair leader's barrier
+        if constexpr (CL != 1) mbar_arrive_cluster(tempty_bar(acc), lead);   // the pair leader's barrier
         else mbar_arrive(tempty_bar(acc));
       }
       acc ^= 1;
@@ -356,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   }
 
   tc_fence_before();
-  if constexpr (kCG != 1) cluster_sync_all(); else __syncthreads();   // peer smem/TMEM stay live until here
+  if constexpr (CL != 1) cluster_sync_all(); else __syncthreads();   // peer smem/TMEM stay live until here
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<MMA_CG>(tmem_base, TMEM_COLS);
@@ -378,20 +384,20 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
   if (!configured) {
     VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG>()));
-    max_units = sm_count() / kCG;
-    if (kCG > 2) {   // clusters of 4 do not tile every GPC: ask how many fit (33 on a 148-SM B200)
+    max_units = sm_count() / Cfg<kCG>::CL;
+    if (Cfg<kCG>::CL > 2) {   // clusters of 4 do not tile every GPC: ask how many fit (33 on a 148-SM B200)
       int n = 0;
       cudaLaunchConfig_t cfg{};
       cfg.blockDim = dim3(NUM_THREADS);
       cfg.dynamicSmemBytes = smem_bytes<kCG>();
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = kCG;
+      attr[0].val.clusterDim.x = Cfg<kCG>::CL;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      cfg.gridDim = dim3(sm_count() / kCG * kCG);
+      cfg.gridDim = dim3(sm_count() / Cfg<kCG>::CL * Cfg<kCG>::CL);
       if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, &cfg) == cudaSuccess && n > 0)
         max_units = n < max_units ? n : max_units;
       else
@@ -399,10 +405,10 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
     }
     configured = true;
   }
-  const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, BN);
+  const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, Cfg<kCG>::BN_);
   const int units = tiles < max_units ? tiles : max_units;
-  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, dim3(units * kCG), dim3(NUM_THREADS), smem_bytes<kCG>(),
-                        stream, kCG, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off, cls));
+  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, dim3(units * Cfg<kCG>::CL), dim3(NUM_THREADS), smem_bytes<kCG>(),
+                        stream, Cfg<kCG>::CL, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off, cls));
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -419,10 +425,12 @@ int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& t
     if (drop.threshold != 0) {
       if (cta_group == 4)
         return fail(VITB200_ERR_UNSUPPORTED, "gemm_tc: dropout is not built for the opt-in cluster-of-4 mode");
+      if (cta_group == 64) return launch_cg<kEpi, kDT, 64, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
       if (cta_group == 1) return launch_cg<kEpi, kDT, 1, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
       return launch_cg<kEpi, kDT, 2, true>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
     }
   }
+  if (cta_group == 64) return launch_cg<kEpi, kDT, 64, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
   if (cta_group == 4) return launch_cg<kEpi, kDT, 4, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
   if (cta_group == 2) return launch_cg<kEpi, kDT, 2, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
   return launch_cg<kEpi, kDT, 1, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, drop, cls_off, cls);
@@ -453,21 +461,32 @@ int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap&
 
 }  // namespace
 
-int gemm_tc_cta_group(int M) {
-  // VITB200_GEMM_CTA_GROUP=1|2|4 overrides (A/B tests).  Pairs pay off with >= 2 row blocks.  The
-  // weight-multicast cluster of two pairs (4) cuts the L2 reads per flop by a quarter but measured
-  // no faster per SM and only 33 such clusters fit a 148-SM B200 ("What bounds the GEMM"):
-  // it stays opt-in.
-  const char* e = getenv("VITB200_GEMM_CTA_GROUP");
-  if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) return e[0] - '0';
-  return M > GEMM_BM ? 2 : 1;
+int gemm_tc_cta_group(int M) { return gemm_tc_tile_mode(M, 1 << 20); }
+
+// Tile mode for an [M, N] output.  VITB200_GEMM_CTA_GROUP=1|2|4|64 overrides (A/B tests).  Measured
+// (profiles/r01_gemm.md): CTA pairs (256x256) win from M = 1576 rows up on every ViT shape; at one or
+// two row blocks (a forward at batch 1) the 128x64 single-CTA tiles are 15-25 % faster because they
+// spread the weight matrix over four times as many SMs, and lose badly beyond that (their MMAs run
+// at a quarter of the rate).  The weight-multicast cluster of two pairs (4) is no faster per SM and
+// fits only 33 clusters on 148 SMs: opt-in only.
+int gemm_tc_tile_mode(int M, int N) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("VITB200_GEMM_CTA_GROUP");
+    const int v = e ? atoi(e) : 0;
+    forced = (v == 1 || v == 2 || v == 4 || v == 64) ? v : 0;
+  }
+  if (forced) return forced;
+  if (M <= 2 * GEMM_BM) return N > GEMM_BN ? 64 : 1;
+  return 2;
 }
 
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tpi, int dtype, int cta_group, const Dropout& drop,
                    int cls_off, const float* cls) {
-  if (cta_group != 1 && cta_group != 2 && cta_group != 4) return fail(VITB200_ERR_INVALID, "gemm_tc: cta_group must be 1, 2 or 4");
+  if (cta_group != 1 && cta_group != 2 && cta_group != 4 && cta_group != 64)
+    return fail(VITB200_ERR_INVALID, "gemm_tc: tile mode must be 1, 2, 4 or 64");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
   if ((N % 8) != 0 || (K % 8) != 0)
     return fail(VITB200_ERR_INVALID, "gemm_tc: N and K must be multiples of 8");
