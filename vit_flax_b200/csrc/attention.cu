@@ -7,8 +7,10 @@
 // softmax is the online (running max / running sum) form.
 //
 // This generation uses warp-level mma.sync (HMMA) with ldmatrix operands and a
-// double-buffered cp.async K/V stream; each warp owns 16 query rows.  A
-// tcgen05/TMEM generation replaces it once the GEMM path is tuned.
+// double-buffered cp.async K/V stream; each warp owns 16 query rows.  The tcgen05/TMEM kernels
+// (attention_tc5.cu for T <= 208, attention_tc5m.cu beyond) have replaced it on the hot path;
+// it stays reachable with VITB200_ATTENTION=hmma as an independent implementation for A/B tests
+// (tests/test_gpu_kernels.py runs both at every shape).
 #include <cstdlib>
 
 #include "common.h"

@@ -14,13 +14,16 @@
 //                    tcgen05.ld -> fused math -> swizzled smem slab -> TMA store
 //                    (16-bit outputs, fp32 head) or TMA reduce-add into the fp32 residual
 //                    stream (x += acc + bias happens in L2; the SM never reads x).
-// kCG = 2 pairs two CTAs (cluster of 2, `cta_group::2`): the pair computes a 256x256 tile, each
-// CTA loading its 128 rows of A and its 128-row half of Wt; only the leader CTA issues MMAs, smem
-// traffic per SM drops from 192 to 128 B/clk (the 1-CTA form is smem-bandwidth bound at ~62 %
-// tensor-pipe activity, profiles/r01_gemm_ncu.md).
-// Pipelines: smem ring (3 stages (5 in pair mode), full/empty mbarriers) between TMA and MMA; TMEM double buffer
-// (tfull/tempty mbarriers) between MMA and epilogue, so the epilogue of tile i overlaps the MMAs
-// of tile i+1; two slab buffers per epilogue group so a slab drains while the next is filled.
+// Tile modes (template kCG): 2 = CTA pair (cluster of 2, `cta_group::2`) on a 256x256 tile -- each
+// CTA loads its 128 rows of A and its 128-row half of Wt, only the leader issues MMAs -- is the
+// production mode: the single-CTA 128x256 form (1) is smem-bandwidth bound at ~62 % tensor-pipe
+// activity.  64 = single CTA on 128x64 tiles for problems of one or two row blocks; 4 = cluster of
+// two pairs sharing a multicast weight tile (opt-in, profiles/r01_gemm.md).
+// Pipelines: smem ring (3 / 5 / 6 stages for modes 1 / 2,4 / 64; full/empty mbarriers) between TMA
+// and MMA; TMEM double buffer (tfull/tempty mbarriers) between MMA and epilogue, so the epilogue of
+// tile i overlaps the MMAs of tile i+1; two slab buffers per epilogue group so a slab drains while
+// the next is filled.  Dropout (template kDrop) is applied in the epilogues that have an
+// nn.Dropout behind them in the reference (ptx.cuh: dropout4).
 #include <cstdlib>
 
 #include "common.h"

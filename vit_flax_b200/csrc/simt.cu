@@ -1,9 +1,9 @@
 // simt.cu -- the CUDA-core kernels of the path:
-//   K2  LayerNorm (warp-shuffle, vectorised; fp32 in, bf16 or fp32 out)     vit.py:31,163
-//   K1a patchify + fp32->bf16 cast (im2col folded into the mandatory cast)   vit.py:146
-//   K1b cls rows                                                             vit.py:151-153
+//   K2  LayerNorm (warp-shuffle, vectorised; fp32 in, 16-bit or fp32 out)    vit.py:31,163
+//   K1a patchify + fp32->16-bit cast (im2col folded into the mandatory cast) vit.py:146
+//   K1b cls rows (fp32 mode; the tensor-core path writes them in the patch GEMM) vit.py:151-153
 //   K5a pool (cls / mean) + head LayerNorm                                   vit.py:159-163
-//   K7  weight pack (fp32 [K,N] -> bf16 [N,Kpad])
+//   K7  weight pack (fp32 [K,N] -> 16-bit [N,Kpad])
 //   fp32 validation mode: SIMT GEMM with the same fused epilogues and a
 //   straightforward fp32 attention (tolerance 1e-4 against the oracle).
 #include <cstdlib>
