@@ -358,12 +358,16 @@ def run_b200(args) -> None:
             "roofline": {
                 "kernel": "gemm_tc_kernel (tcgen05 GEMM family: patch, to_qkv, to_out, ff1, ff2, head)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic(),
                 "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": gemm_launches, "ms_per_step": gemm_ms_in_region,
                 "share_of_step": gemm_share, "isolated_ms_per_step": gemm_ms,
                 "isolated_tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12,
                 "algorithmic_flops_per_step": gemm_flops,
+                "per_launch": {"flops": gemm_flops / max(1, gemm_launches),
+                               "ms": gemm_ms_in_region / max(1, gemm_launches)},
+                "by_epilogue_isolated_tflops": {c: fl[c] * B / (prof[c][0] * 1e-3) / 1e12 for c in gemm_cats
+                                                if prof[c][0] > 0},
                 "traffic_note": "dram bytes of ONE FF1 launch (ncu --set full, profiles/r01_gemm.md); algorithmic 392 MB",
             },
             "kernels_ms": {k: round(v[0], 4) for k, v in prof.items()},
