@@ -325,14 +325,24 @@ def run_b200(args) -> None:
     cpu = None
     if rank == 0:
         from oracle import vit_torch
-        k = 4
+        import torch as _t
+        _t.set_num_threads(os.cpu_count() or 1)
+        k = min(32, B)
         want = vit_torch.vit_forward(vit_torch.tree_to_torch(variables), images[:k].cpu().numpy(), **C2).numpy()
         got = logits_all[start:start + k].cpu().numpy()
+        srt = np.sort(want, axis=1)
+        margin = srt[:, -1] - srt[:, -2]                     # oracle top-1 margin per image
+        agree = got.argmax(1) == want.argmax(1)
+        confident = margin > 2 * 2e-2
         parity = {"images": k, "max_abs_err": float(np.abs(got - want).max()), "tolerance": 2e-2,
-                  "top1_agree": float((got.argmax(1) == want.argmax(1)).mean())}
+                  "top1_agree": float(agree.mean()),
+                  "top1_agree_where_margin_gt_2tol": float(agree[confident].mean()) if confident.any() else None,
+                  "images_with_margin_gt_2tol": int(confident.sum()),
+                  "note": "random-init weights: top-1 margins are ~exponential with mean 0.27, so the raw "
+                          "agreement measures luck at margins below the error (SURVEY.md H3)"}
         if other_line is not None:
             lg = other_line.pop("logits")
-            other_line["max_abs_err"] = float(np.abs(lg - want).max())
+            other_line["max_abs_err"] = float(np.abs(lg - want[:4]).max())
             other_line["note"] = ("bf16 operands: weight rounding alone moves these logits by 1.9e-2 (DESIGN.md, "
                                   "Operand format)" if other == "bf16" else "fp16 operands")
         if world == 1 and not args.no_cpu_baseline:
