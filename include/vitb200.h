@@ -159,6 +159,9 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 #define VITB200_EPI_BIAS_RESID_F32  2  /* C_f32 += acc + bias  (in place)      (vit.py:51/82 + 39)   */
 #define VITB200_EPI_BIAS_F32        3  /* C_f32 = acc + bias                   (head, vit.py:165)    */
 #define VITB200_EPI_PATCH_F32       4  /* C_f32[b*T+1+t] = acc + bias + pos[1+t]  (vit.py:147-153)   */
+#define VITB200_EPI_TOKENS_F32      5  /* A in token layout (row b*T+t; t = 0 the class-token slot):
+                                        * C_f32[b*T+t] = t == 0 && cls ? cls + pos[0]
+                                        *                              : acc + bias + pos[t]  (vit.py:147-153) */
 
 /* tcgen05 GEMM: acc[M,N] = A[M,K] (16-bit row-major) x Wt[N,K]^T (16-bit row-major, i.e. the
  * transposed Flax kernel), fp32 accumulation in TMEM.  dtype = VITB200_DT_BF16 | _F16.
@@ -167,12 +170,19 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bias,
                     void* C, int M, int N, int K, int epilogue,
                     const float* aux, int tokens_per_image, int dtype);
-/* Same with the Dropout that follows the Dense in the reference (epilogues 1, 2 and 4 only):
+/* Same with the Dropout that follows the Dense in the reference (epilogues 1, 2, 4 and 5 only):
  * rate in [0, 1), key / site as in vitb200_set_dropout_key.                                   */
 int vitb200_gemm_tc_dropout(void* stream, const void* A, const void* Wt, const float* bias,
                             void* C, int M, int N, int K, int epilogue,
                             const float* aux, int tokens_per_image, int dtype,
                             float rate, uint64_t key, uint32_t site);
+/* Same with the class-token row source of EPI_TOKENS (`cls` [N] fp32 or NULL; ignored by the other
+ * epilogues except EPI_PATCH, where a non-NULL cls also writes row b*T = cls + pos[0]).
+ * For EPI_TOKENS `tokens_per_image` = T (rows per image of A and C) and `aux` = pos_embedding [T, N]. */
+int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const float* bias,
+                           void* C, int M, int N, int K, int epilogue,
+                           const float* aux, int tokens_per_image, const float* cls, int dtype,
+                           float rate, uint64_t key, uint32_t site);
 /* SIMT fp32 GEMM (validation mode): acc = A[M,K] x W[K,N] (Flax layout).
  * The two "_16" epilogues write fp32 here.                                  */
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias,
@@ -194,6 +204,12 @@ int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch,
  * feature f = (p1*pw + p2)*C + c, zero padded to Kpad. */
 int vitb200_patchify(void* stream, const float* images, void* patches, int batch,
                      int H, int W, int C, int ph, int pw, int Kpad, int out_dtype);
+/* Same with the image layout (nchw = 1: [batch,C,H,W], simple_vit.py:125) and the token layout of
+ * the forward (cls_slot = 1: patch t of image b goes to row b*(Np+1) + 1 + t; row b*(Np+1), the
+ * class-token slot consumed by EPI_TOKENS, is left untouched). */
+int vitb200_patchify_tokens(void* stream, const float* images, void* patches, int batch,
+                            int H, int W, int C, int ph, int pw, int Kpad, int out_dtype,
+                            int nchw, int cls_slot);
 /* cls rows (vit.py:151-153): x[b*T + 0, :] = cls + pos[0] */
 int vitb200_cls_rows(void* stream, const float* cls, const float* pos, float* x,
                      int batch, int T, int dim);

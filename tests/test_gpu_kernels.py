@@ -235,6 +235,61 @@ def test_patchify(lib, H, W, ph, pw, Cc, out):
     assert not got[:, K0:].any()                                          # zero padding
 
 
+@pytest.mark.parametrize("H,W,ph,pw,Cc", [(224, 224, 16, 16, 3), (16, 32, 8, 16, 3), (32, 32, 8, 8, 1), (24, 24, 8, 8, 5)])
+@pytest.mark.parametrize("nchw", [0, 1])
+def test_patchify_token_layout(lib, H, W, ph, pw, Cc, nchw):
+    """The forward's layout: patch t of image b at row b*(Np+1)+1+t, the class-token slot rows untouched
+    (all three kernels: float4 rows, float2 rows, generic / NCHW)."""
+    B = 3
+    dt, tdt, _ = DT16["fp16"]
+    x = np.random.default_rng(H + pw + Cc).standard_normal((B, H, W, Cc)).astype(np.float32)
+    K0 = ph * pw * Cc
+    Kpad = (K0 + 63) // 64 * 64
+    Np = (H // ph) * (W // pw)
+    y = torch.full((B, Np + 1, Kpad), 9.0, dtype=tdt, device="cuda")
+    xd = dev(np.ascontiguousarray(x.transpose(0, 3, 1, 2)) if nchw else x)
+    _lib.check(lib.vitb200_patchify_tokens(stream(), xd.data_ptr(), y.data_ptr(), B, H, W, Cc, ph, pw, Kpad, dt, nchw, 1))
+    torch.cuda.synchronize()
+    want = torch.as_tensor(vit_numpy.patchify(x, ph, pw).reshape(B, Np, K0)).to(tdt).float().numpy()
+    got = y.float().cpu().numpy()
+    np.testing.assert_array_equal(got[:, 1:, :K0], want)
+    assert not got[:, 1:, K0:].any()
+    assert (got[:, 0] == 9.0).all()
+
+
+@pytest.mark.parametrize("cta_group", ["1", "2", "64"])
+@pytest.mark.parametrize("B,T,K,D", [(3, 17, 192, 64), (5, 197, 768, 768)])
+@pytest.mark.parametrize("with_cls", [True, False])
+@pytest.mark.parametrize("rate", [0.0, 0.25])
+def test_gemm_tc_tokens_epilogue(lib, cta_group, B, T, K, D, with_cls, rate, monkeypatch):
+    """vit.py:147-155 as ONE GEMM over the B*T token rows: row b*T+t = patches @ W + bias + pos[t];
+    with a class token, row b*T = cls + pos[0] whatever the slot row of A holds; emb dropout on all rows."""
+    from oracle import philox
+    monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
+    dt, tdt, _ = DT16["fp16"]
+    rng = np.random.default_rng(B * T + K)
+    A = dev(rng.standard_normal((B, T, K)), tdt)
+    if with_cls:
+        A[:, 0] = float("nan")                                            # the slot rows must never reach the output
+    Wt = dev(rng.standard_normal((D, K)) / np.sqrt(K), tdt)
+    bias, cls, pos = dev(rng.standard_normal(D) + 3.0), dev(rng.standard_normal(D) + 3.0), dev(rng.standard_normal((T, D)))
+    x = torch.full((B * T, D), 7.0, device="cuda")
+    key, site = 0xFEEDFACE12345678, 0
+    _lib.check(lib.vitb200_gemm_tc_tokens(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), x.data_ptr(),
+                                          B * T, D, K, _lib.EPI_TOKENS_F32, pos.data_ptr(), T,
+                                          cls.data_ptr() if with_cls else None, dt, rate, key, site))
+    torch.cuda.synchronize()
+    want = torch.nan_to_num(A.double()) @ Wt.double().t() + bias.double() + pos.double()
+    if with_cls:
+        want[:, 0] = cls.double() + pos.double()[0]
+    want = want.view(B * T, D)
+    if rate:
+        keep = torch.as_tensor(philox.keep_mask((B * T, D), rate, site, key), device="cuda")
+        want = torch.where(keep, want / (1 - rate), 0.0)
+    assert torch.isfinite(x).all()
+    assert (x.double() - want).abs().max().item() < 3e-4
+
+
 def test_cls_rows_and_pool_layernorm(lib):
     B, T, D = 3, 17, 96
     rng = np.random.default_rng(1)

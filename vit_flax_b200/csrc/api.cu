@@ -202,7 +202,10 @@ int alloc_workspace(vitb200_model* m) {
   int rc;
   if ((rc = m->x.alloc(R * c.dim))) return rc;
   if (m->tc) {
-    if ((rc = m->patches_h.alloc(Rp * m->K0pad))) return rc;
+    // token layout: one row per token, the class-token slot in front of every image never written
+    // by patchify and never used as data by the TOKENS epilogue; zeroed once so the MMA reads defined bits
+    if ((rc = m->patches_h.alloc(R * m->K0pad))) return rc;
+    VB_CUDA(cudaMemset(m->patches_h.p, 0, R * m->K0pad * sizeof(uint16_t)));
     if ((rc = m->xn_h.alloc(R * c.dim))) return rc;
     if ((rc = m->qkv_h.alloc(R * 3 * m->inner))) return rc;
     if ((rc = m->o_h.alloc(R * m->inner))) return rc;
@@ -224,11 +227,11 @@ int get_act_maps(vitb200_model* m, int batch, const ActMaps** out) {
   auto it = m->act_maps.find(batch);
   if (it == m->act_maps.end()) {
     const auto& c = m->cfg;
-    const int64_t R = int64_t(batch) * m->T, Rp = int64_t(batch) * m->Np;
+    const int64_t R = int64_t(batch) * m->T;
     ActMaps am;
     int rc;
     const int dt = m->dt;
-    if ((rc = make_tmap_2d(&am.patches, m->patches_h.p, Rp, m->K0pad, m->K0pad, GEMM_BM, dt))) return rc;
+    if ((rc = make_tmap_2d(&am.patches, m->patches_h.p, R, m->K0pad, m->K0pad, GEMM_BM, dt))) return rc;
     if ((rc = make_tmap_2d(&am.xn, m->xn_h.p, R, c.dim, c.dim, GEMM_BM, dt))) return rc;
     if ((rc = make_tmap_2d(&am.o, m->o_h.p, R, m->inner, m->inner, GEMM_BM, dt))) return rc;
     if ((rc = make_tmap_2d(&am.h, m->hid_h.p, R, c.mlp_dim, c.mlp_dim, GEMM_BM, dt))) return rc;
@@ -278,24 +281,24 @@ __global__ void add_f32_into_f32_kernel(const float* __restrict__ a, float* __re
 // ---- the forward schedule, bf16 / tcgen05 flavour ---------------------------
 int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
   const auto& c = m->cfg;
-  const int D = c.dim, I = m->inner, T = m->T, Np = m->Np;
-  const int R = batch * T, Rp = batch * Np;
+  const int D = c.dim, I = m->inner, T = m->T;
+  const int R = batch * T;
   const ActMaps* am;
   int rc;
   if ((rc = get_act_maps(m, batch, &am))) return rc;
   // tile mode per GEMM shape (pairs for anything that fills the machine, small tiles otherwise)
-  const int cgp = gemm_tc_tile_mode(Rp, D), cgh = gemm_tc_tile_mode(batch, c.num_classes);
+  const int cgp = gemm_tc_tile_mode(R, D), cgh = gemm_tc_tile_mode(batch, c.num_classes);
   const int cg_qkv = gemm_tc_tile_mode(R, 3 * I), cg_d = gemm_tc_tile_mode(R, D), cg_ff1 = gemm_tc_tile_mode(R, c.mlp_dim);
-  // vit.py:146  patchify (+ fp32->bf16 cast, zero pad to K0pad)
+  // vit.py:146  patchify (+ fp32->16-bit cast, zero pad to K0pad) into the token layout: row b*T+cls+t
   mark(m, st, VITB200_CAT_PATCHIFY);
   if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
-                            c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw))) return rc;
-  // vit.py:147-153  Dense_0 + bias, placed at row b*T+1+t, + pos_embedding[1+t]
+                            c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
+  // vit.py:147-153  Dense_0 + bias + pos_embedding[t] over all B*T token rows; the class-token row of
+  // every image (t = 0) is cls + pos_embedding[0], written by the same epilogue
   mark(m, st, VITB200_CAT_GEMM_PATCH);
-  if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), nullptr, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
-                             Rp, D, m->K0pad, VITB200_EPI_PATCH_F32, leaf_ptr(m, m->leaf_pos), Np, m->dt, cgp,
+  if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), &am->c_x, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+                             R, D, m->K0pad, VITB200_EPI_TOKENS_F32, leaf_ptr(m, m->leaf_pos), T, m->dt, cgp,
                              m->drop(c.emb_dropout, 0), m->cls_off, leaf_ptr(m, m->leaf_cls)))) return rc;
-  // (the class-token rows b*T = cls + pos[0] are written by the same epilogue: vit.py:151-153)
   for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
     Layer& L = m->layers[l];
     // Residual(PreNorm(Attention))  vit.py:31,39,62-87
@@ -665,6 +668,13 @@ int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bi
 int vitb200_gemm_tc_dropout(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
                             int K, int epilogue, const float* aux, int tokens_per_image, int dtype,
                             float rate, uint64_t key, uint32_t site) {
+  return vitb200_gemm_tc_tokens(stream, A, Wt, bias, C, M, N, K, epilogue, aux, tokens_per_image, nullptr, dtype,
+                                rate, key, site);
+}
+
+int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
+                           int K, int epilogue, const float* aux, int tokens_per_image, const float* cls, int dtype,
+                           float rate, uint64_t key, uint32_t site) {
   if (!(rate >= 0.f && rate < 1.f)) return fail(VITB200_ERR_INVALID, "gemm_tc: dropout rate must be in [0, 1)");
   Dropout drop;
   if (rate > 0.f) {
@@ -690,7 +700,7 @@ int vitb200_gemm_tc_dropout(void* stream, const void* A, const void* Wt, const f
   const bool direct = epilogue == VITB200_EPI_PATCH_F32;
   if (!direct && (rc = make_tmap_2d(&tc, C, M, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
   return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, direct ? nullptr : &tc, bias, C, M, N, K, epilogue,
-                        aux, tokens_per_image, dtype, cg, drop);
+                        aux, tokens_per_image, dtype, cg, drop, 1, cls);
 }
 
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias, float* C, int M, int N,
@@ -719,6 +729,15 @@ int vitb200_patchify(void* stream, const float* images, void* patches, int batch
                      int pw, int Kpad, int out_dtype) {
   if (!images || !patches) return fail(VITB200_ERR_INVALID, "patchify: null pointer");
   return launch_patchify(static_cast<cudaStream_t>(stream), images, patches, batch, H, W, C, ph, pw, Kpad, out_dtype);
+}
+
+int vitb200_patchify_tokens(void* stream, const float* images, void* patches, int batch, int H, int W, int C, int ph,
+                            int pw, int Kpad, int out_dtype, int nchw, int cls_slot) {
+  if (!images || !patches) return fail(VITB200_ERR_INVALID, "patchify: null pointer");
+  if ((nchw != 0 && nchw != 1) || (cls_slot != 0 && cls_slot != 1))
+    return fail(VITB200_ERR_INVALID, "patchify: nchw and cls_slot are 0 or 1");
+  return launch_patchify(static_cast<cudaStream_t>(stream), images, patches, batch, H, W, C, ph, pw, Kpad, out_dtype,
+                         nchw, cls_slot);
 }
 
 int vitb200_cls_rows(void* stream, const float* cls, const float* pos, float* x, int batch, int T, int dim) {

@@ -113,7 +113,7 @@ int launch_attention_tc5m(cudaStream_t stream, const void* qkv, void* out, int b
 int launch_attention_f32(cudaStream_t stream, const float* qkv, float* out, int batch, int T,
                          int heads);
 int launch_patchify(cudaStream_t stream, const float* images, void* patches, int batch, int H,
-                    int W, int C, int ph, int pw, int Kpad, int out_dtype, int nchw = 0);
+                    int W, int C, int ph, int pw, int Kpad, int out_dtype, int nchw = 0, int tok_off = 0);
 int launch_cls_rows(cudaStream_t stream, const float* cls, const float* pos, float* x, int batch,
                     int T, int dim, const Dropout& drop = Dropout());
 int launch_pool_layernorm(cudaStream_t stream, const float* x, const float* scale,

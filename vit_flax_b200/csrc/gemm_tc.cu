@@ -326,14 +326,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           } else {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_row + uint32_t(s * SLAB_COLS), r);
+            // TOKENS: output row = token row b*T + t; t = 0 is the class-token row when cls is given
+            // (vit.py:151-153: concat([cls, x]) + pos_embedding), every other row a patch row
+            const int tok = kEpi == VITB200_EPI_TOKENS_F32 ? (m_row0 + lrow) % tpi : 0;
+            const bool cls_row = kEpi == VITB200_EPI_TOKENS_F32 && cls != nullptr && tok == 0;
+            const float* pos_row = aux + int64_t(tok) * N;
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {              // 4 fp32 columns -> one 16-byte chunk
               const int nb = n0 + j * 4;
               float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (nb < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + nb));
-              float o0 = __uint_as_float(r[j * 4 + 0]) + b4.x, o1 = __uint_as_float(r[j * 4 + 1]) + b4.y;
-              float o2 = __uint_as_float(r[j * 4 + 2]) + b4.z, o3 = __uint_as_float(r[j * 4 + 3]) + b4.w;
+              if (nb < N) b4 = __ldg(reinterpret_cast<const float4*>((cls_row ? cls : bias) + nb));
+              float o0 = __uint_as_float(r[j * 4 + 0]), o1 = __uint_as_float(r[j * 4 + 1]);
+              float o2 = __uint_as_float(r[j * 4 + 2]), o3 = __uint_as_float(r[j * 4 + 3]);
+              if constexpr (kEpi == VITB200_EPI_TOKENS_F32) {
+                if (cls_row) o0 = o1 = o2 = o3 = 0.f;   // the slot row of the patch matrix holds no data
+                if (nb < N) {
+                  const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos_row + nb));
+                  b4.x += p4.x; b4.y += p4.y; b4.z += p4.z; b4.w += p4.w;
+                }
+              }
+              o0 += b4.x; o1 += b4.y; o2 += b4.z; o3 += b4.w;
+              if constexpr (kDrop && kEpi == VITB200_EPI_TOKENS_F32)      // emb dropout (vit.py:155)
+                dropout4(drop, int64_t(m_row0 + lrow) * N + nb, o0, o1, o2, o3);
               if constexpr (kDrop && kEpi == VITB200_EPI_BIAS_RESID_F32)   // Dropout after to_out / FF Dense_1
                 dropout4(drop, int64_t(m_row0 + lrow) * N + nb, o0, o1, o2, o3);   // (vit.py:52,83), before the residual add
               st_shared_v4(srow + (uint32_t(j ^ sw) << 4), __float_as_uint(o0), __float_as_uint(o1),
@@ -423,7 +438,7 @@ int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& t
   // dropout variants exist for the epilogues that have a Dropout behind them and for the two
   // production tile modes; the opt-in cluster-of-4 mode falls back to pairs when dropout is on
   constexpr bool kCanDrop = kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_RESID_F32 ||
-                            kEpi == VITB200_EPI_PATCH_F32;
+                            kEpi == VITB200_EPI_PATCH_F32 || kEpi == VITB200_EPI_TOKENS_F32;
   if constexpr (kCanDrop) {
     if (drop.threshold != 0) {
       if (cta_group == 4)
@@ -457,6 +472,10 @@ int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap&
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
       return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
+    case VITB200_EPI_TOKENS_F32:
+      if (aux == nullptr || tpi <= 0)
+        return fail(VITB200_ERR_INVALID, "gemm_tc: TOKENS epilogue needs pos_embedding and tokens per image");
+      return launch_one<VITB200_EPI_TOKENS_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     default:
       return fail(VITB200_ERR_INVALID, "gemm_tc: unknown epilogue");
   }
@@ -498,12 +517,11 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
   if (epilogue != VITB200_EPI_PATCH_F32 && tmC == nullptr)
     return fail(VITB200_ERR_INVALID, "gemm_tc: output tensor map missing");
   const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
+  const float* cls_p = (cls_off == 1 && (epilogue == VITB200_EPI_PATCH_F32 || epilogue == VITB200_EPI_TOKENS_F32)) ? cls : nullptr;
   if (dtype == DT_BF16)
-    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off,
-                                 cls_off == 1 && epilogue == VITB200_EPI_PATCH_F32 ? cls : nullptr);
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off, cls_p);
   if (dtype == DT_F16)
-    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off,
-                                 cls_off == 1 && epilogue == VITB200_EPI_PATCH_F32 ? cls : nullptr);
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off, cls_p);
   return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 

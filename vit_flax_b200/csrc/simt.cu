@@ -148,10 +148,13 @@ int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b,
 
 // -------------------------------------------------------------- patchify (K1a)
 // out[(b*Np + t), f], f = (p1*pw + p2)*C + c  <-  x[b, hh*ph+p1, ww*pw+p2, c]; zero pad f >= K0.
+// tok_off = 1 writes the TOKEN layout instead: row b*(Np+1) + 1 + t, leaving row b*(Np+1) (the image's
+// class-token slot, never written, never used as data) so that the patch GEMM's output rows are the
+// token rows themselves (VITB200_EPI_TOKENS_F32).
 template <int kDT>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
-                int C, int ph, int pw, int Kpad, int nchw) {
+                int C, int ph, int pw, int Kpad, int nchw, int tok_off) {
   pdl_launch_dependents();
   pdl_wait();
   const int gw = W / pw, gh = H / ph;
@@ -179,10 +182,12 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
         v[e] = 0.f;
       }
     }
+    // token layout (tok_off = 1): image b's patches start one row late, behind its class-token row
+    const int64_t o = i + (int64_t(b) + 1) * tok_off * pairs_per_row;
     if constexpr (kDT != DT_F32) {
-      reinterpret_cast<uint32_t*>(out)[i] = pack2<kDT>(v[0], v[1]);
+      reinterpret_cast<uint32_t*>(out)[o] = pack2<kDT>(v[0], v[1]);
     } else {
-      reinterpret_cast<float2*>(out)[i] = make_float2(v[0], v[1]);
+      reinterpret_cast<float2*>(out)[o] = make_float2(v[0], v[1]);
     }
   }
 }
@@ -195,7 +200,7 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
 template <int kDT>
 __global__ void __launch_bounds__(256)
 patchify_rows_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int H, int W,
-                     int C, int ph, int pw, int Kpad) {   // NHWC only; NCHW goes through patchify_kernel
+                     int C, int ph, int pw, int Kpad, int tok_off) {   // NHWC only; NCHW goes through patchify_kernel
   pdl_launch_dependents();
   pdl_wait();
   const int gw = W / pw, gh = H / ph;
@@ -212,7 +217,7 @@ patchify_rows_kernel(const float* __restrict__ img, void* __restrict__ out, int 
     const float2 v = __ldcs(reinterpret_cast<const float2*>(img) + i);
     const int x = t * 2;
     const int ww = x / seg, rem = x - ww * seg;
-    const int64_t o = ((int64_t(b) * gh + hh) * gw + ww) * Kpad + p1 * seg + rem;   // even
+    const int64_t o = ((int64_t(b) * gh + hh) * gw + ww + (int64_t(b) + 1) * tok_off) * Kpad + p1 * seg + rem;   // even
     if constexpr (kDT != DT_F32) reinterpret_cast<uint32_t*>(out)[o >> 1] = pack2<kDT>(v.x, v.y);
     else reinterpret_cast<float2*>(out)[o >> 1] = v;
   }
@@ -221,7 +226,7 @@ patchify_rows_kernel(const float* __restrict__ img, void* __restrict__ out, int 
     for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < npad; i += int64_t(gridDim.x) * blockDim.x) {
       const int64_t patch = i / pad_pairs;
       const int k = int(i - patch * pad_pairs);
-      const int64_t o = patch * Kpad + K0 + 2 * k;
+      const int64_t o = (patch + (patch / (gh * gw) + 1) * tok_off) * Kpad + K0 + 2 * k;
       if constexpr (kDT != DT_F32) reinterpret_cast<uint32_t*>(out)[o >> 1] = 0u;
       else reinterpret_cast<float2*>(out)[o >> 1] = make_float2(0.f, 0.f);
     }
@@ -234,7 +239,7 @@ patchify_rows_kernel(const float* __restrict__ img, void* __restrict__ out, int 
 template <int kDT>
 __global__ void __launch_bounds__(256)
 patchify_row4_kernel(const float* __restrict__ img, void* __restrict__ out, int rows, int H, int W, int C,
-                     int ph, int pw, int Kpad) {
+                     int ph, int pw, int Kpad, int tok_off) {
   pdl_launch_dependents();
   pdl_wait();
   const int gw = W / pw, gh = H / ph;
@@ -258,7 +263,7 @@ patchify_row4_kernel(const float* __restrict__ img, void* __restrict__ out, int 
         if (r >= rows) break;
         const int b = r / H, y = r - b * H;
         const int hh = y / ph, p1 = y - hh * ph;
-        const int64_t o = ((int64_t(b) * gh + hh) * gw + ww) * Kpad + p1 * (seg4 << 2) + (rem4 << 2);   // multiple of 4
+        const int64_t o = ((int64_t(b) * gh + hh) * gw + ww + (b + 1) * tok_off) * Kpad + p1 * (seg4 << 2) + (rem4 << 2);   // multiple of 4
         if constexpr (kDT != DT_F32) {
           uint2 p;
           p.x = pack2<kDT>(v[u].x, v[u].y);
@@ -277,7 +282,7 @@ patchify_row4_kernel(const float* __restrict__ img, void* __restrict__ out, int 
         const int b = r / H, y = r - b * H;
         const int hh = y / ph, p1 = y - hh * ph;
         if (p1 != ph - 1) continue;
-        const int64_t patch0 = (int64_t(b) * gh + hh) * gw;
+        const int64_t patch0 = (int64_t(b) * gh + hh) * gw + (b + 1) * tok_off;
         for (int t = threadIdx.x; t < gw * pad2; t += blockDim.x) {
           const int ww = t / pad2, k = t - ww * pad2;
           const int64_t o = (patch0 + ww) * Kpad + K0 + 2 * k;
@@ -540,7 +545,7 @@ int launch_layernorm(cudaStream_t st, const float* x, const float* g, const floa
 }
 
 int launch_patchify(cudaStream_t st, const float* images, void* patches, int batch, int H, int W,
-                    int C, int ph, int pw, int Kpad, int out_dtype, int nchw) {
+                    int C, int ph, int pw, int Kpad, int out_dtype, int nchw, int tok_off) {
   if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || ph <= 0 || pw <= 0)
     return fail(VITB200_ERR_INVALID, "patchify: empty problem");
   if (H % ph != 0 || W % pw != 0)
@@ -551,20 +556,20 @@ int launch_patchify(cudaStream_t st, const float* images, void* patches, int bat
       (reinterpret_cast<uintptr_t>(patches) & 15) == 0 && int64_t(batch) * H < (int64_t(1) << 31)) {
     const int n4 = (W * C) >> 2;
     const int threads = n4 >= 256 ? 256 : ((n4 + 31) / 32) * 32;
-    VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_row4_kernel<kDT>, dim3(unsigned(std::min<int64_t>(int64_t(batch) * H, int64_t(sm_count()) * 8))), dim3(threads), 0, st, 1, images, patches, batch * H, H, W, C, ph, pw, Kpad)));
+    VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_row4_kernel<kDT>, dim3(unsigned(std::min<int64_t>(int64_t(batch) * H, int64_t(sm_count()) * 8))), dim3(threads), 0, st, 1, images, patches, batch * H, H, W, C, ph, pw, Kpad, tok_off)));
     VB_LAUNCH_CHECK("patchify_row4_kernel");
     return 0;
   }
   if (!nchw && ((pw * C) & 1) == 0 && (reinterpret_cast<uintptr_t>(images) & 7) == 0) {
     const int64_t total = int64_t(batch) * H * ((W * C) >> 1);
     const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
-    VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_rows_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad)));
+    VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_rows_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad, tok_off)));
     VB_LAUNCH_CHECK("patchify_rows_kernel");
     return 0;
   }
   const int64_t total = int64_t(batch) * (H / ph) * (W / pw) * (Kpad / 2);
   const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16));
-  VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad, nchw)));
+  VB_DT_DISPATCH(out_dtype, (launch_kernel(patchify_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, images, patches, batch, H, W, C, ph, pw, Kpad, nchw, tok_off)));
   VB_LAUNCH_CHECK("patchify_kernel");
   return 0;
 }
