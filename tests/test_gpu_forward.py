@@ -166,6 +166,36 @@ def test_device_path_equals_host_path_and_is_batch_independent():
     assert np.abs(y_host[:8] - want).max() < TOL["fp16"]
 
 
+def test_graph_replay_equals_direct_launches():
+    """Small batches replay the forward as an instantiated CUDA graph (api.cu forward_graph), one per
+    (batch, images, logits) triple; the profiled forward always launches directly.  Both must give the
+    same bits, across re-captures (more buffer pairs than the cache holds) and after a weight reload."""
+    from vit_flax_b200.engine import Engine
+    cfg = dict(C2, depth=3)
+    eng = Engine(precision="fp16", max_batch=8, **cfg)
+    eng.load_params(perturb_params(init_params(seed=3, **cfg), seed=4))
+    rng = np.random.default_rng(0)
+    xs = [torch.as_tensor(rng.standard_normal((b, 224, 224, 3)).astype(np.float32), device="cuda")
+          for b in (4, 4, 4, 4, 4, 4, 1, 8)]                    # six pairs at batch 4 > 4 cached graphs
+    outs = [torch.empty((x.shape[0], 1000), device="cuda") for x in xs]
+    for rnd in range(3):                                        # capture, replay, replay after eviction
+        for x, o in zip(xs, outs):
+            o.zero_()
+            eng.forward(x, out=o)
+            direct = torch.empty_like(o)
+            eng.profile_forward(x, out=direct)
+            torch.cuda.synchronize()
+            assert torch.equal(o, direct), f"round {rnd}, batch {x.shape[0]}"
+    before = outs[0].clone()
+    eng.load_params(perturb_params(init_params(seed=7, **cfg), seed=8))   # old graphs must not survive
+    eng.forward(xs[0], out=outs[0])
+    direct = torch.empty_like(outs[0])
+    eng.profile_forward(xs[0], out=direct)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], direct) and not torch.equal(outs[0], before)
+    eng.close()
+
+
 def test_apply_stream_matches_apply():
     """Pipelined host path (two batches in flight, H2D overlapping the forward) == blocking path."""
     cfg = dict(C2, depth=2)

@@ -123,6 +123,22 @@ struct vitb200_model {
   std::map<int, ActMaps> act_maps;
   std::vector<std::pair<int, cudaEvent_t>>* prof = nullptr;   // per-launch marks while profiling
 
+  // CUDA graphs of the forward for launch-bound problem sizes (small batches): one instantiated graph
+  // per (batch, images pointer, logits pointer), a few per batch size, replayed with one cudaGraphLaunch
+  struct FwdGraph {
+    const float* images = nullptr;
+    float* logits = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
+  };
+  struct GraphSlot {
+    std::vector<FwdGraph> entries;
+    int captures = 0;          // a caller that never repeats its buffers stops being captured
+  };
+  std::map<int, GraphSlot> graphs;
+  cudaStream_t capture_stream = nullptr;
+  uint64_t graph_clock = 0;
+
   ~vitb200_model() {
     for (auto& l : leaves)
       if (l.dev) cudaFree(l.dev);
@@ -130,6 +146,10 @@ struct vitb200_model {
     free_dense(patch);
     free_dense(head);
     for (auto& L : layers) { free_dense(L.qkv); free_dense(L.out); free_dense(L.ff1); free_dense(L.ff2); }
+    for (auto& g : graphs)
+      for (auto& e : g.second.entries)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+    if (capture_stream) cudaStreamDestroy(capture_stream);
     x.release();
     patches_h.release(); xn_h.release(); qkv_h.release(); o_h.release(); hid_h.release(); pooled_h.release();
     patches_f.release(); xn_f.release(); qkv_f.release(); o_f.release(); hid_f.release(); pooled_f.release();
@@ -531,9 +551,80 @@ int vitb200_finalize_params(vitb200_model* m, void* stream) {
     if (m->head_tc && (rc = pack_dense(m, m->head, st))) return rc;
   }
   VB_CUDA(cudaStreamSynchronize(st));
+  // graphs captured before a reload hold the old tensor maps and leaf pointers
+  for (auto& g : m->graphs)
+    for (auto& e : g.second.entries)
+      if (e.exec) cudaGraphExecDestroy(e.exec);
+  m->graphs.clear();
   m->finalized = true;
   return 0;
 }
+
+// ---- graph replay of the forward (launch-bound sizes) -------------------------------------------
+// At batch 1 the 88 kernels of a ViT-B/16 forward take less time on the GPU than their launches do
+// on the CPU; replaying them as one instantiated graph (programmatic-dependent-launch edges are kept
+// by stream capture) removes the per-launch cost.  Large batches gain nothing (the GPU is the
+// bottleneck) and are launched directly.  VITB200_GRAPH=0 turns graphs off, =1 forces them for every size.
+namespace {
+constexpr int64_t kGraphMaxRows = 8192;      // token rows; above this a forward is GPU-bound
+constexpr size_t kGraphsPerBatch = 4;        // (images, logits) pairs kept per batch size
+constexpr int kGraphMaxCaptures = 16;        // per batch size; beyond this the caller's buffers do not repeat
+
+int graph_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VITB200_GRAPH");
+    mode = e ? (atoi(e) == 0 ? 0 : 2) : 1;   // 0 off, 1 auto (small sizes), 2 always
+  }
+  return mode;
+}
+
+bool graph_eligible(vitb200_model* m, cudaStream_t st, int batch) {
+  const int mode = graph_mode();
+  if (mode == 0 || m->prof) return false;
+  if (m->cfg.dropout > 0.f || m->cfg.emb_dropout > 0.f) return false;   // the key is a kernel argument
+  if (mode == 1 && int64_t(batch) * m->T > kGraphMaxRows) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cs != cudaStreamCaptureStatusNone) return false;                  // the caller is building its own graph
+  auto it = m->graphs.find(batch);
+  return it == m->graphs.end() || it->second.captures <= kGraphMaxCaptures;
+}
+
+int forward_graph(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
+  vitb200_model::GraphSlot& slot = m->graphs[batch];
+  vitb200_model::FwdGraph* hit = nullptr;
+  for (auto& e : slot.entries)
+    if (e.images == images && e.logits == logits) hit = &e;
+  if (!hit) {
+    if (++slot.captures > kGraphMaxCaptures) return forward_tc(m, st, images, batch, logits);
+    if (!m->capture_stream) VB_CUDA(cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking));
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot capture)
+    VB_CUDA(cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = forward_tc(m, m->capture_stream, images, batch, logits);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(m->capture_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return cuda_fail(ce, "forward: cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return cuda_fail(ie, "forward: cudaGraphInstantiate");
+    if (slot.entries.size() >= kGraphsPerBatch) {       // evict the least recently used pair
+      size_t lru = 0;
+      for (size_t i = 1; i < slot.entries.size(); ++i)
+        if (slot.entries[i].last_use < slot.entries[lru].last_use) lru = i;
+      cudaGraphExecDestroy(slot.entries[lru].exec);
+      slot.entries.erase(slot.entries.begin() + lru);
+    }
+    slot.entries.push_back({images, logits, exec, 0});
+    hit = &slot.entries.back();
+  }
+  hit->last_use = ++m->graph_clock;
+  VB_CUDA(cudaGraphLaunch(hit->exec, st));
+  return 0;
+}
+}  // namespace
 
 int vitb200_set_dropout_key(vitb200_model* m, uint64_t key) {
   if (!m) return fail(VITB200_ERR_INVALID, "set_dropout_key: null model");
@@ -547,7 +638,9 @@ int vitb200_forward(vitb200_model* m, void* stream, const float* images_dev, int
   if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "forward: batch must be in [1, max_batch]");
   DeviceGuard guard(m->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return m->tc ? forward_tc(m, st, images_dev, batch, logits_dev) : forward_f32(m, st, images_dev, batch, logits_dev);
+  if (!m->tc) return forward_f32(m, st, images_dev, batch, logits_dev);
+  if (graph_eligible(m, st, batch)) return forward_graph(m, st, images_dev, batch, logits_dev);
+  return forward_tc(m, st, images_dev, batch, logits_dev);
 }
 
 int vitb200_forward_host(vitb200_model* m, void* stream, const float* images_host, int batch, float* logits_host) {
