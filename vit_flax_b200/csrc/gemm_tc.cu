@@ -492,13 +492,10 @@ int gemm_tc_cta_group(int M) { return gemm_tc_tile_mode(M, 1 << 20); }
 // at a quarter of the rate).  The weight-multicast cluster of two pairs (4) is no faster per SM and
 // fits only 33 clusters on 148 SMs: opt-in only.
 int gemm_tc_tile_mode(int M, int N) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("VITB200_GEMM_CTA_GROUP");
-    const int v = e ? atoi(e) : 0;
-    forced = (v == 1 || v == 2 || v == 4 || v == 64) ? v : 0;
-  }
-  if (forced) return forced;
+  // read on every call (a getenv per GEMM launch is noise): the per-kernel tests switch modes in-process
+  const char* e = getenv("VITB200_GEMM_CTA_GROUP");
+  const int forced = e ? atoi(e) : 0;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 64) return forced;
   if (M <= 2 * GEMM_BM) return N > GEMM_BN ? 64 : 1;
   return 2;
 }
