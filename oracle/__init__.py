@@ -13,5 +13,9 @@ is cross-checked by two independent restatements (numpy float64 in
 ``vit_numpy.py``, torch-CPU float32 in ``vit_torch.py``), an einops check of the
 patchify order, and the known answers the reference does document (output shape
 ``(1, 1000)`` -- README.md:34 -- and the parameter counts implied by
-vit.py:142-165).
+vit.py:142-165).  A third-party implementation of the same architecture
+(HuggingFace ``transformers`` ViTForImageClassification, configured like vit.py
+and loaded through an explicit weight-layout mapping) reproduces the oracle's
+logits to 1e-10 in float64 (tests/test_oracle.py) -- independent evidence, not a
+run of the reference.
 """

@@ -119,3 +119,55 @@ def test_philox_known_answer_and_dropout_semantics():
     np.testing.assert_allclose(y[kept], 1.0 / 0.75, rtol=1e-6)
     np.testing.assert_array_equal(y, philox.dropout(x, 0.25, 3, 42))          # same key, same mask
     assert (philox.dropout(x, 0.25, 4, 42) != y).any() and (philox.dropout(x, 0.25, 3, 43) != y).any()
+
+
+def test_oracle_matches_third_party_vit_with_mapped_weights():
+    """Independent pin: HuggingFace ``transformers`` ViTForImageClassification (written by other people,
+    from the same paper) configured like vit.py -- pre-norm blocks, tanh GELU (nn.gelu default), LayerNorm
+    eps 1e-6, no qkv bias (vit.py:68), head_dim 64, cls pooling -- and loaded with a reference-layout
+    params tree through the layout mapping below must give the oracle's logits.  This does not replace
+    a run of the Flax reference (impossible here), but it rules out a shared misreading of the
+    architecture in oracle/vit_numpy.py and oracle/vit_torch.py."""
+    tr = pytest.importorskip("transformers")
+    cfg = dict(image_size=32, patch_size=8, num_classes=10, dim=128, depth=2, heads=2, mlp_dim=256)   # inner = dim
+    P, D, I = cfg["patch_size"], cfg["dim"], 64 * cfg["heads"]
+    v = perturb_params(init_params(seed=11, **cfg), seed=12)
+    p = v["params"]
+    hf_cfg = tr.ViTConfig(hidden_size=D, num_hidden_layers=cfg["depth"], num_attention_heads=cfg["heads"],
+                          intermediate_size=cfg["mlp_dim"], hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6,
+                          qkv_bias=False, image_size=cfg["image_size"], patch_size=P, num_labels=cfg["num_classes"],
+                          hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    hf = tr.ViTForImageClassification(hf_cfg).double().eval()
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    sd = {
+        "vit.embeddings.cls_token": t(p["cls"]),
+        "vit.embeddings.position_embeddings": t(p["pos_embedding"]),
+        # Dense_0 kernel [(p1 p2 c), D] (vit.py:146-147) -> conv weight [D, c, p1, p2]
+        "vit.embeddings.patch_embeddings.projection.weight": t(p["Dense_0"]["kernel"]).reshape(P, P, 3, D).permute(3, 2, 0, 1),
+        "vit.embeddings.patch_embeddings.projection.bias": t(p["Dense_0"]["bias"]),
+        "vit.layernorm.weight": t(p["LayerNorm_0"]["scale"]), "vit.layernorm.bias": t(p["LayerNorm_0"]["bias"]),
+        "classifier.weight": t(p["Dense_1"]["kernel"]).T, "classifier.bias": t(p["Dense_1"]["bias"]),
+    }
+    tp = p["Transformer_0"]
+    for l in range(cfg["depth"]):
+        pre = f"vit.encoder.layer.{l}."
+        qkv = t(tp[f"Attention_{l}"]["Dense_0"]["kernel"])                     # [D, 3*inner], q | k | v (vit.py:69)
+        for i, name in enumerate(("query", "key", "value")):
+            sd[pre + f"attention.attention.{name}.weight"] = qkv[:, i * I:(i + 1) * I].T
+        sd[pre + "attention.output.dense.weight"] = t(tp[f"Attention_{l}"]["Dense_1"]["kernel"]).T
+        sd[pre + "attention.output.dense.bias"] = t(tp[f"Attention_{l}"]["Dense_1"]["bias"])
+        sd[pre + "intermediate.dense.weight"] = t(tp[f"FeedForward_{l}"]["Dense_0"]["kernel"]).T
+        sd[pre + "intermediate.dense.bias"] = t(tp[f"FeedForward_{l}"]["Dense_0"]["bias"])
+        sd[pre + "output.dense.weight"] = t(tp[f"FeedForward_{l}"]["Dense_1"]["kernel"]).T
+        sd[pre + "output.dense.bias"] = t(tp[f"FeedForward_{l}"]["Dense_1"]["bias"])
+        for hf_name, ours in (("layernorm_before", f"PreNorm_{2 * l}"), ("layernorm_after", f"PreNorm_{2 * l + 1}")):
+            sd[pre + hf_name + ".weight"] = t(tp[ours]["LayerNorm_0"]["scale"])
+            sd[pre + hf_name + ".bias"] = t(tp[ours]["LayerNorm_0"]["bias"])
+    missing, unexpected = hf.load_state_dict({k: x.contiguous() for k, x in sd.items()}, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    img = images_for(cfg, 3, seed=13)
+    with torch.no_grad():
+        want = hf(pixel_values=torch.as_tensor(img, dtype=torch.float64).permute(0, 3, 1, 2)).logits.numpy()
+    got = vit_numpy.vit_forward(v, img, **cfg)
+    assert np.abs(want).max() > 0.1                                            # a non-trivial comparison
+    np.testing.assert_allclose(got, want, atol=1e-10)
