@@ -150,6 +150,23 @@ int vitb200_profile_forward(vitb200_model* m, void* stream, const float* images_
  * host) -- parity checks of Transformer.__call__ (vit.py:98-112).            */
 int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int batch);
 
+/* ---- training: forward that keeps its activations + backward -----
+ * Nothing in the reference trains (no jax.grad anywhere in vit_flax), so these have no reference
+ * counterpart; they are the two halves of jax.vjp(lambda p: ViT.apply(p, img), params).
+ * Built for the bf16 / fp16 modes, dropout rates 0, at most 208 tokens per image, dim <= 1280;
+ * anything else returns VITB200_ERR_UNSUPPORTED.  Activations (about 5.4 KB per token and layer for
+ * ViT-B) and one fp32 gradient per leaf are allocated for max_batch on the first call.           */
+int vitb200_train_forward(vitb200_model* m, void* stream, const float* images_dev, int batch,
+                          float* logits_dev);
+/* dlogits_dev: [batch, num_classes] fp32, the cotangent of the logits of the last train_forward.
+ * 16-bit intermediates: with fp16 operands scale dlogits up (and the gradients down) yourself
+ * when its entries are below ~1e-4 (loss scaling); gradients are linear in dlogits.             */
+int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits_dev, int batch);
+/* gradient of one leaf (flax path, same shape as the parameter) -> host; synchronises the stream */
+int vitb200_get_grad(vitb200_model* m, void* stream, const char* path, float* host_out);
+/* device pointer of the same gradient (valid until the model is destroyed; overwritten by backward) */
+int vitb200_grad_device(vitb200_model* m, const char* path, float** dev_out);
+
 /* ---- per-kernel entry points (unit parity tests, ncu) -------------------
  * All pointers are DEVICE pointers.                                         */
 
@@ -162,6 +179,7 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 #define VITB200_EPI_TOKENS_F32      5  /* A in token layout (row b*T+t; t = 0 the class-token slot):
                                         * C_f32[b*T+t] = t == 0 && cls ? cls + pos[0]
                                         *                              : acc + bias + pos[t]  (vit.py:147-153) */
+#define VITB200_EPI_BIAS_16         6  /* C_16 = acc + bias  (FF pre-activation kept for the backward pass) */
 
 /* tcgen05 GEMM: acc[M,N] = A[M,K] (16-bit row-major) x Wt[N,K]^T (16-bit row-major, i.e. the
  * transposed Flax kernel), fp32 accumulation in TMEM.  dtype = VITB200_DT_BF16 | _F16.
@@ -199,6 +217,14 @@ int vitb200_layernorm(void* stream, const float* x, const float* scale, const fl
 int vitb200_attention_tc(void* stream, const void* qkv, void* out, int batch, int T, int heads,
                          int dtype);
 int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads);
+
+/* adjoint of vitb200_attention_tc for T <= 208: (qkv, d_out [batch*T, heads*64]) -> dqkv [batch*T, 3*heads*64] */
+int vitb200_attention_bwd(void* stream, const void* qkv, const void* d_out, void* dqkv,
+                          int batch, int T, int heads, int dtype);
+/* adjoint of vitb200_layernorm: dx (+)= d/dx, dscale += , dbias += ; dy is 16-bit of `dtype`, dim <= 1280 */
+int vitb200_layernorm_bwd(void* stream, const void* dy, const float* x, const float* scale,
+                          float* dx, float* dscale, float* dbias, int rows, int dim, int dtype,
+                          float eps, int accumulate);
 
 /* patchify (vit.py:146): images [batch,H,W,C] fp32 -> patches [batch*Np, Kpad] of out_dtype,
  * feature f = (p1*pw + p2)*C + c, zero padded to Kpad. */

@@ -62,8 +62,7 @@ def _ff(x, p, dt=None):
     return _r(h, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"]                           # vit.py:51
 
 
-@torch.no_grad()
-def vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, depth,
+def _vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, depth,
                 heads, mlp_dim, pool="cls", operand_dtype=None):
     """``params_t``: the ``params`` sub-tree already converted by ``tree_to_torch``.
     ``operand_dtype`` (torch.bfloat16 / torch.float16 / None): emulate 16-bit GEMM operands."""
@@ -84,3 +83,30 @@ def vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, d
     x = x.mean(dim=1) if pool == "mean" else x[:, 0]                       # vit.py:159
     x = _ln(x, p["LayerNorm_0"])                                           # vit.py:163
     return _r(x, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"]   # vit.py:165
+
+
+vit_forward = torch.no_grad()(_vit_forward)
+
+
+def vit_vjp(variables, images, dlogits, *, dtype=torch.float64, **cfg):
+    """The checker of the backward pass: ``jax.vjp(lambda p: ViT.apply(p, img), params)[1](dlogits)``
+    restated as torch autograd (float64) through the forward above.  Returns ``(logits, grads)``
+    as numpy, ``grads`` a tree shaped like ``variables['params']``."""
+    tree = variables["params"] if "params" in variables else variables
+
+    def conv(t):
+        if isinstance(t, dict) or hasattr(t, "items"):
+            return {k: conv(v) for k, v in t.items()}
+        return torch.as_tensor(t).to(dtype).clone().requires_grad_(True)
+
+    p = conv(tree)
+    with torch.enable_grad():
+        logits = _vit_forward({"params": p}, images, **cfg)
+        (logits * torch.as_tensor(dlogits).to(dtype)).sum().backward()
+
+    def grads(t):
+        if isinstance(t, dict):
+            return {k: grads(v) for k, v in t.items()}
+        return (t.grad if t.grad is not None else torch.zeros_like(t)).detach().numpy()
+
+    return logits.detach().numpy(), grads(p)

@@ -1,0 +1,187 @@
+"""Backward pass on a real B200 against autograd through the CPU oracle.
+
+The reference never differentiates its forward, so the checker is ``oracle/vit_torch.vit_vjp``:
+float64 torch autograd through the restatement of vit.py (itself pinned by tests/test_oracle.py,
+including a finite-difference check of this function).  The CUDA path runs 16-bit GEMM operands
+and keeps 16-bit activations / activation gradients, so gradients are compared leaf by leaf as
+max|g - g_ref| / max|g_ref| with the tolerance stated in each test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_torch
+from vit_flax_b200 import ViT, _lib, init_params, perturb_params
+from vit_flax_b200._lib import VitB200Error
+from vit_flax_b200.engine import Engine
+from vit_flax_b200.params import flatten_params
+from vit_flax_b200.runtime import clear_cache
+from _util import C2, TINY, images_for
+
+pytestmark = pytest.mark.gpu
+
+DT16 = {"bf16": (_lib.DT_BF16, torch.bfloat16), "fp16": (_lib.DT_F16, torch.float16)}
+
+
+@pytest.fixture(scope="module")
+def lib(lib_built):
+    assert lib_built.vitb200_device_count() >= 1, "no sm_100 device"
+    return lib_built
+
+
+@pytest.fixture(autouse=True)
+def _fresh_cache():
+    yield
+    clear_cache()
+    torch.cuda.empty_cache()
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel_err(got, want):
+    want = np.asarray(want, dtype=np.float64)
+    return float(np.abs(np.asarray(got, dtype=np.float64) - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+@pytest.mark.parametrize("batch,T,heads", [(2, 197, 3), (1, 208, 1), (3, 64, 2), (2, 17, 2), (1, 100, 1), (40, 197, 12)])
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+def test_attention_bwd(lib, batch, T, heads, fmt):
+    """Adjoint of vit.py:69-79 per (image, head): dq, dk, dv from (q, k, v, d_out), all 16-bit."""
+    dt, tdt = DT16[fmt]
+    inner = heads * 64
+    g = torch.Generator().manual_seed(T * 7 + heads)
+    qkv = (torch.randn((batch * T, 3 * inner), generator=g) * 1.2).to(tdt).cuda()
+    d_out = torch.randn((batch * T, inner), generator=g).to(tdt).cuda()
+    dqkv = torch.full((batch * T, 3 * inner), 9.0, dtype=tdt, device="cuda")
+    _lib.check(lib.vitb200_attention_bwd(stream(), qkv.data_ptr(), d_out.data_ptr(), dqkv.data_ptr(), batch, T, heads, dt))
+    torch.cuda.synchronize()
+    x = qkv.double().view(batch, T, 3, heads, 64).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)   # [3, B, h, T, 64]
+    o = torch.softmax(x[0] @ x[1].transpose(-1, -2) / 8.0, dim=-1) @ x[2]                                      # vit.py:73-78
+    (o * d_out.double().view(batch, T, heads, 64).permute(0, 2, 1, 3)).sum().backward()
+    want = x.grad.permute(1, 3, 0, 2, 4).reshape(batch * T, 3 * inner)
+    assert torch.isfinite(dqkv.float()).all()
+    err = rel_err(dqkv.float().cpu().numpy(), want.cpu().numpy())
+    assert err < (1.5e-2 if fmt == "fp16" else 5e-2), err
+
+
+@pytest.mark.parametrize("rows,dim", [(300, 768), (65, 128), (10, 1280), (33, 192), (1, 64)])
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_layernorm_bwd(lib, rows, dim, accumulate):
+    dt, tdt = DT16["fp16"]
+    g = torch.Generator().manual_seed(rows + dim)
+    x = (torch.randn((rows, dim), generator=g) * 2 + 0.5).cuda()
+    gamma = (torch.randn(dim, generator=g) * 0.5 + 1).cuda()
+    dy = torch.randn((rows, dim), generator=g).to(tdt).cuda()
+    dx0 = torch.randn((rows, dim), generator=g).cuda()
+    dx = dx0.clone()
+    dgamma, dbeta = torch.full((dim,), 2.0, device="cuda"), torch.full((dim,), -1.0, device="cuda")
+    _lib.check(lib.vitb200_layernorm_bwd(stream(), dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), dx.data_ptr(),
+                                         dgamma.data_ptr(), dbeta.data_ptr(), rows, dim, dt, 1e-6, accumulate))
+    torch.cuda.synchronize()
+    xr = x.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    br = torch.zeros(dim, dtype=torch.float64, device="cuda", requires_grad=True)
+    (torch.nn.functional.layer_norm(xr, (dim,), gr, br, eps=1e-6) * dy.double()).sum().backward()
+    want_dx = xr.grad + (dx0.double() if accumulate else 0)
+    assert (dx.double() - want_dx).abs().max().item() < 2e-4 * max(1.0, want_dx.abs().max().item())
+    assert (dgamma.double() - 2.0 - gr.grad).abs().max().item() < 1e-4 * max(1.0, gr.grad.abs().max().item())   # accumulates
+    assert (dbeta.double() + 1.0 - br.grad).abs().max().item() < 1e-4 * max(1.0, br.grad.abs().max().item())
+
+
+def _check_grads(eng, variables, cfg, img, dl, pool, tol, logits):
+    want_logits, want = vit_torch.vit_vjp(variables, img, dl, pool=pool, **cfg)
+    assert np.abs(logits - want_logits).max() < (2e-2 if tol <= 2e-2 else 5e-2)      # forward tolerance of the format (test_gpu_forward.py)
+    got = eng.grads()
+    ref = flatten_params({"params": want})
+    assert set(got) == set(ref)
+    errs = {k: rel_err(got[k], ref[k]) for k in ref}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < tol, (worst, errs[worst], sorted(errs.items(), key=lambda kv: -kv[1])[:5])
+    return errs
+
+
+@pytest.mark.parametrize("pool", ["cls", "mean"])
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_backward_tiny(pool, precision):
+    """Every leaf of a small ViT (ragged everything: T = 17, dim 192, batch 5)."""
+    cfg = dict(image_size=32, patch_size=8, num_classes=24, dim=192, depth=2, heads=2, mlp_dim=256)
+    variables = perturb_params(init_params(seed=21, **cfg), seed=22)
+    img = images_for(cfg, 5, seed=23)
+    dl = np.random.default_rng(24).standard_normal((5, 24)).astype(np.float32)
+    eng = Engine(precision=precision, max_batch=8, pool=pool, **cfg)
+    eng.load_params(variables)
+    logits = eng.train_forward(torch.as_tensor(img, device="cuda"))
+    eng.backward(torch.as_tensor(dl, device="cuda"))
+    torch.cuda.synchronize()
+    _check_grads(eng, variables, cfg, img, dl, pool, 2e-2 if precision == "fp16" else 8e-2, logits.cpu().numpy())
+    # a second backward of the same forward gives the same gradients (buffers are re-zeroed, nothing accumulates)
+    g1 = eng.grads()
+    eng.backward(torch.as_tensor(dl, device="cuda"))
+    g2 = eng.grads()
+    for k in g1:
+        assert rel_err(g2[k], g1[k]) < 1e-5, k
+    eng.close()
+
+
+def test_backward_vit_b16_dims():
+    """ViT-B/16 geometry (T = 197, dim 768, 12 heads, mlp 3072) at depth 2, batch 4."""
+    cfg = dict(C2, depth=2)
+    variables = perturb_params(init_params(seed=31, **cfg), seed=32)
+    img = images_for(cfg, 4, seed=33)
+    dl = np.random.default_rng(34).standard_normal((4, 1000)).astype(np.float32)
+    eng = Engine(precision="fp16", max_batch=4, **cfg)
+    eng.load_params(variables)
+    x = torch.as_tensor(img, device="cuda")
+    logits = eng.train_forward(x)
+    eng.backward(torch.as_tensor(dl, device="cuda"))
+    torch.cuda.synchronize()
+    _check_grads(eng, variables, cfg, img, dl, "cls", 2e-2, logits.cpu().numpy())
+    assert np.abs(logits.cpu().numpy() - eng.forward(x).cpu().numpy()).max() < 5e-3      # train_forward == forward up to 16-bit rounding
+    eng.close()
+
+
+def test_vjp_api_and_loss_scaling():
+    """ViT.vjp mirrors jax.vjp(lambda p: v.apply(p, x), params); tiny cotangents survive fp16 through the scaling."""
+    cfg = dict(TINY)
+    v = ViT(**cfg)
+    variables = perturb_params(init_params(seed=41, **cfg), seed=42)
+    img = images_for(cfg, 3, seed=43)
+    dl = (np.random.default_rng(44).standard_normal((3, cfg["num_classes"])) * 1e-7).astype(np.float32)
+    logits, vjp_fn = v.vjp(variables, img)
+    assert isinstance(logits, np.ndarray) and logits.shape == (3, cfg["num_classes"])
+    grads = vjp_fn(dl)
+    _, want = vit_torch.vit_vjp(variables, img, dl, **cfg)
+    got, ref = flatten_params(grads), flatten_params({"params": want})
+    assert set(got) == set(ref)
+    for k in ref:
+        assert got[k].shape == ref[k].shape and got[k].dtype == np.float32
+        assert rel_err(got[k], ref[k]) < 2e-2, k
+    with pytest.raises(NotImplementedError):
+        ViT(dropout=0.1, **cfg).vjp(variables, img)
+    with pytest.raises(ValueError):
+        vjp_fn(dl[:2])
+
+
+def test_backward_errors():
+    cfg = dict(image_size=64, patch_size=4, num_classes=8, dim=64, depth=1, heads=2, mlp_dim=64)   # T = 257 > 208
+    eng = Engine(precision="fp16", max_batch=1, **cfg)
+    eng.load_params(init_params(seed=1, **cfg))
+    with pytest.raises(VitB200Error, match="208 tokens"):
+        eng.train_forward(torch.zeros((1, 64, 64, 3), device="cuda"))
+    eng.close()
+    eng = Engine(precision="fp16", max_batch=2, **TINY)
+    eng.load_params(init_params(seed=1, **TINY))
+    with pytest.raises(VitB200Error, match="train_forward first"):
+        eng.backward(torch.zeros((2, TINY["num_classes"]), device="cuda"))
+    eng.train_forward(torch.zeros((2, 32, 32, 3), device="cuda"))
+    with pytest.raises(VitB200Error, match="batch differs"):
+        eng.backward(torch.zeros((1, TINY["num_classes"]), device="cuda"))
+    eng.close()
+    eng = Engine(precision="fp32", max_batch=1, **TINY)
+    eng.load_params(init_params(seed=1, **TINY))
+    with pytest.raises(VitB200Error, match="bf16/fp16"):
+        eng.train_forward(torch.zeros((1, 32, 32, 3), device="cuda"))
+    eng.close()

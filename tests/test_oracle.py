@@ -171,3 +171,35 @@ def test_oracle_matches_third_party_vit_with_mapped_weights():
     got = vit_numpy.vit_forward(v, img, **cfg)
     assert np.abs(want).max() > 0.1                                            # a non-trivial comparison
     np.testing.assert_allclose(got, want, atol=1e-10)
+
+
+def test_vjp_oracle_matches_finite_differences():
+    """oracle/vit_torch.vit_vjp (float64 autograd through the restatement) is the checker of the CUDA
+    backward pass; pin it with central differences on a few entries of every kind of leaf."""
+    cfg = dict(image_size=16, patch_size=8, num_classes=8, dim=64, depth=2, heads=2, mlp_dim=96)
+    v = perturb_params(init_params(seed=51, **cfg), seed=52)
+    img = images_for(cfg, 2, seed=53)
+    dl = np.random.default_rng(54).standard_normal((2, 8))
+    for pool in ("cls", "mean"):
+        _, g = vit_torch.vit_vjp(v, img, dl, pool=pool, **cfg)
+        probes = [(("cls",), (0, 0, 5)), (("pos_embedding",), (0, 2, 7)), (("Dense_0", "kernel"), (17, 3)),
+                  (("Transformer_0", "Attention_1", "Dense_0", "kernel"), (4, 100)),
+                  (("Transformer_0", "PreNorm_1", "LayerNorm_0", "scale"), (9,)),
+                  (("Transformer_0", "FeedForward_0", "Dense_0", "bias"), (11,)), (("Dense_1", "kernel"), (6, 2))]
+        for path, idx in probes:
+            import copy
+            eps = 1e-5
+            vals = []
+            for sgn in (1, -1):
+                w = copy.deepcopy(v)
+                w64 = vit_torch.tree_to_torch(w, torch.float64)
+                node = w64["params"]
+                for k in path[:-1]:
+                    node = node[k]
+                node[path[-1]][idx] += sgn * eps
+                vals.append(float((vit_torch.vit_forward(w64, img, pool=pool, **cfg).numpy() * dl).sum()))
+            fd = (vals[0] - vals[1]) / (2 * eps)
+            ref = g
+            for k in path:
+                ref = ref[k]
+            assert abs(fd - ref[idx]) < 1e-6 * max(1.0, abs(fd)), (pool, path, fd, ref[idx])

@@ -20,7 +20,7 @@ PRECISIONS = {"bf16": PREC_BF16, "fp32": PREC_FP32, "fp16": PREC_FP16}
 POOL_CLS, POOL_MEAN = 0, 1
 CATEGORIES = ["patchify", "gemm_patch", "cls_rows", "layernorm", "gemm_qkv", "attention", "gemm_out",
               "gemm_ff1", "gemm_ff2", "pool_ln", "gemm_head"]
-EPI_STORE_16, EPI_BIAS_GELU_16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32, EPI_TOKENS_F32 = range(6)
+EPI_STORE_16, EPI_BIAS_GELU_16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32, EPI_TOKENS_F32, EPI_BIAS_16 = range(7)
 
 
 class Config(C.Structure):
@@ -64,6 +64,12 @@ SIGNATURES = {
     "vitb200_wait_host": (_i, [_vp]),
     "vitb200_profile_forward": (_i, [_vp, _vp, _fp, _i, _fp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vitb200_debug_tokens": (_i, [_vp, _vp, _fp, _i]),
+    "vitb200_train_forward": (_i, [_vp, _vp, _fp, _i, _fp]),
+    "vitb200_backward": (_i, [_vp, _vp, _fp, _i]),
+    "vitb200_get_grad": (_i, [_vp, _vp, C.c_char_p, _fp]),
+    "vitb200_grad_device": (_i, [_vp, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "vitb200_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "vitb200_layernorm_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, C.c_float, _i]),
     "vitb200_gemm_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i]),
     "vitb200_gemm_tc_dropout": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i, C.c_float, C.c_uint64, C.c_uint32]),
     "vitb200_gemm_tc_tokens": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _fp, _i, C.c_float, C.c_uint64, C.c_uint32]),

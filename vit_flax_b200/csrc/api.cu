@@ -32,6 +32,7 @@ struct DenseW {
   int leaf_kernel = -1, leaf_bias = -1;   // indices into leaves
   int K = 0, N = 0, Kpad = 0;
   uint16_t* wt = nullptr;                 // bf16/fp16 [N, Kpad] (tensor-core modes)
+  uint16_t* wf = nullptr;                 // bf16/fp16 [K, N], the Flax layout: the "W^T" operand of dX = dY W^T (backward only)
   CUtensorMap tm{};                       // box 256 x 64 over wt (one CTA per tile)
   CUtensorMap tm2{};                      // box 128 x 64 over wt (CTA pair per tile)
   CUtensorMap tm4{};                      // box 64 x 64 over wt (cluster of two pairs, multicast)
@@ -139,10 +140,26 @@ struct vitb200_model {
   cudaStream_t capture_stream = nullptr;
   uint64_t graph_clock = 0;
 
+  // training (train_forward / backward): activations kept per layer, gradient workspace, leaf gradients
+  struct TrainLayer { DevBuf<uint16_t> xn1, qkv, o, xn2, pre, hid; };
+  struct TrainState {
+    int fwd_batch = 0;                    // batch of the last train_forward (0 = none to differentiate)
+    std::vector<DevBuf<float>> xs;        // residual stream before every LayerNorm + after the last layer
+    std::vector<TrainLayer> layers;
+    DevBuf<float> dx, pooled_ln, dpl, zeros, grads;
+    DevBuf<uint16_t> dy16, dhid16, dxn16, do16, dqkv16, tA, tB;
+    std::vector<size_t> grad_off;         // per leaf: element offset into grads
+  };
+  std::unique_ptr<TrainState> train;
+
   ~vitb200_model() {
     for (auto& l : leaves)
       if (l.dev) cudaFree(l.dev);
-    auto free_dense = [](DenseW& d) { if (d.wt) cudaFree(d.wt); d.wt = nullptr; };
+    auto free_dense = [](DenseW& d) {
+      if (d.wt) cudaFree(d.wt);
+      if (d.wf) cudaFree(d.wf);
+      d.wt = d.wf = nullptr;
+    };
     free_dense(patch);
     free_dense(head);
     for (auto& L : layers) { free_dense(L.qkv); free_dense(L.out); free_dense(L.ff1); free_dense(L.ff2); }
@@ -272,6 +289,7 @@ int pack_dense(vitb200_model* m, DenseW& d, cudaStream_t st) {
     VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.wt), size_t(d.N) * d.Kpad * sizeof(uint16_t)));
   int rc = launch_pack_weight(st, m->leaves[d.leaf_kernel].dev, d.wt, d.K, d.N, d.Kpad, m->dt);
   if (rc) return rc;
+  if (d.wf && (rc = launch_cast16(st, m->leaves[d.leaf_kernel].dev, d.wf, int64_t(d.K) * d.N, m->dt))) return rc;
   if ((rc = make_tmap_2d(&d.tm, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN, m->dt))) return rc;
   if ((rc = make_tmap_2d(&d.tm2, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN / 2, m->dt))) return rc;
   return make_tmap_2d(&d.tm4, d.wt, d.N, d.Kpad, d.Kpad, GEMM_BN / 4, m->dt);
@@ -752,6 +770,217 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
   return 0;
 }
 
+// ---- training: a forward that keeps its activations, and the backward pass ----
+// Nothing in the reference trains, so there is no reference API to mirror; the C entry points are
+// the two halves of jax.vjp(lambda p: ViT.apply(p, img), params): train_forward returns the logits,
+// backward takes their cotangent and fills one fp32 gradient per parameter leaf.
+namespace {
+
+inline float* grad_ptr(vitb200_model* m, int leaf) { return leaf >= 0 ? m->train->grads.p + m->train->grad_off[leaf] : nullptr; }
+
+// C[c_rows <= M, N] = epilogue(A[M, K] x Wt[N, ldw]^T) with tensor maps encoded per call (host side, ~1 us each)
+int gemm16(vitb200_model* m, cudaStream_t st, const void* A, int M, int K, const void* Wt, int ldw, int N, void* C,
+           int c_rows, int epi, const float* bias, const float* aux = nullptr, int tpi = 0, const float* cls = nullptr) {
+  CUtensorMap ta, tb, tc;
+  int rc;
+  const int cg = gemm_tc_tile_mode(M, N);
+  const bool out16 = epi == VITB200_EPI_STORE_16 || epi == VITB200_EPI_BIAS_GELU_16 || epi == VITB200_EPI_BIAS_16;
+  if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, m->dt))) return rc;
+  if ((rc = make_tmap_2d(&tb, Wt, N, ldw, ldw, cg == 64 ? 64 : GEMM_BN / cg, m->dt))) return rc;
+  if ((rc = make_tmap_2d(&tc, C, c_rows, N, N, GEMM_BM, out16 ? m->dt : VITB200_DT_F32))) return rc;
+  return launch_gemm_tc(st, ta, tb, &tc, bias, C, M, N, K, epi, aux, tpi, m->dt, cg, Dropout(), m->cls_off, cls);
+}
+
+// dW[Dx (first c_rows rows), Dy] += X[R, Dx]^T dY[R, Dy]: both operands transposed into K-major scratch
+// (zero padded to a multiple of 64 rows), then one GEMM whose epilogue reduce-adds into the gradient leaf
+int wgrad(vitb200_model* m, cudaStream_t st, const void* X, int Dx, const void* dY, int Dy, int R, float* dW, int c_rows) {
+  auto& ts = *m->train;
+  const int Rpad = int(round_up(R, 64));
+  int rc;
+  if ((rc = launch_transpose16(st, X, ts.tA.p, R, Dx, Rpad))) return rc;
+  if ((rc = launch_transpose16(st, dY, ts.tB.p, R, Dy, Rpad))) return rc;
+  return gemm16(m, st, ts.tA.p, Dx, Rpad, ts.tB.p, Rpad, Dy, dW, c_rows, VITB200_EPI_BIAS_RESID_F32, ts.zeros.p);
+}
+
+int train_supported(const vitb200_model* m) {
+  const auto& c = m->cfg;
+  if (!m->tc) return fail(VITB200_ERR_UNSUPPORTED, "train: the backward pass is built for the bf16/fp16 modes only");
+  if (c.dropout > 0.f || c.emb_dropout > 0.f) return fail(VITB200_ERR_UNSUPPORTED, "train: dropout > 0 is not built for the backward pass");
+  if (!m->project_out) return fail(VITB200_ERR_UNSUPPORTED, "train: heads == 1 with dim == 64 (identity to_out) is not built");
+  if (m->T > attention_bwd_max_tokens()) return fail(VITB200_ERR_UNSUPPORTED, "train: more than 208 tokens per image is not built for the backward pass");
+  if (c.dim > 1280) return fail(VITB200_ERR_UNSUPPORTED, "train: dim > 1280 is not built for the backward pass");
+  return 0;
+}
+
+int ensure_train(vitb200_model* m, cudaStream_t st) {
+  if (m->train) return 0;
+  const auto& c = m->cfg;
+  std::unique_ptr<vitb200_model::TrainState> ts(new vitb200_model::TrainState());
+  const size_t B = size_t(c.max_batch), R = B * m->T, Rpad = size_t(round_up(int64_t(R), 64));
+  const size_t D = size_t(c.dim), I = size_t(m->inner), H = size_t(c.mlp_dim);
+  int rc;
+  ts->xs.resize(2 * size_t(c.depth) + 1);
+  for (auto& x : ts->xs) if ((rc = x.alloc(R * D))) return rc;
+  ts->layers.resize(size_t(c.depth));
+  for (auto& L : ts->layers) {
+    if ((rc = L.xn1.alloc(R * D)) || (rc = L.qkv.alloc(R * 3 * I)) || (rc = L.o.alloc(R * I)) ||
+        (rc = L.xn2.alloc(R * D)) || (rc = L.pre.alloc(R * H)) || (rc = L.hid.alloc(R * H))) return rc;
+  }
+  if ((rc = ts->dx.alloc(R * D)) || (rc = ts->pooled_ln.alloc(B * D)) || (rc = ts->dpl.alloc(B * D))) return rc;
+  if ((rc = ts->dy16.alloc(R * D)) || (rc = ts->dhid16.alloc(R * H)) || (rc = ts->dxn16.alloc(R * D)) ||
+      (rc = ts->do16.alloc(R * I)) || (rc = ts->dqkv16.alloc(R * 3 * I))) return rc;
+  const size_t dx_max = std::max(std::max(H, D), std::max(I, size_t(m->K0pad))), dy_max = std::max(std::max(H, D), 3 * I);
+  if ((rc = ts->tA.alloc(dx_max * Rpad)) || (rc = ts->tB.alloc(dy_max * Rpad))) return rc;
+  const size_t nz = std::max(std::max(dx_max, dy_max), size_t(c.num_classes));
+  if ((rc = ts->zeros.alloc(nz))) return rc;
+  VB_CUDA(cudaMemsetAsync(ts->zeros.p, 0, nz * sizeof(float), st));
+  size_t total = 0;
+  for (const auto& l : m->leaves) {
+    ts->grad_off.push_back(total);
+    total += size_t(round_up(l.numel(), 64));        // 256-byte aligned leaves (TMA reduce-add targets)
+  }
+  if ((rc = ts->grads.alloc(total))) return rc;
+  VB_CUDA(cudaMemsetAsync(ts->grads.p, 0, total * sizeof(float), st));
+  // Flax-layout 16-bit weight copies for the dgrad GEMMs
+  auto make_wf = [&](DenseW& d) -> int {
+    if (d.leaf_kernel < 0) return 0;
+    VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.wf), size_t(d.K) * d.N * sizeof(uint16_t)));
+    return launch_cast16(st, m->leaves[d.leaf_kernel].dev, d.wf, int64_t(d.K) * d.N, m->dt);
+  };
+  for (auto& L : m->layers)
+    if ((rc = make_wf(L.qkv)) || (rc = make_wf(L.out)) || (rc = make_wf(L.ff1)) || (rc = make_wf(L.ff2))) return rc;
+  m->train = std::move(ts);
+  return 0;
+}
+
+}  // namespace
+
+int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, int batch, float* logits) {
+  if (!m || !images || !logits) return fail(VITB200_ERR_INVALID, "train_forward: null argument");
+  if (!m->finalized) return fail(VITB200_ERR_PARAM_MISSING, "train_forward: call finalize_params first");
+  if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "train_forward: batch must be in [1, max_batch]");
+  int rc;
+  if ((rc = train_supported(m))) return rc;
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_train(m, st))) return rc;
+  auto& ts = *m->train;
+  ts.fwd_batch = 0;
+  const auto& c = m->cfg;
+  const int D = c.dim, I = m->inner, T = m->T, H = c.mlp_dim, R = batch * T;
+  const size_t xbytes = size_t(R) * D * sizeof(float);
+  if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels, c.patch_h, c.patch_w,
+                            m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
+  if ((rc = gemm16(m, st, m->patches_h.p, R, m->K0pad, m->patch.wt, m->patch.Kpad, D, ts.xs[0].p, R, VITB200_EPI_TOKENS_F32,
+                   leaf_ptr(m, m->patch.leaf_bias), leaf_ptr(m, m->leaf_pos), T, leaf_ptr(m, m->leaf_cls)))) return rc;
+  for (int l = 0; l < c.depth; ++l) {
+    Layer& L = m->layers[l];
+    auto& S = ts.layers[l];
+    float* x0 = ts.xs[2 * l].p;
+    float* x1 = ts.xs[2 * l + 1].p;
+    float* x2 = ts.xs[2 * l + 2].p;
+    // x1 = x0 + to_out(attention(to_qkv(LN1(x0))));  x0 stays behind as the saved LayerNorm input
+    if ((rc = launch_layernorm(st, x0, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), S.xn1.p, R, D, m->dt, m->eps))) return rc;
+    VB_CUDA(cudaMemcpyAsync(x1, x0, xbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = gemm16(m, st, S.xn1.p, R, D, L.qkv.wt, L.qkv.Kpad, 3 * I, S.qkv.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
+    if ((rc = launch_attention_tc(st, S.qkv.p, S.o.p, batch, T, c.heads, m->dt))) return rc;
+    if ((rc = gemm16(m, st, S.o.p, R, I, L.out.wt, L.out.Kpad, D, x1, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.out.leaf_bias)))) return rc;
+    // x2 = x1 + ff2(gelu(ff1(LN2(x1)))), the pre-activation kept for gelu'
+    if ((rc = launch_layernorm(st, x1, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), S.xn2.p, R, D, m->dt, m->eps))) return rc;
+    VB_CUDA(cudaMemcpyAsync(x2, x1, xbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = gemm16(m, st, S.xn2.p, R, D, L.ff1.wt, L.ff1.Kpad, H, S.pre.p, R, VITB200_EPI_BIAS_16, leaf_ptr(m, L.ff1.leaf_bias)))) return rc;
+    if ((rc = launch_gelu_fwd(st, S.pre.p, S.hid.p, int64_t(R) * H, m->dt))) return rc;
+    if ((rc = gemm16(m, st, S.hid.p, R, H, L.ff2.wt, L.ff2.Kpad, D, x2, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.ff2.leaf_bias)))) return rc;
+  }
+  const float* xf = ts.xs[2 * size_t(c.depth)].p;
+  if ((rc = launch_pool_layernorm(st, xf, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), ts.pooled_ln.p,
+                                  batch, T, D, c.pool, VITB200_DT_F32, m->eps))) return rc;
+  if (m->head_tc) {
+    if ((rc = launch_pool_layernorm(st, xf, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p,
+                                    batch, T, D, c.pool, m->dt, m->eps))) return rc;
+    if ((rc = gemm16(m, st, m->pooled_h.p, batch, D, m->head.wt, m->head.Kpad, c.num_classes, logits, batch, VITB200_EPI_BIAS_F32,
+                     leaf_ptr(m, m->head.leaf_bias)))) return rc;
+  } else {
+    if ((rc = launch_gemm_f32(st, ts.pooled_ln.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits,
+                              batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
+  }
+  ts.fwd_batch = batch;
+  return 0;
+}
+
+int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int batch) {
+  if (!m || !dlogits) return fail(VITB200_ERR_INVALID, "backward: null argument");
+  if (!m->train || m->train->fwd_batch == 0) return fail(VITB200_ERR_INVALID, "backward: call train_forward first");
+  if (batch != m->train->fwd_batch) return fail(VITB200_ERR_INVALID, "backward: batch differs from the last train_forward");
+  if (!m->finalized) return fail(VITB200_ERR_PARAM_MISSING, "backward: parameters changed since train_forward");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto& ts = *m->train;
+  const auto& c = m->cfg;
+  const int D = c.dim, I = m->inner, T = m->T, H = c.mlp_dim, R = batch * T, dt = m->dt;
+  int rc;
+  VB_CUDA(cudaMemsetAsync(ts.grads.p, 0, ts.grads.n * sizeof(float), st));
+  // head: logits = LN(pool(x)) Wh + bh   (vit.py:159-165)
+  if ((rc = launch_head_bwd(st, ts.pooled_ln.p, dlogits, leaf_ptr(m, m->head.leaf_kernel), grad_ptr(m, m->head.leaf_kernel),
+                            grad_ptr(m, m->head.leaf_bias), ts.dpl.p, batch, D, c.num_classes))) return rc;
+  if ((rc = launch_pool_ln_bwd(st, ts.xs[2 * size_t(c.depth)].p, ts.dpl.p, leaf_ptr(m, m->leaf_head_scale), ts.dx.p,
+                               grad_ptr(m, m->leaf_head_scale), grad_ptr(m, m->leaf_head_bias), batch, T, D, c.pool, m->eps))) return rc;
+  for (int l = c.depth - 1; l >= 0; --l) {
+    Layer& L = m->layers[l];
+    auto& S = ts.layers[l];
+    // ---- x2 = x1 + Dense_1(gelu(Dense_0(LN2(x1))))   (vit.py:39,47-53) ----
+    if ((rc = launch_cast16(st, ts.dx.p, ts.dy16.p, int64_t(R) * D, dt))) return rc;
+    if ((rc = launch_colsum(st, ts.dx.p, grad_ptr(m, L.ff2.leaf_bias), R, D, VITB200_DT_F32))) return rc;
+    if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.ff2.wf, D, H, ts.dhid16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
+    if ((rc = wgrad(m, st, S.hid.p, H, ts.dy16.p, D, R, grad_ptr(m, L.ff2.leaf_kernel), H))) return rc;
+    if ((rc = launch_gelu_bwd(st, S.pre.p, ts.dhid16.p, ts.dhid16.p, int64_t(R) * H, dt))) return rc;
+    if ((rc = launch_colsum(st, ts.dhid16.p, grad_ptr(m, L.ff1.leaf_bias), R, H, dt))) return rc;
+    if ((rc = gemm16(m, st, ts.dhid16.p, R, H, L.ff1.wf, H, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
+    if ((rc = wgrad(m, st, S.xn2.p, D, ts.dhid16.p, H, R, grad_ptr(m, L.ff1.leaf_kernel), D))) return rc;
+    if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l + 1].p, leaf_ptr(m, L.ln2_scale), ts.dx.p, grad_ptr(m, L.ln2_scale),
+                            grad_ptr(m, L.ln2_bias), R, D, dt, m->eps, 1))) return rc;
+    // ---- x1 = x0 + to_out(attention(to_qkv(LN1(x0))))   (vit.py:39,62-87) ----
+    if ((rc = launch_cast16(st, ts.dx.p, ts.dy16.p, int64_t(R) * D, dt))) return rc;
+    if ((rc = launch_colsum(st, ts.dx.p, grad_ptr(m, L.out.leaf_bias), R, D, VITB200_DT_F32))) return rc;
+    if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.out.wf, D, I, ts.do16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
+    if ((rc = wgrad(m, st, S.o.p, I, ts.dy16.p, D, R, grad_ptr(m, L.out.leaf_kernel), I))) return rc;
+    if ((rc = launch_attention_bwd(st, S.qkv.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt))) return rc;
+    if ((rc = gemm16(m, st, ts.dqkv16.p, R, 3 * I, L.qkv.wf, 3 * I, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
+    if ((rc = wgrad(m, st, S.xn1.p, D, ts.dqkv16.p, 3 * I, R, grad_ptr(m, L.qkv.leaf_kernel), D))) return rc;
+    if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l].p, leaf_ptr(m, L.ln1_scale), ts.dx.p, grad_ptr(m, L.ln1_scale),
+                            grad_ptr(m, L.ln1_bias), R, D, dt, m->eps, 1))) return rc;
+  }
+  // ---- tokens = concat(cls, patches W + b) + pos   (vit.py:147-153) ----
+  if ((rc = launch_token_grads(st, ts.dx.p, grad_ptr(m, m->leaf_pos), grad_ptr(m, m->leaf_cls), grad_ptr(m, m->patch.leaf_bias),
+                               batch, T, D, m->cls_off))) return rc;
+  if ((rc = launch_cast16(st, ts.dx.p, ts.dy16.p, int64_t(R) * D, dt))) return rc;
+  // the class-token slot rows of the patch matrix are zero, so their dx rows add nothing to dW
+  if ((rc = wgrad(m, st, m->patches_h.p, m->K0pad, ts.dy16.p, D, R, grad_ptr(m, m->patch.leaf_kernel), m->K0))) return rc;
+  return 0;
+}
+
+int vitb200_get_grad(vitb200_model* m, void* stream, const char* path, float* host_out) {
+  if (!m || !path || !host_out) return fail(VITB200_ERR_INVALID, "get_grad: null argument");
+  if (!m->train) return fail(VITB200_ERR_INVALID, "get_grad: no backward pass has run");
+  auto it = m->index.find(path);
+  if (it == m->index.end()) return fail(VITB200_ERR_INVALID, std::string("get_grad: unknown parameter path '") + path + "'");
+  DeviceGuard guard(m->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VB_CUDA(cudaMemcpyAsync(host_out, grad_ptr(m, it->second), size_t(m->leaves[it->second].numel()) * sizeof(float),
+                          cudaMemcpyDeviceToHost, st));
+  VB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int vitb200_grad_device(vitb200_model* m, const char* path, float** dev_out) {
+  if (!m || !path || !dev_out) return fail(VITB200_ERR_INVALID, "grad_device: null argument");
+  if (!m->train) return fail(VITB200_ERR_INVALID, "grad_device: no backward pass has run");
+  auto it = m->index.find(path);
+  if (it == m->index.end()) return fail(VITB200_ERR_INVALID, std::string("grad_device: unknown parameter path '") + path + "'");
+  *dev_out = grad_ptr(m, it->second);
+  return 0;
+}
+
 // ---- per-kernel entry points ------------------------------------------------
 int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N,
                     int K, int epilogue, const float* aux, int tokens_per_image, int dtype) {
@@ -789,7 +1018,7 @@ int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const fl
   if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, dtype))) return rc;
   const int cg = gemm_tc_tile_mode(M, N);
   if ((rc = make_tmap_2d(&tb, Wt, N, K, K, cg == 64 ? 64 : GEMM_BN / cg, dtype))) return rc;
-  const bool out16 = epilogue == VITB200_EPI_STORE_16 || epilogue == VITB200_EPI_BIAS_GELU_16;
+  const bool out16 = epilogue == VITB200_EPI_STORE_16 || epilogue == VITB200_EPI_BIAS_GELU_16 || epilogue == VITB200_EPI_BIAS_16;
   const bool direct = epilogue == VITB200_EPI_PATCH_F32;
   if (!direct && (rc = make_tmap_2d(&tc, C, M, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
   return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, direct ? nullptr : &tc, bias, C, M, N, K, epilogue,
@@ -816,6 +1045,19 @@ int vitb200_attention_tc(void* stream, const void* qkv, void* out, int batch, in
 int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads) {
   if (!qkv || !out) return fail(VITB200_ERR_INVALID, "attention_f32: null pointer");
   return launch_attention_f32(static_cast<cudaStream_t>(stream), qkv, out, batch, T, heads);
+}
+
+int vitb200_attention_bwd(void* stream, const void* qkv, const void* d_out, void* dqkv, int batch, int T, int heads,
+                          int dtype) {
+  if (!qkv || !d_out || !dqkv) return fail(VITB200_ERR_INVALID, "attention_bwd: null pointer");
+  return launch_attention_bwd(static_cast<cudaStream_t>(stream), qkv, d_out, dqkv, batch, T, heads, dtype);
+}
+
+int vitb200_layernorm_bwd(void* stream, const void* dy, const float* x, const float* scale, float* dx, float* dscale,
+                          float* dbias, int rows, int dim, int dtype, float eps, int accumulate) {
+  if (!dy || !x || !scale || !dx || !dscale || !dbias) return fail(VITB200_ERR_INVALID, "layernorm_bwd: null pointer");
+  return launch_ln_bwd(static_cast<cudaStream_t>(stream), dy, x, scale, dx, dscale, dbias, rows, dim, dtype,
+                       eps > 0.f ? eps : 1e-6f, accumulate);
 }
 
 int vitb200_patchify(void* stream, const float* images, void* patches, int batch, int H, int W, int C, int ph,

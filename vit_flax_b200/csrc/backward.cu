@@ -1,0 +1,689 @@
+// backward.cu -- kernels of the backward pass: everything that is not a GEMM.
+//
+// The reference never differentiates its forward (nothing in vit_flax trains), so there is no
+// reference code to cite beyond the forward lines each kernel is the adjoint of:
+//   attention_bwd_kernel   adjoint of vit.py:69-79 (softmax(q k^T / 8) v per image and head)
+//   ln_bwd_kernel          adjoint of nn.LayerNorm() (vit.py:31,163)
+//   gelu_fwd / gelu_bwd    nn.gelu (tanh form, vit.py:49) on the stored pre-activation
+//   pool_ln_bwd_kernel     adjoint of vit.py:159-163 (cls / mean pool + LayerNorm)
+//   token_grad kernels     adjoint of vit.py:151-153 (cls concat + pos_embedding broadcast over the batch)
+//   transpose16 / cast16 / colsum: operand preparation for the weight-gradient GEMMs and the bias gradients
+// The GEMMs (dgrad: dX = dY W^T, wgrad: dW = X^T dY) run on the tcgen05 kernel of gemm_tc.cu.
+#include <algorithm>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vb {
+
+namespace {
+
+template <int kDT>
+__device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
+  lo = to_f32<kDT>(uint16_t(v & 0xFFFFu));
+  hi = to_f32<kDT>(uint16_t(v >> 16));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ elementwise
+template <int kDT>
+__global__ void __launch_bounds__(256)
+cast16_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int64_t n8) {   // n8 = elements / 8
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+    uint4 o;
+    o.x = pack2<kDT>(a.x, a.y); o.y = pack2<kDT>(a.z, a.w);
+    o.z = pack2<kDT>(b.x, b.y); o.w = pack2<kDT>(b.z, b.w);
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+
+__device__ __forceinline__ float gelu_tanh_ref(float x) {   // nn.gelu default (vit.py:49)
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.0f + tanhf(k0 * x * fmaf(k1 * x, x, 1.0f)));
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float t = tanhf(k0 * x * fmaf(k1 * x, x, 1.0f));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * fmaf(3.0f * k1 * x, x, 1.0f);
+}
+
+template <int kDT, bool kBwd>
+__global__ void __launch_bounds__(256)
+gelu_kernel(const uint16_t* __restrict__ pre, const uint16_t* __restrict__ dhid, uint16_t* __restrict__ out, int64_t n8) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+    const uint4 p = reinterpret_cast<const uint4*>(pre)[i];
+    uint4 d = make_uint4(0, 0, 0, 0);
+    if constexpr (kBwd) d = reinterpret_cast<const uint4*>(dhid)[i];
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w}, dw[4] = {d.x, d.y, d.z, d.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a, b;
+      unpack2<kDT>(pw[j], a, b);
+      if constexpr (kBwd) {
+        float da, db;
+        unpack2<kDT>(dw[j], da, db);
+        ow[j] = pack2<kDT>(da * gelu_tanh_grad(a), db * gelu_tanh_grad(b));
+      } else {
+        ow[j] = pack2<kDT>(gelu_tanh_ref(a), gelu_tanh_ref(b));
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
+// out[c, r] = in[r, c] for r < rows, 0 for rows <= r < rows_pad  (16-bit elements, 64x64 tiles)
+__global__ void __launch_bounds__(256)
+transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int rows, int cols, int rows_pad) {
+  __shared__ uint16_t tile[64][66];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + 2 * tx;
+    uint32_t v = 0;
+    if (r < rows && c < cols) v = *reinterpret_cast<const uint32_t*>(in + int64_t(r) * cols + c);   // cols is even
+    tile[ty + i * 8][2 * tx] = uint16_t(v & 0xFFFFu);
+    tile[ty + i * 8][2 * tx + 1] = uint16_t(v >> 16);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + 2 * tx;
+    if (c < cols && r < rows_pad) {
+      const uint32_t v = uint32_t(tile[2 * tx][ty + i * 8]) | (uint32_t(tile[2 * tx + 1][ty + i * 8]) << 16);
+      *reinterpret_cast<uint32_t*>(out + int64_t(c) * rows_pad + r) = v;      // rows_pad is even
+    }
+  }
+}
+
+// out[c] += sum_r in[r, c]   (bias gradients); two columns per thread, rows strided over blockIdx.y
+template <int kDT>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * tx;
+  float a = 0.f, b = 0.f;
+  if (c < cols) {
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+      if constexpr (kDT == DT_F32) {
+        const float2 v = *reinterpret_cast<const float2*>(static_cast<const float*>(in) + int64_t(r) * cols + c);
+        a += v.x; b += v.y;
+      } else {
+        float x, y;
+        unpack2<kDT>(*reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(in) + int64_t(r) * cols + c), x, y);
+        a += x; b += y;
+      }
+    }
+  }
+  red[ty][2 * tx] = a;
+  red[ty][2 * tx + 1] = b;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { a += red[j][2 * tx]; b += red[j][2 * tx + 1]; }
+    atomicAdd(out + c, a);
+    atomicAdd(out + c + 1, b);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dx[r,:] += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum_r dy * xhat,
+// dbeta += sum_r dy.  One warp per row; every lane owns columns lane + 32 k and keeps its share of
+// dgamma / dbeta in registers over all the rows of the warp.
+constexpr int LN_KMAX = 40;   // dim <= 1280
+
+template <int kDT>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+              float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim,
+              float eps, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float gam[LN_KMAX], ag[LN_KMAX], ab[LN_KMAX];
+#pragma unroll
+  for (int k = 0; k < LN_KMAX; ++k) {
+    const int c = lane + 32 * k;
+    gam[k] = c < dim ? gamma[c] : 0.f;
+    ag[k] = 0.f;
+    ab[k] = 0.f;
+  }
+  const float inv_d = 1.0f / float(dim);
+  for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+    const float* xr = x + int64_t(r) * dim;
+    const uint16_t* dr = dy + int64_t(r) * dim;
+    float xv[LN_KMAX], dv[LN_KMAX];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_KMAX; ++k) {
+      const int c = lane + 32 * k;
+      xv[k] = c < dim ? xr[c] : 0.f;
+      dv[k] = c < dim ? to_f32<kDT>(dr[c]) : 0.f;
+      s += xv[k];
+      ss += xv[k] * xv[k];
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const float mean = s * inv_d;
+    const float rstd = rsqrtf(fmaxf(0.f, ss * inv_d - mean * mean) + eps);   // flax: var = max(0, E[x^2] - E[x]^2)
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_KMAX; ++k) {
+      const float xh = (xv[k] - mean) * rstd, g = dv[k] * gam[k];
+      xv[k] = xh;
+      a += g;
+      b += g * xh;
+      ag[k] += dv[k] * xh;     // zero beyond dim (dv = 0)
+      ab[k] += dv[k];
+    }
+    a = warp_sum(a) * inv_d;
+    b = warp_sum(b) * inv_d;
+    float* dxr = dx + int64_t(r) * dim;
+#pragma unroll
+    for (int k = 0; k < LN_KMAX; ++k) {
+      const int c = lane + 32 * k;
+      if (c < dim) {
+        const float v = rstd * (dv[k] * gam[k] - a - xv[k] * b);
+        dxr[c] = accumulate ? dxr[c] + v : v;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LN_KMAX; ++k) {
+    const int c = lane + 32 * k;
+    if (c < dim) {
+      atomicAdd(dgamma + c, ag[k]);
+      atomicAdd(dbeta + c, ab[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ head: pool + LayerNorm backward
+// One block per image.  pooled = x[b, 0] (cls) or mean_t x[b, t]; dpl = gradient wrt LayerNorm(pooled).
+// Writes the whole dx of the image: cls -> row 0 gets the pooled gradient, the others 0; mean -> every
+// row gets 1/T of it.
+__global__ void __launch_bounds__(256)
+pool_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dpl, const float* __restrict__ gamma,
+                   float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int dim,
+                   int pool_mean, float eps) {
+  extern __shared__ float sh[];          // pooled[dim], g[dim], red[64]
+  float* pooled = sh;
+  float* gv = sh + dim;
+  float* red = sh + 2 * dim;
+  const int b = blockIdx.x;
+  const float* xb = x + int64_t(b) * T * dim;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float v;
+    if (pool_mean) {
+      v = 0.f;
+      for (int t = 0; t < T; ++t) v += xb[int64_t(t) * dim + c];
+      v /= float(T);
+    } else {
+      v = xb[c];
+    }
+    pooled[c] = v;
+  }
+  __syncthreads();
+  auto block_sum2 = [&](float& a, float& c2) {
+    a = warp_sum(a);
+    c2 = warp_sum(c2);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) { red[w] = a; red[32 + w] = c2; }
+    __syncthreads();
+    float ra = 0.f, rc = 0.f;
+    for (int i = 0; i < int(blockDim.x >> 5); ++i) { ra += red[i]; rc += red[32 + i]; }
+    a = ra;
+    c2 = rc;
+  };
+  float s = 0.f, ss = 0.f;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) { s += pooled[c]; ss += pooled[c] * pooled[c]; }
+  block_sum2(s, ss);
+  const float mean = s / float(dim);
+  const float rstd = rsqrtf(fmaxf(0.f, ss / float(dim) - mean * mean) + eps);
+  float a = 0.f, bb = 0.f;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    const float xh = (pooled[c] - mean) * rstd, d = dpl[int64_t(b) * dim + c], g = d * gamma[c];
+    pooled[c] = xh;
+    gv[c] = g;
+    a += g;
+    bb += g * xh;
+    atomicAdd(dgamma + c, d * xh);
+    atomicAdd(dbeta + c, d);
+  }
+  block_sum2(a, bb);
+  a /= float(dim);
+  bb /= float(dim);
+  __syncthreads();
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) gv[c] = rstd * (gv[c] - a - pooled[c] * bb) * (pool_mean ? 1.0f / float(T) : 1.0f);
+  __syncthreads();
+  float* dxb = dx + int64_t(b) * T * dim;
+  for (int64_t i = threadIdx.x; i < int64_t(T) * dim; i += blockDim.x) {
+    const int t = int(i / dim), c = int(i - int64_t(t) * dim);
+    dxb[i] = (pool_mean || t == 0) ? gv[c] : 0.f;
+  }
+}
+
+// head Dense backward (fp32, tiny): dW[d, c] += sum_b pl[b, d] dl[b, c];  dpl[b, d] = sum_c dl[b, c] W[d, c]
+__global__ void __launch_bounds__(256)
+head_wgrad_kernel(const float* __restrict__ pl, const float* __restrict__ dl, float* __restrict__ dW, int batch,
+                  int dim, int classes) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y;
+  if (c >= classes) return;
+  float acc = 0.f;
+  for (int b = 0; b < batch; ++b) acc += pl[int64_t(b) * dim + d] * dl[int64_t(b) * classes + c];
+  dW[int64_t(d) * classes + c] += acc;
+}
+__global__ void __launch_bounds__(256)
+head_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ W, float* __restrict__ dpl, int batch,
+                  int dim, int classes) {
+  // one warp per (b, d): lanes stride over the classes
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= batch * dim) return;
+  const int b = gw / dim, d = gw - b * dim;
+  float acc = 0.f;
+  for (int c = lane; c < classes; c += 32) acc += dl[int64_t(b) * classes + c] * W[int64_t(d) * classes + c];
+  acc = warp_sum(acc);
+  if (lane == 0) dpl[gw] = acc;
+}
+
+// ------------------------------------------------------------------ token gradients
+// dpos[t, d] += sum_b dx[b, t, d]
+__global__ void __launch_bounds__(256)
+pos_grad_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int batch, int T, int dim) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (d >= dim) return;
+  float acc = 0.f;
+  for (int b = 0; b < batch; ++b) acc += dx[(int64_t(b) * T + t) * dim + d];
+  dpos[int64_t(t) * dim + d] += acc;
+}
+// after pos_grad on a zeroed dpos: dcls = dpos[0] (cls_off = 1), dbias = sum_{t >= cls_off} dpos[t]
+__global__ void __launch_bounds__(256)
+cls_bias_grad_kernel(const float* __restrict__ dpos, float* __restrict__ dcls, float* __restrict__ dbias, int T,
+                     int dim, int cls_off) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dim) return;
+  float acc = 0.f;
+  for (int t = cls_off; t < T; ++t) acc += dpos[int64_t(t) * dim + d];
+  dbias[d] += acc;
+  if (cls_off && dcls) dcls[d] += dpos[d];
+}
+
+// ------------------------------------------------------------------ attention backward
+// One CTA per (image, head), T <= 208.  q, k, v, dO tiles and the T x T probability matrix live in
+// shared memory; all five matmuls run on mma.sync with ldmatrix operands:
+//   A   P = softmax(q k^T / 8)                       -> smem (16-bit)
+//   A2  dV = P^T dO                                  (P read transposed)
+//   B   dP = dO v^T;  D_i = sum_j P_ij dP_ij;  dS = P o (dP - D) / 8 -> smem (over P);  dQ = dS k
+//   C   dK = dS^T q
+// Padded query rows carry dO = 0, padded key columns P = 0, so neither contributes.
+constexpr int DH = 64;
+constexpr int ROW_BYTES = DH * 2;
+constexpr int ABW_MAX_T = 208;
+constexpr int ABW_MAX_NT = ABW_MAX_T / 8;     // 26 score n-tiles of 8 keys
+
+__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
+  return base + uint32_t(row) * ROW_BYTES + (uint32_t(chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void load_rows(uint32_t sbase, const uint16_t* g, int64_t ld, int nrows, int row_limit) {
+  for (int i = threadIdx.x; i < nrows * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    const bool ok = r < row_limit;
+    cp_async16(swz(sbase, r, c), g + int64_t(ok ? r : 0) * ld + c * 8, ok);
+  }
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// acc[8][4] (16 rows x 64 columns) = M^T[rows m0.., all q] . X[q, 64], M = the smem score matrix
+template <int kDT>
+__device__ __forceinline__ void mma_transposed_scores(float (&acc)[8][4], uint32_t sP, int pitch, int m0, uint32_t sX,
+                                                      int nblk, int lane) {
+  const int mi = lane >> 3, r = lane & 7;
+  for (int qs = 0; qs < nblk; ++qs) {
+    uint32_t a[4];
+    ldmatrix_x4_trans(sP + uint32_t(qs * 16 + (mi >> 1) * 8 + r) * pitch + uint32_t(m0 + (mi & 1) * 8) * 2, a[0], a[1], a[2], a[3]);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4_trans(swz(sX, qs * 16 + (mi & 1) * 8 + r, dp * 2 + (mi >> 1)), b0, b1, b2, b3);
+      mma_16816<kDT>(acc[2 * dp], a, b0, b1);
+      mma_16816<kDT>(acc[2 * dp + 1], a, b2, b3);
+    }
+  }
+}
+
+template <int kDT>
+__device__ __forceinline__ void store_tile_16x64(const float (&acc)[8][4], uint16_t* gbase, int64_t ld, int row0, int T,
+                                                 int lane) {
+  const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * tg;
+    if (row0 + g < T) *reinterpret_cast<uint32_t*>(gbase + int64_t(row0 + g) * ld + c) = pack2<kDT>(acc[nt][0], acc[nt][1]);
+    if (row0 + g + 8 < T) *reinterpret_cast<uint32_t*>(gbase + int64_t(row0 + g + 8) * ld + c) = pack2<kDT>(acc[nt][2], acc[nt][3]);
+  }
+}
+
+template <int kDT>
+__global__ void __launch_bounds__(256, 1)
+attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ d_out, uint16_t* __restrict__ dqkv,
+                     int T, int heads, int TP, int pitch) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tg = lane & 3, mi = lane >> 3, r8 = lane & 7;
+  const int bh = blockIdx.x, b = bh / heads, h = bh - b * heads;
+  const int inner = heads * DH;
+  const int64_t ld = 3 * int64_t(inner);
+  const uint16_t* qbase = qkv + int64_t(b) * T * ld + h * DH;
+  uint16_t* dqbase = dqkv + int64_t(b) * T * ld + h * DH;
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + uint32_t(TP) * ROW_BYTES, sV = sK + uint32_t(TP) * ROW_BYTES;
+  const uint32_t sD = sV + uint32_t(TP) * ROW_BYTES, sP = sD + uint32_t(TP) * ROW_BYTES;
+  load_rows(sQ, qbase, ld, TP, T);
+  load_rows(sK, qbase + inner, ld, TP, T);
+  load_rows(sV, qbase + 2 * inner, ld, TP, T);
+  load_rows(sD, d_out + int64_t(b) * T * inner + h * DH, inner, TP, T);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int nblk = TP >> 4, ntiles = TP >> 3;
+  const float sl2 = 0.125f * 1.4426950408889634f;   // dim_head^-0.5 * log2(e)
+
+  // ---- A: P = softmax(q k^T / 8) -> smem ----
+  for (int qb = warp; qb < nblk; qb += nw) {
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldmatrix_x4(swz(sQ, qb * 16 + (mi & 1) * 8 + r8, ks * 2 + (mi >> 1)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+    float s[ABW_MAX_NT][4];
+#pragma unroll
+    for (int nt = 0; nt < ABW_MAX_NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+#pragma unroll
+    for (int p = 0; p < ABW_MAX_NT / 2; ++p) {
+      if (p < nblk) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(swz(sK, p * 16 + (mi >> 1) * 8 + r8, ks * 2 + (mi & 1)), b0, b1, b2, b3);
+          mma_16816<kDT>(s[2 * p], qf[ks], b0, b1);
+          mma_16816<kDT>(s[2 * p + 1], qf[ks], b2, b3);
+        }
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
+      if (nt < ntiles) {
+        const int c0 = nt * 8 + 2 * tg;
+        if (c0 >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (c0 + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
+      if (nt < ntiles) {
+        s[nt][0] = ex2_approx((s[nt][0] - mx0) * sl2);
+        s[nt][1] = ex2_approx((s[nt][1] - mx0) * sl2);
+        s[nt][2] = ex2_approx((s[nt][2] - mx1) * sl2);
+        s[nt][3] = ex2_approx((s[nt][3] - mx1) * sl2);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const uint32_t pa = sP + uint32_t(qb * 16 + g) * pitch + uint32_t(2 * tg) * 2, pb = pa + 8u * pitch;
+#pragma unroll
+    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
+      if (nt < ntiles) {
+        sts32(pa + nt * 16, pack2<kDT>(s[nt][0] * i0, s[nt][1] * i0));
+        sts32(pb + nt * 16, pack2<kDT>(s[nt][2] * i1, s[nt][3] * i1));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- A2: dV = P^T dO ----
+  for (int kb = warp; kb < nblk; kb += nw) {
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    mma_transposed_scores<kDT>(acc, sP, pitch, kb * 16, sD, nblk, lane);
+    store_tile_16x64<kDT>(acc, dqbase + 2 * inner, ld, kb * 16, T, lane);
+  }
+  __syncthreads();
+
+  // ---- B: dP = dO v^T, dS = P o (dP - D) / 8 (over P, own rows), dQ = dS k ----
+  for (int qb = warp; qb < nblk; qb += nw) {
+    uint32_t dof[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldmatrix_x4(swz(sD, qb * 16 + (mi & 1) * 8 + r8, ks * 2 + (mi >> 1)), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
+    float dp[ABW_MAX_NT][4];
+#pragma unroll
+    for (int nt = 0; nt < ABW_MAX_NT; ++nt) { dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
+#pragma unroll
+    for (int p = 0; p < ABW_MAX_NT / 2; ++p) {
+      if (p < nblk) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(swz(sV, p * 16 + (mi >> 1) * 8 + r8, ks * 2 + (mi & 1)), b0, b1, b2, b3);
+          mma_16816<kDT>(dp[2 * p], dof[ks], b0, b1);
+          mma_16816<kDT>(dp[2 * p + 1], dof[ks], b2, b3);
+        }
+      }
+    }
+    const uint32_t pa = sP + uint32_t(qb * 16 + g) * pitch + uint32_t(2 * tg) * 2, pb = pa + 8u * pitch;
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
+      if (nt < ntiles) {
+        float p0, p1, p2, p3;
+        unpack2<kDT>(lds32(pa + nt * 16), p0, p1);
+        unpack2<kDT>(lds32(pb + nt * 16), p2, p3);
+        d0 += p0 * dp[nt][0] + p1 * dp[nt][1];
+        d1 += p2 * dp[nt][2] + p3 * dp[nt][3];
+      }
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    uint32_t dsf[ABW_MAX_NT / 2][4];
+#pragma unroll
+    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
+      if (nt < ntiles) {
+        float p0, p1, p2, p3;
+        unpack2<kDT>(lds32(pa + nt * 16), p0, p1);
+        unpack2<kDT>(lds32(pb + nt * 16), p2, p3);
+        const uint32_t va = pack2<kDT>(p0 * (dp[nt][0] - d0) * 0.125f, p1 * (dp[nt][1] - d0) * 0.125f);
+        const uint32_t vb = pack2<kDT>(p2 * (dp[nt][2] - d1) * 0.125f, p3 * (dp[nt][3] - d1) * 0.125f);
+        sts32(pa + nt * 16, va);
+        sts32(pb + nt * 16, vb);
+        if ((nt & 1) == 0) { dsf[nt >> 1][0] = va; dsf[nt >> 1][1] = vb; }
+        else               { dsf[nt >> 1][2] = va; dsf[nt >> 1][3] = vb; }
+      }
+    }
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < ABW_MAX_NT / 2; ++j) {
+      if (j < nblk) {
+#pragma unroll
+        for (int dpi = 0; dpi < 4; ++dpi) {
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(swz(sK, j * 16 + (mi & 1) * 8 + r8, dpi * 2 + (mi >> 1)), b0, b1, b2, b3);
+          mma_16816<kDT>(dq[2 * dpi], dsf[j], b0, b1);
+          mma_16816<kDT>(dq[2 * dpi + 1], dsf[j], b2, b3);
+        }
+      }
+    }
+    store_tile_16x64<kDT>(dq, dqbase, ld, qb * 16, T, lane);
+  }
+  __syncthreads();
+
+  // ---- C: dK = dS^T q ----
+  for (int kb = warp; kb < nblk; kb += nw) {
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    mma_transposed_scores<kDT>(acc, sP, pitch, kb * 16, sQ, nblk, lane);
+    store_tile_16x64<kDT>(acc, dqbase + inner, ld, kb * 16, T, lane);
+  }
+}
+
+inline unsigned grid_for(int64_t work_items, int per_block) {
+  return unsigned(std::min<int64_t>((work_items + per_block - 1) / per_block, int64_t(sm_count()) * 16));
+}
+
+}  // namespace
+
+#define VB_DT_DISPATCH_ANY(dt, CALL)                                                    \
+  switch (dt) {                                                                        \
+    case DT_F32: { constexpr int kDT = DT_F32; CALL; break; }                          \
+    case DT_BF16: { constexpr int kDT = DT_BF16; CALL; break; }                        \
+    case DT_F16: { constexpr int kDT = DT_F16; CALL; break; }                          \
+    default: return fail(VITB200_ERR_INVALID, "dtype must be VITB200_DT_F32/BF16/F16"); \
+  }
+
+#define VB_DT16_DISPATCH(dt, CALL)                                                     \
+  switch (dt) {                                                                        \
+    case DT_BF16: { constexpr int kDT = DT_BF16; CALL; break; }                        \
+    case DT_F16: { constexpr int kDT = DT_F16; CALL; break; }                          \
+    default: return fail(VITB200_ERR_INVALID, "dtype must be VITB200_DT_BF16/F16");   \
+  }
+
+int launch_cast16(cudaStream_t st, const float* x, void* y, int64_t n, int dtype) {
+  if (n <= 0 || (n & 7)) return fail(VITB200_ERR_INVALID, "cast16: element count must be a positive multiple of 8");
+  VB_DT16_DISPATCH(dtype, (cast16_kernel<kDT><<<grid_for(n / 8, 256), 256, 0, st>>>(x, static_cast<uint16_t*>(y), n / 8)));
+  VB_LAUNCH_CHECK("cast16_kernel");
+  return 0;
+}
+
+int launch_gelu_fwd(cudaStream_t st, const void* pre, void* hid, int64_t n, int dtype) {
+  if (n <= 0 || (n & 7)) return fail(VITB200_ERR_INVALID, "gelu: element count must be a positive multiple of 8");
+  VB_DT16_DISPATCH(dtype, (gelu_kernel<kDT, false><<<grid_for(n / 8, 256), 256, 0, st>>>(
+                              static_cast<const uint16_t*>(pre), nullptr, static_cast<uint16_t*>(hid), n / 8)));
+  VB_LAUNCH_CHECK("gelu_kernel(fwd)");
+  return 0;
+}
+
+int launch_gelu_bwd(cudaStream_t st, const void* pre, const void* dhid, void* dpre, int64_t n, int dtype) {
+  if (n <= 0 || (n & 7)) return fail(VITB200_ERR_INVALID, "gelu: element count must be a positive multiple of 8");
+  VB_DT16_DISPATCH(dtype, (gelu_kernel<kDT, true><<<grid_for(n / 8, 256), 256, 0, st>>>(
+                              static_cast<const uint16_t*>(pre), static_cast<const uint16_t*>(dhid),
+                              static_cast<uint16_t*>(dpre), n / 8)));
+  VB_LAUNCH_CHECK("gelu_kernel(bwd)");
+  return 0;
+}
+
+int launch_transpose16(cudaStream_t st, const void* in, void* out, int rows, int cols, int rows_pad) {
+  if (rows <= 0 || cols <= 0 || rows_pad < rows || (cols & 1) || (rows_pad & 1))
+    return fail(VITB200_ERR_INVALID, "transpose16: cols and rows_pad must be even, rows_pad >= rows");
+  dim3 grid(unsigned((rows_pad + 63) / 64), unsigned((cols + 63) / 64));
+  transpose16_kernel<<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), rows, cols, rows_pad);
+  VB_LAUNCH_CHECK("transpose16_kernel");
+  return 0;
+}
+
+int launch_colsum(cudaStream_t st, const void* in, float* out, int rows, int cols, int dtype) {
+  if (rows <= 0 || cols <= 0 || (cols & 1)) return fail(VITB200_ERR_INVALID, "colsum: cols must be even");
+  const int gx = (cols + 63) / 64;
+  const int gy = std::max(1, std::min((rows + 63) / 64, std::max(1, 8 * sm_count() / gx)));
+  dim3 grid{unsigned(gx), unsigned(gy)};
+  VB_DT_DISPATCH_ANY(dtype, (colsum_kernel<kDT><<<grid, 256, 0, st>>>(in, out, rows, cols)));
+  VB_LAUNCH_CHECK("colsum_kernel");
+  return 0;
+}
+
+int launch_ln_bwd(cudaStream_t st, const void* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                  float* dbeta, int rows, int dim, int dtype, float eps, int accumulate) {
+  if (rows <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "ln_bwd: empty problem");
+  if (dim > 32 * LN_KMAX) return fail(VITB200_ERR_UNSUPPORTED, "ln_bwd: dim > 1280 is not built");
+  const int grid = std::min((rows + 7) / 8, sm_count() * 4);
+  VB_DT16_DISPATCH(dtype, (ln_bwd_kernel<kDT><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(dy), x, gamma, dx, dgamma,
+                                                                  dbeta, rows, dim, eps, accumulate)));
+  VB_LAUNCH_CHECK("ln_bwd_kernel");
+  return 0;
+}
+
+int launch_pool_ln_bwd(cudaStream_t st, const float* x, const float* dpl, const float* gamma, float* dx,
+                       float* dgamma, float* dbeta, int batch, int T, int dim, int pool_mean, float eps) {
+  if (batch <= 0 || T <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "pool_ln_bwd: empty problem");
+  const size_t smem = (2 * size_t(dim) + 64) * sizeof(float);
+  pool_ln_bwd_kernel<<<batch, 256, smem, st>>>(x, dpl, gamma, dx, dgamma, dbeta, T, dim, pool_mean, eps);
+  VB_LAUNCH_CHECK("pool_ln_bwd_kernel");
+  return 0;
+}
+
+int launch_head_bwd(cudaStream_t st, const float* pl, const float* dl, const float* W, float* dW, float* dbias,
+                    float* dpl, int batch, int dim, int classes) {
+  if (batch <= 0 || dim <= 0 || classes <= 0) return fail(VITB200_ERR_INVALID, "head_bwd: empty problem");
+  head_wgrad_kernel<<<dim3(unsigned((classes + 255) / 256), unsigned(dim)), 256, 0, st>>>(pl, dl, dW, batch, dim, classes);
+  VB_LAUNCH_CHECK("head_wgrad_kernel");
+  head_dgrad_kernel<<<unsigned((int64_t(batch) * dim * 32 + 255) / 256), 256, 0, st>>>(dl, W, dpl, batch, dim, classes);
+  VB_LAUNCH_CHECK("head_dgrad_kernel");
+  // dbias[c] += sum_b dl[b, c]  (classes may be odd: one column per thread)
+  pos_grad_kernel<<<dim3(unsigned((classes + 255) / 256), 1), 256, 0, st>>>(dl, dbias, batch, 1, classes);
+  VB_LAUNCH_CHECK("pos_grad_kernel(head bias)");
+  return 0;
+}
+
+int launch_token_grads(cudaStream_t st, const float* dx, float* dpos, float* dcls, float* dbias, int batch, int T,
+                       int dim, int cls_off) {
+  if (batch <= 0 || T <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "token_grads: empty problem");
+  pos_grad_kernel<<<dim3(unsigned((dim + 255) / 256), unsigned(T)), 256, 0, st>>>(dx, dpos, batch, T, dim);
+  VB_LAUNCH_CHECK("pos_grad_kernel");
+  cls_bias_grad_kernel<<<unsigned((dim + 255) / 256), 256, 0, st>>>(dpos, dcls, dbias, T, dim, cls_off);
+  VB_LAUNCH_CHECK("cls_bias_grad_kernel");
+  return 0;
+}
+
+int attention_bwd_max_tokens() { return ABW_MAX_T; }
+
+int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, int batch, int T, int heads,
+                         int dtype) {
+  if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
+  if (T > ABW_MAX_T) return fail(VITB200_ERR_UNSUPPORTED, "attention_bwd: more than 208 tokens is not built");
+  const int TP = (T + 15) / 16 * 16, pitch = TP * 2 + 16;
+  const int nblk = TP / 16, rounds = (nblk + 7) / 8, nw = (nblk + rounds - 1) / rounds;
+  const size_t smem = size_t(4) * TP * ROW_BYTES + size_t(TP) * pitch;
+  static bool configured = false;
+  if (!configured) {
+    VB_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VB_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  VB_DT16_DISPATCH(dtype, (attention_bwd_kernel<kDT><<<unsigned(batch * heads), nw * 32, smem, st>>>(
+                              static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(d_out),
+                              static_cast<uint16_t*>(dqkv), T, heads, TP, pitch)));
+  VB_LAUNCH_CHECK("attention_bwd_kernel");
+  return 0;
+}
+
+}  // namespace vb

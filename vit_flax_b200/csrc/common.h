@@ -122,4 +122,25 @@ int launch_pool_layernorm(cudaStream_t stream, const float* x, const float* scal
 int launch_pack_weight(cudaStream_t stream, const float* W, void* Wt, int K, int N, int Kpad,
                        int dtype);
 
+// ---- backward pass (backward.cu); 16-bit buffers are of type `dtype` (VITB200_DT_BF16 / _F16) ----
+int launch_cast16(cudaStream_t stream, const float* x, void* y, int64_t n, int dtype);
+int launch_gelu_fwd(cudaStream_t stream, const void* pre, void* hid, int64_t n, int dtype);
+int launch_gelu_bwd(cudaStream_t stream, const void* pre, const void* dhid, void* dpre, int64_t n, int dtype);
+// out[c, r] = in[r, c], r < rows; zero for rows <= r < rows_pad (the K padding of the wgrad GEMMs)
+int launch_transpose16(cudaStream_t stream, const void* in, void* out, int rows, int cols, int rows_pad);
+// out[c] += sum_r in[r, c]; dtype may be VITB200_DT_F32
+int launch_colsum(cudaStream_t stream, const void* in, float* out, int rows, int cols, int dtype);
+// dx (+)= LayerNorm backward of dy (16-bit) at input x; dgamma / dbeta accumulate
+int launch_ln_bwd(cudaStream_t stream, const void* dy, const float* x, const float* gamma, float* dx,
+                  float* dgamma, float* dbeta, int rows, int dim, int dtype, float eps, int accumulate);
+int launch_pool_ln_bwd(cudaStream_t stream, const float* x, const float* dpl, const float* gamma, float* dx,
+                       float* dgamma, float* dbeta, int batch, int T, int dim, int pool_mean, float eps);
+int launch_head_bwd(cudaStream_t stream, const float* pl, const float* dl, const float* W, float* dW,
+                    float* dbias, float* dpl, int batch, int dim, int classes);
+int launch_token_grads(cudaStream_t stream, const float* dx, float* dpos, float* dcls, float* dbias, int batch,
+                       int T, int dim, int cls_off);
+int attention_bwd_max_tokens();
+int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* d_out, void* dqkv, int batch, int T,
+                         int heads, int dtype);
+
 }  // namespace vb

@@ -78,7 +78,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const float* __restrict__ bias, void* __restrict__ Cout,
                int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop, int cls_off,
                const float* __restrict__ cls) {
-  constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16);
+  constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_16);
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
   constexpr int SLABS_PER_TILE = Cfg<kCG>::BN_ / SLAB_COLS;
@@ -301,6 +301,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]);
+                if constexpr (kEpi == VITB200_EPI_BIAS_16) {   // pre-activation kept for the backward pass
+                  const int nb = n0 + half * 32 + j * 8;
+                  if (nb < N) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + nb + 4));
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                  }
+                }
                 if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16) {
                   const int nb = n0 + half * 32 + j * 8;
                   float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
@@ -472,6 +481,8 @@ int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap&
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: PATCH epilogue needs pos_embedding and tokens");
       return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
+    case VITB200_EPI_BIAS_16:
+      return launch_one<VITB200_EPI_BIAS_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     case VITB200_EPI_TOKENS_F32:
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: TOKENS epilogue needs pos_embedding and tokens per image");

@@ -108,6 +108,42 @@ class Engine:
                                             images.data_ptr(), b, out.data_ptr()))
         return out
 
+    # -- training --------------------------------------
+    def train_forward(self, images, out=None):
+        """Forward that keeps every activation the backward pass needs; same arguments as ``forward``.
+        (The FeedForward pre-activation is rounded to 16 bits before the GELU here, so the logits can
+        differ from ``forward``'s in the last 16-bit digit.)"""
+        torch = self._torch
+        self._check_images(images.shape)
+        if images.dtype != torch.float32 or not images.is_cuda or not images.is_contiguous():
+            raise ValueError("train_forward expects a contiguous float32 CUDA tensor")
+        b = images.shape[0]
+        if out is None:
+            out = torch.empty((b, self.num_classes), dtype=torch.float32, device=images.device)
+        _lib.check(self.lib.vitb200_train_forward(self.handle, _stream_ptr(torch, images.device),
+                                                  images.data_ptr(), b, out.data_ptr()))
+        return out
+
+    def backward(self, dlogits) -> None:
+        """Cotangent of the logits of the last ``train_forward`` (fp32 CUDA tensor [B, classes]) ->
+        one fp32 gradient per parameter leaf, read with ``grads()`` / ``grad_tensor(path)``."""
+        torch = self._torch
+        if dlogits.dtype != torch.float32 or not dlogits.is_cuda or not dlogits.is_contiguous() or dlogits.dim() != 2 \
+                or dlogits.shape[1] != self.num_classes:
+            raise ValueError(f"backward expects a contiguous float32 CUDA tensor [B, {self.num_classes}]")
+        _lib.check(self.lib.vitb200_backward(self.handle, _stream_ptr(torch, dlogits.device),
+                                             dlogits.data_ptr(), int(dlogits.shape[0])))
+
+    def grads(self) -> Dict[str, np.ndarray]:
+        """{flax path: float32 ndarray} of the last backward pass."""
+        out = {}
+        for path, shape in self.param_table().items():
+            a = np.empty(shape, np.float32)
+            _lib.check(self.lib.vitb200_get_grad(self.handle, _stream_ptr(self._torch, self.device),
+                                                 path.encode(), a.ctypes.data))
+            out[path] = a
+        return out
+
     def forward_host(self, images: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """End-to-end path: host fp32 images in, host fp32 logits out (H2D + D2H inside)."""
         images = np.ascontiguousarray(images, dtype=np.float32)

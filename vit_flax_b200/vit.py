@@ -133,6 +133,43 @@ class ViT:
             return eng.forward(xin)
         return eng.forward_host(np.asarray(x, dtype=np.float32))
 
+    def vjp(self, variables: Any, x: Any, *, precision: Optional[str] = None, device: Optional[int] = None,
+            max_batch: Optional[int] = None):
+        """``jax.vjp(lambda p: v.apply(p, x), variables)`` (ours: nothing in the reference trains).
+
+        Returns ``(logits, vjp_fn)``; ``vjp_fn(dlogits)`` gives ``{'params': tree}`` of float32
+        gradients with the reference's names and shapes.  Host arrays in -> numpy out, CUDA tensors
+        in -> CUDA logits out (gradients always come back as numpy).  With fp16 operands the
+        cotangent is scaled to unit magnitude on the way in and the gradients back on the way out
+        (loss scaling: the map is linear)."""
+        from .runtime import get_engine
+        if self.dropout != 0.0 or self.emb_dropout != 0.0:
+            raise NotImplementedError("vjp: the backward pass is built for dropout rates 0.0")
+        import torch
+        is_torch_cuda = hasattr(x, "is_cuda") and bool(x.is_cuda)
+        channels = self._validate(tuple(x.shape) if hasattr(x, "shape") else np.shape(x))
+        batch = int(x.shape[0])
+        if device is None:
+            device = x.device.index if is_torch_cuda and x.device.index is not None else _current_device()
+        eng = get_engine(self, channels, precision or _DEFAULT_PRECISION, device, max_batch or batch, variables, False)
+        dev = torch.device("cuda", device)
+        xin = x if is_torch_cuda else torch.as_tensor(np.asarray(x, dtype=np.float32), device=dev)
+        xin = xin if (xin.dtype == torch.float32 and xin.is_contiguous()) else xin.float().contiguous()
+        logits = eng.train_forward(xin)
+
+        def vjp_fn(dlogits):
+            d = dlogits if hasattr(dlogits, "is_cuda") else torch.as_tensor(np.asarray(dlogits, dtype=np.float32))
+            d = d.to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(d.shape) != (batch, self.num_classes):
+                raise ValueError(f"vjp_fn expects a cotangent of shape ({batch}, {self.num_classes})")
+            peak = float(d.abs().max())
+            scale = 1.0 if peak == 0.0 or not np.isfinite(peak) else float(2.0 ** -np.round(np.log2(peak)))
+            eng.backward(d * scale if scale != 1.0 else d)
+            from .checkpoint import _unflatten
+            return {"params": _unflatten({k: g / np.float32(scale) for k, g in eng.grads().items()})}
+
+        return (logits if is_torch_cuda else logits.cpu().numpy()), vjp_fn
+
     def apply_stream(self, variables: Any, batches, *, precision: Optional[str] = None,
                      device: Optional[int] = None, max_batch: int = 256):
         """Serving-style extension of ``apply`` (ours, not in the reference): iterate host batches
