@@ -184,7 +184,9 @@ int vitb200_grad_device(vitb200_model* m, const char* path, float** dev_out);
 /* tcgen05 GEMM: acc[M,N] = A[M,K] (16-bit row-major) x Wt[N,K]^T (16-bit row-major, i.e. the
  * transposed Flax kernel), fp32 accumulation in TMEM.  dtype = VITB200_DT_BF16 | _F16.
  * K % 8 == 0, N % 8 == 0.  `aux` = pos_embedding [T, N] fp32 and `tokens_per_image` = T-1 for
- * EPI_PATCH.                                                                                  */
+ * EPI_PATCH.  For EPI_BIAS_RESID_F32, `tokens_per_image` > 1 is a split-K factor: that many CTAs
+ * share a tile's K range and their partial sums meet in the reduce-add (used by the weight-gradient
+ * GEMMs, whose outputs have few tiles and a very long K).                                       */
 int vitb200_gemm_tc(void* stream, const void* A, const void* Wt, const float* bias,
                     void* C, int M, int N, int K, int epilogue,
                     const float* aux, int tokens_per_image, int dtype);

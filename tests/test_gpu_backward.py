@@ -143,6 +143,40 @@ def test_backward_vit_b16_dims():
     eng.close()
 
 
+def test_backward_vit_b16_full_depth_and_full_batch_properties():
+    """Full ViT-B/16: (1) all 12 layers against the oracle at batch 2; (2) at BASELINE's batch 256, where the
+    float64 oracle would take minutes, the properties a VJP must have: linear in the cotangent, and additive
+    over the batch (gradients of 256 images = sum of the gradients of its two halves)."""
+    cfg = dict(C2)
+    variables = perturb_params(init_params(seed=61, **cfg), seed=62)
+    eng = Engine(precision="fp16", max_batch=256, **cfg)
+    eng.load_params(variables)
+    img = images_for(cfg, 256, seed=63)
+    dl = (np.random.default_rng(64).standard_normal((256, 1000)) / 16).astype(np.float32)
+    x, d = torch.as_tensor(img, device="cuda"), torch.as_tensor(dl, device="cuda")
+    logits = eng.train_forward(x[:2].contiguous())
+    eng.backward(d[:2].contiguous())
+    _check_grads(eng, variables, cfg, img[:2], dl[:2], "cls", 3e-2, logits.cpu().numpy())
+    keys = ["Dense_0/kernel", "pos_embedding", "cls", "Transformer_0/Attention_0/Dense_0/kernel",
+            "Transformer_0/FeedForward_5/Dense_1/kernel", "Transformer_0/PreNorm_23/LayerNorm_0/scale",
+            "Transformer_0/FeedForward_11/Dense_0/bias", "Dense_1/kernel"]
+
+    def grads_of(lo, hi, scale=1.0):
+        eng.train_forward(x[lo:hi].contiguous())
+        eng.backward((d[lo:hi] * scale).contiguous())
+        return {k: torch.as_tensor(eng.grad_tensor(k)).clone() for k in keys}
+
+    full = grads_of(0, 256)
+    a, b = grads_of(0, 128), grads_of(128, 256)
+    twice = grads_of(0, 256, 2.0)
+    for k in keys:
+        ref = full[k].double()
+        assert torch.isfinite(ref).all() and ref.abs().max() > 0
+        assert ((a[k].double() + b[k].double()) - ref).abs().max() / ref.abs().max() < 5e-3, k     # additive over the batch
+        assert (twice[k].double() - 2 * ref).abs().max() / ref.abs().max() < 5e-3, k                # linear in dlogits
+    eng.close()
+
+
 def test_vjp_api_and_loss_scaling():
     """ViT.vjp mirrors jax.vjp(lambda p: v.apply(p, x), params); tiny cotangents survive fp16 through the scaling."""
     cfg = dict(TINY)

@@ -103,6 +103,25 @@ def test_gemm_tc_patch_epilogue(lib, cta_group, B, Np, K, D, monkeypatch):
     assert torch.all(got[:, 0] == 7.0)                                    # cls rows untouched
 
 
+@pytest.mark.parametrize("cta_group", ["1", "2", "64"])
+@pytest.mark.parametrize("M,N,K,splits", [(768, 768, 12608, 16), (300, 520, 1000, 5), (128, 64, 640, 64), (520, 264, 72, 3)])
+def test_gemm_tc_split_k(lib, cta_group, M, N, K, splits, monkeypatch):
+    """EPI_BIAS_RESID_F32 with a split-K factor (the weight-gradient GEMMs): C += A Wt^T + bias exactly once,
+    whatever the factor (clamped to the number of k-blocks) and the tile mode."""
+    monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
+    dt, tdt, _ = DT16["fp16"]
+    rng = np.random.default_rng(M + K)
+    A = dev(rng.standard_normal((M, K)), tdt)
+    Wt = dev(rng.standard_normal((N, K)) / np.sqrt(K), tdt)
+    bias, resid = dev(rng.standard_normal(N)), dev(rng.standard_normal((M, N)))
+    out = resid.clone()
+    _lib.check(lib.vitb200_gemm_tc(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                   M, N, K, _lib.EPI_BIAS_RESID_F32, None, splits, dt))
+    torch.cuda.synchronize()
+    want = A.double() @ Wt.double().t() + bias.double() + resid.double()
+    assert (out.double() - want).abs().max().item() < 3e-4
+
+
 def test_gemm_tc_rejects_bad_arguments(lib):
     a = torch.zeros((8, 16), dtype=torch.bfloat16, device="cuda")
     rc = lib.vitb200_gemm_tc(stream(), a.data_ptr(), a.data_ptr(), None, a.data_ptr(), 8, 8, 12, 0, None, 0, _lib.DT_BF16)

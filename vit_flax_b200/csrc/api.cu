@@ -799,7 +799,13 @@ int wgrad(vitb200_model* m, cudaStream_t st, const void* X, int Dx, const void* 
   int rc;
   if ((rc = launch_transpose16(st, X, ts.tA.p, R, Dx, Rpad))) return rc;
   if ((rc = launch_transpose16(st, dY, ts.tB.p, R, Dy, Rpad))) return rc;
-  return gemm16(m, st, ts.tA.p, Dx, Rpad, ts.tB.p, Rpad, Dy, dW, c_rows, VITB200_EPI_BIAS_RESID_F32, ts.zeros.p);
+  // split-K so that the few output tiles of a weight gradient (9 for 768 x 768) become about two waves of work;
+  // the partial sums meet in the epilogue's TMA reduce-add
+  const int cg = gemm_tc_tile_mode(Dx, Dy);
+  const int tm = cg == 2 ? 2 * GEMM_BM : GEMM_BM, tn = cg == 64 ? 64 : GEMM_BN, units = cg == 2 ? sm_count() / 2 : sm_count();
+  const int mn_tiles = ceil_div(Dx, tm) * ceil_div(Dy, tn);
+  const int splits = std::max(1, 2 * units / mn_tiles);
+  return gemm16(m, st, ts.tA.p, Dx, Rpad, ts.tB.p, Rpad, Dy, dW, c_rows, VITB200_EPI_BIAS_RESID_F32, ts.zeros.p, nullptr, splits);
 }
 
 int train_supported(const vitb200_model* m) {

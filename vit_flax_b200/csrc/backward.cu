@@ -135,38 +135,41 @@ colsum_kernel(const void* __restrict__ in, float* __restrict__ out, int rows, in
 }
 
 // ------------------------------------------------------------------ LayerNorm backward
-// dx[r,:] += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum_r dy * xhat,
-// dbeta += sum_r dy.  One warp per row; every lane owns columns lane + 32 k and keeps its share of
-// dgamma / dbeta in registers over all the rows of the warp.
-constexpr int LN_KMAX = 40;   // dim <= 1280
-
-template <int kDT>
-__global__ void __launch_bounds__(256)
+// dx[r,:] (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum_r dy * xhat,
+// dbeta += sum_r dy.  One warp per row, float4 / 8-byte accesses: lane owns columns 4 (lane + 32 k) .. +3,
+// k < KV (dim <= 128 KV), and keeps its share of dgamma / dbeta in registers over all the rows of the
+// warp; the warps of a block are reduced through shared memory, so a column sees one atomic per block.
+template <int kDT, int KV>
+__global__ void __launch_bounds__(128)
 ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim,
               float eps, int accumulate) {
+  extern __shared__ float red[];            // [2][dim]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  float gam[LN_KMAX], ag[LN_KMAX], ab[LN_KMAX];
+  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 ag[KV], ab[KV];
 #pragma unroll
-  for (int k = 0; k < LN_KMAX; ++k) {
-    const int c = lane + 32 * k;
-    gam[k] = c < dim ? gamma[c] : 0.f;
-    ag[k] = 0.f;
-    ab[k] = 0.f;
-  }
+  for (int k = 0; k < KV; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float inv_d = 1.0f / float(dim);
   for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
     const float* xr = x + int64_t(r) * dim;
     const uint16_t* dr = dy + int64_t(r) * dim;
-    float xv[LN_KMAX], dv[LN_KMAX];
+    float4 xv[KV], dv[KV];
     float s = 0.f, ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_KMAX; ++k) {
-      const int c = lane + 32 * k;
-      xv[k] = c < dim ? xr[c] : 0.f;
-      dv[k] = c < dim ? to_f32<kDT>(dr[c]) : 0.f;
-      s += xv[k];
-      ss += xv[k] * xv[k];
+    for (int k = 0; k < KV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < dim) {
+        xv[k] = *reinterpret_cast<const float4*>(xr + c);
+        const uint2 d2 = *reinterpret_cast<const uint2*>(dr + c);
+        unpack2<kDT>(d2.x, dv[k].x, dv[k].y);
+        unpack2<kDT>(d2.y, dv[k].z, dv[k].w);
+      } else {
+        xv[k] = dv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      s += (xv[k].x + xv[k].y) + (xv[k].z + xv[k].w);
+      ss += (xv[k].x * xv[k].x + xv[k].y * xv[k].y) + (xv[k].z * xv[k].z + xv[k].w * xv[k].w);
     }
     s = warp_sum(s);
     ss = warp_sum(ss);
@@ -174,33 +177,49 @@ ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, cons
     const float rstd = rsqrtf(fmaxf(0.f, ss * inv_d - mean * mean) + eps);   // flax: var = max(0, E[x^2] - E[x]^2)
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_KMAX; ++k) {
-      const float xh = (xv[k] - mean) * rstd, g = dv[k] * gam[k];
-      xv[k] = xh;
-      a += g;
-      b += g * xh;
-      ag[k] += dv[k] * xh;     // zero beyond dim (dv = 0)
-      ab[k] += dv[k];
+    for (int k = 0; k < KV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < dim) gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      xv[k].x = (xv[k].x - mean) * rstd; xv[k].y = (xv[k].y - mean) * rstd;
+      xv[k].z = (xv[k].z - mean) * rstd; xv[k].w = (xv[k].w - mean) * rstd;
+      ag[k].x += dv[k].x * xv[k].x; ag[k].y += dv[k].y * xv[k].y; ag[k].z += dv[k].z * xv[k].z; ag[k].w += dv[k].w * xv[k].w;
+      ab[k].x += dv[k].x; ab[k].y += dv[k].y; ab[k].z += dv[k].z; ab[k].w += dv[k].w;
+      dv[k].x *= gm.x; dv[k].y *= gm.y; dv[k].z *= gm.z; dv[k].w *= gm.w;      // g = dy * gamma (0 beyond dim)
+      a += (dv[k].x + dv[k].y) + (dv[k].z + dv[k].w);
+      b += (dv[k].x * xv[k].x + dv[k].y * xv[k].y) + (dv[k].z * xv[k].z + dv[k].w * xv[k].w);
     }
     a = warp_sum(a) * inv_d;
     b = warp_sum(b) * inv_d;
     float* dxr = dx + int64_t(r) * dim;
 #pragma unroll
-    for (int k = 0; k < LN_KMAX; ++k) {
-      const int c = lane + 32 * k;
+    for (int k = 0; k < KV; ++k) {
+      const int c = 4 * (lane + 32 * k);
       if (c < dim) {
-        const float v = rstd * (dv[k] * gam[k] - a - xv[k] * b);
-        dxr[c] = accumulate ? dxr[c] + v : v;
+        float4 v;
+        v.x = rstd * (dv[k].x - a - xv[k].x * b); v.y = rstd * (dv[k].y - a - xv[k].y * b);
+        v.z = rstd * (dv[k].z - a - xv[k].z * b); v.w = rstd * (dv[k].w - a - xv[k].w * b);
+        if (accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(dxr + c);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *reinterpret_cast<float4*>(dxr + c) = v;
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < LN_KMAX; ++k) {
-    const int c = lane + 32 * k;
+  for (int k = 0; k < KV; ++k) {
+    const int c = 4 * (lane + 32 * k);
     if (c < dim) {
-      atomicAdd(dgamma + c, ag[k]);
-      atomicAdd(dbeta + c, ab[k]);
+      atomicAdd(red + c, ag[k].x); atomicAdd(red + c + 1, ag[k].y); atomicAdd(red + c + 2, ag[k].z); atomicAdd(red + c + 3, ag[k].w);
+      atomicAdd(red + dim + c, ab[k].x); atomicAdd(red + dim + c + 1, ab[k].y);
+      atomicAdd(red + dim + c + 2, ab[k].z); atomicAdd(red + dim + c + 3, ab[k].w);
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[dim + i]);
   }
 }
 
@@ -621,14 +640,27 @@ int launch_colsum(cudaStream_t st, const void* in, float* out, int rows, int col
   return 0;
 }
 
+template <int kDT, int KV>
+int launch_ln_bwd_t(cudaStream_t st, const void* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                    float* dbeta, int rows, int dim, float eps, int accumulate) {
+  const int grid = std::min((rows + 3) / 4, sm_count() * 4);   // 128-thread blocks: 3-4 resident per SM at 158 registers
+  ln_bwd_kernel<kDT, KV><<<grid, 128, 2 * size_t(dim) * sizeof(float), st>>>(static_cast<const uint16_t*>(dy), x, gamma, dx,
+                                                                           dgamma, dbeta, rows, dim, eps, accumulate);
+  VB_LAUNCH_CHECK("ln_bwd_kernel");
+  return 0;
+}
+
 int launch_ln_bwd(cudaStream_t st, const void* dy, const float* x, const float* gamma, float* dx, float* dgamma,
                   float* dbeta, int rows, int dim, int dtype, float eps, int accumulate) {
   if (rows <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "ln_bwd: empty problem");
-  if (dim > 32 * LN_KMAX) return fail(VITB200_ERR_UNSUPPORTED, "ln_bwd: dim > 1280 is not built");
-  const int grid = std::min((rows + 7) / 8, sm_count() * 4);
-  VB_DT16_DISPATCH(dtype, (ln_bwd_kernel<kDT><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(dy), x, gamma, dx, dgamma,
-                                                                  dbeta, rows, dim, eps, accumulate)));
-  VB_LAUNCH_CHECK("ln_bwd_kernel");
+  if (dim & 3) return fail(VITB200_ERR_INVALID, "ln_bwd: dim must be a multiple of 4");
+  if (dim > 1280) return fail(VITB200_ERR_UNSUPPORTED, "ln_bwd: dim > 1280 is not built");
+#define VB_LN_BWD(KV) VB_DT16_DISPATCH(dtype, return (launch_ln_bwd_t<kDT, KV>(st, dy, x, gamma, dx, dgamma, dbeta, rows, dim, eps, accumulate)))
+  if (dim <= 256) { VB_LN_BWD(2); }
+  else if (dim <= 768) { VB_LN_BWD(6); }
+  else if (dim <= 1024) { VB_LN_BWD(8); }
+  else { VB_LN_BWD(10); }
+#undef VB_LN_BWD
   return 0;
 }
 

@@ -113,8 +113,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   const int lane = threadIdx.x & 31;
   const int m_tiles = ((M + TILE_M - 1) / TILE_M + PAIRS - 1) / PAIRS;   // cluster steps along M
   const int n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
+  // split-K (BIAS_RESID_F32 only, `tpi` carries the factor): split sp of a tile accumulates k-blocks
+  // [sp * kb_per, min(num_kb, (sp + 1) * kb_per)) and reduce-adds its partial sum; split 0 adds the bias
+  const int splits = (kEpi == VITB200_EPI_BIAS_RESID_F32 && tpi > 1) ? tpi : 1;
+  const int kb_per = (num_kb + splits - 1) / splits;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * splits;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -146,10 +151,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int sp = tile / mn_tiles, t2 = tile - sp * mn_tiles;
+        const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
+        const int kb0 = sp * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         const int a_row = (m_blk * PAIRS + int(pair)) * TILE_M + int(rank) * BM;
         const int b_row = n_blk * BN + int(rank) * Cfg<kCG>::B_ROWS + int(pair) * Cfg<kCG>::B_LOAD_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (dbg & 1) {   // timing experiment: no loads, the MMAs chew on stale smem
             if (rank == 0) mbar_arrive(full_bar(stage));
@@ -195,7 +202,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
         else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (tile / mn_tiles) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a0 = sA + stage * A_BYTES, b0 = sB + stage * B_BYTES;
@@ -203,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int k = 0; k < BK / UMMA_K; ++k) {
             umma_bf16_ss<MMA_CG>(d_tmem, umma_desc_k_sw128(a0 + k * UMMA_K * 2),
                               umma_desc_k_sw128(b0 + k * UMMA_K * 2), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
+                              (kb != kb0 || k != 0) ? 1u : 0u);
           }
           // smem slot free (in both CTAs) once these MMAs retire
           if constexpr (CL != 1) umma_commit_cg2_mc(empty_bar(stage), all_mask);
@@ -229,7 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     uint32_t acc_phase = 0;
     int buf = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int sp = tile / mn_tiles, t2 = tile - sp * mn_tiles;
+      const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
       const int m_row0 = (m_blk * PAIRS + int(pair)) * TILE_M + int(rank) * BM;   // first output row of this CTA
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -345,7 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int j = 0; j < 8; ++j) {              // 4 fp32 columns -> one 16-byte chunk
               const int nb = n0 + j * 4;
               float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (nb < N) b4 = __ldg(reinterpret_cast<const float4*>((cls_row ? cls : bias) + nb));
+              if (nb < N && sp == 0) b4 = __ldg(reinterpret_cast<const float4*>((cls_row ? cls : bias) + nb));
               float o0 = __uint_as_float(r[j * 4 + 0]), o1 = __uint_as_float(r[j * 4 + 1]);
               float o2 = __uint_as_float(r[j * 4 + 2]), o3 = __uint_as_float(r[j * 4 + 3]);
               if constexpr (kEpi == VITB200_EPI_TOKENS_F32) {
@@ -432,7 +441,8 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
     }
     configured = true;
   }
-  const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, Cfg<kCG>::BN_);
+  const int splits = (kEpi == VITB200_EPI_BIAS_RESID_F32 && tpi > 1) ? tpi : 1;
+  const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, Cfg<kCG>::BN_) * splits;
   const int units = tiles < max_units ? tiles : max_units;
   VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, dim3(units * Cfg<kCG>::CL), dim3(NUM_THREADS), smem_bytes<kCG>(),
                         stream, Cfg<kCG>::CL, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off, cls));
@@ -524,6 +534,13 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
     return fail(VITB200_ERR_INVALID, "gemm_tc: epilogue needs a bias");
   if (epilogue != VITB200_EPI_PATCH_F32 && tmC == nullptr)
     return fail(VITB200_ERR_INVALID, "gemm_tc: output tensor map missing");
+  if (epilogue == VITB200_EPI_BIAS_RESID_F32) {
+    // `tpi` = split-K factor: clamp so that every split owns at least one k-block
+    const int num_kb = ceil_div(K, GEMM_BK);
+    int sp = tpi < 1 ? 1 : (tpi > num_kb ? num_kb : tpi);
+    sp = ceil_div(num_kb, ceil_div(num_kb, sp));
+    tpi = sp;
+  }
   const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
   const float* cls_p = (cls_off == 1 && (epilogue == VITB200_EPI_PATCH_F32 || epilogue == VITB200_EPI_TOKENS_F32)) ? cls : nullptr;
   if (dtype == DT_BF16)

@@ -134,6 +134,20 @@ class Engine:
         _lib.check(self.lib.vitb200_backward(self.handle, _stream_ptr(torch, dlogits.device),
                                              dlogits.data_ptr(), int(dlogits.shape[0])))
 
+    def grad_tensor(self, path: str):
+        """The gradient of one leaf as a CUDA tensor viewing the library's buffer (overwritten by the
+        next ``backward``; clone it to keep it)."""
+        torch = self._torch
+        shape = self.param_table()[path]
+        ptr = C.c_void_p()
+        _lib.check(self.lib.vitb200_grad_device(self.handle, path.encode(), C.byref(ptr)))
+        n = int(np.prod(shape))
+
+        class _Buf:   # __cuda_array_interface__ view: no copy, no ownership
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr.value), False), "version": 2}
+        torch.cuda.current_stream(self.device).synchronize()
+        return torch.as_tensor(_Buf(), device=self.device).view(*shape)
+
     def grads(self) -> Dict[str, np.ndarray]:
         """{flax path: float32 ndarray} of the last backward pass."""
         out = {}
