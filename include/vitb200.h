@@ -220,6 +220,11 @@ int vitb200_attention_tc(void* stream, const void* qkv, void* out, int batch, in
                          int dtype);
 int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads);
 
+/* weight gradient dW[M, N] += X[K, M]^T dY[K, N]: X and dY are the row-major 16-bit activations
+ * (K = rows, any count; M, N % 8 == 0), read as MN-major tcgen05 operands; `splits` CTAs share a
+ * tile's K range (<= 1: none) and meet in the fp32 reduce-add.  dW must be initialised (it accumulates). */
+int vitb200_gemm_tc_wgrad(void* stream, const void* X, const void* dY, float* dW,
+                          int M, int N, int K, int splits, int dtype);
 /* adjoint of vitb200_attention_tc for T <= 208: (qkv, d_out [batch*T, heads*64]) -> dqkv [batch*T, 3*heads*64] */
 int vitb200_attention_bwd(void* stream, const void* qkv, const void* d_out, void* dqkv,
                           int batch, int T, int heads, int dtype);

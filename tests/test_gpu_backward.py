@@ -67,6 +67,26 @@ def test_attention_bwd(lib, batch, T, heads, fmt):
     assert err < (1.5e-2 if fmt == "fp16" else 5e-2), err
 
 
+@pytest.mark.parametrize("cta_group", ["1", "2", "64"])
+@pytest.mark.parametrize("M,N,K,splits", [(768, 768, 12608, 16), (3072, 768, 985, 4), (192, 264, 85, 2), (640, 768, 788, 1),
+                                          (64, 64, 1000, 7), (128, 2304, 197, 3)])
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+def test_gemm_tc_wgrad(lib, cta_group, M, N, K, splits, fmt, monkeypatch):
+    """dW += X^T dY with X [K, M] and dY [K, N] row-major (MN-major tcgen05 operands, K = the row index,
+    ragged K tails zero-filled by TMA), in every tile mode and with split-K."""
+    monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
+    dt, tdt = DT16[fmt]
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn((K, M), generator=g).to(tdt).cuda()
+    dY = (torch.randn((K, N), generator=g) / np.sqrt(K)).to(tdt).cuda()
+    dW0 = torch.randn((M, N), generator=g).cuda()
+    dW = dW0.clone()
+    _lib.check(lib.vitb200_gemm_tc_wgrad(stream(), X.data_ptr(), dY.data_ptr(), dW.data_ptr(), M, N, K, splits, dt))
+    torch.cuda.synchronize()
+    want = X.double().t() @ dY.double() + dW0.double()
+    assert (dW.double() - want).abs().max().item() < 3e-4
+
+
 @pytest.mark.parametrize("rows,dim", [(300, 768), (65, 128), (10, 1280), (33, 192), (1, 64)])
 @pytest.mark.parametrize("accumulate", [0, 1])
 def test_layernorm_bwd(lib, rows, dim, accumulate):

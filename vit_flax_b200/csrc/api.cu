@@ -791,21 +791,29 @@ int gemm16(vitb200_model* m, cudaStream_t st, const void* A, int M, int K, const
   return launch_gemm_tc(st, ta, tb, &tc, bias, C, M, N, K, epi, aux, tpi, m->dt, cg, Dropout(), m->cls_off, cls);
 }
 
-// dW[Dx (first c_rows rows), Dy] += X[R, Dx]^T dY[R, Dy]: both operands transposed into K-major scratch
-// (zero padded to a multiple of 64 rows), then one GEMM whose epilogue reduce-adds into the gradient leaf
+// dW[Dx (first c_rows rows), Dy] += X[R, Dx]^T dY[R, Dy]: the GEMM reads both row-major activations as
+// MN-major operands (K = the row index), split-K so that the few output tiles of a weight gradient
+// (9 for 768 x 768) become about two waves of work; the partial sums meet in the TMA reduce-add.
+// VITB200_WGRAD_TRANSPOSE=1 keeps the first implementation (explicit transposed copies + the K-major GEMM).
 int wgrad(vitb200_model* m, cudaStream_t st, const void* X, int Dx, const void* dY, int Dy, int R, float* dW, int c_rows) {
   auto& ts = *m->train;
-  const int Rpad = int(round_up(R, 64));
-  int rc;
-  if ((rc = launch_transpose16(st, X, ts.tA.p, R, Dx, Rpad))) return rc;
-  if ((rc = launch_transpose16(st, dY, ts.tB.p, R, Dy, Rpad))) return rc;
-  // split-K so that the few output tiles of a weight gradient (9 for 768 x 768) become about two waves of work;
-  // the partial sums meet in the epilogue's TMA reduce-add
-  const int cg = gemm_tc_tile_mode(Dx, Dy);
+  const int cg = gemm_tc_tile_mode(Dx, Dy) == 4 ? 2 : gemm_tc_tile_mode(Dx, Dy);
   const int tm = cg == 2 ? 2 * GEMM_BM : GEMM_BM, tn = cg == 64 ? 64 : GEMM_BN, units = cg == 2 ? sm_count() / 2 : sm_count();
   const int mn_tiles = ceil_div(Dx, tm) * ceil_div(Dy, tn);
   const int splits = std::max(1, 2 * units / mn_tiles);
-  return gemm16(m, st, ts.tA.p, Dx, Rpad, ts.tB.p, Rpad, Dy, dW, c_rows, VITB200_EPI_BIAS_RESID_F32, ts.zeros.p, nullptr, splits);
+  static const bool via_transpose = [] { const char* e = getenv("VITB200_WGRAD_TRANSPOSE"); return e && e[0] == '1'; }();
+  int rc;
+  if (via_transpose) {
+    const int Rpad = int(round_up(R, 64));
+    if ((rc = launch_transpose16(st, X, ts.tA.p, R, Dx, Rpad))) return rc;
+    if ((rc = launch_transpose16(st, dY, ts.tB.p, R, Dy, Rpad))) return rc;
+    return gemm16(m, st, ts.tA.p, Dx, Rpad, ts.tB.p, Rpad, Dy, dW, c_rows, VITB200_EPI_BIAS_RESID_F32, ts.zeros.p, nullptr, splits);
+  }
+  CUtensorMap tx, ty, tc;
+  if ((rc = make_tmap_2d(&tx, X, R, Dx, Dx, 64, m->dt))) return rc;
+  if ((rc = make_tmap_2d(&ty, dY, R, Dy, Dy, 64, m->dt))) return rc;
+  if ((rc = make_tmap_2d(&tc, dW, c_rows, Dy, Dy, GEMM_BM, VITB200_DT_F32))) return rc;
+  return launch_gemm_tc_wgrad(st, tx, ty, tc, ts.zeros.p, dW, Dx, Dy, R, splits, m->dt, cg);
 }
 
 int train_supported(const vitb200_model* m) {
@@ -1051,6 +1059,21 @@ int vitb200_attention_tc(void* stream, const void* qkv, void* out, int batch, in
 int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch, int T, int heads) {
   if (!qkv || !out) return fail(VITB200_ERR_INVALID, "attention_f32: null pointer");
   return launch_attention_f32(static_cast<cudaStream_t>(stream), qkv, out, batch, T, heads);
+}
+
+int vitb200_gemm_tc_wgrad(void* stream, const void* X, const void* dY, float* dW, int M, int N, int K, int splits, int dtype) {
+  if (!X || !dY || !dW) return fail(VITB200_ERR_INVALID, "gemm_tc_wgrad: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0 || (M % 8) != 0 || (N % 8) != 0)
+    return fail(VITB200_ERR_INVALID, "gemm_tc_wgrad: M and N must be positive multiples of 8");
+  if (dtype != VITB200_DT_BF16 && dtype != VITB200_DT_F16) return fail(VITB200_ERR_INVALID, "gemm_tc_wgrad: dtype must be bf16 or fp16");
+  const int mode = gemm_tc_tile_mode(M, N);
+  const int cg = mode == 4 ? 2 : mode;
+  CUtensorMap tx, ty, tc;
+  int rc;
+  if ((rc = make_tmap_2d(&tx, X, K, M, M, 64, dtype))) return rc;
+  if ((rc = make_tmap_2d(&ty, dY, K, N, N, 64, dtype))) return rc;
+  if ((rc = make_tmap_2d(&tc, dW, M, N, N, GEMM_BM, VITB200_DT_F32))) return rc;
+  return launch_gemm_tc_wgrad(static_cast<cudaStream_t>(stream), tx, ty, tc, nullptr, dW, M, N, K, splits, dtype, cg);
 }
 
 int vitb200_attention_bwd(void* stream, const void* qkv, const void* d_out, void* dqkv, int batch, int T, int heads,

@@ -90,6 +90,10 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tokens_per_image, int dtype, int cta_group,
                    const Dropout& drop = Dropout(), int cls_off = 1, const float* cls = nullptr);
+// Weight gradient C[M, N] += X[K, M]^T dY[K, N] (fp32 C, TMA reduce-add, split-K `splits`): tmX / tmdY are maps
+// over the ROW-MAJOR activations with 64-row x 64-column boxes (MN-major operands, no transposed copies)
+int launch_gemm_tc_wgrad(cudaStream_t stream, const CUtensorMap& tmX, const CUtensorMap& tmdY, const CUtensorMap& tmC,
+                         const float* zero_bias, float* C, int M, int N, int K, int splits, int dtype, int cta_group);
 // `cls` (PATCH epilogue, cls_off == 1): also write the class-token rows b*T = cls + pos[0]
 // 1 = one CTA per 128x256 tile (Wt box 256 rows), 2 = CTA pair per 256x256 tile (Wt box 128 rows),
 // 4 = cluster of two pairs sharing a multicast weight tile (Wt box 64 rows).

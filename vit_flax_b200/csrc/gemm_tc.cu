@@ -70,7 +70,12 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.0f + tanh_approx(u));
 }
 
-template <int kEpi, int kDT, int kCG, bool kDrop>
+// kMN (weight gradients, dW = X^T dY): both operands are read MN-major straight from the row-major
+// activations -- tmA over X [K rows, M cols], tmB over dY [K rows, N cols], boxes of 64 rows x 64
+// columns -- so the K dimension of the GEMM is the ROW index and no transposed copy is needed.  A
+// stage then holds, per operand, one 8 KB box per 64-column atom (LBO = 8 KB between atoms, 1 KB
+// between 8-row groups); rows past K are zero-filled by TMA.
+template <int kEpi, int kDT, int kCG, bool kDrop, bool kMN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmB,
@@ -162,8 +167,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             if (rank == 0) mbar_arrive(full_bar(stage));
           } else if constexpr (CL == 1) {
             mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(sA + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, a_row);
-            tma_load_2d(sB + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, b_row);
+            if constexpr (kMN) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sA + stage * A_BYTES + j * 8192, &tmA, full_bar(stage), a_row + j * 64, kb * BK);
+#pragma unroll
+              for (int j = 0; j < Cfg<kCG>::B_ROWS / 64; ++j)
+                tma_load_2d(sB + stage * B_BYTES + j * 8192, &tmB, full_bar(stage), b_row + j * 64, kb * BK);
+            } else {
+              tma_load_2d(sA + stage * A_BYTES, &tmA, full_bar(stage), kb * BK, a_row);
+              tma_load_2d(sB + stage * B_BYTES, &tmB, full_bar(stage), kb * BK, b_row);
+            }
           } else {
             // Both CTAs' loads complete on the pair LEADER's full barrier (the MMA issuer waits there).
             // Only the leader arrives, arming the bytes of both CTAs: the peer's complete_tx may
@@ -172,6 +186,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             // cluster-scope release costs >1000 cycles per stage (profiles/r01_gemm_pair.md).
             const uint32_t lead_full = mapa_shared(full_bar(stage), lead);
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            if constexpr (kMN) {
+              static_assert(!kMN || CL <= 2, "MN-major operands are not built for the multicast cluster");
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d_cg2(sA + stage * A_BYTES + j * 8192, &tmA, lead_full, a_row + j * 64, kb * BK);
+#pragma unroll
+              for (int j = 0; j < Cfg<kCG>::B_ROWS / 64; ++j)
+                tma_load_2d_cg2(sB + stage * B_BYTES + j * 8192, &tmB, lead_full, b_row + j * 64, kb * BK);
+            } else {
             tma_load_2d_cg2(sA + stage * A_BYTES, &tmA, lead_full, kb * BK, a_row);
             if constexpr (CL == 2) {
               tma_load_2d_cg2(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, b_row);
@@ -180,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
               // CTA of equal rank in the other pair; each destination signals its own pair leader.
               tma_load_2d_cg2_mc(sB + stage * B_BYTES + pair * (Cfg<kCG>::B_LOAD_ROWS * BK * 2), &tmB,
                                  lead_full, kb * BK, b_row, uint16_t(0x5u << rank));
+            }
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -190,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only in pair mode) =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_16(TILE_M, BN, kDT == DT_F16 ? 0 : 1);
+      constexpr uint32_t idesc = umma_idesc_16(TILE_M, BN, kDT == DT_F16 ? 0 : 1, kMN ? 1 : 0, kMN ? 1 : 0);
       const uint16_t pair_mask = uint16_t(0x3u << lead);               // both CTAs of this pair
       const uint16_t all_mask = uint16_t((1u << CL) - 1u);             // every CTA whose smem the stage's loads touch
       int stage = 0;
@@ -209,6 +233,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           const uint32_t a0 = sA + stage * A_BYTES, b0 = sB + stage * B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
+            if constexpr (kMN)   // 16 K-rows of 128 B further per step
+              umma_bf16_ss<MMA_CG>(d_tmem, umma_desc_mn_sw128_wide(a0 + k * UMMA_K * 128, 8192),
+                                   umma_desc_mn_sw128_wide(b0 + k * UMMA_K * 128, 8192), idesc,
+                                   (kb != kb0 || k != 0) ? 1u : 0u);
+            else
             umma_bf16_ss<MMA_CG>(d_tmem, umma_desc_k_sw128(a0 + k * UMMA_K * 2),
                               umma_desc_k_sw128(b0 + k * UMMA_K * 2), idesc,
                               (kb != kb0 || k != 0) ? 1u : 0u);
@@ -354,7 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int j = 0; j < 8; ++j) {              // 4 fp32 columns -> one 16-byte chunk
               const int nb = n0 + j * 4;
               float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (nb < N && sp == 0) b4 = __ldg(reinterpret_cast<const float4*>((cls_row ? cls : bias) + nb));
+              if (nb < N && sp == 0 && bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>((cls_row ? cls : bias) + nb));
               float o0 = __uint_as_float(r[j * 4 + 0]), o1 = __uint_as_float(r[j * 4 + 1]);
               float o2 = __uint_as_float(r[j * 4 + 2]), o3 = __uint_as_float(r[j * 4 + 3]);
               if constexpr (kEpi == VITB200_EPI_TOKENS_F32) {
@@ -411,14 +440,14 @@ int gemm_dbg() {   // VITB200_GEMM_DBG bit 0: no TMA loads, bit 1: no output sto
   return v;
 }
 
-template <int kEpi, int kDT, int kCG, bool kDrop>
+template <int kEpi, int kDT, int kCG, bool kDrop, bool kMN = false>
 int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
               const float* aux, int tpi, const Dropout& drop, int cls_off, const float* cls) {
   static bool configured = false;   // per-process; attribute is per-function, device-agnostic
   static int max_units = 0;         // clusters (CTAs for kCG == 1) that can be resident at once
   if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>,
+    VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG, kDrop, kMN>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG>()));
     max_units = sm_count() / Cfg<kCG>::CL;
     if (Cfg<kCG>::CL > 2) {   // clusters of 4 do not tile every GPC: ask how many fit (33 on a 148-SM B200)
@@ -434,7 +463,7 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       cfg.gridDim = dim3(sm_count() / Cfg<kCG>::CL * Cfg<kCG>::CL);
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, &cfg) == cudaSuccess && n > 0)
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<kEpi, kDT, kCG, kDrop, kMN>, &cfg) == cudaSuccess && n > 0)
         max_units = n < max_units ? n : max_units;
       else
         cudaGetLastError();
@@ -444,7 +473,7 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
   const int splits = (kEpi == VITB200_EPI_BIAS_RESID_F32 && tpi > 1) ? tpi : 1;
   const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, Cfg<kCG>::BN_) * splits;
   const int units = tiles < max_units ? tiles : max_units;
-  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop>, dim3(units * Cfg<kCG>::CL), dim3(NUM_THREADS), smem_bytes<kCG>(),
+  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop, kMN>, dim3(units * Cfg<kCG>::CL), dim3(NUM_THREADS), smem_bytes<kCG>(),
                         stream, Cfg<kCG>::CL, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off, cls));
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
@@ -519,6 +548,26 @@ int gemm_tc_tile_mode(int M, int N) {
   if (forced == 1 || forced == 2 || forced == 4 || forced == 64) return forced;
   if (M <= 2 * GEMM_BM) return N > GEMM_BN ? 64 : 1;
   return 2;
+}
+
+int launch_gemm_tc_wgrad(cudaStream_t stream, const CUtensorMap& tmX, const CUtensorMap& tmdY, const CUtensorMap& tmC,
+                         const float* zero_bias, float* C, int M, int N, int K, int splits, int dtype, int cta_group) {   // zero_bias may be null
+  if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc_wgrad: empty problem");
+  if ((M % 8) != 0 || (N % 8) != 0) return fail(VITB200_ERR_INVALID, "gemm_tc_wgrad: M and N must be multiples of 8");
+  const int num_kb = ceil_div(K, GEMM_BK);
+  int sp = splits < 1 ? 1 : (splits > num_kb ? num_kb : splits);
+  sp = ceil_div(num_kb, ceil_div(num_kb, sp));
+  constexpr int E = VITB200_EPI_BIAS_RESID_F32;
+#define VB_WGRAD(DT)                                                                                                     \
+  do {                                                                                                                   \
+    if (cta_group == 64) return launch_cg<E, DT, 64, false, true>(stream, tmX, tmdY, tmC, zero_bias, C, M, N, K, nullptr, sp, Dropout(), 1, nullptr); \
+    if (cta_group == 1) return launch_cg<E, DT, 1, false, true>(stream, tmX, tmdY, tmC, zero_bias, C, M, N, K, nullptr, sp, Dropout(), 1, nullptr);   \
+    return launch_cg<E, DT, 2, false, true>(stream, tmX, tmdY, tmC, zero_bias, C, M, N, K, nullptr, sp, Dropout(), 1, nullptr);                        \
+  } while (0)
+  if (dtype == DT_BF16) VB_WGRAD(DT_BF16);
+  if (dtype == DT_F16) VB_WGRAD(DT_F16);
+#undef VB_WGRAD
+  return fail(VITB200_ERR_INVALID, "gemm_tc_wgrad: dtype must be bf16 or fp16");
 }
 
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,

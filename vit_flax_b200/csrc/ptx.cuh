@@ -334,12 +334,19 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t addr) {
   return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) |
          (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32, K-major A; B major selectable.
+// The same for an operand several 64-element atoms wide along MN: atom j starts `lbo_bytes` after
+// atom j-1 (canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in 16-bit elements).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_wide(uint32_t addr, uint32_t lbo_bytes) {
+  return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32; operand majors selectable.
 // `fmt`: 0 = F16, 1 = BF16 (UMMA F16F32Format).
-__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fmt, int b_mn_major = 0) {
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fmt, int b_mn_major = 0, int a_mn_major = 0) {
   return (1u << 4)                       // D format  : F32
          | (uint32_t(fmt) << 7)          // A format
          | (uint32_t(fmt) << 10)         // B format
+         | (uint32_t(a_mn_major) << 15)  // A major   : 0 = K, 1 = MN
          | (uint32_t(b_mn_major) << 16)  // B major   : 0 = K, 1 = MN
          | (uint32_t(N >> 3) << 17)      // N >> 3
          | (uint32_t(M >> 4) << 24);     // M >> 4
