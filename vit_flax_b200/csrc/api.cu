@@ -882,7 +882,6 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
   ts.fwd_batch = 0;
   const auto& c = m->cfg;
   const int D = c.dim, I = m->inner, T = m->T, H = c.mlp_dim, R = batch * T;
-  const size_t xbytes = size_t(R) * D * sizeof(float);
   if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels, c.patch_h, c.patch_w,
                             m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
   if ((rc = gemm16(m, st, m->patches_h.p, R, m->K0pad, m->patch.wt, m->patch.Kpad, D, ts.xs[0].p, R, VITB200_EPI_TOKENS_F32,
@@ -894,14 +893,12 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
     float* x1 = ts.xs[2 * l + 1].p;
     float* x2 = ts.xs[2 * l + 2].p;
     // x1 = x0 + to_out(attention(to_qkv(LN1(x0))));  x0 stays behind as the saved LayerNorm input
-    if ((rc = launch_layernorm(st, x0, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), S.xn1.p, R, D, m->dt, m->eps))) return rc;
-    VB_CUDA(cudaMemcpyAsync(x1, x0, xbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_layernorm(st, x0, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), S.xn1.p, R, D, m->dt, m->eps, x1))) return rc;
     if ((rc = gemm16(m, st, S.xn1.p, R, D, L.qkv.wt, L.qkv.Kpad, 3 * I, S.qkv.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = launch_attention_tc(st, S.qkv.p, S.o.p, batch, T, c.heads, m->dt))) return rc;
     if ((rc = gemm16(m, st, S.o.p, R, I, L.out.wt, L.out.Kpad, D, x1, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.out.leaf_bias)))) return rc;
     // x2 = x1 + ff2(gelu(ff1(LN2(x1)))), the pre-activation kept for gelu'
-    if ((rc = launch_layernorm(st, x1, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), S.xn2.p, R, D, m->dt, m->eps))) return rc;
-    VB_CUDA(cudaMemcpyAsync(x2, x1, xbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_layernorm(st, x1, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), S.xn2.p, R, D, m->dt, m->eps, x2))) return rc;
     if ((rc = gemm16(m, st, S.xn2.p, R, D, L.ff1.wt, L.ff1.Kpad, H, S.pre.p, R, VITB200_EPI_BIAS_16, leaf_ptr(m, L.ff1.leaf_bias)))) return rc;
     if ((rc = launch_gelu_fwd(st, S.pre.p, S.hid.p, int64_t(R) * H, m->dt))) return rc;
     if ((rc = gemm16(m, st, S.hid.p, R, H, L.ff2.wt, L.ff2.Kpad, D, x2, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.ff2.leaf_bias)))) return rc;
@@ -943,19 +940,16 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
     Layer& L = m->layers[l];
     auto& S = ts.layers[l];
     // ---- x2 = x1 + Dense_1(gelu(Dense_0(LN2(x1))))   (vit.py:39,47-53) ----
-    if ((rc = launch_cast16(st, ts.dx.p, ts.dy16.p, int64_t(R) * D, dt))) return rc;
-    if ((rc = launch_colsum(st, ts.dx.p, grad_ptr(m, L.ff2.leaf_bias), R, D, VITB200_DT_F32))) return rc;
+    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.ff2.leaf_bias), R, D, dt))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.ff2.wf, D, H, ts.dhid16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.hid.p, H, ts.dy16.p, D, R, grad_ptr(m, L.ff2.leaf_kernel), H))) return rc;
-    if ((rc = launch_gelu_bwd(st, S.pre.p, ts.dhid16.p, ts.dhid16.p, int64_t(R) * H, dt))) return rc;
-    if ((rc = launch_colsum(st, ts.dhid16.p, grad_ptr(m, L.ff1.leaf_bias), R, H, dt))) return rc;
+    if ((rc = launch_gelu_bwd_colsum(st, S.pre.p, ts.dhid16.p, ts.dhid16.p, grad_ptr(m, L.ff1.leaf_bias), R, H, dt))) return rc;
     if ((rc = gemm16(m, st, ts.dhid16.p, R, H, L.ff1.wf, H, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.xn2.p, D, ts.dhid16.p, H, R, grad_ptr(m, L.ff1.leaf_kernel), D))) return rc;
     if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l + 1].p, leaf_ptr(m, L.ln2_scale), ts.dx.p, grad_ptr(m, L.ln2_scale),
                             grad_ptr(m, L.ln2_bias), R, D, dt, m->eps, 1))) return rc;
     // ---- x1 = x0 + to_out(attention(to_qkv(LN1(x0))))   (vit.py:39,62-87) ----
-    if ((rc = launch_cast16(st, ts.dx.p, ts.dy16.p, int64_t(R) * D, dt))) return rc;
-    if ((rc = launch_colsum(st, ts.dx.p, grad_ptr(m, L.out.leaf_bias), R, D, VITB200_DT_F32))) return rc;
+    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.out.leaf_bias), R, D, dt))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.out.wf, D, I, ts.do16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.o.p, I, ts.dy16.p, D, R, grad_ptr(m, L.out.leaf_kernel), I))) return rc;
     if ((rc = launch_attention_bwd(st, S.qkv.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt))) return rc;

@@ -78,6 +78,64 @@ gelu_kernel(const uint16_t* __restrict__ pre, const uint16_t* __restrict__ dhid,
   }
 }
 
+// Fused row passes with a column sum (the bias gradients ride along with a pass that is needed anyway):
+//   MODE 0: y16 = cast(x32),                      sums += x32          (dy for the GEMMs + db of to_out / FF Dense_1)
+//   MODE 1: out16 = dhid16 * gelu'(pre16),        sums += out16        (gelu backward + db of FF Dense_0)
+// A thread owns 8 consecutive columns and walks rows blockIdx.y * 8 + ty, + 8 gridDim.y, ...; a block covers
+// 256 columns; the 8 row lanes of a block meet in shared memory, then one atomic per column and block.
+template <int kDT, int MODE>
+__global__ void __launch_bounds__(256)
+rowpass_colsum_kernel(const void* __restrict__ in0, const uint16_t* __restrict__ in1, uint16_t* __restrict__ out,
+                      float* __restrict__ sums, int rows, int cols) {
+  __shared__ float red[8][256];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + tx * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < cols) {
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+      const int64_t o = int64_t(r) * cols + c;
+      float v[8];
+      if constexpr (MODE == 0) {
+        const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(in0) + o);
+        const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(in0) + o + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+        const uint4 p = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(in0) + o);
+        const uint4 d = *reinterpret_cast<const uint4*>(in1 + o);
+        const uint32_t pw[4] = {p.x, p.y, p.z, p.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a, b, da, db;
+          unpack2<kDT>(pw[j], a, b);
+          unpack2<kDT>(dw[j], da, db);
+          v[2 * j] = da * gelu_tanh_grad(a);
+          v[2 * j + 1] = db * gelu_tanh_grad(b);
+        }
+      }
+      uint4 w;
+      w.x = pack2<kDT>(v[0], v[1]); w.y = pack2<kDT>(v[2], v[3]); w.z = pack2<kDT>(v[4], v[5]); w.w = pack2<kDT>(v[6], v[7]);
+      *reinterpret_cast<uint4*>(out + o) = w;
+      if constexpr (MODE == 1) {   // the bias gradient is the sum of what the GEMMs will see: the rounded values
+        unpack2<kDT>(w.x, v[0], v[1]); unpack2<kDT>(w.y, v[2], v[3]); unpack2<kDT>(w.z, v[4], v[5]); unpack2<kDT>(w.w, v[6], v[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    atomicAdd(sums + col, t);
+  }
+}
+
 // out[c, r] = in[r, c] for r < rows, 0 for rows <= r < rows_pad  (16-bit elements, 64x64 tiles)
 __global__ void __launch_bounds__(256)
 transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int rows, int cols, int rows_pad) {
@@ -169,12 +227,17 @@ ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, cons
         xv[k] = dv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       s += (xv[k].x + xv[k].y) + (xv[k].z + xv[k].w);
-      ss += (xv[k].x * xv[k].x + xv[k].y * xv[k].y) + (xv[k].z * xv[k].z + xv[k].w * xv[k].w);
     }
-    s = warp_sum(s);
-    ss = warp_sum(ss);
-    const float mean = s * inv_d;
-    const float rstd = rsqrtf(fmaxf(0.f, ss * inv_d - mean * mean) + eps);   // flax: var = max(0, E[x^2] - E[x]^2)
+    const float mean = warp_sum(s) * inv_d;
+    ss = 0.f;                                 // same two-pass variance as the forward kernel (simt.cu)
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      if (4 * (lane + 32 * k) < dim) {
+        const float p = xv[k].x - mean, q = xv[k].y - mean, u = xv[k].z - mean, w = xv[k].w - mean;
+        ss += (p * p + q * q) + (u * u + w * w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int k = 0; k < KV; ++k) {
@@ -618,6 +681,29 @@ int launch_gelu_bwd(cudaStream_t st, const void* pre, const void* dhid, void* dp
                               static_cast<const uint16_t*>(pre), static_cast<const uint16_t*>(dhid),
                               static_cast<uint16_t*>(dpre), n / 8)));
   VB_LAUNCH_CHECK("gelu_kernel(bwd)");
+  return 0;
+}
+
+static dim3 rowpass_grid(int rows, int cols) {
+  const int gx = (cols + 255) / 256;
+  const int gy = std::max(1, std::min((rows + 7) / 8, std::max(1, 4 * sm_count() / gx)));
+  return dim3(unsigned(gx), unsigned(gy));
+}
+
+int launch_cast16_colsum(cudaStream_t st, const float* x, void* y, float* sums, int rows, int cols, int dtype) {
+  if (rows <= 0 || cols <= 0 || (cols & 7)) return fail(VITB200_ERR_INVALID, "cast16_colsum: cols must be a positive multiple of 8");
+  VB_DT16_DISPATCH(dtype, (rowpass_colsum_kernel<kDT, 0><<<rowpass_grid(rows, cols), 256, 0, st>>>(
+                              x, nullptr, static_cast<uint16_t*>(y), sums, rows, cols)));
+  VB_LAUNCH_CHECK("rowpass_colsum_kernel(cast)");
+  return 0;
+}
+
+int launch_gelu_bwd_colsum(cudaStream_t st, const void* pre, const void* dhid, void* dpre, float* sums, int rows, int cols,
+                           int dtype) {
+  if (rows <= 0 || cols <= 0 || (cols & 7)) return fail(VITB200_ERR_INVALID, "gelu_bwd_colsum: cols must be a positive multiple of 8");
+  VB_DT16_DISPATCH(dtype, (rowpass_colsum_kernel<kDT, 1><<<rowpass_grid(rows, cols), 256, 0, st>>>(
+                              pre, static_cast<const uint16_t*>(dhid), static_cast<uint16_t*>(dpre), sums, rows, cols)));
+  VB_LAUNCH_CHECK("rowpass_colsum_kernel(gelu_bwd)");
   return 0;
 }
 

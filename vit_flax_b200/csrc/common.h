@@ -105,7 +105,8 @@ int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const f
                     float* C, int M, int N, int K, int epilogue, const float* aux,
                     int tokens_per_image, const Dropout& drop = Dropout(), int cls_off = 1);
 int launch_layernorm(cudaStream_t stream, const float* x, const float* scale, const float* bias,
-                     void* y, int rows, int dim, int out_dtype, float eps = 1e-6f);
+                     void* y, int rows, int dim, int out_dtype, float eps = 1e-6f, float* copy = nullptr);
+// `copy` (training): the kernel also writes x to `copy`, the residual buffer the following GEMM adds into
 int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
                         int heads, int dtype);
 bool attention_tc5_supports(int T);
@@ -130,6 +131,10 @@ int launch_pack_weight(cudaStream_t stream, const float* W, void* Wt, int K, int
 int launch_cast16(cudaStream_t stream, const float* x, void* y, int64_t n, int dtype);
 int launch_gelu_fwd(cudaStream_t stream, const void* pre, void* hid, int64_t n, int dtype);
 int launch_gelu_bwd(cudaStream_t stream, const void* pre, const void* dhid, void* dpre, int64_t n, int dtype);
+// fused passes: y16 = cast(x), sums[c] += sum_r x[r, c]  /  dpre = dhid * gelu'(pre), sums[c] += sum_r dpre[r, c]
+int launch_cast16_colsum(cudaStream_t stream, const float* x, void* y, float* sums, int rows, int cols, int dtype);
+int launch_gelu_bwd_colsum(cudaStream_t stream, const void* pre, const void* dhid, void* dpre, float* sums, int rows,
+                           int cols, int dtype);
 // out[c, r] = in[r, c], r < rows; zero for rows <= r < rows_pad (the K padding of the wgrad GEMMs)
 int launch_transpose16(cudaStream_t stream, const void* in, void* out, int rows, int cols, int rows_pad);
 // out[c] += sum_r in[r, c]; dtype may be VITB200_DT_F32

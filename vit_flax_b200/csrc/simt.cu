@@ -34,7 +34,8 @@ __device__ __forceinline__ float warp_max(float v) {
 template <int NV, int kDT>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                      const float* __restrict__ bias, void* __restrict__ y, int rows, int dim, int reverse, float eps) {
+                      const float* __restrict__ bias, void* __restrict__ y, int rows, int dim, int reverse, float eps,
+                      float* __restrict__ copy) {   // copy != null (training): also x -> copy, the next residual buffer
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,6 +53,7 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ sca
     const int c = i * 32 + lane;
     if (c < nvec) {
       v[i] = __ldcs(xr + c);
+      if (copy != nullptr) reinterpret_cast<float4*>(copy + int64_t(row) * dim)[c] = v[i];
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -127,20 +129,21 @@ int ln_reverse() {
 
 template <int kDT>
 int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b, void* y, int rows,
-                int dim, float eps) {
+                int dim, float eps, float* copy) {
   const int grid = ceil_div(rows, 8);
   const bool vec = (dim % 4 == 0) && dim <= 2048 &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                      reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
-  if (!vec) {
+  if (!vec || (reinterpret_cast<uintptr_t>(copy) & 15) != 0) {
+    if (copy != nullptr) VB_CUDA(cudaMemcpyAsync(copy, x, size_t(rows) * dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
     VB_CUDA(launch_kernel(layernorm_generic_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, eps));
   } else {
     const int nv = ceil_div(dim, 128);
-    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
-    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
-    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
-    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
-    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps));
+    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
   }
   VB_LAUNCH_CHECK("layernorm");
   return 0;
@@ -538,9 +541,9 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   }
 
 int launch_layernorm(cudaStream_t st, const float* x, const float* g, const float* b, void* y,
-                     int rows, int dim, int out_dtype, float eps) {
+                     int rows, int dim, int out_dtype, float eps, float* copy) {
   if (rows <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "layernorm: empty problem");
-  VB_DT_DISPATCH(out_dtype, return launch_ln_t<kDT>(st, x, g, b, y, rows, dim, eps));
+  VB_DT_DISPATCH(out_dtype, return launch_ln_t<kDT>(st, x, g, b, y, rows, dim, eps, copy));
   return 0;
 }
 
