@@ -320,6 +320,35 @@ def run_b200(args) -> None:
                       "steps": 10, "logits": out2[:4].cpu().numpy()}
         eng2.close()
 
+    # ---- the training step (train_forward + backward, no optimiser), for the record ----
+    train_line = None
+    if rank == 0 and world == 1 and not args.no_train:
+        dl = torch.randn((B, 1000), dtype=torch.float32, device=dev) / B
+        lt = torch.empty((B, 1000), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            eng.train_forward(images, out=lt)
+            eng.backward(dl)
+        torch.cuda.synchronize()
+        n_tr = 8
+        l0 = launch_count()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * n_tr + 1)]
+        evs[0].record()
+        for i in range(n_tr):
+            eng.train_forward(images, out=lt)
+            evs[2 * i + 1].record()
+            eng.backward(dl)
+            evs[2 * i + 2].record()
+        torch.cuda.synchronize()
+        tf = sum(evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(n_tr)) / n_tr
+        tb = sum(evs[2 * i + 1].elapsed_time(evs[2 * i + 2]) for i in range(n_tr)) / n_tr
+        gnorm = float(eng.grad_tensor("Transformer_0/Attention_0/Dense_0/kernel").double().norm())
+        train_line = {"value": B / ((tf + tb) * 1e-3), "unit": "images/s", "steps": n_tr,
+                      "train_forward_ms": round(tf, 3), "backward_ms": round(tb, 3),
+                      "model_tflops": 3 * flops_per_image(C2)["total"] * B / ((tf + tb) * 1e-3) / 1e12,
+                      "launches_per_step": int((launch_count() - l0) // n_tr), "grad_norm_finite": bool(np.isfinite(gnorm)),
+                      "note": "vjp of the forward wrt every parameter leaf (activations kept, no optimiser, no dropout); "
+                              "FLOPs counted as 3x the forward; parity: tests/test_gpu_backward.py against float64 autograd"}
+
     # ---- in-run parity spot check against the CPU oracle (checker only) ----
     parity = None
     cpu = None
@@ -385,6 +414,7 @@ def run_b200(args) -> None:
                         "last3": round(sum(per_step[-3:]) / max(1, len(per_step[-3:])), 3),
                         "note": "back-to-back forwards hit the 1000 W cap after ~50 ms: SM clock 1.97 -> ~1.5 GHz"},
             "other_operand_format": other_line,
+            "train_step": train_line,
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": int(host_np[0].nbytes), "d2h_bytes_per_step": int(B * 1000 * 4),
                     "steps": e2e_steps,
@@ -414,6 +444,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--cpu-images", type=int, default=64, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (forward + backward) record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

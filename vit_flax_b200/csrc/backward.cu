@@ -195,94 +195,112 @@ colsum_kernel(const void* __restrict__ in, float* __restrict__ out, int rows, in
 // ------------------------------------------------------------------ LayerNorm backward
 // dx[r,:] (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum_r dy * xhat,
 // dbeta += sum_r dy.  One warp per row, float4 / 8-byte accesses: lane owns columns 4 (lane + 32 k) .. +3,
-// k < KV (dim <= 128 KV), and keeps its share of dgamma / dbeta in registers over all the rows of the
-// warp; the warps of a block are reduced through shared memory, so a column sees one atomic per block.
+// k < KV (dim <= 128 KV).  The kernel is a pure HBM stream (14 bytes per element), so what matters is
+// bytes in flight: the loads of the warp's NEXT row (x, dy, dx) are issued before the current row is
+// reduced, and dgamma / dbeta accumulate in a warp-private shared-memory strip (no atomics, no
+// registers) that the block folds into one atomic per column at the end.
 template <int kDT, int KV>
 __global__ void __launch_bounds__(128)
 ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim,
               float eps, int accumulate) {
-  extern __shared__ float red[];            // [2][dim]
+  extern __shared__ float4 acc_sm[];        // [warps][2][dim / 4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  float4 ag[KV], ab[KV];
-#pragma unroll
-  for (int k = 0; k < KV; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nvec = dim >> 2;
+  float4* ag = acc_sm + size_t(warp) * 2 * nvec;
+  float4* ab = ag + nvec;
+  for (int i = lane; i < 2 * nvec; i += 32) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
   const float inv_d = 1.0f / float(dim);
-  for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
-    const float* xr = x + int64_t(r) * dim;
-    const uint16_t* dr = dy + int64_t(r) * dim;
-    float4 xv[KV], dv[KV];
+  const int stride = gridDim.x * nw;
+  int r = blockIdx.x * nw + warp;
+  float4 nx[KV], no[KV];
+  uint2 nd[KV];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec && row < rows) {
+        nx[k] = reinterpret_cast<const float4*>(x + int64_t(row) * dim)[c];
+        nd[k] = reinterpret_cast<const uint2*>(dy + int64_t(row) * dim)[c];
+        no[k] = accumulate ? reinterpret_cast<const float4*>(dx + int64_t(row) * dim)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        nx[k] = no[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nd[k] = make_uint2(0u, 0u);
+      }
+    }
+  };
+  fetch(r);
+  for (; r < rows; r += stride) {
+    float4 xv[KV], dv[KV], ov[KV];
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      xv[k] = nx[k];
+      ov[k] = no[k];
+      unpack2<kDT>(nd[k].x, dv[k].x, dv[k].y);
+      unpack2<kDT>(nd[k].y, dv[k].z, dv[k].w);
+    }
+    fetch(r + stride);                        // in flight while this row is reduced
     float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int k = 0; k < KV; ++k) {
-      const int c = 4 * (lane + 32 * k);
-      if (c < dim) {
-        xv[k] = *reinterpret_cast<const float4*>(xr + c);
-        const uint2 d2 = *reinterpret_cast<const uint2*>(dr + c);
-        unpack2<kDT>(d2.x, dv[k].x, dv[k].y);
-        unpack2<kDT>(d2.y, dv[k].z, dv[k].w);
-      } else {
-        xv[k] = dv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       s += (xv[k].x + xv[k].y) + (xv[k].z + xv[k].w);
+      ss += (xv[k].x * xv[k].x + xv[k].y * xv[k].y) + (xv[k].z * xv[k].z + xv[k].w * xv[k].w);
     }
-    const float mean = warp_sum(s) * inv_d;
-    ss = 0.f;                                 // same two-pass variance as the forward kernel (simt.cu)
 #pragma unroll
-    for (int k = 0; k < KV; ++k) {
-      if (4 * (lane + 32 * k) < dim) {
-        const float p = xv[k].x - mean, q = xv[k].y - mean, u = xv[k].z - mean, w = xv[k].w - mean;
-        ss += (p * p + q * q) + (u * u + w * w);
-      }
+    for (int o = 16; o > 0; o >>= 1) {       // the two reductions share their shuffle latency
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
     }
-    const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+    const float mean = s * inv_d;
+    const float rstd = rsqrtf(fmaxf(0.f, ss * inv_d - mean * mean) + eps);   // flax: var = max(0, E[x^2] - E[x]^2)
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int k = 0; k < KV; ++k) {
-      const int c = 4 * (lane + 32 * k);
-      float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < dim) gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      xv[k].x = (xv[k].x - mean) * rstd; xv[k].y = (xv[k].y - mean) * rstd;
-      xv[k].z = (xv[k].z - mean) * rstd; xv[k].w = (xv[k].w - mean) * rstd;
-      ag[k].x += dv[k].x * xv[k].x; ag[k].y += dv[k].y * xv[k].y; ag[k].z += dv[k].z * xv[k].z; ag[k].w += dv[k].w * xv[k].w;
-      ab[k].x += dv[k].x; ab[k].y += dv[k].y; ab[k].z += dv[k].z; ab[k].w += dv[k].w;
-      dv[k].x *= gm.x; dv[k].y *= gm.y; dv[k].z *= gm.z; dv[k].w *= gm.w;      // g = dy * gamma (0 beyond dim)
-      a += (dv[k].x + dv[k].y) + (dv[k].z + dv[k].w);
-      b += (dv[k].x * xv[k].x + dv[k].y * xv[k].y) + (dv[k].z * xv[k].z + dv[k].w * xv[k].w);
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        xv[k].x = (xv[k].x - mean) * rstd; xv[k].y = (xv[k].y - mean) * rstd;
+        xv[k].z = (xv[k].z - mean) * rstd; xv[k].w = (xv[k].w - mean) * rstd;
+        float4 g4 = ag[c], b4 = ab[c];
+        g4.x += dv[k].x * xv[k].x; g4.y += dv[k].y * xv[k].y; g4.z += dv[k].z * xv[k].z; g4.w += dv[k].w * xv[k].w;
+        b4.x += dv[k].x; b4.y += dv[k].y; b4.z += dv[k].z; b4.w += dv[k].w;
+        ag[c] = g4;
+        ab[c] = b4;
+        dv[k].x *= gm.x; dv[k].y *= gm.y; dv[k].z *= gm.z; dv[k].w *= gm.w;      // g = dy * gamma
+        a += (dv[k].x + dv[k].y) + (dv[k].z + dv[k].w);
+        b += (dv[k].x * xv[k].x + dv[k].y * xv[k].y) + (dv[k].z * xv[k].z + dv[k].w * xv[k].w);
+      }
     }
-    a = warp_sum(a) * inv_d;
-    b = warp_sum(b) * inv_d;
-    float* dxr = dx + int64_t(r) * dim;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    a *= inv_d;
+    b *= inv_d;
+    float4* dxr = reinterpret_cast<float4*>(dx + int64_t(r) * dim);
 #pragma unroll
     for (int k = 0; k < KV; ++k) {
-      const int c = 4 * (lane + 32 * k);
-      if (c < dim) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
         float4 v;
-        v.x = rstd * (dv[k].x - a - xv[k].x * b); v.y = rstd * (dv[k].y - a - xv[k].y * b);
-        v.z = rstd * (dv[k].z - a - xv[k].z * b); v.w = rstd * (dv[k].w - a - xv[k].w * b);
-        if (accumulate) {
-          const float4 o = *reinterpret_cast<const float4*>(dxr + c);
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-        *reinterpret_cast<float4*>(dxr + c) = v;
+        v.x = ov[k].x + rstd * (dv[k].x - a - xv[k].x * b); v.y = ov[k].y + rstd * (dv[k].y - a - xv[k].y * b);
+        v.z = ov[k].z + rstd * (dv[k].z - a - xv[k].z * b); v.w = ov[k].w + rstd * (dv[k].w - a - xv[k].w * b);
+        dxr[c] = v;
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < KV; ++k) {
-    const int c = 4 * (lane + 32 * k);
-    if (c < dim) {
-      atomicAdd(red + c, ag[k].x); atomicAdd(red + c + 1, ag[k].y); atomicAdd(red + c + 2, ag[k].z); atomicAdd(red + c + 3, ag[k].w);
-      atomicAdd(red + dim + c, ab[k].x); atomicAdd(red + dim + c + 1, ab[k].y);
-      atomicAdd(red + dim + c + 2, ab[k].z); atomicAdd(red + dim + c + 3, ab[k].w);
-    }
-  }
   __syncthreads();
+  const float* accf = reinterpret_cast<const float*>(acc_sm);
   for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[dim + i]);
+    float tg = 0.f, tb = 0.f;
+    for (int w = 0; w < nw; ++w) {
+      tg += accf[size_t(w) * 2 * dim + i];
+      tb += accf[size_t(w) * 2 * dim + dim + i];
+    }
+    atomicAdd(dgamma + i, tg);
+    atomicAdd(dbeta + i, tb);
   }
 }
 
@@ -729,8 +747,8 @@ int launch_colsum(cudaStream_t st, const void* in, float* out, int rows, int col
 template <int kDT, int KV>
 int launch_ln_bwd_t(cudaStream_t st, const void* dy, const float* x, const float* gamma, float* dx, float* dgamma,
                     float* dbeta, int rows, int dim, float eps, int accumulate) {
-  const int grid = std::min((rows + 3) / 4, sm_count() * 4);   // 128-thread blocks: 3-4 resident per SM at 158 registers
-  ln_bwd_kernel<kDT, KV><<<grid, 128, 2 * size_t(dim) * sizeof(float), st>>>(static_cast<const uint16_t*>(dy), x, gamma, dx,
+  const int grid = std::min((rows + 3) / 4, sm_count() * 3);   // persistent: 128-thread blocks, two to three resident per SM
+  ln_bwd_kernel<kDT, KV><<<grid, 128, 4 * 2 * size_t(dim) * sizeof(float), st>>>(static_cast<const uint16_t*>(dy), x, gamma, dx,
                                                                            dgamma, dbeta, rows, dim, eps, accumulate);
   VB_LAUNCH_CHECK("ln_bwd_kernel");
   return 0;
