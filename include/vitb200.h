@@ -225,8 +225,9 @@ int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch,
  * tile's K range (<= 1: none) and meet in the fp32 reduce-add.  dW must be initialised (it accumulates). */
 int vitb200_gemm_tc_wgrad(void* stream, const void* X, const void* dY, float* dW,
                           int M, int N, int K, int splits, int dtype);
-/* adjoint of vitb200_attention_tc for T <= 208: (qkv, d_out [batch*T, heads*64]) -> dqkv [batch*T, 3*heads*64] */
-int vitb200_attention_bwd(void* stream, const void* qkv, const void* d_out, void* dqkv,
+/* adjoint of vitb200_attention_tc for T <= 208: (qkv, out = the forward's output, d_out [batch*T, heads*64])
+ * -> dqkv [batch*T, 3*heads*64] */
+int vitb200_attention_bwd(void* stream, const void* qkv, const void* out, const void* d_out, void* dqkv,
                           int batch, int T, int heads, int dtype);
 /* adjoint of vitb200_layernorm: dx (+)= d/dx, dscale += , dbias += ; dy is 16-bit of `dtype`, dim <= 1280 */
 int vitb200_layernorm_bwd(void* stream, const void* dy, const float* x, const float* scale,

@@ -56,7 +56,9 @@ def test_attention_bwd(lib, batch, T, heads, fmt):
     qkv = (torch.randn((batch * T, 3 * inner), generator=g) * 1.2).to(tdt).cuda()
     d_out = torch.randn((batch * T, inner), generator=g).to(tdt).cuda()
     dqkv = torch.full((batch * T, 3 * inner), 9.0, dtype=tdt, device="cuda")
-    _lib.check(lib.vitb200_attention_bwd(stream(), qkv.data_ptr(), d_out.data_ptr(), dqkv.data_ptr(), batch, T, heads, dt))
+    out = torch.empty((batch * T, inner), dtype=tdt, device="cuda")             # the forward's output, as train_forward keeps it
+    _lib.check(lib.vitb200_attention_tc(stream(), qkv.data_ptr(), out.data_ptr(), batch, T, heads, dt))
+    _lib.check(lib.vitb200_attention_bwd(stream(), qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), dqkv.data_ptr(), batch, T, heads, dt))
     torch.cuda.synchronize()
     x = qkv.double().view(batch, T, 3, heads, 64).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)   # [3, B, h, T, 64]
     o = torch.softmax(x[0] @ x[1].transpose(-1, -2) / 8.0, dim=-1) @ x[2]                                      # vit.py:73-78

@@ -69,7 +69,7 @@ SIGNATURES = {
     "vitb200_get_grad": (_i, [_vp, _vp, C.c_char_p, _fp]),
     "vitb200_grad_device": (_i, [_vp, C.c_char_p, C.POINTER(C.c_void_p)]),
     "vitb200_gemm_tc_wgrad": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i]),
-    "vitb200_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "vitb200_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "vitb200_layernorm_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, C.c_float, _i]),
     "vitb200_gemm_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i]),
     "vitb200_gemm_tc_dropout": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i, C.c_float, C.c_uint64, C.c_uint32]),

@@ -952,7 +952,7 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
     if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.out.leaf_bias), R, D, dt))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.out.wf, D, I, ts.do16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.o.p, I, ts.dy16.p, D, R, grad_ptr(m, L.out.leaf_kernel), I))) return rc;
-    if ((rc = launch_attention_bwd(st, S.qkv.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt))) return rc;
+    if ((rc = launch_attention_bwd(st, S.qkv.p, S.o.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt))) return rc;
     if ((rc = gemm16(m, st, ts.dqkv16.p, R, 3 * I, L.qkv.wf, 3 * I, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.xn1.p, D, ts.dqkv16.p, 3 * I, R, grad_ptr(m, L.qkv.leaf_kernel), D))) return rc;
     if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l].p, leaf_ptr(m, L.ln1_scale), ts.dx.p, grad_ptr(m, L.ln1_scale),
@@ -1070,10 +1070,10 @@ int vitb200_gemm_tc_wgrad(void* stream, const void* X, const void* dY, float* dW
   return launch_gemm_tc_wgrad(static_cast<cudaStream_t>(stream), tx, ty, tc, nullptr, dW, M, N, K, splits, dtype, cg);
 }
 
-int vitb200_attention_bwd(void* stream, const void* qkv, const void* d_out, void* dqkv, int batch, int T, int heads,
-                          int dtype) {
-  if (!qkv || !d_out || !dqkv) return fail(VITB200_ERR_INVALID, "attention_bwd: null pointer");
-  return launch_attention_bwd(static_cast<cudaStream_t>(stream), qkv, d_out, dqkv, batch, T, heads, dtype);
+int vitb200_attention_bwd(void* stream, const void* qkv, const void* out, const void* d_out, void* dqkv, int batch, int T,
+                          int heads, int dtype) {
+  if (!qkv || !out || !d_out || !dqkv) return fail(VITB200_ERR_INVALID, "attention_bwd: null pointer");
+  return launch_attention_bwd(static_cast<cudaStream_t>(stream), qkv, out, d_out, dqkv, batch, T, heads, dtype);
 }
 
 int vitb200_layernorm_bwd(void* stream, const void* dy, const float* x, const float* scale, float* dx, float* dscale,

@@ -477,10 +477,34 @@ __device__ __forceinline__ void store_tile_16x64(const float (&acc)[8][4], uint1
   }
 }
 
+// One 64-key chunk of a 16-row score block: acc[8][4] = rows(sA frag af) . X[keys ch*64 .. +63]^T
 template <int kDT>
-__global__ void __launch_bounds__(256, 1)
-attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ d_out, uint16_t* __restrict__ dqkv,
-                     int T, int heads, int TP, int pitch) {
+__device__ __forceinline__ void score_chunk(float (&acc)[8][4], const uint32_t (&af)[4][4], uint32_t sX, int ch, int nblk,
+                                            int lane) {
+  const int mi = lane >> 3, r8 = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (ch * 4 + p < nblk) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(swz(sX, (ch * 4 + p) * 16 + (mi >> 1) * 8 + r8, ks * 2 + (mi & 1)), b0, b1, b2, b3);
+        mma_16816<kDT>(acc[2 * p], af[ks], b0, b1);
+        mma_16816<kDT>(acc[2 * p + 1], af[ks], b2, b3);
+      }
+    }
+  }
+}
+
+// One warp per 16-row block (13 at T = 197).  Phase A keeps its 16 x T score block in registers; phase B
+// works on 64-key chunks with D_i = sum_d dO_id O_id taken from the attention output kept by the forward
+// (instead of a full row of dP), so the kernel fits 13 warps (allocated as 16: 128 registers each).
+template <int kDT>
+__global__ void __launch_bounds__(416, 1)
+attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ o_fwd, const uint16_t* __restrict__ d_out,
+                     uint16_t* __restrict__ dqkv, int T, int heads, int TP, int pitch) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tg = lane & 3, mi = lane >> 3, r8 = lane & 7;
@@ -494,12 +518,13 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
   const uint32_t sD = sV + uint32_t(TP) * ROW_BYTES, sP = sD + uint32_t(TP) * ROW_BYTES;
   load_rows(sQ, qbase, ld, TP, T);
   load_rows(sK, qbase + inner, ld, TP, T);
-  load_rows(sV, qbase + 2 * inner, ld, TP, T);
+  cp_async_commit();
+  load_rows(sV, qbase + 2 * inner, ld, TP, T);     // v and dO land while phase A runs on q and k
   load_rows(sD, d_out + int64_t(b) * T * inner + h * DH, inner, TP, T);
   cp_async_commit();
-  cp_async_wait<0>();
+  cp_async_wait<1>();
   __syncthreads();
-  const int nblk = TP >> 4, ntiles = TP >> 3;
+  const int nblk = TP >> 4, nch = (TP + 63) >> 6;
   const float sl2 = 0.125f * 1.4426950408889634f;   // dim_head^-0.5 * log2(e)
 
   // ---- A: P = softmax(q k^T / 8) -> smem ----
@@ -508,6 +533,7 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
       ldmatrix_x4(swz(sQ, qb * 16 + (mi & 1) * 8 + r8, ks * 2 + (mi >> 1)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+    // the whole 16 x TP score block lives in registers (104 at T = 197..208): one q k^T, one exp sweep
     float s[ABW_MAX_NT][4];
 #pragma unroll
     for (int nt = 0; nt < ABW_MAX_NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
@@ -523,29 +549,29 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
         }
       }
     }
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < ntiles) {
+      if (nt < 2 * nblk) {
         const int c0 = nt * 8 + 2 * tg;
         if (c0 >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
         if (c0 + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
       }
     }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < ntiles) {
-        s[nt][0] = ex2_approx((s[nt][0] - mx0) * sl2);
-        s[nt][1] = ex2_approx((s[nt][1] - mx0) * sl2);
-        s[nt][2] = ex2_approx((s[nt][2] - mx1) * sl2);
-        s[nt][3] = ex2_approx((s[nt][3] - mx1) * sl2);
+      if (nt < 2 * nblk) {
+        s[nt][0] = ex2_approx((s[nt][0] - m0) * sl2);
+        s[nt][1] = ex2_approx((s[nt][1] - m0) * sl2);
+        s[nt][2] = ex2_approx((s[nt][2] - m1) * sl2);
+        s[nt][3] = ex2_approx((s[nt][3] - m1) * sl2);
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
       }
@@ -558,12 +584,13 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
     const uint32_t pa = sP + uint32_t(qb * 16 + g) * pitch + uint32_t(2 * tg) * 2, pb = pa + 8u * pitch;
 #pragma unroll
     for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < ntiles) {
+      if (nt < 2 * nblk) {
         sts32(pa + nt * 16, pack2<kDT>(s[nt][0] * i0, s[nt][1] * i0));
         sts32(pb + nt * 16, pack2<kDT>(s[nt][2] * i1, s[nt][3] * i1));
       }
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
 
   // ---- A2: dV = P^T dO ----
@@ -582,64 +609,65 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
       ldmatrix_x4(swz(sD, qb * 16 + (mi & 1) * 8 + r8, ks * 2 + (mi >> 1)), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
-    float dp[ABW_MAX_NT][4];
+    // D_i = sum_d dO[i, d] O[i, d] for rows g and g + 8 of the block (quad = one row pair, 16 columns per lane)
+    float d0 = 0.f, d1 = 0.f;
+    {
+      const int ra = qb * 16 + g, rb = ra + 8;
+      const uint16_t* oa = o_fwd + (int64_t(b) * T + ra) * inner + h * DH;
+      const uint16_t* ob = o_fwd + (int64_t(b) * T + rb) * inner + h * DH;
 #pragma unroll
-    for (int nt = 0; nt < ABW_MAX_NT; ++nt) { dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
-#pragma unroll
-    for (int p = 0; p < ABW_MAX_NT / 2; ++p) {
-      if (p < nblk) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(swz(sV, p * 16 + (mi >> 1) * 8 + r8, ks * 2 + (mi & 1)), b0, b1, b2, b3);
-          mma_16816<kDT>(dp[2 * p], dof[ks], b0, b1);
-          mma_16816<kDT>(dp[2 * p + 1], dof[ks], b2, b3);
+      for (int nt = 0; nt < 8; ++nt) {
+        float x0, x1, y0, y1;
+        if (ra < T) {
+          unpack2<kDT>(lds32(swz(sD, ra, nt) + uint32_t(tg) * 4), x0, x1);
+          unpack2<kDT>(*reinterpret_cast<const uint32_t*>(oa + nt * 8 + 2 * tg), y0, y1);
+          d0 += x0 * y0 + x1 * y1;
+        }
+        if (rb < T) {
+          unpack2<kDT>(lds32(swz(sD, rb, nt) + uint32_t(tg) * 4), x0, x1);
+          unpack2<kDT>(*reinterpret_cast<const uint32_t*>(ob + nt * 8 + 2 * tg), y0, y1);
+          d1 += x0 * y0 + x1 * y1;
         }
       }
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
     }
     const uint32_t pa = sP + uint32_t(qb * 16 + g) * pitch + uint32_t(2 * tg) * 2, pb = pa + 8u * pitch;
-    float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < ntiles) {
-        float p0, p1, p2, p3;
-        unpack2<kDT>(lds32(pa + nt * 16), p0, p1);
-        unpack2<kDT>(lds32(pb + nt * 16), p2, p3);
-        d0 += p0 * dp[nt][0] + p1 * dp[nt][1];
-        d1 += p2 * dp[nt][2] + p3 * dp[nt][3];
-      }
-    }
-    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    uint32_t dsf[ABW_MAX_NT / 2][4];
-#pragma unroll
-    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < ntiles) {
-        float p0, p1, p2, p3;
-        unpack2<kDT>(lds32(pa + nt * 16), p0, p1);
-        unpack2<kDT>(lds32(pb + nt * 16), p2, p3);
-        const uint32_t va = pack2<kDT>(p0 * (dp[nt][0] - d0) * 0.125f, p1 * (dp[nt][1] - d0) * 0.125f);
-        const uint32_t vb = pack2<kDT>(p2 * (dp[nt][2] - d1) * 0.125f, p3 * (dp[nt][3] - d1) * 0.125f);
-        sts32(pa + nt * 16, va);
-        sts32(pb + nt * 16, vb);
-        if ((nt & 1) == 0) { dsf[nt >> 1][0] = va; dsf[nt >> 1][1] = vb; }
-        else               { dsf[nt >> 1][2] = va; dsf[nt >> 1][3] = vb; }
-      }
-    }
     float dq[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+    for (int ch = 0; ch < nch; ++ch) {
+      float dp[8][4];
+      score_chunk<kDT>(dp, dof, sV, ch, nblk, lane);
+      uint32_t dsf[4][4];
 #pragma unroll
-    for (int j = 0; j < ABW_MAX_NT / 2; ++j) {
-      if (j < nblk) {
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t va = 0u, vb = 0u;
+        if (ch * 64 + nt * 8 < TP) {
+          const uint32_t off = uint32_t(ch * 64 + nt * 8) * 2;
+          float p0, p1, p2, p3;
+          unpack2<kDT>(lds32(pa + off), p0, p1);
+          unpack2<kDT>(lds32(pb + off), p2, p3);
+          va = pack2<kDT>(p0 * (dp[nt][0] - d0) * 0.125f, p1 * (dp[nt][1] - d0) * 0.125f);
+          vb = pack2<kDT>(p2 * (dp[nt][2] - d1) * 0.125f, p3 * (dp[nt][3] - d1) * 0.125f);
+          sts32(pa + off, va);
+          sts32(pb + off, vb);
+        }
+        if ((nt & 1) == 0) { dsf[nt >> 1][0] = va; dsf[nt >> 1][1] = vb; }
+        else               { dsf[nt >> 1][2] = va; dsf[nt >> 1][3] = vb; }
+      }
 #pragma unroll
-        for (int dpi = 0; dpi < 4; ++dpi) {
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4_trans(swz(sK, j * 16 + (mi & 1) * 8 + r8, dpi * 2 + (mi >> 1)), b0, b1, b2, b3);
-          mma_16816<kDT>(dq[2 * dpi], dsf[j], b0, b1);
-          mma_16816<kDT>(dq[2 * dpi + 1], dsf[j], b2, b3);
+      for (int p = 0; p < 4; ++p) {
+        if (ch * 4 + p < nblk) {
+#pragma unroll
+          for (int dpi = 0; dpi < 4; ++dpi) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(swz(sK, (ch * 4 + p) * 16 + (mi & 1) * 8 + r8, dpi * 2 + (mi >> 1)), b0, b1, b2, b3);
+            mma_16816<kDT>(dq[2 * dpi], dsf[p], b0, b1);
+            mma_16816<kDT>(dq[2 * dpi + 1], dsf[p], b2, b3);
+          }
         }
       }
     }
@@ -802,12 +830,12 @@ int launch_token_grads(cudaStream_t st, const float* dx, float* dpos, float* dcl
 
 int attention_bwd_max_tokens() { return ABW_MAX_T; }
 
-int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, int batch, int T, int heads,
-                         int dtype) {
+int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv, int batch, int T,
+                         int heads, int dtype) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
   if (T > ABW_MAX_T) return fail(VITB200_ERR_UNSUPPORTED, "attention_bwd: more than 208 tokens is not built");
   const int TP = (T + 15) / 16 * 16, pitch = TP * 2 + 16;
-  const int nblk = TP / 16, rounds = (nblk + 7) / 8, nw = (nblk + rounds - 1) / rounds;
+  const int nblk = TP / 16, nw = nblk;                        // one warp per 16-row block (<= 13)
   const size_t smem = size_t(4) * TP * ROW_BYTES + size_t(TP) * pitch;
   static bool configured = false;
   if (!configured) {
@@ -816,8 +844,8 @@ int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* d_out, vo
     configured = true;
   }
   VB_DT16_DISPATCH(dtype, (attention_bwd_kernel<kDT><<<unsigned(batch * heads), nw * 32, smem, st>>>(
-                              static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(d_out),
-                              static_cast<uint16_t*>(dqkv), T, heads, TP, pitch)));
+                              static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(o_fwd),
+                              static_cast<const uint16_t*>(d_out), static_cast<uint16_t*>(dqkv), T, heads, TP, pitch)));
   VB_LAUNCH_CHECK("attention_bwd_kernel");
   return 0;
 }

@@ -149,7 +149,8 @@ int launch_head_bwd(cudaStream_t stream, const float* pl, const float* dl, const
 int launch_token_grads(cudaStream_t stream, const float* dx, float* dpos, float* dcls, float* dbias, int batch,
                        int T, int dim, int cls_off);
 int attention_bwd_max_tokens();
-int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* d_out, void* dqkv, int batch, int T,
-                         int heads, int dtype);
+// o_fwd: the attention output of the forward pass (rowsum(dO o O) replaces a full row of dP)
+int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
+                         int batch, int T, int heads, int dtype);
 
 }  // namespace vb
