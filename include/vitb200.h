@@ -164,6 +164,9 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images_de
 int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits_dev, int batch);
 /* gradient of one leaf (flax path, same shape as the parameter) -> host; synchronises the stream */
 int vitb200_get_grad(vitb200_model* m, void* stream, const char* path, float* host_out);
+/* all leaf gradients as ONE contiguous fp32 buffer (leaves 256-byte aligned, padding zero): the unit of
+ * the data-parallel gradient all-reduce -- one collective per step instead of one per leaf            */
+int vitb200_grads_buffer(vitb200_model* m, float** dev_out, int64_t* count);
 /* device pointer of the same gradient (valid until the model is destroyed; overwritten by backward) */
 int vitb200_grad_device(vitb200_model* m, const char* path, float** dev_out);
 

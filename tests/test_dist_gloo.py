@@ -60,3 +60,44 @@ def test_sharded_logits_world2_gloo(global_batch):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, (global_batch, 5)), (1, True, (global_batch, 5))]
+
+
+def _grad_worker(rank, world, port, q):
+    """Data-parallel backward on CPU: each rank differentiates the oracle on its batch shard; the
+    all-reduced gradient buffer must equal the gradient of the whole batch (the VJP is additive)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import vit_torch
+        from vit_flax_b200 import init_params, perturb_params
+        from vit_flax_b200.dist import all_reduce_grads
+        from vit_flax_b200.params import flatten_params
+        cfg = dict(image_size=16, patch_size=8, num_classes=8, dim=64, depth=1, heads=2, mlp_dim=64)
+        v = perturb_params(init_params(seed=1, **cfg), seed=2)
+        rng = np.random.default_rng(3)
+        img = rng.standard_normal((6, 16, 16, 3)).astype(np.float32)
+        dl = rng.standard_normal((6, 8))
+        s, e = shard_range(6, world, rank)
+        _, g_local = vit_torch.vit_vjp(v, img[s:e], dl[s:e], **cfg)
+        keys = sorted(flatten_params({"params": g_local}))
+        flat = torch.cat([torch.as_tensor(flatten_params({"params": g_local})[k]).reshape(-1) for k in keys])
+        all_reduce_grads(flat)
+        _, g_all = vit_torch.vit_vjp(v, img, dl, **cfg)
+        want = torch.cat([torch.as_tensor(flatten_params({"params": g_all})[k]).reshape(-1) for k in keys])
+        q.put((rank, bool(torch.allclose(flat, want, rtol=1e-9, atol=1e-12))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_reduce_grads_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

@@ -67,6 +67,7 @@ SIGNATURES = {
     "vitb200_train_forward": (_i, [_vp, _vp, _fp, _i, _fp]),
     "vitb200_backward": (_i, [_vp, _vp, _fp, _i]),
     "vitb200_get_grad": (_i, [_vp, _vp, C.c_char_p, _fp]),
+    "vitb200_grads_buffer": (_i, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "vitb200_grad_device": (_i, [_vp, C.c_char_p, C.POINTER(C.c_void_p)]),
     "vitb200_gemm_tc_wgrad": (_i, [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i]),
     "vitb200_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),

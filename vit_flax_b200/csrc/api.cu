@@ -980,6 +980,14 @@ int vitb200_get_grad(vitb200_model* m, void* stream, const char* path, float* ho
   return 0;
 }
 
+int vitb200_grads_buffer(vitb200_model* m, float** dev_out, int64_t* count) {
+  if (!m || !dev_out || !count) return fail(VITB200_ERR_INVALID, "grads_buffer: null argument");
+  if (!m->train) return fail(VITB200_ERR_INVALID, "grads_buffer: no train_forward has run");
+  *dev_out = m->train->grads.p;
+  *count = int64_t(m->train->grads.n);
+  return 0;
+}
+
 int vitb200_grad_device(vitb200_model* m, const char* path, float** dev_out) {
   if (!m || !path || !dev_out) return fail(VITB200_ERR_INVALID, "grad_device: null argument");
   if (!m->train) return fail(VITB200_ERR_INVALID, "grad_device: no backward pass has run");

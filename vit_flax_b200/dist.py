@@ -1,4 +1,4 @@
-"""Batch-sharded forward across the GPUs of one node.
+"""Batch-sharded forward (and data-parallel backward) across the GPUs of one node.
 
 Images are independent (no op of vit.py mixes the batch axis), so rank r takes
 the contiguous shard ``[start, stop)`` of the global batch, weights are
@@ -61,3 +61,17 @@ def sharded_logits(forward_local: Callable[[torch.Tensor, torch.Tensor], None],
     rows = [padded[r, : shard_range(global_batch, world, r)[1] - shard_range(global_batch, world, r)[0]]
             for r in range(world)]
     return torch.cat(rows, dim=0)
+
+
+def all_reduce_grads(grads_flat: torch.Tensor, group: Optional[dist.ProcessGroup] = None, average: bool = False) -> torch.Tensor:
+    """Data-parallel backward: every rank ran ``train_forward`` / ``backward`` on its batch shard; the
+    parameter gradients of the global batch are their SUM (the VJP is additive over the batch), so the
+    one exchange step is an all-reduce of the contiguous gradient buffer (``Engine.grads_flat()``,
+    346 MB for ViT-B/16) -- a single NCCL collective, reduced in the NVSwitch when NVLS is up.
+    In place; ``average`` divides by the world size (a mean-over-global-batch loss whose cotangent
+    each rank scaled by its LOCAL batch)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(grads_flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            grads_flat.div_(dist.get_world_size(group))
+    return grads_flat

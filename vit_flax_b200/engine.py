@@ -148,6 +148,17 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         return torch.as_tensor(_Buf(), device=self.device).view(*shape)
 
+    def grads_flat(self):
+        """Every leaf gradient as one contiguous fp32 CUDA tensor (a view of the library's buffer):
+        what a data-parallel step all-reduces (``vit_flax_b200.dist.all_reduce_grads``)."""
+        torch = self._torch
+        ptr, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.vitb200_grads_buffer(self.handle, C.byref(ptr), C.byref(n)))
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<f4", "data": (int(ptr.value), False), "version": 2}
+        return torch.as_tensor(_Buf(), device=self.device)
+
     def grads(self) -> Dict[str, np.ndarray]:
         """{flax path: float32 ndarray} of the last backward pass."""
         out = {}
