@@ -153,8 +153,9 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 /* ---- training: forward that keeps its activations + backward -----
  * Nothing in the reference trains (no jax.grad anywhere in vit_flax), so these have no reference
  * counterpart; they are the two halves of jax.vjp(lambda p: ViT.apply(p, img), params).
- * Built for the bf16 / fp16 modes, dropout rates 0, at most 208 tokens per image, dim <= 1280;
- * anything else returns VITB200_ERR_UNSUPPORTED.  Activations (about 5.4 KB per token and layer for
+ * Built for the bf16 / fp16 modes, at most 208 tokens per image, dim <= 1280; anything else returns
+ * VITB200_ERR_UNSUPPORTED.  With dropout rates > 0 the forward draws its masks from the key of
+ * vitb200_set_dropout_key and the backward replays them (they are pure functions of key, site, element).  Activations (about 5.4 KB per token and layer for
  * ViT-B) and one fp32 gradient per leaf are allocated for max_batch on the first call.           */
 int vitb200_train_forward(vitb200_model* m, void* stream, const float* images_dev, int batch,
                           float* logits_dev);

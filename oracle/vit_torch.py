@@ -39,7 +39,20 @@ def _ln(x, p):
     return F.layer_norm(x, (x.shape[-1],), p["scale"], p["bias"], eps=1e-6)
 
 
-def _attention(x, p, heads, dim, dt=None):
+def _drop(x, drop, site):
+    """``nn.Dropout(rate)(x, deterministic=False)`` with the Philox masks of libvitb200 (oracle/philox.py);
+    ``drop`` = None or (rate, key); x is [..., cols], rows = the flattened leading axes."""
+    if drop is None or drop[0] == 0.0:
+        return x
+    import numpy as np
+    from . import philox
+    flat_shape = (int(x.numel() // x.shape[-1]), int(x.shape[-1]))
+    keep = torch.as_tensor(philox.keep_mask(flat_shape, drop[0], site, drop[1])).view(x.shape)
+    inv = float(np.float32(1.0) / (np.float32(1.0) - np.float32(drop[0])))      # the kernels scale in fp32
+    return torch.where(keep, x * inv, torch.zeros((), dtype=x.dtype))
+
+
+def _attention(x, p, heads, dim, dt=None, drop=None, site=0):
     b, n, _ = x.shape
     qkv = _r(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt), dt)               # vit.py:68
     q, k, v = qkv.chunk(3, dim=-1)                                         # vit.py:69
@@ -53,17 +66,18 @@ def _attention(x, p, heads, dim, dt=None):
         o = (_r(e, dt) @ v) / e.sum(dim=-1, keepdim=True)
     o = _r(o.transpose(1, 2).reshape(b, n, heads * DIM_HEAD), dt)          # vit.py:79
     if not (heads == 1 and DIM_HEAD == dim):                               # vit.py:65
-        o = F.linear(o, _r(p["Dense_1"]["kernel"], dt).t(), p["Dense_1"]["bias"])  # vit.py:82
+        o = _drop(F.linear(o, _r(p["Dense_1"]["kernel"], dt).t(), p["Dense_1"]["bias"]), drop, site)  # vit.py:82-83
     return o
 
 
-def _ff(x, p, dt=None):
+def _ff(x, p, dt=None, drop=None, site=0):
     h = F.gelu(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt) + p["Dense_0"]["bias"], approximate="tanh")  # vit.py:48-49
-    return _r(h, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"]                           # vit.py:51
+    h = _drop(h, drop, site)                                                                           # vit.py:50
+    return _drop(_r(h, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"], drop, site + 1)    # vit.py:51-52
 
 
 def _vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, depth,
-                heads, mlp_dim, pool="cls", operand_dtype=None):
+                heads, mlp_dim, pool="cls", operand_dtype=None, dropout=0.0, emb_dropout=0.0, dropout_key=None):
     """``params_t``: the ``params`` sub-tree already converted by ``tree_to_torch``.
     ``operand_dtype`` (torch.bfloat16 / torch.float16 / None): emulate 16-bit GEMM operands."""
     dt = operand_dtype
@@ -76,10 +90,13 @@ def _vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, 
     x = _r(x, dt) @ _r(p["Dense_0"]["kernel"], dt) + p["Dense_0"]["bias"]  # vit.py:147
     x = torch.cat([p["cls"].expand(b, -1, -1), x], dim=1)                  # vit.py:151-152
     x = x + p["pos_embedding"][:, : x.shape[1]]                            # vit.py:153
+    # dropout sites as in include/vitb200.h: 0 emb, 1+3l after to_out, 2+3l after gelu, 3+3l after FF Dense_1
+    x = _drop(x, (emb_dropout, dropout_key) if emb_dropout else None, 0)   # vit.py:155
+    drop = (dropout, dropout_key) if dropout else None
     tp = p["Transformer_0"]
     for l in range(depth):                                                 # vit.py:108-110
-        x = _attention(_ln(x, tp[f"PreNorm_{2 * l}"]["LayerNorm_0"]), tp[f"Attention_{l}"], heads, dim, dt) + x
-        x = _ff(_ln(x, tp[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"]), tp[f"FeedForward_{l}"], dt) + x
+        x = _attention(_ln(x, tp[f"PreNorm_{2 * l}"]["LayerNorm_0"]), tp[f"Attention_{l}"], heads, dim, dt, drop, 1 + 3 * l) + x
+        x = _ff(_ln(x, tp[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"]), tp[f"FeedForward_{l}"], dt, drop, 2 + 3 * l) + x
     x = x.mean(dim=1) if pool == "mean" else x[:, 0]                       # vit.py:159
     x = _ln(x, p["LayerNorm_0"])                                           # vit.py:163
     return _r(x, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"]   # vit.py:165

@@ -215,10 +215,41 @@ def test_vjp_api_and_loss_scaling():
     for k in ref:
         assert got[k].shape == ref[k].shape and got[k].dtype == np.float32
         assert rel_err(got[k], ref[k]) < 2e-2, k
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="dropout"):                     # rates > 0 need the 'dropout' rng, like apply
         ViT(dropout=0.1, **cfg).vjp(variables, img)
     with pytest.raises(ValueError):
         vjp_fn(dl[:2])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 2e-2), ("bf16", 8e-2)])
+def test_backward_with_dropout_replays_the_forward_masks(precision, tol):
+    """vit.py:50,52,83,155 with rates > 0: train_forward drops with the Philox masks of the 'dropout' key and
+    the backward replays them (nothing is stored); the oracle differentiates the same dropped forward."""
+    cfg = dict(image_size=32, patch_size=8, num_classes=16, dim=128, depth=2, heads=2, mlp_dim=256)
+    rate, emb_rate, key = 0.2, 0.1, 0x0123456789ABCDEF
+    variables = perturb_params(init_params(seed=71, **cfg), seed=72)
+    img = images_for(cfg, 6, seed=73)
+    dl = np.random.default_rng(74).standard_normal((6, 16)).astype(np.float32)
+    eng = Engine(precision=precision, max_batch=8, dropout=rate, emb_dropout=emb_rate, **cfg)
+    eng.load_params(variables)
+    eng.set_dropout_key(key)
+    x = torch.as_tensor(img, device="cuda")
+    logits = eng.train_forward(x).cpu().numpy()
+    assert np.abs(logits - eng.forward(x).cpu().numpy()).max() < 2e-2          # the same masks as the inference-path dropout
+    eng.set_dropout_key(key + 1)                                               # backward must use the FORWARD's key
+    eng.backward(torch.as_tensor(dl, device="cuda"))
+    want_logits, want = vit_torch.vit_vjp(variables, img, dl, dropout=rate, emb_dropout=emb_rate, dropout_key=key, **cfg)
+    assert np.abs(logits - want_logits).max() < (2e-2 if precision == "fp16" else 5e-2)
+    got, ref = eng.grads(), flatten_params({"params": want})
+    errs = {k: rel_err(got[k], ref[k]) for k in ref}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < tol, (worst, errs[worst])
+    # and through the module surface
+    v = ViT(dropout=rate, emb_dropout=emb_rate, **cfg)
+    _, vjp_fn = v.vjp(variables, img, rngs={"dropout": 5}, precision=precision)
+    g = flatten_params(vjp_fn(dl))
+    assert all(np.isfinite(a).all() for a in g.values()) and set(g) == set(ref)
+    eng.close()
 
 
 def test_backward_errors():

@@ -144,6 +144,7 @@ struct vitb200_model {
   struct TrainLayer { DevBuf<uint16_t> xn1, qkv, o, xn2, pre, hid; };
   struct TrainState {
     int fwd_batch = 0;                    // batch of the last train_forward (0 = none to differentiate)
+    uint64_t fwd_key = 0;                 // 'dropout' rng key of that forward: the backward replays its masks
     std::vector<DevBuf<float>> xs;        // residual stream before every LayerNorm + after the last layer
     std::vector<TrainLayer> layers;
     DevBuf<float> dx, pooled_ln, dpl, zeros, grads;
@@ -780,7 +781,8 @@ inline float* grad_ptr(vitb200_model* m, int leaf) { return leaf >= 0 ? m->train
 
 // C[c_rows <= M, N] = epilogue(A[M, K] x Wt[N, ldw]^T) with tensor maps encoded per call (host side, ~1 us each)
 int gemm16(vitb200_model* m, cudaStream_t st, const void* A, int M, int K, const void* Wt, int ldw, int N, void* C,
-           int c_rows, int epi, const float* bias, const float* aux = nullptr, int tpi = 0, const float* cls = nullptr) {
+           int c_rows, int epi, const float* bias, const float* aux = nullptr, int tpi = 0, const float* cls = nullptr,
+           const Dropout& drop = Dropout()) {
   CUtensorMap ta, tb, tc;
   int rc;
   const int cg = gemm_tc_tile_mode(M, N);
@@ -788,7 +790,7 @@ int gemm16(vitb200_model* m, cudaStream_t st, const void* A, int M, int K, const
   if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, m->dt))) return rc;
   if ((rc = make_tmap_2d(&tb, Wt, N, ldw, ldw, cg == 64 ? 64 : GEMM_BN / cg, m->dt))) return rc;
   if ((rc = make_tmap_2d(&tc, C, c_rows, N, N, GEMM_BM, out16 ? m->dt : VITB200_DT_F32))) return rc;
-  return launch_gemm_tc(st, ta, tb, &tc, bias, C, M, N, K, epi, aux, tpi, m->dt, cg, Dropout(), m->cls_off, cls);
+  return launch_gemm_tc(st, ta, tb, &tc, bias, C, M, N, K, epi, aux, tpi, m->dt, cg, drop, m->cls_off, cls);
 }
 
 // dW[Dx (first c_rows rows), Dy] += X[R, Dx]^T dY[R, Dy]: the GEMM reads both row-major activations as
@@ -819,7 +821,6 @@ int wgrad(vitb200_model* m, cudaStream_t st, const void* X, int Dx, const void* 
 int train_supported(const vitb200_model* m) {
   const auto& c = m->cfg;
   if (!m->tc) return fail(VITB200_ERR_UNSUPPORTED, "train: the backward pass is built for the bf16/fp16 modes only");
-  if (c.dropout > 0.f || c.emb_dropout > 0.f) return fail(VITB200_ERR_UNSUPPORTED, "train: dropout > 0 is not built for the backward pass");
   if (!m->project_out) return fail(VITB200_ERR_UNSUPPORTED, "train: heads == 1 with dim == 64 (identity to_out) is not built");
   if (m->T > attention_bwd_max_tokens()) return fail(VITB200_ERR_UNSUPPORTED, "train: more than 208 tokens per image is not built for the backward pass");
   if (c.dim > 1280) return fail(VITB200_ERR_UNSUPPORTED, "train: dim > 1280 is not built for the backward pass");
@@ -885,7 +886,8 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
   if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels, c.patch_h, c.patch_w,
                             m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
   if ((rc = gemm16(m, st, m->patches_h.p, R, m->K0pad, m->patch.wt, m->patch.Kpad, D, ts.xs[0].p, R, VITB200_EPI_TOKENS_F32,
-                   leaf_ptr(m, m->patch.leaf_bias), leaf_ptr(m, m->leaf_pos), T, leaf_ptr(m, m->leaf_cls)))) return rc;
+                   leaf_ptr(m, m->patch.leaf_bias), leaf_ptr(m, m->leaf_pos), T, leaf_ptr(m, m->leaf_cls),
+                   m->drop(c.emb_dropout, 0)))) return rc;
   for (int l = 0; l < c.depth; ++l) {
     Layer& L = m->layers[l];
     auto& S = ts.layers[l];
@@ -896,12 +898,14 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
     if ((rc = launch_layernorm(st, x0, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), S.xn1.p, R, D, m->dt, m->eps, x1))) return rc;
     if ((rc = gemm16(m, st, S.xn1.p, R, D, L.qkv.wt, L.qkv.Kpad, 3 * I, S.qkv.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = launch_attention_tc(st, S.qkv.p, S.o.p, batch, T, c.heads, m->dt))) return rc;
-    if ((rc = gemm16(m, st, S.o.p, R, I, L.out.wt, L.out.Kpad, D, x1, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.out.leaf_bias)))) return rc;
+    if ((rc = gemm16(m, st, S.o.p, R, I, L.out.wt, L.out.Kpad, D, x1, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.out.leaf_bias),
+                     nullptr, 0, nullptr, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     // x2 = x1 + ff2(gelu(ff1(LN2(x1)))), the pre-activation kept for gelu'
     if ((rc = launch_layernorm(st, x1, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), S.xn2.p, R, D, m->dt, m->eps, x2))) return rc;
     if ((rc = gemm16(m, st, S.xn2.p, R, D, L.ff1.wt, L.ff1.Kpad, H, S.pre.p, R, VITB200_EPI_BIAS_16, leaf_ptr(m, L.ff1.leaf_bias)))) return rc;
-    if ((rc = launch_gelu_fwd(st, S.pre.p, S.hid.p, int64_t(R) * H, m->dt))) return rc;
-    if ((rc = gemm16(m, st, S.hid.p, R, H, L.ff2.wt, L.ff2.Kpad, D, x2, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.ff2.leaf_bias)))) return rc;
+    if ((rc = launch_gelu_fwd(st, S.pre.p, S.hid.p, int64_t(R) * H, m->dt, m->drop(c.dropout, 2 + 3 * l)))) return rc;
+    if ((rc = gemm16(m, st, S.hid.p, R, H, L.ff2.wt, L.ff2.Kpad, D, x2, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.ff2.leaf_bias),
+                     nullptr, 0, nullptr, m->drop(c.dropout, 3 + 3 * l)))) return rc;
   }
   const float* xf = ts.xs[2 * size_t(c.depth)].p;
   if ((rc = launch_pool_layernorm(st, xf, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), ts.pooled_ln.p,
@@ -916,6 +920,7 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
                               batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
   }
   ts.fwd_batch = batch;
+  ts.fwd_key = m->dropout_key;
   return 0;
 }
 
@@ -930,6 +935,10 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
   const auto& c = m->cfg;
   const int D = c.dim, I = m->inner, T = m->T, H = c.mlp_dim, R = batch * T, dt = m->dt;
   int rc;
+  // the nn.Dropout masks of the forward are pure functions of (key, site, element): replayed, never stored
+  const uint64_t cur_key = m->dropout_key;
+  m->dropout_key = ts.fwd_key;
+  struct KeyRestore { vitb200_model* m; uint64_t k; ~KeyRestore() { m->dropout_key = k; } } restore{m, cur_key};
   VB_CUDA(cudaMemsetAsync(ts.grads.p, 0, ts.grads.n * sizeof(float), st));
   // head: logits = LN(pool(x)) Wh + bh   (vit.py:159-165)
   if ((rc = launch_head_bwd(st, ts.pooled_ln.p, dlogits, leaf_ptr(m, m->head.leaf_kernel), grad_ptr(m, m->head.leaf_kernel),
@@ -940,16 +949,17 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
     Layer& L = m->layers[l];
     auto& S = ts.layers[l];
     // ---- x2 = x1 + Dense_1(gelu(Dense_0(LN2(x1))))   (vit.py:39,47-53) ----
-    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.ff2.leaf_bias), R, D, dt))) return rc;
+    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.ff2.leaf_bias), R, D, dt, m->drop(c.dropout, 3 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.ff2.wf, D, H, ts.dhid16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.hid.p, H, ts.dy16.p, D, R, grad_ptr(m, L.ff2.leaf_kernel), H))) return rc;
-    if ((rc = launch_gelu_bwd_colsum(st, S.pre.p, ts.dhid16.p, ts.dhid16.p, grad_ptr(m, L.ff1.leaf_bias), R, H, dt))) return rc;
+    if ((rc = launch_gelu_bwd_colsum(st, S.pre.p, ts.dhid16.p, ts.dhid16.p, grad_ptr(m, L.ff1.leaf_bias), R, H, dt,
+                                     m->drop(c.dropout, 2 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dhid16.p, R, H, L.ff1.wf, H, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.xn2.p, D, ts.dhid16.p, H, R, grad_ptr(m, L.ff1.leaf_kernel), D))) return rc;
     if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l + 1].p, leaf_ptr(m, L.ln2_scale), ts.dx.p, grad_ptr(m, L.ln2_scale),
                             grad_ptr(m, L.ln2_bias), R, D, dt, m->eps, 1))) return rc;
     // ---- x1 = x0 + to_out(attention(to_qkv(LN1(x0))))   (vit.py:39,62-87) ----
-    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.out.leaf_bias), R, D, dt))) return rc;
+    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.out.leaf_bias), R, D, dt, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.out.wf, D, I, ts.do16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.o.p, I, ts.dy16.p, D, R, grad_ptr(m, L.out.leaf_kernel), I))) return rc;
     if ((rc = launch_attention_bwd(st, S.qkv.p, S.o.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt))) return rc;
@@ -958,7 +968,8 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
     if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l].p, leaf_ptr(m, L.ln1_scale), ts.dx.p, grad_ptr(m, L.ln1_scale),
                             grad_ptr(m, L.ln1_bias), R, D, dt, m->eps, 1))) return rc;
   }
-  // ---- tokens = concat(cls, patches W + b) + pos   (vit.py:147-153) ----
+  // ---- tokens = Dropout(concat(cls, patches W + b) + pos)   (vit.py:147-155) ----
+  if ((rc = launch_mask_inplace(st, ts.dx.p, int64_t(R) * D, m->drop(c.emb_dropout, 0)))) return rc;
   if ((rc = launch_token_grads(st, ts.dx.p, grad_ptr(m, m->leaf_pos), grad_ptr(m, m->leaf_cls), grad_ptr(m, m->patch.leaf_bias),
                                batch, T, D, m->cls_off))) return rc;
   if ((rc = launch_cast16(st, ts.dx.p, ts.dy16.p, int64_t(R) * D, dt))) return rc;

@@ -55,13 +55,15 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 
 template <int kDT, bool kBwd>
 __global__ void __launch_bounds__(256)
-gelu_kernel(const uint16_t* __restrict__ pre, const uint16_t* __restrict__ dhid, uint16_t* __restrict__ out, int64_t n8) {
+gelu_kernel(const uint16_t* __restrict__ pre, const uint16_t* __restrict__ dhid, uint16_t* __restrict__ out, int64_t n8,
+            Dropout drop) {   // forward: nn.Dropout behind the GELU (vit.py:50), flat element index = 8 i
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
     const uint4 p = reinterpret_cast<const uint4*>(pre)[i];
     uint4 d = make_uint4(0, 0, 0, 0);
     if constexpr (kBwd) d = reinterpret_cast<const uint4*>(dhid)[i];
     const uint32_t pw[4] = {p.x, p.y, p.z, p.w}, dw[4] = {d.x, d.y, d.z, d.w};
     uint32_t ow[4];
+    float v[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float a, b;
@@ -69,11 +71,19 @@ gelu_kernel(const uint16_t* __restrict__ pre, const uint16_t* __restrict__ dhid,
       if constexpr (kBwd) {
         float da, db;
         unpack2<kDT>(dw[j], da, db);
-        ow[j] = pack2<kDT>(da * gelu_tanh_grad(a), db * gelu_tanh_grad(b));
+        v[2 * j] = da * gelu_tanh_grad(a);
+        v[2 * j + 1] = db * gelu_tanh_grad(b);
       } else {
-        ow[j] = pack2<kDT>(gelu_tanh_ref(a), gelu_tanh_ref(b));
+        v[2 * j] = gelu_tanh_ref(a);
+        v[2 * j + 1] = gelu_tanh_ref(b);
       }
     }
+    if (drop.threshold != 0) {
+      dropout4(drop, i * 8, v[0], v[1], v[2], v[3]);
+      dropout4(drop, i * 8 + 4, v[4], v[5], v[6], v[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ow[j] = pack2<kDT>(v[2 * j], v[2 * j + 1]);
     reinterpret_cast<uint4*>(out)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
@@ -86,7 +96,8 @@ gelu_kernel(const uint16_t* __restrict__ pre, const uint16_t* __restrict__ dhid,
 template <int kDT, int MODE>
 __global__ void __launch_bounds__(256)
 rowpass_colsum_kernel(const void* __restrict__ in0, const uint16_t* __restrict__ in1, uint16_t* __restrict__ out,
-                      float* __restrict__ sums, int rows, int cols) {
+                      float* __restrict__ sums, int rows, int cols, Dropout drop) {   // drop: the mask of the forward's nn.Dropout
+                                                                                      // at this tensor (flat index r * cols + c), replayed
   __shared__ float red[8][256];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + tx * 8;
@@ -114,6 +125,10 @@ rowpass_colsum_kernel(const void* __restrict__ in0, const uint16_t* __restrict__
           v[2 * j + 1] = db * gelu_tanh_grad(b);
         }
       }
+      if (drop.threshold != 0) {
+        dropout4(drop, o, v[0], v[1], v[2], v[3]);
+        dropout4(drop, o + 4, v[4], v[5], v[6], v[7]);
+      }
       uint4 w;
       w.x = pack2<kDT>(v[0], v[1]); w.y = pack2<kDT>(v[2], v[3]); w.z = pack2<kDT>(v[4], v[5]); w.w = pack2<kDT>(v[6], v[7]);
       *reinterpret_cast<uint4*>(out + o) = w;
@@ -133,6 +148,16 @@ rowpass_colsum_kernel(const void* __restrict__ in0, const uint16_t* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
     atomicAdd(sums + col, t);
+  }
+}
+
+// x[i] = mask(i) ? x[i] / keep : 0 in place (the embedding dropout, vit.py:155, in the backward pass)
+__global__ void __launch_bounds__(256)
+mask_inplace_kernel(float* __restrict__ x, int64_t n4, Dropout drop) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    dropout4(drop, i * 4, v.x, v.y, v.z, v.w);
+    reinterpret_cast<float4*>(x)[i] = v;
   }
 }
 
@@ -713,10 +738,18 @@ int launch_cast16(cudaStream_t st, const float* x, void* y, int64_t n, int dtype
   return 0;
 }
 
-int launch_gelu_fwd(cudaStream_t st, const void* pre, void* hid, int64_t n, int dtype) {
+int launch_mask_inplace(cudaStream_t st, float* x, int64_t n, const Dropout& drop) {
+  if (drop.threshold == 0) return 0;
+  if (n <= 0 || (n & 3)) return fail(VITB200_ERR_INVALID, "mask_inplace: element count must be a positive multiple of 4");
+  mask_inplace_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(x, n / 4, drop);
+  VB_LAUNCH_CHECK("mask_inplace_kernel");
+  return 0;
+}
+
+int launch_gelu_fwd(cudaStream_t st, const void* pre, void* hid, int64_t n, int dtype, const Dropout& drop) {
   if (n <= 0 || (n & 7)) return fail(VITB200_ERR_INVALID, "gelu: element count must be a positive multiple of 8");
   VB_DT16_DISPATCH(dtype, (gelu_kernel<kDT, false><<<grid_for(n / 8, 256), 256, 0, st>>>(
-                              static_cast<const uint16_t*>(pre), nullptr, static_cast<uint16_t*>(hid), n / 8)));
+                              static_cast<const uint16_t*>(pre), nullptr, static_cast<uint16_t*>(hid), n / 8, drop)));
   VB_LAUNCH_CHECK("gelu_kernel(fwd)");
   return 0;
 }
@@ -725,7 +758,7 @@ int launch_gelu_bwd(cudaStream_t st, const void* pre, const void* dhid, void* dp
   if (n <= 0 || (n & 7)) return fail(VITB200_ERR_INVALID, "gelu: element count must be a positive multiple of 8");
   VB_DT16_DISPATCH(dtype, (gelu_kernel<kDT, true><<<grid_for(n / 8, 256), 256, 0, st>>>(
                               static_cast<const uint16_t*>(pre), static_cast<const uint16_t*>(dhid),
-                              static_cast<uint16_t*>(dpre), n / 8)));
+                              static_cast<uint16_t*>(dpre), n / 8, Dropout())));
   VB_LAUNCH_CHECK("gelu_kernel(bwd)");
   return 0;
 }
@@ -736,19 +769,20 @@ static dim3 rowpass_grid(int rows, int cols) {
   return dim3(unsigned(gx), unsigned(gy));
 }
 
-int launch_cast16_colsum(cudaStream_t st, const float* x, void* y, float* sums, int rows, int cols, int dtype) {
+int launch_cast16_colsum(cudaStream_t st, const float* x, void* y, float* sums, int rows, int cols, int dtype,
+                         const Dropout& drop) {
   if (rows <= 0 || cols <= 0 || (cols & 7)) return fail(VITB200_ERR_INVALID, "cast16_colsum: cols must be a positive multiple of 8");
   VB_DT16_DISPATCH(dtype, (rowpass_colsum_kernel<kDT, 0><<<rowpass_grid(rows, cols), 256, 0, st>>>(
-                              x, nullptr, static_cast<uint16_t*>(y), sums, rows, cols)));
+                              x, nullptr, static_cast<uint16_t*>(y), sums, rows, cols, drop)));
   VB_LAUNCH_CHECK("rowpass_colsum_kernel(cast)");
   return 0;
 }
 
 int launch_gelu_bwd_colsum(cudaStream_t st, const void* pre, const void* dhid, void* dpre, float* sums, int rows, int cols,
-                           int dtype) {
+                           int dtype, const Dropout& drop) {
   if (rows <= 0 || cols <= 0 || (cols & 7)) return fail(VITB200_ERR_INVALID, "gelu_bwd_colsum: cols must be a positive multiple of 8");
   VB_DT16_DISPATCH(dtype, (rowpass_colsum_kernel<kDT, 1><<<rowpass_grid(rows, cols), 256, 0, st>>>(
-                              pre, static_cast<const uint16_t*>(dhid), static_cast<uint16_t*>(dpre), sums, rows, cols)));
+                              pre, static_cast<const uint16_t*>(dhid), static_cast<uint16_t*>(dpre), sums, rows, cols, drop)));
   VB_LAUNCH_CHECK("rowpass_colsum_kernel(gelu_bwd)");
   return 0;
 }

@@ -129,12 +129,14 @@ int launch_pack_weight(cudaStream_t stream, const float* W, void* Wt, int K, int
 
 // ---- backward pass (backward.cu); 16-bit buffers are of type `dtype` (VITB200_DT_BF16 / _F16) ----
 int launch_cast16(cudaStream_t stream, const float* x, void* y, int64_t n, int dtype);
-int launch_gelu_fwd(cudaStream_t stream, const void* pre, void* hid, int64_t n, int dtype);
+int launch_gelu_fwd(cudaStream_t stream, const void* pre, void* hid, int64_t n, int dtype, const Dropout& drop = Dropout());
+int launch_mask_inplace(cudaStream_t stream, float* x, int64_t n, const Dropout& drop);
 int launch_gelu_bwd(cudaStream_t stream, const void* pre, const void* dhid, void* dpre, int64_t n, int dtype);
 // fused passes: y16 = cast(x), sums[c] += sum_r x[r, c]  /  dpre = dhid * gelu'(pre), sums[c] += sum_r dpre[r, c]
-int launch_cast16_colsum(cudaStream_t stream, const float* x, void* y, float* sums, int rows, int cols, int dtype);
+int launch_cast16_colsum(cudaStream_t stream, const float* x, void* y, float* sums, int rows, int cols, int dtype,
+                         const Dropout& drop = Dropout());
 int launch_gelu_bwd_colsum(cudaStream_t stream, const void* pre, const void* dhid, void* dpre, float* sums, int rows,
-                           int cols, int dtype);
+                           int cols, int dtype, const Dropout& drop = Dropout());
 // out[c, r] = in[r, c], r < rows; zero for rows <= r < rows_pad (the K padding of the wgrad GEMMs)
 int launch_transpose16(cudaStream_t stream, const void* in, void* out, int rows, int cols, int rows_pad);
 // out[c] += sum_r in[r, c]; dtype may be VITB200_DT_F32

@@ -133,19 +133,19 @@ class ViT:
             return eng.forward(xin)
         return eng.forward_host(np.asarray(x, dtype=np.float32))
 
-    def vjp(self, variables: Any, x: Any, *, precision: Optional[str] = None, device: Optional[int] = None,
-            max_batch: Optional[int] = None):
+    def vjp(self, variables: Any, x: Any, rngs: Any = None, *, precision: Optional[str] = None,
+            device: Optional[int] = None, max_batch: Optional[int] = None):
         """``jax.vjp(lambda p: v.apply(p, x), variables)`` (ours: nothing in the reference trains).
 
         Returns ``(logits, vjp_fn)``; ``vjp_fn(dlogits)`` gives ``{'params': tree}`` of float32
         gradients with the reference's names and shapes.  Host arrays in -> numpy out, CUDA tensors
         in -> CUDA logits out (gradients always come back as numpy).  With fp16 operands the
         cotangent is scaled to unit magnitude on the way in and the gradients back on the way out
-        (loss scaling: the map is linear)."""
+        (loss scaling: the map is linear).  With dropout rates > 0 pass ``rngs={'dropout': key}``: the
+        forward drops with that key's masks and ``vjp_fn`` differentiates that same dropped forward."""
         from .runtime import get_engine
-        if self.dropout != 0.0 or self.emb_dropout != 0.0:
-            raise NotImplementedError("vjp: the backward pass is built for dropout rates 0.0")
         import torch
+        key = self._dropout_key(rngs)          # rates > 0 need rngs={'dropout': key}, like apply
         is_torch_cuda = hasattr(x, "is_cuda") and bool(x.is_cuda)
         channels = self._validate(tuple(x.shape) if hasattr(x, "shape") else np.shape(x))
         batch = int(x.shape[0])
@@ -155,6 +155,8 @@ class ViT:
         dev = torch.device("cuda", device)
         xin = x if is_torch_cuda else torch.as_tensor(np.asarray(x, dtype=np.float32), device=dev)
         xin = xin if (xin.dtype == torch.float32 and xin.is_contiguous()) else xin.float().contiguous()
+        if key is not None:
+            eng.set_dropout_key(key)           # the backward replays the masks of this key
         logits = eng.train_forward(xin)
 
         def vjp_fn(dlogits):
