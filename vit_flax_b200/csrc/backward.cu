@@ -43,13 +43,15 @@ cast16_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int64_t n8)
   }
 }
 
+// tanh.approx (one MUFU op, 2^-11 relative) as in the forward GEMM epilogue: with tanhf these passes were
+// issue-bound (72 % issue-slot utilisation, profiles/r01_backward.md) instead of HBM-bound
 __device__ __forceinline__ float gelu_tanh_ref(float x) {   // nn.gelu default (vit.py:49)
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * x * (1.0f + tanhf(k0 * x * fmaf(k1 * x, x, 1.0f)));
+  return 0.5f * x * (1.0f + tanh_approx(k0 * x * fmaf(k1 * x, x, 1.0f)));
 }
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float t = tanhf(k0 * x * fmaf(k1 * x, x, 1.0f));
+  const float t = tanh_approx(k0 * x * fmaf(k1 * x, x, 1.0f));
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * fmaf(3.0f * k1 * x, x, 1.0f);
 }
 
