@@ -1,6 +1,7 @@
 """Isolated timings of the backward kernels that have per-kernel C entry points, at ViT-B/16 batch-256 sizes.
     python profiles/run_bwd_kernels.py"""
 import ctypes as C
+import os
 import sys
 from pathlib import Path
 
@@ -45,6 +46,11 @@ o = torch.randn((R, heads * 64), device="cuda").to(tdt)
 timeit("attention_bwd batch 256, T 197, 12 heads",
        lambda: _lib.check(lib.vitb200_attention_bwd(st(), qkv.data_ptr(), o.data_ptr(), do.data_ptr(), dqkv.data_ptr(), B, T, heads, dt)),
        flops=5 * 2 * T * T * 64 * B * heads)   # useful flops: 5 matmuls (the kernel runs 6)
+os.environ["VITB200_ATTN_BWD"] = "flash"
+timeit("attention_bwd (streamed kernels), same problem",
+       lambda: _lib.check(lib.vitb200_attention_bwd(st(), qkv.data_ptr(), o.data_ptr(), do.data_ptr(), dqkv.data_ptr(), B, T, heads, dt)),
+       flops=5 * 2 * T * T * 64 * B * heads)
+os.environ.pop("VITB200_ATTN_BWD")
 for (M, N, name) in ((D, 3 * D, "to_qkv"), (D, D, "to_out"), (D, H, "ff1"), (H, D, "ff2")):
     X = torch.randn((R, M), device="cuda").to(tdt)
     dY = torch.randn((R, N), device="cuda").to(tdt)

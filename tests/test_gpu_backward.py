@@ -46,10 +46,20 @@ def rel_err(got, want):
     return float(np.abs(np.asarray(got, dtype=np.float64) - want).max() / max(np.abs(want).max(), 1e-30))
 
 
-@pytest.mark.parametrize("batch,T,heads", [(2, 197, 3), (1, 208, 1), (3, 64, 2), (2, 17, 2), (1, 100, 1), (40, 197, 12)])
+@pytest.mark.parametrize("batch,T,heads", [(2, 197, 3), (1, 208, 1), (3, 64, 2), (2, 17, 2), (1, 100, 1), (40, 197, 12),
+                                           (2, 257, 2), (1, 1025, 1), (3, 300, 2), (2, 209, 1)])
 @pytest.mark.parametrize("fmt", ["fp16", "bf16"])
-def test_attention_bwd(lib, batch, T, heads, fmt):
-    """Adjoint of vit.py:69-79 per (image, head): dq, dk, dv from (q, k, v, d_out), all 16-bit."""
+@pytest.mark.parametrize("impl", ["auto", "flash"])
+def test_attention_bwd(lib, batch, T, heads, fmt, impl, monkeypatch):
+    """Adjoint of vit.py:69-79 per (image, head): dq, dk, dv from (q, k, v, d_out), all 16-bit.  auto = the
+    shared-memory-resident kernel up to T = 208 and the streamed (flash-style) kernels beyond; flash forces the
+    latter at every shape, so both implementations are checked wherever both exist."""
+    if impl == "flash":
+        if T > 208:
+            pytest.skip("auto already runs the streamed kernels here")
+        monkeypatch.setenv("VITB200_ATTN_BWD", "flash")
+    else:
+        monkeypatch.delenv("VITB200_ATTN_BWD", raising=False)
     dt, tdt = DT16[fmt]
     inner = heads * 64
     g = torch.Generator().manual_seed(T * 7 + heads)
@@ -252,13 +262,22 @@ def test_backward_with_dropout_replays_the_forward_masks(precision, tol):
     eng.close()
 
 
-def test_backward_errors():
-    cfg = dict(image_size=64, patch_size=4, num_classes=8, dim=64, depth=1, heads=2, mlp_dim=64)   # T = 257 > 208
-    eng = Engine(precision="fp16", max_batch=1, **cfg)
-    eng.load_params(init_params(seed=1, **cfg))
-    with pytest.raises(VitB200Error, match="208 tokens"):
-        eng.train_forward(torch.zeros((1, 64, 64, 3), device="cuda"))
+def test_backward_more_than_208_tokens():
+    """T = 257 (the token count of ViT-H/14 at 224 px): the forward runs the streamed tcgen05 attention and the
+    backward the streamed adjoint kernels."""
+    cfg = dict(image_size=64, patch_size=4, num_classes=8, dim=128, depth=2, heads=2, mlp_dim=128)
+    variables = perturb_params(init_params(seed=81, **cfg), seed=82)
+    img = images_for(cfg, 3, seed=83)
+    dl = np.random.default_rng(84).standard_normal((3, 8)).astype(np.float32)
+    eng = Engine(precision="fp16", max_batch=4, **cfg)
+    eng.load_params(variables)
+    logits = eng.train_forward(torch.as_tensor(img, device="cuda"))
+    eng.backward(torch.as_tensor(dl, device="cuda"))
+    _check_grads(eng, variables, cfg, img, dl, "cls", 2e-2, logits.cpu().numpy())
     eng.close()
+
+
+def test_backward_errors():
     eng = Engine(precision="fp16", max_batch=2, **TINY)
     eng.load_params(init_params(seed=1, **TINY))
     with pytest.raises(VitB200Error, match="train_forward first"):

@@ -147,7 +147,7 @@ struct vitb200_model {
     uint64_t fwd_key = 0;                 // 'dropout' rng key of that forward: the backward replays its masks
     std::vector<DevBuf<float>> xs;        // residual stream before every LayerNorm + after the last layer
     std::vector<TrainLayer> layers;
-    DevBuf<float> dx, pooled_ln, dpl, zeros, grads;
+    DevBuf<float> dx, pooled_ln, dpl, zeros, grads, attn_ws;
     DevBuf<uint16_t> dy16, dhid16, dxn16, do16, dqkv16, tA, tB;
     std::vector<size_t> grad_off;         // per leaf: element offset into grads
   };
@@ -822,7 +822,6 @@ int train_supported(const vitb200_model* m) {
   const auto& c = m->cfg;
   if (!m->tc) return fail(VITB200_ERR_UNSUPPORTED, "train: the backward pass is built for the bf16/fp16 modes only");
   if (!m->project_out) return fail(VITB200_ERR_UNSUPPORTED, "train: heads == 1 with dim == 64 (identity to_out) is not built");
-  if (m->T > attention_bwd_max_tokens()) return fail(VITB200_ERR_UNSUPPORTED, "train: more than 208 tokens per image is not built for the backward pass");
   if (c.dim > 1280) return fail(VITB200_ERR_UNSUPPORTED, "train: dim > 1280 is not built for the backward pass");
   return 0;
 }
@@ -844,6 +843,8 @@ int ensure_train(vitb200_model* m, cudaStream_t st) {
   if ((rc = ts->dx.alloc(R * D)) || (rc = ts->pooled_ln.alloc(B * D)) || (rc = ts->dpl.alloc(B * D))) return rc;
   if ((rc = ts->dy16.alloc(R * D)) || (rc = ts->dhid16.alloc(R * H)) || (rc = ts->dxn16.alloc(R * D)) ||
       (rc = ts->do16.alloc(R * I)) || (rc = ts->dqkv16.alloc(R * 3 * I))) return rc;
+  if (attention_bwd_needs_workspace(m->T) &&
+      (rc = ts->attn_ws.alloc(attention_bwd_flash_workspace_floats(c.max_batch, m->T, c.heads)))) return rc;
   const size_t dx_max = std::max(std::max(H, D), std::max(I, size_t(m->K0pad))), dy_max = std::max(std::max(H, D), 3 * I);
   if ((rc = ts->tA.alloc(dx_max * Rpad)) || (rc = ts->tB.alloc(dy_max * Rpad))) return rc;
   const size_t nz = std::max(std::max(dx_max, dy_max), size_t(c.num_classes));
@@ -962,7 +963,7 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
     if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.out.leaf_bias), R, D, dt, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.out.wf, D, I, ts.do16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.o.p, I, ts.dy16.p, D, R, grad_ptr(m, L.out.leaf_kernel), I))) return rc;
-    if ((rc = launch_attention_bwd(st, S.qkv.p, S.o.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt))) return rc;
+    if ((rc = launch_attention_bwd(st, S.qkv.p, S.o.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt, ts.attn_ws.p))) return rc;
     if ((rc = gemm16(m, st, ts.dqkv16.p, R, 3 * I, L.qkv.wf, 3 * I, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.xn1.p, D, ts.dqkv16.p, 3 * I, R, grad_ptr(m, L.qkv.leaf_kernel), D))) return rc;
     if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l].p, leaf_ptr(m, L.ln1_scale), ts.dx.p, grad_ptr(m, L.ln1_scale),

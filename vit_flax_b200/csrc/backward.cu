@@ -10,6 +10,7 @@
 //   transpose16 / cast16 / colsum: operand preparation for the weight-gradient GEMMs and the bias gradients
 // The GEMMs (dgrad: dX = dY W^T, wgrad: dW = X^T dY) run on the tcgen05 kernel of gemm_tc.cu.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -866,10 +867,26 @@ int launch_token_grads(cudaStream_t st, const float* dx, float* dpos, float* dcl
 
 int attention_bwd_max_tokens() { return ABW_MAX_T; }
 
+// 0 = the shared-memory-resident kernel when T <= 208 and the streamed one beyond (default), 1 = always streamed
+// (VITB200_ATTN_BWD=flash, A/B tests)
+static int attn_bwd_force_flash() {
+  const char* e = getenv("VITB200_ATTN_BWD");
+  return e && e[0] == 'f';
+}
+
+bool attention_bwd_needs_workspace(int T) { return T > ABW_MAX_T || attn_bwd_force_flash(); }
+
 int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv, int batch, int T,
-                         int heads, int dtype) {
+                         int heads, int dtype, float* workspace) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
-  if (T > ABW_MAX_T) return fail(VITB200_ERR_UNSUPPORTED, "attention_bwd: more than 208 tokens is not built");
+  if (attention_bwd_needs_workspace(T)) {
+    if (workspace != nullptr) return launch_attention_bwd_flash(st, qkv, o_fwd, d_out, dqkv, workspace, batch, T, heads, dtype);
+    float* ws = nullptr;                     // per-kernel entry point: stream-ordered scratch
+    VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), attention_bwd_flash_workspace_floats(batch, T, heads) * sizeof(float), st));
+    const int rc = launch_attention_bwd_flash(st, qkv, o_fwd, d_out, dqkv, ws, batch, T, heads, dtype);
+    cudaFreeAsync(ws, st);
+    return rc;
+  }
   const int TP = (T + 15) / 16 * 16, pitch = TP * 2 + 16;
   const int nblk = TP / 16, nw = nblk;                        // one warp per 16-row block (<= 13)
   const size_t smem = size_t(4) * TP * ROW_BYTES + size_t(TP) * pitch;

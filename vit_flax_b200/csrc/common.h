@@ -152,7 +152,14 @@ int launch_token_grads(cudaStream_t stream, const float* dx, float* dpos, float*
                        int T, int dim, int cls_off);
 int attention_bwd_max_tokens();
 // o_fwd: the attention output of the forward pass (rowsum(dO o O) replaces a full row of dP)
+// T <= 208: one CTA per (image, head) with everything in shared memory; beyond (or VITB200_ATTN_BWD=flash): the
+// streamed kernels of attention_bwd_flash.cu, which need `workspace` (attention_bwd_flash_workspace_floats floats;
+// null = stream-ordered scratch allocated per call)
 int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
-                         int batch, int T, int heads, int dtype);
+                         int batch, int T, int heads, int dtype, float* workspace = nullptr);
+bool attention_bwd_needs_workspace(int T);
+size_t attention_bwd_flash_workspace_floats(int batch, int T, int heads);
+int launch_attention_bwd_flash(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
+                               float* workspace, int batch, int T, int heads, int dtype);
 
 }  // namespace vb
