@@ -153,8 +153,7 @@ int vitb200_debug_tokens(vitb200_model* m, void* stream, float* tokens_host, int
 /* ---- training: forward that keeps its activations + backward -----
  * Nothing in the reference trains (no jax.grad anywhere in vit_flax), so these have no reference
  * counterpart; they are the two halves of jax.vjp(lambda p: ViT.apply(p, img), params).
- * Built for the bf16 / fp16 modes, at most 208 tokens per image, dim <= 1280; anything else returns
- * VITB200_ERR_UNSUPPORTED.  With dropout rates > 0 the forward draws its masks from the key of
+ * Built for the bf16 / fp16 modes and dim <= 1280; anything else returns VITB200_ERR_UNSUPPORTED.  With dropout rates > 0 the forward draws its masks from the key of
  * vitb200_set_dropout_key and the backward replays them (they are pure functions of key, site, element).  Activations (about 5.4 KB per token and layer for
  * ViT-B) and one fp32 gradient per leaf are allocated for max_batch on the first call.           */
 int vitb200_train_forward(vitb200_model* m, void* stream, const float* images_dev, int batch,
@@ -229,8 +228,9 @@ int vitb200_attention_f32(void* stream, const float* qkv, float* out, int batch,
  * tile's K range (<= 1: none) and meet in the fp32 reduce-add.  dW must be initialised (it accumulates). */
 int vitb200_gemm_tc_wgrad(void* stream, const void* X, const void* dY, float* dW,
                           int M, int N, int K, int splits, int dtype);
-/* adjoint of vitb200_attention_tc for T <= 208: (qkv, out = the forward's output, d_out [batch*T, heads*64])
- * -> dqkv [batch*T, 3*heads*64] */
+/* adjoint of vitb200_attention_tc: (qkv, out = the forward's output, d_out [batch*T, heads*64])
+ * -> dqkv [batch*T, 3*heads*64]; T <= 208 runs one shared-memory-resident kernel, larger T the streamed kernels
+ * (with stream-ordered scratch here; the model path owns its workspace) */
 int vitb200_attention_bwd(void* stream, const void* qkv, const void* out, const void* d_out, void* dqkv,
                           int batch, int T, int heads, int dtype);
 /* adjoint of vitb200_layernorm: dx (+)= d/dx, dscale += , dbias += ; dy is 16-bit of `dtype`, dim <= 1280 */

@@ -7,14 +7,14 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tests"))
-from _util import C2, C3  # noqa: E402
+from _util import C2, C3, C4, C5  # noqa: E402
 from vit_flax_b200 import init_params, perturb_params  # noqa: E402
 from vit_flax_b200.engine import Engine  # noqa: E402
 
 name, batch = sys.argv[1], int(sys.argv[2])
 dtype = sys.argv[3] if len(sys.argv) > 3 else "fp16"
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-cfg = dict(C2=C2, C3=C3)[name]
+cfg = dict(C2=C2, C3=C3, C4=C4, C5=C5)[name]
 eng = Engine(precision=dtype, max_batch=batch, **cfg)
 eng.load_params(perturb_params(init_params(seed=1, **cfg), seed=2))
 s = cfg["image_size"]

@@ -170,11 +170,10 @@ attn_bwd_stats_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restri
 
 // ------------------------------------------------------------------ main
 template <int kDT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 attn_bwd_flash_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ d_out, const float* __restrict__ lse2,
                       const float* __restrict__ dsum, uint16_t* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int heads) {
-  __shared__ __align__(128) uint8_t smem[5 * TILE_BYTES];
-  __shared__ float s_lse[TILE], s_d[TILE];
+  extern __shared__ __align__(128) uint8_t smem[];     // K, V, dS^T staging, 2 x (Q, dO) tiles, 2 x (lse2, D)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3, mi = lane >> 3, r8 = lane & 7;
   const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads, k0 = blockIdx.x * TILE;
   const int inner = heads * DH;
@@ -182,9 +181,20 @@ attn_bwd_flash_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restri
   const uint16_t* qbase = qkv + int64_t(b) * T * ld + h * DH;
   const uint16_t* dobase = d_out + int64_t(b) * T * inner + h * DH;
   uint16_t* dqbase = dqkv + int64_t(b) * T * ld + h * DH;
-  const uint32_t sK = smem_u32(smem), sV = sK + TILE_BYTES, sQ = sV + TILE_BYTES, sD = sQ + TILE_BYTES, sT = sD + TILE_BYTES;
+  const uint32_t sK = smem_u32(smem), sV = sK + TILE_BYTES, sT = sV + TILE_BYTES, sQD = sT + TILE_BYTES;
+  float* s_stat = reinterpret_cast<float*>(smem + 7 * TILE_BYTES);     // [2][2][TILE]
+  auto fetch_q_tile = [&](int q0, int buf) {
+    load_tile(sQD + buf * 2 * TILE_BYTES, qbase, ld, q0, T);
+    load_tile(sQD + buf * 2 * TILE_BYTES + TILE_BYTES, dobase, inner, q0, T);
+    if (threadIdx.x < TILE) {
+      const int q = q0 + threadIdx.x;
+      s_stat[buf * 2 * TILE + threadIdx.x] = q < T ? lse2[int64_t(bh) * T + q] : INFINITY;     // P = 0 for padded query rows
+      s_stat[buf * 2 * TILE + TILE + threadIdx.x] = q < T ? dsum[int64_t(bh) * T + q] : 0.f;
+    }
+  };
   load_tile(sK, qbase + inner, ld, k0, T);
   load_tile(sV, qbase + 2 * inner, ld, k0, T);
+  fetch_q_tile(0, 0);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -200,18 +210,14 @@ attn_bwd_flash_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restri
   const float sl2 = 0.125f * 1.4426950408889634f;
   const bool key_a = k0 + warp * 16 + g < T, key_b = k0 + warp * 16 + g + 8 < T;
 
-  for (int q0 = 0; q0 < T; q0 += TILE) {
-    __syncthreads();                       // the previous tile's Q / dO / dS^T are no longer read
-    load_tile(sQ, qbase, ld, q0, T);
-    load_tile(sD, dobase, inner, q0, T);
+  int buf = 0;
+  for (int q0 = 0; q0 < T; q0 += TILE, buf ^= 1) {
+    // the next tile streams in while this one is processed (its buffer was last read two syncs ago)
+    if (q0 + TILE < T) fetch_q_tile(q0 + TILE, buf ^ 1);
     cp_async_commit();
-    if (threadIdx.x < TILE) {
-      const int q = q0 + threadIdx.x;
-      s_lse[threadIdx.x] = q < T ? lse2[int64_t(bh) * T + q] : INFINITY;     // P = 0 for padded query rows
-      s_d[threadIdx.x] = q < T ? dsum[int64_t(bh) * T + q] : 0.f;
-    }
-    cp_async_wait<0>();
-    __syncthreads();
+    const uint32_t sQ = sQD + buf * 2 * TILE_BYTES, sD = sQ + TILE_BYTES;
+    const float* s_lse = s_stat + buf * 2 * TILE;
+    const float* s_d = s_lse + TILE;
     // S^T = K_w Q^T, P^T = exp2(S^T * sl2 - lse2[q])
     float st[8][4];
     mma_abt<kDT>(st, kf, sQ, lane);
@@ -263,15 +269,12 @@ attn_bwd_flash_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restri
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int c = h * DH + nt * 8 + 2 * tg;
-      if (qa < T) {
-        atomicAdd(dq_acc + (int64_t(b) * T + qa) * inner + c, dq[nt][0]);
-        atomicAdd(dq_acc + (int64_t(b) * T + qa) * inner + c + 1, dq[nt][1]);
-      }
-      if (qb < T) {
-        atomicAdd(dq_acc + (int64_t(b) * T + qb) * inner + c, dq[nt][2]);
-        atomicAdd(dq_acc + (int64_t(b) * T + qb) * inner + c + 1, dq[nt][3]);
-      }
+      // one 8-byte vector atomic per column pair (sm_90+)
+      if (qa < T) atomicAdd(reinterpret_cast<float2*>(dq_acc + (int64_t(b) * T + qa) * inner + c), make_float2(dq[nt][0], dq[nt][1]));
+      if (qb < T) atomicAdd(reinterpret_cast<float2*>(dq_acc + (int64_t(b) * T + qb) * inner + c), make_float2(dq[nt][2], dq[nt][3]));
     }
+    cp_async_wait<0>();                     // the next tile has landed ...
+    __syncthreads();                        // ... for everyone, and this tile's Q / dO / dS^T are no longer read
   }
   // dK, dV of this warp's 16 keys
   const int ka = k0 + warp * 16 + g, kb = ka + 8;
@@ -330,16 +333,23 @@ int launch_attention_bwd_flash(cudaStream_t st, const void* qkv, const void* o_f
   const uint16_t* d16 = static_cast<const uint16_t*>(d_out);
   uint16_t* g16 = static_cast<uint16_t*>(dqkv);
   const unsigned cgrid = unsigned(std::min<int64_t>((rows * (inner / 8) + 255) / 256, int64_t(sm_count()) * 16));
+  constexpr size_t kMainSmem = 7 * TILE_BYTES + 2 * 2 * TILE * sizeof(float);     // 57 KB: three CTAs per SM
+  static bool configured = false;
+  if (!configured) {
+    VB_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMainSmem)));
+    VB_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMainSmem)));
+    configured = true;
+  }
   if (dtype == DT_F16) {
     attn_bwd_stats_kernel<DT_F16><<<grid, 128, 0, st>>>(q16, o16, d16, lse2, dsum, T, heads);
     VB_LAUNCH_CHECK("attn_bwd_stats_kernel");
-    attn_bwd_flash_kernel<DT_F16><<<grid, 128, 0, st>>>(q16, d16, lse2, dsum, g16, dq_acc, T, heads);
+    attn_bwd_flash_kernel<DT_F16><<<grid, 128, kMainSmem, st>>>(q16, d16, lse2, dsum, g16, dq_acc, T, heads);
     VB_LAUNCH_CHECK("attn_bwd_flash_kernel");
     dq_convert_kernel<DT_F16><<<cgrid, 256, 0, st>>>(dq_acc, g16, rows, inner);
   } else {
     attn_bwd_stats_kernel<DT_BF16><<<grid, 128, 0, st>>>(q16, o16, d16, lse2, dsum, T, heads);
     VB_LAUNCH_CHECK("attn_bwd_stats_kernel");
-    attn_bwd_flash_kernel<DT_BF16><<<grid, 128, 0, st>>>(q16, d16, lse2, dsum, g16, dq_acc, T, heads);
+    attn_bwd_flash_kernel<DT_BF16><<<grid, 128, kMainSmem, st>>>(q16, d16, lse2, dsum, g16, dq_acc, T, heads);
     VB_LAUNCH_CHECK("attn_bwd_flash_kernel");
     dq_convert_kernel<DT_BF16><<<cgrid, 256, 0, st>>>(dq_acc, g16, rows, inner);
   }

@@ -334,11 +334,10 @@ ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, cons
 
 // ------------------------------------------------------------------ head: pool + LayerNorm backward
 // One block per image.  pooled = x[b, 0] (cls) or mean_t x[b, t]; dpl = gradient wrt LayerNorm(pooled).
-// Writes the whole dx of the image: cls -> row 0 gets the pooled gradient, the others 0; mean -> every
-// row gets 1/T of it.
+// The gradient wrt the pooled vector replaces dpl (same buffer is fine: each block owns its row).
 __global__ void __launch_bounds__(256)
-pool_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dpl, const float* __restrict__ gamma,
-                   float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int dim,
+pool_ln_bwd_kernel(const float* __restrict__ x, const float* dpl, const float* __restrict__ gamma,
+                   float* dpl_out, float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int dim,
                    int pool_mean, float eps) {
   extern __shared__ float sh[];          // pooled[dim], g[dim], red[64]
   float* pooled = sh;
@@ -391,10 +390,22 @@ pool_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dpl, c
   __syncthreads();
   for (int c = threadIdx.x; c < dim; c += blockDim.x) gv[c] = rstd * (gv[c] - a - pooled[c] * bb) * (pool_mean ? 1.0f / float(T) : 1.0f);
   __syncthreads();
-  float* dxb = dx + int64_t(b) * T * dim;
-  for (int64_t i = threadIdx.x; i < int64_t(T) * dim; i += blockDim.x) {
-    const int t = int(i / dim), c = int(i - int64_t(t) * dim);
-    dxb[i] = (pool_mean || t == 0) ? gv[c] : 0.f;
+  // the pooled gradient goes back over dpl; pool_scatter_kernel spreads it over the image's token rows
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) dpl_out[int64_t(b) * dim + c] = gv[c];
+}
+
+// dx[b, t, :] = pooled gradient of image b for every t (mean pool, already divided by T) or for t = 0 only (cls), else 0
+__global__ void __launch_bounds__(256)
+pool_scatter_kernel(const float* __restrict__ dpooled, float* __restrict__ dx, int64_t total4, int T, int dim, int pool_mean) {
+  const int per_row = dim >> 2;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = i / per_row;
+    const int c4 = int(i - row * per_row);
+    const int64_t b = row / T;
+    const int t = int(row - b * T);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pool_mean || t == 0) v = reinterpret_cast<const float4*>(dpooled + b * dim)[c4];
+    reinterpret_cast<float4*>(dx)[i] = v;
   }
 }
 
@@ -431,16 +442,17 @@ pos_grad_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int batc
   for (int b = 0; b < batch; ++b) acc += dx[(int64_t(b) * T + t) * dim + d];
   dpos[int64_t(t) * dim + d] += acc;
 }
-// after pos_grad on a zeroed dpos: dcls = dpos[0] (cls_off = 1), dbias = sum_{t >= cls_off} dpos[t]
+// after pos_grad on a zeroed dpos: dcls = dpos[0] (cls_off = 1), dbias = sum_{t >= cls_off} dpos[t]; the token rows
+// are split over blockIdx.y (one atomic per column and slice)
 __global__ void __launch_bounds__(256)
 cls_bias_grad_kernel(const float* __restrict__ dpos, float* __restrict__ dcls, float* __restrict__ dbias, int T,
                      int dim, int cls_off) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= dim) return;
   float acc = 0.f;
-  for (int t = cls_off; t < T; ++t) acc += dpos[int64_t(t) * dim + d];
-  dbias[d] += acc;
-  if (cls_off && dcls) dcls[d] += dpos[d];
+  for (int t = cls_off + blockIdx.y; t < T; t += gridDim.y) acc += dpos[int64_t(t) * dim + d];
+  atomicAdd(dbias + d, acc);
+  if (blockIdx.y == 0 && cls_off && dcls) dcls[d] += dpos[d];
 }
 
 // ------------------------------------------------------------------ attention backward
@@ -833,12 +845,16 @@ int launch_ln_bwd(cudaStream_t st, const void* dy, const float* x, const float* 
   return 0;
 }
 
-int launch_pool_ln_bwd(cudaStream_t st, const float* x, const float* dpl, const float* gamma, float* dx,
+int launch_pool_ln_bwd(cudaStream_t st, const float* x, float* dpl, const float* gamma, float* dx,
                        float* dgamma, float* dbeta, int batch, int T, int dim, int pool_mean, float eps) {
-  if (batch <= 0 || T <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "pool_ln_bwd: empty problem");
+  if (batch <= 0 || T <= 0 || dim <= 0 || (dim & 3)) return fail(VITB200_ERR_INVALID, "pool_ln_bwd: dim must be a positive multiple of 4");
   const size_t smem = (2 * size_t(dim) + 64) * sizeof(float);
-  pool_ln_bwd_kernel<<<batch, 256, smem, st>>>(x, dpl, gamma, dx, dgamma, dbeta, T, dim, pool_mean, eps);
+  pool_ln_bwd_kernel<<<batch, 256, smem, st>>>(x, dpl, gamma, dpl, dgamma, dbeta, T, dim, pool_mean, eps);
   VB_LAUNCH_CHECK("pool_ln_bwd_kernel");
+  // dx of the whole batch: cls -> row 0 of every image gets the pooled gradient, the others 0; mean -> every row 1/T of it
+  const int64_t total4 = int64_t(batch) * T * (dim >> 2);
+  pool_scatter_kernel<<<grid_for(total4, 256), 256, 0, st>>>(dpl, dx, total4, T, dim, pool_mean);
+  VB_LAUNCH_CHECK("pool_scatter_kernel");
   return 0;
 }
 
@@ -860,7 +876,7 @@ int launch_token_grads(cudaStream_t st, const float* dx, float* dpos, float* dcl
   if (batch <= 0 || T <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "token_grads: empty problem");
   pos_grad_kernel<<<dim3(unsigned((dim + 255) / 256), unsigned(T)), 256, 0, st>>>(dx, dpos, batch, T, dim);
   VB_LAUNCH_CHECK("pos_grad_kernel");
-  cls_bias_grad_kernel<<<unsigned((dim + 255) / 256), 256, 0, st>>>(dpos, dcls, dbias, T, dim, cls_off);
+  cls_bias_grad_kernel<<<dim3(unsigned((dim + 255) / 256), unsigned(std::min(T, 32))), 256, 0, st>>>(dpos, dcls, dbias, T, dim, cls_off);
   VB_LAUNCH_CHECK("cls_bias_grad_kernel");
   return 0;
 }

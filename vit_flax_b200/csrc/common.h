@@ -144,7 +144,8 @@ int launch_colsum(cudaStream_t stream, const void* in, float* out, int rows, int
 // dx (+)= LayerNorm backward of dy (16-bit) at input x; dgamma / dbeta accumulate
 int launch_ln_bwd(cudaStream_t stream, const void* dy, const float* x, const float* gamma, float* dx,
                   float* dgamma, float* dbeta, int rows, int dim, int dtype, float eps, int accumulate);
-int launch_pool_ln_bwd(cudaStream_t stream, const float* x, const float* dpl, const float* gamma, float* dx,
+// dpl: in = gradient wrt LayerNorm(pooled), out = gradient wrt pooled (overwritten)
+int launch_pool_ln_bwd(cudaStream_t stream, const float* x, float* dpl, const float* gamma, float* dx,
                        float* dgamma, float* dbeta, int batch, int T, int dim, int pool_mean, float eps);
 int launch_head_bwd(cudaStream_t stream, const float* pl, const float* dl, const float* W, float* dW,
                     float* dbias, float* dpl, int batch, int dim, int classes);
