@@ -61,3 +61,50 @@ def test_vit_b16_shape_and_rejections():
 
 def test_posemb_matches_oracle():
     np.testing.assert_allclose(posemb_sincos_2d(7, 5, 64), simple_vit_numpy.posemb_sincos_2d(7, 5, 64), atol=1e-6)
+
+
+def test_simple_vit_vjp_matches_finite_differences_of_the_oracle():
+    """SimpleViT.vjp (NCHW patchify, no class token, sin/cos table, bias-free LayerNorms, mean pool -- the same
+    backward kernels under three config switches).  The numpy oracle has no autograd, so every leaf is checked at
+    its largest-gradient entries against central differences of the float64 oracle."""
+    import copy
+    cfg = SMALL
+    v = SimpleViT(**cfg)
+    img = np.random.default_rng(5).standard_normal((4, 3, 32, 64)).astype(np.float32)
+    params = _perturbed(v, img, 6)
+    dl = np.random.default_rng(7).standard_normal((4, cfg["num_classes"]))
+    logits, vjp_fn = v.vjp(params, img)
+    assert np.abs(logits - simple_vit_numpy.simple_vit_forward(params, img, **cfg)).max() < 2e-2
+    grads = vjp_fn(dl.astype(np.float32))
+
+    def leaves(tree, prefix=()):
+        for k, x in tree.items():
+            if isinstance(x, dict):
+                yield from leaves(x, prefix + (k,))
+            else:
+                yield prefix + (k,), x
+
+    def get(tree, path):
+        for k in path:
+            tree = tree[k]
+        return tree
+
+    f = lambda p: float((simple_vit_numpy.simple_vit_forward(p, img, **cfg) * dl).sum())
+    got = dict(leaves(grads["params"]))
+    assert set(got) == set(dict(leaves(params["params"])))           # same tree as the parameters
+    for path, g in got.items():
+        assert g.shape == get(params["params"], path).shape and g.dtype == np.float32
+        scale = np.abs(g).max()
+        assert scale > 0, path
+        for flat_idx in np.argsort(np.abs(g).ravel())[-2:]:
+            idx = np.unravel_index(flat_idx, g.shape)
+            vals = []
+            for sgn in (1, -1):
+                p2 = copy.deepcopy(params)
+                leaf = get(p2["params"], path[:-1])
+                a = np.asarray(leaf[path[-1]], dtype=np.float64).copy()
+                a[idx] += sgn * 1e-4
+                leaf[path[-1]] = a
+                vals.append(f(p2))
+            fd = (vals[0] - vals[1]) / 2e-4
+            assert abs(g[idx] - fd) < 3e-2 * scale, (path, idx, g[idx], fd)

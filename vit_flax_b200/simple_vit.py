@@ -109,10 +109,7 @@ class SimpleViT:
             "LayerNorm_0": {"scale": f(head["layers_0"]["scale"]), "bias": z(self.dim)},
             "Dense_1": {k: f(v) for k, v in head["layers_1"].items()}}}
 
-    # ------------------------------------------------------------------- apply
-    def apply(self, variables: Any, img: Any, rngs: Any = None, *, precision: Optional[str] = None,
-              device: Optional[int] = None, max_batch: Optional[int] = None):
-        """``v.apply(params, img)`` -> logits ``[B, num_classes]`` float32; ``img`` is NCHW."""
+    def _engine(self, variables, img, precision, device, max_batch):
         from . import vit as _vit
         from .engine import Engine
         is_cuda = hasattr(img, "is_cuda") and bool(img.is_cuda)
@@ -135,6 +132,55 @@ class SimpleViT:
             eng.load_params(self._engine_tree(variables))
             loaded = id(variables)
         _ENGINES[key] = (eng, loaded)
+        return eng
+
+    def _grads_tree(self, flat: Dict[str, np.ndarray]) -> Dict[str, Any]:
+        """Engine gradients (vit.py leaf names) -> the SimpleViT pytree; the gradients of leaves SimpleViT does
+        not have (zero biases, the fixed sin/cos table, the unused cls) are dropped."""
+        t = {}
+        for l in range(self.depth):
+            pre = "Transformer_0/"
+            t[f"Attention_{l}"] = {"LayerNorm_0": {"scale": flat[pre + f"PreNorm_{2 * l}/LayerNorm_0/scale"]},
+                                   "Dense_0": {"kernel": flat[pre + f"Attention_{l}/Dense_0/kernel"]},
+                                   "Dense_1": {"kernel": flat[pre + f"Attention_{l}/Dense_1/kernel"]}}
+            t[f"FeedForward_{l}"] = {"LayerNorm_0": {"scale": flat[pre + f"PreNorm_{2 * l + 1}/LayerNorm_0/scale"]},
+                                     "Dense_0": {k: flat[pre + f"FeedForward_{l}/Dense_0/{k}"] for k in ("kernel", "bias")},
+                                     "Dense_1": {k: flat[pre + f"FeedForward_{l}/Dense_1/{k}"] for k in ("kernel", "bias")}}
+        return {"params": {"Dense_0": {k: flat[f"Dense_0/{k}"] for k in ("kernel", "bias")},
+                           "Transformer_0": t,
+                           "Sequential_0": {"layers_0": {"scale": flat["LayerNorm_0/scale"]},
+                                            "layers_1": {k: flat[f"Dense_1/{k}"] for k in ("kernel", "bias")}}}}
+
+    def vjp(self, variables: Any, img: Any, *, precision: Optional[str] = None, device: Optional[int] = None,
+            max_batch: Optional[int] = None):
+        """``jax.vjp(lambda p: v.apply(p, img), variables)`` (ours; simple_vit.py never differentiates):
+        ``(logits, vjp_fn)``, ``vjp_fn(dlogits)`` -> ``{'params': tree}`` of float32 gradients in SimpleViT's names."""
+        import torch
+        is_cuda = hasattr(img, "is_cuda") and bool(img.is_cuda)
+        eng = self._engine(variables, img, precision, device, max_batch)
+        batch = int(img.shape[0])
+        x = img if is_cuda else torch.as_tensor(np.asarray(img, dtype=np.float32), device=eng.device)
+        x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
+        logits = eng.train_forward(x)
+
+        def vjp_fn(dlogits):
+            d = dlogits if hasattr(dlogits, "is_cuda") else torch.as_tensor(np.asarray(dlogits, dtype=np.float32))
+            d = d.to(device=eng.device, dtype=torch.float32).contiguous()
+            if tuple(d.shape) != (batch, self.num_classes):
+                raise ValueError(f"vjp_fn expects a cotangent of shape ({batch}, {self.num_classes})")
+            peak = float(d.abs().max())
+            scale = 1.0 if peak == 0.0 or not np.isfinite(peak) else float(2.0 ** -np.round(np.log2(peak)))
+            eng.backward(d * scale if scale != 1.0 else d)
+            return self._grads_tree({k: g / np.float32(scale) for k, g in eng.grads().items()})
+
+        return (logits if is_cuda else logits.cpu().numpy()), vjp_fn
+
+    # ------------------------------------------------------------------- apply
+    def apply(self, variables: Any, img: Any, rngs: Any = None, *, precision: Optional[str] = None,
+              device: Optional[int] = None, max_batch: Optional[int] = None):
+        """``v.apply(params, img)`` -> logits ``[B, num_classes]`` float32; ``img`` is NCHW."""
+        is_cuda = hasattr(img, "is_cuda") and bool(img.is_cuda)
+        eng = self._engine(variables, img, precision, device, max_batch)
         if is_cuda:
             import torch
             x = img if (img.dtype == torch.float32 and img.is_contiguous()) else img.float().contiguous()
