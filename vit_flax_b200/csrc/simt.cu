@@ -31,7 +31,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ------------------------------------------------------------- LayerNorm (K2)
 // One warp per row, the row lives in registers (<= 16 float4 per lane => dim <= 2048).
-template <int NV, int kDT>
+template <int NV, int kDT, bool kCopy>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                       const float* __restrict__ bias, void* __restrict__ y, int rows, int dim, int reverse, float eps,
@@ -53,7 +53,7 @@ layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ sca
     const int c = i * 32 + lane;
     if (c < nvec) {
       v[i] = __ldcs(xr + c);
-      if (copy != nullptr) reinterpret_cast<float4*>(copy + int64_t(row) * dim)[c] = v[i];
+      if constexpr (kCopy) reinterpret_cast<float4*>(copy + int64_t(row) * dim)[c] = v[i];
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -139,11 +139,16 @@ int launch_ln_t(cudaStream_t st, const float* x, const float* g, const float* b,
     VB_CUDA(launch_kernel(layernorm_generic_kernel<kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, eps));
   } else {
     const int nv = ceil_div(dim, 128);
-    if (nv <= 4) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
-    else if (nv <= 6) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
-    else if (nv <= 8) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
-    else if (nv <= 10) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
-    else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+    if (nv <= 4) { if (copy) VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT, true>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+                   else VB_CUDA(launch_kernel(layernorm_rows_kernel<4, kDT, false>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy)); }
+    else if (nv <= 6) { if (copy) VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT, true>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+                        else VB_CUDA(launch_kernel(layernorm_rows_kernel<6, kDT, false>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy)); }
+    else if (nv <= 8) { if (copy) VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT, true>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+                        else VB_CUDA(launch_kernel(layernorm_rows_kernel<8, kDT, false>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy)); }
+    else if (nv <= 10) { if (copy) VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT, true>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+                         else VB_CUDA(launch_kernel(layernorm_rows_kernel<10, kDT, false>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy)); }
+    else { if (copy) VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT, true>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy));
+           else VB_CUDA(launch_kernel(layernorm_rows_kernel<16, kDT, false>, dim3(grid), dim3(256), 0, st, 1, x, g, b, y, rows, dim, ln_reverse(), eps, copy)); }
   }
   VB_LAUNCH_CHECK("layernorm");
   return 0;
