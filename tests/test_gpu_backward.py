@@ -291,3 +291,23 @@ def test_backward_errors():
     with pytest.raises(VitB200Error, match="bf16/fp16"):
         eng.train_forward(torch.zeros((1, 32, 32, 3), device="cuda"))
     eng.close()
+
+
+def test_training_state_is_freed_with_the_model():
+    """The activations / gradient workspace of train_forward (GBs at real sizes) must go away with the model."""
+    cfg = dict(C2, depth=2)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free0 = torch.cuda.mem_get_info()[0]
+    eng = Engine(precision="fp16", max_batch=32, **cfg)
+    eng.load_params(init_params(seed=1, **cfg))
+    x = torch.zeros((32, 224, 224, 3), device="cuda")
+    eng.train_forward(x)
+    eng.backward(torch.zeros((32, 1000), device="cuda"))
+    torch.cuda.synchronize()
+    used = free0 - torch.cuda.mem_get_info()[0]
+    assert used > 400 << 20                                   # the training state is there
+    eng.close()
+    del x
+    torch.cuda.empty_cache()
+    assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20    # and gone (allow allocator / context slack)
