@@ -311,3 +311,30 @@ def test_training_state_is_freed_with_the_model():
     del x
     torch.cuda.empty_cache()
     assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20    # and gone (allow allocator / context slack)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_backward_config_fuzz(seed):
+    """Random small configs with ragged everything (dim not a multiple of 64, odd class counts -> fp32 head path,
+    non-square patches, T on both sides of 208, both pools, both formats, batch 1..5) against the autograd oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    ph, pw = int(rng.choice([4, 8])), int(rng.choice([4, 8, 16]))
+    gh, gw = int(rng.integers(1, 9)), int(rng.integers(1, 5))
+    if seed in (3, 6):
+        ph, pw, gh, gw = 4, 4, 15, 15                                       # T = 226 > 208: streamed attention adjoint
+    heads = int(rng.choice([1, 2, 3]))
+    dim = int(rng.choice([72, 128, 200]))
+    cfg = dict(image_size=(gh * ph, gw * pw), patch_size=(ph, pw), num_classes=int(rng.choice([5, 8, 13, 24])), dim=dim,
+               depth=int(rng.integers(1, 3)), heads=heads, mlp_dim=int(rng.choice([64, 136, 256])))
+    pool = str(rng.choice(["cls", "mean"]))
+    precision = "fp16" if seed % 3 else "bf16"
+    batch = int(rng.integers(1, 6))
+    variables = perturb_params(init_params(seed=seed, **cfg), seed=seed + 50)
+    img = images_for(cfg, batch, seed=seed + 100)
+    dl = rng.standard_normal((batch, cfg["num_classes"])).astype(np.float32)
+    eng = Engine(precision=precision, max_batch=batch + int(rng.integers(0, 3)), pool=pool, **cfg)
+    eng.load_params(variables)
+    logits = eng.train_forward(torch.as_tensor(img, device="cuda"))
+    eng.backward(torch.as_tensor(dl, device="cuda"))
+    _check_grads(eng, variables, cfg, img, dl, pool, 2e-2 if precision == "fp16" else 8e-2, logits.cpu().numpy())
+    eng.close()
