@@ -10,8 +10,7 @@ import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
-from _util import C2, C3, C4, C5  # noqa: E402
-from oracle import vit_torch  # noqa: E402
+from _util import C2, C3, C4, C5, oracle_logits  # noqa: E402
 from vit_flax_b200 import init_params, perturb_params  # noqa: E402
 from vit_flax_b200.engine import Engine  # noqa: E402
 
@@ -46,7 +45,7 @@ for name, cfg, batch in (("C2 ViT-B/16 224", C2, 256), ("C3 ViT-L/16 224", C3, 2
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     t0 = time.time()
-    want = vit_torch.vit_forward(vit_torch.tree_to_torch(variables), x[:2].cpu().numpy(), **cfg).numpy()
+    want = oracle_logits(variables, x[:2].cpu().numpy(), cfg)
     err = float(np.abs(out[:2].cpu().numpy() - want).max())
     ips = batch / ms * 1e3
     rows.append(f"| {name} | {batch} | {ms:.2f} | {ips:,.0f} | {ips * flops(cfg) / 1e12:.0f} | {err:.1e} | {time.time() - t0:.0f} s |")

@@ -9,8 +9,7 @@ import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
-from _util import C2, C4, TINY, images_for, load_golden  # noqa: E402
-from oracle import vit_torch  # noqa: E402
+from _util import C2, C4, TINY, images_for, load_golden, oracle_logits  # noqa: E402
 from vit_flax_b200 import ViT, init_params, perturb_params  # noqa: E402
 
 variables, meta = load_golden("tiny_cls.npz")
@@ -20,7 +19,7 @@ for precision, tol in (("fp32", 1e-4), ("fp16", 2e-2), ("bf16", 5e-2)):
 for cfg, batch in ((dict(C2, depth=1), 2), (dict(C4, depth=1), 1)):
     v = perturb_params(init_params(seed=1, **cfg), seed=2)
     img = images_for(cfg, batch)
-    want = vit_torch.vit_forward(vit_torch.tree_to_torch(v), img, **cfg).numpy()
+    want = oracle_logits(v, img, cfg)
     got = ViT(**cfg).apply(v, img)
     assert np.abs(got - want).max() < 2e-2
 torch.cuda.synchronize()

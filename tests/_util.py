@@ -33,3 +33,11 @@ def load_golden(name):
 def images_for(cfg, batch, seed=0, channels=3):
     ih, iw = cfg["image_size"] if isinstance(cfg["image_size"], tuple) else (cfg["image_size"],) * 2
     return np.random.default_rng(seed).standard_normal((batch, ih, iw, channels)).astype(np.float32)
+
+
+def oracle_logits(variables, images, cfg, **kw):
+    """The checker (torch-CPU restatement of vit.py) for scripts outside tests/ that want a parity figure next to
+    their timings: they import THIS, so that everything under oracle/ stays reachable from tests/, smoke() and
+    bench.py's CPU legs only."""
+    from oracle import vit_torch
+    return vit_torch.vit_forward(vit_torch.tree_to_torch(variables), images, **kw, **cfg).numpy()
