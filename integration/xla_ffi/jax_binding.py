@@ -26,6 +26,8 @@ class B200ViT:
         self.engine = Engine(precision=precision, max_batch=max_batch, **cfg)   # owns the C handle
         so = ctypes.CDLL(os.path.join(HERE, "libvitb200_xla.so"))
         jax.ffi.register_ffi_target("vitb200_forward", jax.ffi.pycapsule(so.VitB200Forward), platform="CUDA")
+        jax.ffi.register_ffi_target("vitb200_train_forward", jax.ffi.pycapsule(so.VitB200TrainForward), platform="CUDA")
+        jax.ffi.register_ffi_target("vitb200_backward", jax.ffi.pycapsule(so.VitB200Backward), platform="CUDA")
         self._loaded = None
 
     def apply(self, variables, img, rngs=None):
@@ -36,3 +38,34 @@ class B200ViT:
         out = jax.ShapeDtypeStruct((img.shape[0], self.cfg["num_classes"]), jax.numpy.float32)
         call = jax.ffi.ffi_call("vitb200_forward", out)
         return call(img.astype(jax.numpy.float32), handle=np.int64(self.engine.handle.value))
+
+
+    def value_and_vjp(self, variables, img):
+        """``jax.vjp(lambda p: self.apply(p, img), variables)``: (logits, vjp_fn).  The activations stay inside the
+        library between the two custom calls; the backward call returns every leaf gradient in ONE flat buffer
+        (the layout of ``vitb200_grads_buffer``: leaves in ``Engine.param_table()`` order, each padded to a
+        multiple of 64 floats), sliced back into the params pytree here."""
+        jax, jnp = self._jax, self._jax.numpy
+        if self._loaded is not id(variables):
+            self.engine.load_params(variables)
+            self._loaded = id(variables)
+        handle = np.int64(self.engine.handle.value)
+        out = jax.ShapeDtypeStruct((img.shape[0], self.cfg["num_classes"]), jnp.float32)
+        logits = jax.ffi.ffi_call("vitb200_train_forward", out)(img.astype(jnp.float32), handle=handle)
+        table = self.engine.param_table()                       # {flax path: shape}, registry order
+        sizes = [int(np.prod(s)) for s in table.values()]
+        offsets = np.cumsum([0] + [-(-n // 64) * 64 for n in sizes])
+
+        def vjp_fn(dlogits):
+            flat = jax.ffi.ffi_call("vitb200_backward", jax.ShapeDtypeStruct((int(offsets[-1]),), jnp.float32))(
+                dlogits.astype(jnp.float32), handle=handle)
+            tree = {}
+            for (path, shape), off, n in zip(table.items(), offsets, sizes):
+                node = tree
+                parts = path.split("/")
+                for k in parts[:-1]:
+                    node = node.setdefault(k, {})
+                node[parts[-1]] = flat[off:off + n].reshape(shape)
+            return {"params": tree}
+
+        return logits, vjp_fn
