@@ -955,28 +955,39 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
                             grad_ptr(m, m->head.leaf_bias), ts.dpl.p, batch, D, c.num_classes))) return rc;
   if ((rc = launch_pool_ln_bwd(st, ts.xs[2 * size_t(c.depth)].p, ts.dpl.p, leaf_ptr(m, m->leaf_head_scale), ts.dx.p,
                                grad_ptr(m, m->leaf_head_scale), grad_ptr(m, m->leaf_head_bias), batch, T, D, c.pool, m->eps))) return rc;
+  // dy16 = cast(dx) (+ the replayed mask of the Dropout behind FF Dense_1) and its column sums = that bias gradient;
+  // for every later stage the LayerNorm adjoint that produces dx emits both itself
+  if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, m->layers[c.depth - 1].ff2.leaf_bias), R, D, dt,
+                                 m->drop(c.dropout, 3 + 3 * (c.depth - 1))))) return rc;
   for (int l = c.depth - 1; l >= 0; --l) {
     Layer& L = m->layers[l];
     auto& S = ts.layers[l];
     // ---- x2 = x1 + Dense_1(gelu(Dense_0(LN2(x1))))   (vit.py:39,47-53) ----
-    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.ff2.leaf_bias), R, D, dt, m->drop(c.dropout, 3 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.ff2.wf, D, H, ts.dhid16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.hid.p, H, ts.dy16.p, D, R, grad_ptr(m, L.ff2.leaf_kernel), H))) return rc;
     if ((rc = launch_gelu_bwd_colsum(st, S.pre.p, ts.dhid16.p, ts.dhid16.p, grad_ptr(m, L.ff1.leaf_bias), R, H, dt,
                                      m->drop(c.dropout, 2 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dhid16.p, R, H, L.ff1.wf, H, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.xn2.p, D, ts.dhid16.p, H, R, grad_ptr(m, L.ff1.leaf_kernel), D))) return rc;
+    // LayerNorm adjoint; its dx is the cotangent of to_out's output: 16-bit copy + to_out bias gradient ride along
     if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l + 1].p, leaf_ptr(m, L.ln2_scale), ts.dx.p, grad_ptr(m, L.ln2_scale),
-                            grad_ptr(m, L.ln2_bias), R, D, dt, m->eps, 1))) return rc;
+                            grad_ptr(m, L.ln2_bias), R, D, dt, m->eps, 1, ts.dy16.p, grad_ptr(m, L.out.leaf_bias),
+                            m->drop(c.dropout, 1 + 3 * l)))) return rc;
     // ---- x1 = x0 + to_out(attention(to_qkv(LN1(x0))))   (vit.py:39,62-87) ----
-    if ((rc = launch_cast16_colsum(st, ts.dx.p, ts.dy16.p, grad_ptr(m, L.out.leaf_bias), R, D, dt, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.out.wf, D, I, ts.do16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.o.p, I, ts.dy16.p, D, R, grad_ptr(m, L.out.leaf_kernel), I))) return rc;
     if ((rc = launch_attention_bwd(st, S.qkv.p, S.o.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt, ts.attn_ws.p))) return rc;
     if ((rc = gemm16(m, st, ts.dqkv16.p, R, 3 * I, L.qkv.wf, 3 * I, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.xn1.p, D, ts.dqkv16.p, 3 * I, R, grad_ptr(m, L.qkv.leaf_kernel), D))) return rc;
-    if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l].p, leaf_ptr(m, L.ln1_scale), ts.dx.p, grad_ptr(m, L.ln1_scale),
-                            grad_ptr(m, L.ln1_bias), R, D, dt, m->eps, 1))) return rc;
+    // its dx is the cotangent of the previous layer's FF Dense_1 output (layer 0: of the token embedding, handled below)
+    if (l > 0) {
+      if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[2 * l].p, leaf_ptr(m, L.ln1_scale), ts.dx.p, grad_ptr(m, L.ln1_scale),
+                              grad_ptr(m, L.ln1_bias), R, D, dt, m->eps, 1, ts.dy16.p, grad_ptr(m, m->layers[l - 1].ff2.leaf_bias),
+                              m->drop(c.dropout, 3 + 3 * (l - 1))))) return rc;
+    } else {
+      if ((rc = launch_ln_bwd(st, ts.dxn16.p, ts.xs[0].p, leaf_ptr(m, L.ln1_scale), ts.dx.p, grad_ptr(m, L.ln1_scale),
+                              grad_ptr(m, L.ln1_bias), R, D, dt, m->eps, 1))) return rc;
+    }
   }
   // ---- tokens = Dropout(concat(cls, patches W + b) + pos)   (vit.py:147-155) ----
   if ((rc = launch_mask_inplace(st, ts.dx.p, int64_t(R) * D, m->drop(c.emb_dropout, 0)))) return rc;

@@ -231,13 +231,17 @@ template <int kDT, int KV>
 __global__ void __launch_bounds__(128)
 ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim,
-              float eps, int accumulate) {
-  extern __shared__ float4 acc_sm[];        // [warps][2][dim / 4]
+              float eps, int accumulate, uint16_t* __restrict__ dx16, float* __restrict__ dbias_next, Dropout drop) {
+  // dx16 != null: the new dx is also what the NEXT stage's GEMMs consume, so it leaves here as 16 bits too
+  // (with that stage's nn.Dropout mask replayed) and its column sums are that stage's bias gradient --
+  // this replaces a separate cast + column-sum pass over dx
+  extern __shared__ float4 acc_sm[];        // [warps][3][dim / 4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int nvec = dim >> 2;
-  float4* ag = acc_sm + size_t(warp) * 2 * nvec;
+  float4* ag = acc_sm + size_t(warp) * 3 * nvec;
   float4* ab = ag + nvec;
-  for (int i = lane; i < 2 * nvec; i += 32) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4* an = ab + nvec;
+  for (int i = lane; i < 3 * nvec; i += 32) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   const float inv_d = 1.0f / float(dim);
   const int stride = gridDim.x * nw;
@@ -316,19 +320,31 @@ ln_bwd_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x, cons
         v.x = ov[k].x + rstd * (dv[k].x - a - xv[k].x * b); v.y = ov[k].y + rstd * (dv[k].y - a - xv[k].y * b);
         v.z = ov[k].z + rstd * (dv[k].z - a - xv[k].z * b); v.w = ov[k].w + rstd * (dv[k].w - a - xv[k].w * b);
         dxr[c] = v;
+        if (dx16 != nullptr) {
+          if (drop.threshold != 0) dropout4(drop, int64_t(r) * dim + 4 * c, v.x, v.y, v.z, v.w);
+          uint2 w;
+          w.x = pack2<kDT>(v.x, v.y);
+          w.y = pack2<kDT>(v.z, v.w);
+          reinterpret_cast<uint2*>(dx16 + int64_t(r) * dim)[c] = w;
+          float4 s4 = an[c];
+          s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+          an[c] = s4;
+        }
       }
     }
   }
   __syncthreads();
   const float* accf = reinterpret_cast<const float*>(acc_sm);
   for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-    float tg = 0.f, tb = 0.f;
+    float tg = 0.f, tb = 0.f, tn = 0.f;
     for (int w = 0; w < nw; ++w) {
-      tg += accf[size_t(w) * 2 * dim + i];
-      tb += accf[size_t(w) * 2 * dim + dim + i];
+      tg += accf[size_t(w) * 3 * dim + i];
+      tb += accf[size_t(w) * 3 * dim + dim + i];
+      tn += accf[size_t(w) * 3 * dim + 2 * dim + i];
     }
     atomicAdd(dgamma + i, tg);
     atomicAdd(dbeta + i, tb);
+    if (dbias_next != nullptr) atomicAdd(dbias_next + i, tn);
   }
 }
 
@@ -823,20 +839,28 @@ int launch_colsum(cudaStream_t st, const void* in, float* out, int rows, int col
 
 template <int kDT, int KV>
 int launch_ln_bwd_t(cudaStream_t st, const void* dy, const float* x, const float* gamma, float* dx, float* dgamma,
-                    float* dbeta, int rows, int dim, float eps, int accumulate) {
+                    float* dbeta, int rows, int dim, float eps, int accumulate, void* dx16, float* dbias_next,
+                    const Dropout& drop) {
   const int grid = std::min((rows + 3) / 4, sm_count() * 3);   // persistent: 128-thread blocks, two to three resident per SM
-  ln_bwd_kernel<kDT, KV><<<grid, 128, 4 * 2 * size_t(dim) * sizeof(float), st>>>(static_cast<const uint16_t*>(dy), x, gamma, dx,
-                                                                           dgamma, dbeta, rows, dim, eps, accumulate);
+  const size_t smem = 4 * 3 * size_t(dim) * sizeof(float);     // 60 KB at dim 1280
+  static bool configured = false;
+  if (!configured) {
+    VB_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<kDT, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * 1280 * int(sizeof(float))));
+    configured = true;
+  }
+  ln_bwd_kernel<kDT, KV><<<grid, 128, smem, st>>>(static_cast<const uint16_t*>(dy), x, gamma, dx, dgamma, dbeta, rows, dim, eps,
+                                                  accumulate, static_cast<uint16_t*>(dx16), dbias_next, drop);
   VB_LAUNCH_CHECK("ln_bwd_kernel");
   return 0;
 }
 
 int launch_ln_bwd(cudaStream_t st, const void* dy, const float* x, const float* gamma, float* dx, float* dgamma,
-                  float* dbeta, int rows, int dim, int dtype, float eps, int accumulate) {
+                  float* dbeta, int rows, int dim, int dtype, float eps, int accumulate, void* dx16, float* dbias_next,
+                  const Dropout& drop) {
   if (rows <= 0 || dim <= 0) return fail(VITB200_ERR_INVALID, "ln_bwd: empty problem");
   if (dim & 3) return fail(VITB200_ERR_INVALID, "ln_bwd: dim must be a multiple of 4");
   if (dim > 1280) return fail(VITB200_ERR_UNSUPPORTED, "ln_bwd: dim > 1280 is not built");
-#define VB_LN_BWD(KV) VB_DT16_DISPATCH(dtype, return (launch_ln_bwd_t<kDT, KV>(st, dy, x, gamma, dx, dgamma, dbeta, rows, dim, eps, accumulate)))
+#define VB_LN_BWD(KV) VB_DT16_DISPATCH(dtype, return (launch_ln_bwd_t<kDT, KV>(st, dy, x, gamma, dx, dgamma, dbeta, rows, dim, eps, accumulate, dx16, dbias_next, drop)))
   if (dim <= 256) { VB_LN_BWD(2); }
   else if (dim <= 768) { VB_LN_BWD(6); }
   else if (dim <= 1024) { VB_LN_BWD(8); }

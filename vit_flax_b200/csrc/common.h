@@ -143,7 +143,10 @@ int launch_transpose16(cudaStream_t stream, const void* in, void* out, int rows,
 int launch_colsum(cudaStream_t stream, const void* in, float* out, int rows, int cols, int dtype);
 // dx (+)= LayerNorm backward of dy (16-bit) at input x; dgamma / dbeta accumulate
 int launch_ln_bwd(cudaStream_t stream, const void* dy, const float* x, const float* gamma, float* dx,
-                  float* dgamma, float* dbeta, int rows, int dim, int dtype, float eps, int accumulate);
+                  float* dgamma, float* dbeta, int rows, int dim, int dtype, float eps, int accumulate,
+                  void* dx16 = nullptr, float* dbias_next = nullptr, const Dropout& drop = Dropout());
+// dx16 / dbias_next / drop: also emit the new dx as 16 bits for the next stage's GEMMs (that stage's dropout mask
+// replayed) and add its column sums to that stage's bias gradient
 // dpl: in = gradient wrt LayerNorm(pooled), out = gradient wrt pooled (overwritten)
 int launch_pool_ln_bwd(cudaStream_t stream, const float* x, float* dpl, const float* gamma, float* dx,
                        float* dgamma, float* dbeta, int batch, int T, int dim, int pool_mean, float eps);
