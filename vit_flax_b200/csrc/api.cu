@@ -150,9 +150,13 @@ struct vitb200_model {
   uint64_t graph_clock = 0;
 
   // training (train_forward / backward): activations kept per layer, gradient workspace, leaf gradients
-  struct TrainLayer { DevBuf<uint16_t> xn1, qkv, o, xn2, pre, hid; };
+  struct TrainLayer {
+    DevBuf<uint16_t> xn1, qkv, o, xn2, pre;   // pre: [2 * rows_cap, mlp] -- FF pre-activation, then its GELU (hid)
+    uint16_t* hid = nullptr;
+  };
   struct TrainState {
     int fwd_batch = 0;                    // batch of the last train_forward (0 = none to differentiate)
+    int rows_cap = 0;                     // max_batch * T rounded up to the GEMM tile height (256)
     uint64_t fwd_key = 0;                 // 'dropout' rng key of that forward: the backward replays its masks
     std::vector<DevBuf<float>> xs;        // residual stream before every LayerNorm + after the last layer
     std::vector<TrainLayer> layers;
@@ -795,7 +799,8 @@ int gemm16(vitb200_model* m, cudaStream_t st, const void* A, int M, int K, const
   CUtensorMap ta, tb, tc;
   int rc;
   const int cg = gemm_tc_tile_mode(M, N);
-  const bool out16 = epi == VITB200_EPI_STORE_16 || epi == VITB200_EPI_BIAS_GELU_16 || epi == VITB200_EPI_BIAS_16;
+  const bool out16 = epi == VITB200_EPI_STORE_16 || epi == VITB200_EPI_BIAS_GELU_16 || epi == VITB200_EPI_BIAS_16 ||
+                     epi == VITB200_EPI_BIAS_PRE_GELU_16;
   if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, m->dt))) return rc;
   if ((rc = make_tmap_2d(&tb, Wt, N, ldw, ldw, cg == 64 ? 64 : GEMM_BN / cg, m->dt))) return rc;
   if ((rc = make_tmap_2d(&tc, C, c_rows, N, N, GEMM_BM, out16 ? m->dt : VITB200_DT_F32))) return rc;
@@ -845,9 +850,11 @@ int ensure_train(vitb200_model* m, cudaStream_t st) {
   ts->xs.resize(2 * size_t(c.depth) + 1);
   for (auto& x : ts->xs) if ((rc = x.alloc(R * D))) return rc;
   ts->layers.resize(size_t(c.depth));
+  ts->rows_cap = int(round_up(int64_t(R), 2 * GEMM_BM));
   for (auto& L : ts->layers) {
     if ((rc = L.xn1.alloc(R * D)) || (rc = L.qkv.alloc(R * 3 * I)) || (rc = L.o.alloc(R * I)) ||
-        (rc = L.xn2.alloc(R * D)) || (rc = L.pre.alloc(R * H)) || (rc = L.hid.alloc(R * H))) return rc;
+        (rc = L.xn2.alloc(R * D)) || (rc = L.pre.alloc(2 * size_t(ts->rows_cap) * H))) return rc;
+    L.hid = L.pre.p + size_t(ts->rows_cap) * H;
   }
   if ((rc = ts->dx.alloc(R * D)) || (rc = ts->pooled_ln.alloc(B * D)) || (rc = ts->dpl.alloc(B * D))) return rc;
   if ((rc = ts->dy16.alloc(R * D)) || (rc = ts->dhid16.alloc(R * H)) || (rc = ts->dxn16.alloc(R * D)) ||
@@ -912,9 +919,15 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
                      nullptr, 0, nullptr, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     // x2 = x1 + ff2(gelu(ff1(LN2(x1)))), the pre-activation kept for gelu'
     if ((rc = launch_layernorm(st, x1, leaf_ptr(m, L.ln2_scale), leaf_ptr(m, L.ln2_bias), S.xn2.p, R, D, m->dt, m->eps, x2))) return rc;
-    if ((rc = gemm16(m, st, S.xn2.p, R, D, L.ff1.wt, L.ff1.Kpad, H, S.pre.p, R, VITB200_EPI_BIAS_16, leaf_ptr(m, L.ff1.leaf_bias)))) return rc;
-    if ((rc = launch_gelu_fwd(st, S.pre.p, S.hid.p, int64_t(R) * H, m->dt, m->drop(c.dropout, 2 + 3 * l)))) return rc;
-    if ((rc = gemm16(m, st, S.hid.p, R, H, L.ff2.wt, L.ff2.Kpad, D, x2, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.ff2.leaf_bias),
+    static const bool dual = [] { const char* e = getenv("VITB200_TRAIN_DUAL"); return !(e && e[0] == '0'); }();
+    if (dual) {   // one GEMM writes the pre-activation and, rows_cap rows further down the same buffer, its GELU
+      if ((rc = gemm16(m, st, S.xn2.p, R, D, L.ff1.wt, L.ff1.Kpad, H, S.pre.p, 2 * ts.rows_cap, VITB200_EPI_BIAS_PRE_GELU_16,
+                       leaf_ptr(m, L.ff1.leaf_bias), nullptr, ts.rows_cap, nullptr, m->drop(c.dropout, 2 + 3 * l)))) return rc;
+    } else {
+      if ((rc = gemm16(m, st, S.xn2.p, R, D, L.ff1.wt, L.ff1.Kpad, H, S.pre.p, R, VITB200_EPI_BIAS_16, leaf_ptr(m, L.ff1.leaf_bias)))) return rc;
+      if ((rc = launch_gelu_fwd(st, S.pre.p, S.hid, int64_t(R) * H, m->dt, m->drop(c.dropout, 2 + 3 * l)))) return rc;
+    }
+    if ((rc = gemm16(m, st, S.hid, R, H, L.ff2.wt, L.ff2.Kpad, D, x2, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.ff2.leaf_bias),
                      nullptr, 0, nullptr, m->drop(c.dropout, 3 + 3 * l)))) return rc;
   }
   const float* xf = ts.xs[2 * size_t(c.depth)].p;
@@ -964,7 +977,7 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
     auto& S = ts.layers[l];
     // ---- x2 = x1 + Dense_1(gelu(Dense_0(LN2(x1))))   (vit.py:39,47-53) ----
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.ff2.wf, D, H, ts.dhid16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
-    if ((rc = wgrad(m, st, S.hid.p, H, ts.dy16.p, D, R, grad_ptr(m, L.ff2.leaf_kernel), H))) return rc;
+    if ((rc = wgrad(m, st, S.hid, H, ts.dy16.p, D, R, grad_ptr(m, L.ff2.leaf_kernel), H))) return rc;
     if ((rc = launch_gelu_bwd_colsum(st, S.pre.p, ts.dhid16.p, ts.dhid16.p, grad_ptr(m, L.ff1.leaf_bias), R, H, dt,
                                      m->drop(c.dropout, 2 + 3 * l)))) return rc;
     if ((rc = gemm16(m, st, ts.dhid16.p, R, H, L.ff1.wf, H, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
@@ -1066,9 +1079,12 @@ int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const fl
   if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, dtype))) return rc;
   const int cg = gemm_tc_tile_mode(M, N);
   if ((rc = make_tmap_2d(&tb, Wt, N, K, K, cg == 64 ? 64 : GEMM_BN / cg, dtype))) return rc;
-  const bool out16 = epilogue == VITB200_EPI_STORE_16 || epilogue == VITB200_EPI_BIAS_GELU_16 || epilogue == VITB200_EPI_BIAS_16;
+  const bool out16 = epilogue == VITB200_EPI_STORE_16 || epilogue == VITB200_EPI_BIAS_GELU_16 || epilogue == VITB200_EPI_BIAS_16 ||
+                     epilogue == VITB200_EPI_BIAS_PRE_GELU_16;
   const bool direct = epilogue == VITB200_EPI_PATCH_F32;
-  if (!direct && (rc = make_tmap_2d(&tc, C, M, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
+  // PRE_GELU writes its second output tokens_per_image rows below the first: the map covers both
+  const int64_t c_rows = epilogue == VITB200_EPI_BIAS_PRE_GELU_16 ? int64_t(tokens_per_image) + M : M;
+  if (!direct && (rc = make_tmap_2d(&tc, C, c_rows, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
   return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, direct ? nullptr : &tc, bias, C, M, N, K, epilogue,
                         aux, tokens_per_image, dtype, cg, drop, 1, cls);
 }

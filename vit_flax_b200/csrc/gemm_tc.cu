@@ -83,7 +83,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const float* __restrict__ bias, void* __restrict__ Cout,
                int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop, int cls_off,
                const float* __restrict__ cls) {
-  constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_16);
+  constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_16 ||
+                           kEpi == VITB200_EPI_BIAS_PRE_GELU_16);
+  constexpr bool kDual = (kEpi == VITB200_EPI_BIAS_PRE_GELU_16);   // two outputs per slab: pre-activation and GELU
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
   constexpr int SLABS_PER_TILE = Cfg<kCG>::BN_ / SLAB_COLS;
@@ -323,11 +325,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
           const int n0 = n_blk * BN + s * SLAB_COLS;
           if (n0 >= N || (dbg & 4)) break;             // uniform over the group
           const uint32_t slab = sSlab + uint32_t(grp * 2 + buf) * SLAB_BYTES;
-          // the slab buffer used two slabs ago must have been read out by its TMA store
-          if (leader) tma_store_wait_read<1>();
+          // the slab buffer used two slabs ago must have been read out by its TMA store (dual output: both
+          // buffers of the group are filled per slab, so every earlier store must have been read out)
+          if (leader) { if constexpr (kDual) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
           named_bar_sync(1 + grp, 128);
           const uint32_t srow = slab + uint32_t(lrow) * 128u;
           const int sw = lrow & 7;
+          // dual output: the GELU values go to the group's other slab buffer and leave `tpi` rows further down
+          const uint32_t srow2 = sSlab + uint32_t(grp * 2 + (buf ^ 1)) * SLAB_BYTES + uint32_t(lrow) * 128u;
           if constexpr (kOut16) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -339,7 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]);
-                if constexpr (kEpi == VITB200_EPI_BIAS_16) {   // pre-activation kept for the backward pass
+                if constexpr (kEpi == VITB200_EPI_BIAS_16 || kDual) {   // pre-activation kept for the backward pass
                   const int nb = n0 + half * 32 + j * 8;
                   if (nb < N) {
                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
@@ -347,6 +352,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
                     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                   }
+                }
+                if constexpr (kDual) {
+                  // the GELU acts on the ROUNDED pre-activation, which is what the backward differentiates at
+                  const int chunk2 = half * 4 + j;
+                  const uint32_t q0 = pack2<kDT>(v[0], v[1]), q1 = pack2<kDT>(v[2], v[3]), q2 = pack2<kDT>(v[4], v[5]), q3 = pack2<kDT>(v[6], v[7]);
+                  st_shared_v4(srow + (uint32_t(chunk2 ^ sw) << 4), q0, q1, q2, q3);
+                  v[0] = to_f32<kDT>(uint16_t(q0 & 0xFFFFu)); v[1] = to_f32<kDT>(uint16_t(q0 >> 16));
+                  v[2] = to_f32<kDT>(uint16_t(q1 & 0xFFFFu)); v[3] = to_f32<kDT>(uint16_t(q1 >> 16));
+                  v[4] = to_f32<kDT>(uint16_t(q2 & 0xFFFFu)); v[5] = to_f32<kDT>(uint16_t(q2 >> 16));
+                  v[6] = to_f32<kDT>(uint16_t(q3 & 0xFFFFu)); v[7] = to_f32<kDT>(uint16_t(q3 >> 16));
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = gelu_tanh_fast(v[e]);
+                  if constexpr (kDrop) {   // FeedForward's first Dropout (vit.py:50)
+                    const int64_t e0 = int64_t(m_row0 + lrow) * N + n0 + half * 32 + j * 8;
+                    dropout4(drop, e0, v[0], v[1], v[2], v[3]);
+                    dropout4(drop, e0 + 4, v[4], v[5], v[6], v[7]);
+                  }
+                  st_shared_v4(srow2 + (uint32_t(chunk2 ^ sw) << 4), pack2<kDT>(v[0], v[1]), pack2<kDT>(v[2], v[3]),
+                               pack2<kDT>(v[4], v[5]), pack2<kDT>(v[6], v[7]));
+                  continue;
                 }
                 if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16) {
                   const int nb = n0 + half * 32 + j * 8;
@@ -409,6 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
               tma_reduce_add_2d(&tmC, slab, n0, m_row0);          // x += acc + bias
             else
               tma_store_2d(&tmC, slab, n0, m_row0);
+            if constexpr (kDual) tma_store_2d(&tmC, sSlab + uint32_t(grp * 2 + (buf ^ 1)) * SLAB_BYTES, n0, m_row0 + tpi);
             tma_store_commit();
           }
           buf ^= 1;
@@ -485,7 +511,7 @@ int launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& t
                const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off, const float* cls) {
   // dropout variants exist for the epilogues that have a Dropout behind them and for the two
   // production tile modes; the opt-in cluster-of-4 mode falls back to pairs when dropout is on
-  constexpr bool kCanDrop = kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_RESID_F32 ||
+  constexpr bool kCanDrop = kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_RESID_F32 || kEpi == VITB200_EPI_BIAS_PRE_GELU_16 ||
                             kEpi == VITB200_EPI_PATCH_F32 || kEpi == VITB200_EPI_TOKENS_F32;
   if constexpr (kCanDrop) {
     if (drop.threshold != 0) {
@@ -522,6 +548,9 @@ int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap&
       return launch_one<VITB200_EPI_PATCH_F32, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     case VITB200_EPI_BIAS_16:
       return launch_one<VITB200_EPI_BIAS_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
+    case VITB200_EPI_BIAS_PRE_GELU_16:
+      if (tpi < M) return fail(VITB200_ERR_INVALID, "gemm_tc: PRE_GELU epilogue needs the row offset of its second output (>= M)");
+      return launch_one<VITB200_EPI_BIAS_PRE_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
     case VITB200_EPI_TOKENS_F32:
       if (aux == nullptr || tpi <= 0)
         return fail(VITB200_ERR_INVALID, "gemm_tc: TOKENS epilogue needs pos_embedding and tokens per image");
