@@ -55,14 +55,20 @@ def simple_vit_forward(variables, img, *, image_size, patch_size, num_classes, d
     gh, gw = H // ph, W // pw
     # 'b c (h p1) (w p2) -> b h w (p1 p2 c)'                                 simple_vit.py:125
     x = x.reshape(b, c, gh, ph, gw, pw).transpose(0, 2, 4, 3, 5, 1).reshape(b, gh, gw, ph * pw * c)
-    x = dense(x, p["Dense_0"])                                              # simple_vit.py:126
+    # Flax names modules at construction (simple_vit.py:117-120 run before :126): LayerNorm_0 / Dense_0 are the
+    # head, Dense_1 the patch embedding.  The adoption layout (Dense_0 = patch, Sequential_0/layers_*) that round 1
+    # of this repository wrote is accepted too.
+    if "Sequential_0" in p:
+        patch, head_norm, head_dense = p["Dense_0"], p["Sequential_0"]["layers_0"], p["Sequential_0"]["layers_1"]
+    else:
+        patch, head_norm, head_dense = p["Dense_1"], p["LayerNorm_0"], p["Dense_0"]
+    x = dense(x, patch)                                                     # simple_vit.py:126
     x = x.reshape(b, gh * gw, dim) + posemb_sincos_2d(gh, gw, dim, dtype=dtype)   # simple_vit.py:127-128
     tp = p["Transformer_0"]
     for l in range(depth):                                                  # simple_vit.py:92-95
         x = attention(x, tp[f"Attention_{l}"], heads, dim_head) + x
         x = feed_forward(x, tp[f"FeedForward_{l}"]) + x
     x = x.mean(axis=1)                                                      # simple_vit.py:131
-    head = p["Sequential_0"]
-    x = dense(layer_norm_nobias(x, head["layers_0"]), head["layers_1"])     # simple_vit.py:117-120,134
+    x = dense(layer_norm_nobias(x, head_norm), head_dense)                  # simple_vit.py:117-120,134
     assert x.shape == (b, num_classes)
     return x

@@ -60,3 +60,29 @@ def test_chunked_arrays_are_reassembled():
 def test_unknown_extension(tmp_path):
     with pytest.raises(ValueError, match="unknown checkpoint format"):
         load_params(tmp_path / "x.bin")
+
+
+def test_chunked_arrays_use_the_flax_tuple_layout(monkeypatch):
+    """Leaves above the chunk limit: flax writes ``shape`` and ``chunks`` through ``_tuple_to_dict``
+    (``{'0': d0, '1': d1}``).  A hand-built chunk dict in that layout must load, our writer must emit it, and
+    the older list form of ``shape`` stays readable."""
+    from vit_flax_b200 import checkpoint
+    a = np.arange(24, dtype=np.float32).reshape(4, 6)
+
+    def leaf(x):
+        return msgpack.ExtType(1, msgpack.packb((x.shape, x.dtype.name, x.tobytes()), use_bin_type=True))
+
+    flat = a.ravel()
+    flax_style = {"params": {"w": {"__msgpack_chunked_array__": True, "shape": {"0": 4, "1": 6},
+                                   "chunks": {"0": leaf(flat[:10]), "1": leaf(flat[10:20]), "2": leaf(flat[20:])}}}}
+    got = load_params(msgpack.packb(flax_style, use_bin_type=True))
+    np.testing.assert_array_equal(got["params"]["w"], a)
+    list_style = {"w": {"__msgpack_chunked_array__": True, "shape": [4, 6], "chunks": {"0": leaf(flat[:13]), "1": leaf(flat[13:])}}}
+    np.testing.assert_array_equal(load_params(msgpack.packb(list_style, use_bin_type=True))["w"], a)
+    monkeypatch.setattr(checkpoint, "_MAX_CHUNK", 40)            # 10 floats per chunk
+    raw = msgpack.unpackb(msgpack_serialize({"w": a, "b": a[0]}), raw=False, strict_map_key=False)
+    assert raw["w"]["__msgpack_chunked_array__"] is True and raw["w"]["shape"] == {"0": 4, "1": 6}
+    assert sorted(raw["w"]["chunks"]) == ["0", "1", "2"] and not isinstance(raw["b"], dict)
+    back = msgpack_restore(msgpack_serialize({"w": a, "b": a[0]}))
+    np.testing.assert_array_equal(back["w"], a)
+    np.testing.assert_array_equal(back["b"], a[0])

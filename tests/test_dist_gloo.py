@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vit_flax_b200.dist import shard_range, sharded_logits
+from vit_flax_b200.dist import shard_range, sharded_apply_stream, sharded_logits
 
 
 def test_shard_range_partitions_the_batch():
@@ -42,7 +42,15 @@ def _worker(rank, world, port, global_batch, q):
             out.copy_(x @ w)
 
         got = sharded_logits(forward_local, full[s:e], global_batch, classes)
-        q.put((rank, torch.allclose(got, full @ w), tuple(got.shape)))
+        ok = torch.allclose(got, full @ w)
+        if global_batch % world == 0:
+            # the serving loop (host shards in, gathered host logits out, two steps in flight): 5 steps, each with
+            # its own inputs, must come back in order
+            steps = [full[s:e] * (i + 1) for i in range(5)]
+            outs = [y.clone() for y in sharded_apply_stream(forward_local, iter(steps), global_batch, classes, (12,),
+                                                            torch.device("cpu"))]
+            ok = ok and len(outs) == 5 and all(torch.allclose(y, (full * (i + 1)) @ w) for i, y in enumerate(outs))
+        q.put((rank, ok, tuple(got.shape)))
     finally:
         dist.destroy_process_group()
 

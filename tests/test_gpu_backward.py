@@ -338,3 +338,43 @@ def test_backward_config_fuzz(seed):
     eng.backward(torch.as_tensor(dl, device="cuda"))
     _check_grads(eng, variables, cfg, img, dl, pool, 2e-2 if precision == "fp16" else 8e-2, logits.cpu().numpy())
     eng.close()
+
+
+def test_vjp_fn_refuses_a_stale_forward():
+    """vjp_fn closes over the engine of its config (one set of kept activations, a patch workspace shared with
+    the inference forward): any forward / reload in between must make it raise, never return wrong gradients."""
+    cfg = TINY
+    v = ViT(**cfg)
+    variables = perturb_params(init_params(seed=1, **cfg), seed=2)
+    img = images_for(cfg, 3, seed=3)
+    dl = np.ones((3, cfg["num_classes"]), np.float32)
+    _, f1 = v.vjp(variables, img)
+    g1 = flatten_params(f1(dl))
+    _, f2 = v.vjp(variables, img)
+    v.apply(variables, images_for(cfg, 3, seed=4))               # overwrites the patch matrix of the kept forward
+    with pytest.raises(RuntimeError, match="another forward"):
+        f2(dl)
+    _, f3 = v.vjp(variables, img)
+    _, f4 = v.vjp(variables, images_for(cfg, 3, seed=5))         # a second vjp overwrites the kept activations
+    with pytest.raises(RuntimeError, match="another forward"):
+        f3(dl)
+    g4 = flatten_params(f4(dl))
+    assert any(np.abs(g4[k] - g1[k]).max() > 0 for k in g1)
+    _, f5 = v.vjp(variables, img)
+    g5 = flatten_params(f5(dl))
+    for k in g1:
+        np.testing.assert_array_equal(g1[k], g5[k])
+    # the C ABI refuses on its own when an inference forward ran in between
+    from vit_flax_b200._lib import VitB200Error
+    eng = Engine(precision="fp16", max_batch=3, **cfg)
+    eng.load_params(variables)
+    x = torch.as_tensor(img, device="cuda")
+    eng.train_forward(x)
+    eng.forward(x)
+    with pytest.raises(VitB200Error, match="train_forward again"):
+        eng.backward(torch.as_tensor(dl, device="cuda"))
+    eng.close()
+    with pytest.raises(VitB200Error, match="at least one transformer layer"):
+        e0 = Engine(precision="fp16", max_batch=1, **dict(cfg, depth=0))
+        e0.load_params(perturb_params(init_params(seed=1, **dict(cfg, depth=0)), seed=2))
+        e0.train_forward(x[:1].contiguous())

@@ -1,12 +1,21 @@
 """End-to-end parity of ViT.apply on a real B200 against the CPU oracle.
 
 Tolerances are BASELINE.json's: logits max-abs 1e-4 in fp32 mode and 2e-2 on the 16-bit
-tensor-core path.  The default 16-bit operand format is fp16 and it meets 2e-2 at every depth
-and batch size.  bf16 operands meet it on shallow stacks only: rounding the WEIGHTS alone to
-bf16 already moves ViT-B/16 logits by 1.9e-2 (measured on the CPU oracle, DESIGN.md "Operand
-format"), so full-depth bf16 runs are held to that format's own noise floor, stated below.
-Top-1 agreement is checked on images whose oracle top-1 margin exceeds twice the tolerance
-(on random-init weights the raw metric measures luck, not kernels)."""
+tensor-core path.  fp16 operands (the default) meet 2e-2 at every depth and batch size.
+bf16 operands cannot: rounding the Dense kernels ALONE to bf16 moves ViT-B/16 logits by 2.2e-2 and
+rounding every tensor-core operand by 3e-2 (tests/test_oracle.py::test_bf16_operand_floor_on_vit_b16,
+a CPU test of the oracle alone).  bf16 runs are therefore held to a bound DERIVED from the oracle on
+the same inputs instead of a blanket constant:
+
+    |gpu - fp32 oracle| <= max(2e-2, 1.25 x |bf16-emulating oracle - fp32 oracle|)   and
+    |gpu - bf16-emulating oracle| <= 2e-2
+
+i.e. the north-star tolerance wherever the operand format can meet it, otherwise at most 25 % above
+the format's own rounding floor, and always within the north-star tolerance of the reference
+computed with the same operand rounding.
+Top-1 agreement is checked on images whose oracle top-1 margin exceeds twice the error bound
+(on random-init weights the raw metric measures luck, not kernels; the 2048-image
+figures, raw and margin-filtered, are in profiles/r02_parity.md and bench.py's `parity`)."""
 import numpy as np
 import pytest
 import torch
@@ -20,12 +29,17 @@ from _util import C1, C2, C3, C4, C5, TINY, TINY_MEAN, images_for, load_golden
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 5e-2}   # bf16: operand-format noise floor, see docstring
+TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 2e-2}   # BASELINE.json north star; bf16: see bf16_bound()
 # 16-bit run vs the oracle with the SAME operand rounding: what is left is accumulation order and
-# one-ulp rounding flips, so it scales with the format's ulp (bf16's is 8x fp16's; measured on
-# ViT-B/16 depth 12: fp16 2.3e-3, bf16 1.8e-2).
-TOL_VS_EMULATED = {"fp16": 1e-2, "bf16": 4e-2}
+# one-ulp rounding flips (measured on ViT-B/16 depth 12: fp16 2.3e-3, bf16 1.8e-2).
+TOL_VS_EMULATED = {"fp16": 1e-2, "bf16": 2e-2}
 TORCH_DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def bf16_bound(emulated, want):
+    """Error bound of a bf16-operand run against the fp32 oracle `want`, derived from the bf16-emulating
+    oracle on the same inputs (module docstring)."""
+    return max(TOL["bf16"], 1.25 * float(np.abs(emulated - want).max()))
 
 
 def oracle_logits(variables, images, cfg, pool="cls", operand_dtype=None):
@@ -49,7 +63,10 @@ def test_golden_tiny(name, cfg, pool, precision):
     assert launch_count() > before, "no kernels of libvitb200 were launched"
     assert y.shape == meta["logits"].shape and y.dtype == np.float32
     err = np.abs(y - meta["logits"]).max()
-    assert err < TOL[precision], f"{precision}: max abs logit error {err}"
+    tol = TOL[precision]
+    if precision == "bf16":
+        tol = bf16_bound(oracle_logits(variables, meta["images"], cfg, pool, torch.bfloat16), meta["logits"])
+    assert err < tol, f"{precision}: max abs logit error {err} (bound {tol})"
 
 
 def test_golden_tiny_tokens_fp32():
@@ -71,7 +88,10 @@ def test_readme_config_c1(precision):
     y = ViT(**C1).apply(variables, img, precision=precision)
     assert y.shape == (1, 1000)                                 # README.md:34
     err = np.abs(y - meta["logits"]).max()
-    assert err < TOL[precision], f"{precision}: max abs logit error {err}"
+    tol = TOL[precision]
+    if precision == "bf16":
+        tol = bf16_bound(oracle_logits(variables, img, C1, "cls", torch.bfloat16), meta["logits"])
+    assert err < tol, f"{precision}: max abs logit error {err} (bound {tol})"
 
 
 def test_reference_init_zero_image_gives_zero_logits():
@@ -82,11 +102,10 @@ def test_reference_init_zero_image_gives_zero_logits():
         assert np.all(y == 0.0)
 
 
-def _check_16bit(cfg, batch, depth=None, pool="cls", seed=0, precision="fp16", tol=None):
+def _check_16bit(cfg, batch, depth=None, pool="cls", seed=0, precision="fp16"):
     cfg = dict(cfg)
     if depth is not None:
         cfg["depth"] = depth
-    tol = TOL[precision] if tol is None else tol
     variables = perturb_params(init_params(seed=seed + 1, **cfg), seed=seed + 2)
     img = images_for(cfg, batch, seed=seed)
     want = oracle_logits(variables, img, cfg, pool)
@@ -94,9 +113,10 @@ def _check_16bit(cfg, batch, depth=None, pool="cls", seed=0, precision="fp16", t
     err = np.abs(got - want).max()
     emu = oracle_logits(variables, img, cfg, pool, TORCH_DT[precision])
     err_emu = np.abs(got - emu).max()
-    print(f"[parity] {precision} depth={cfg['depth']} batch={batch}: max abs logit error {err:.5f} "
-          f"(vs same-rounding oracle {err_emu:.5f})")
-    assert err < tol, f"{precision}: max abs logit error {err}"
+    tol = bf16_bound(emu, want) if precision == "bf16" else TOL[precision]
+    print(f"[parity] {precision} depth={cfg['depth']} batch={batch}: max abs logit error {err:.5f} (bound {tol:.5f}; "
+          f"same-rounding oracle is {np.abs(emu - want).max():.5f} from fp32, gpu is {err_emu:.5f} from it)")
+    assert err < tol, f"{precision}: max abs logit error {err} (bound {tol})"
     assert err_emu < TOL_VS_EMULATED[precision], f"{precision}: {err_emu} away from the same-rounding oracle"
     srt = np.sort(want, axis=1)
     confident = (srt[:, -1] - srt[:, -2]) > 2 * tol
@@ -127,9 +147,22 @@ def test_vit_l16_512px_reduced_depth(precision):
     _check_16bit(C5, batch=2, depth=2, precision=precision)
 
 
-def test_vit_l16_full_depth_fp16():
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_vit_l16_full_depth(precision):
     """configs[2] model, all 24 layers, 2 images."""
-    _check_16bit(C3, batch=2, precision="fp16")
+    _check_16bit(C3, batch=2, precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_vit_h14_full_depth(precision):
+    """configs[3] model at its full depth 32: T = 257 (streamed-KV attention), K0 = 588, inner 1024 != dim 1280."""
+    _check_16bit(C4, batch=2, precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_vit_l16_512px_full_depth(precision):
+    """configs[4] model at its full depth 24: T = 1025 tokens."""
+    _check_16bit(C5, batch=2, precision=precision)
 
 
 def test_mean_pool():
@@ -280,3 +313,69 @@ def test_vit_l16_full_batch_2048_rows_do_not_overflow():
     want = oracle_logits(variables, x[2044:].cpu().numpy(), cfg)
     assert np.abs(y[2044:].cpu().numpy() - want).max() < TOL["fp16"]
     eng.close()
+
+
+@pytest.mark.parametrize("ext", [".msgpack", ".npz", ".safetensors"])
+def test_checkpoint_file_to_gpu_forward(tmp_path, ext):
+    """SURVEY.md 8f-2 end to end: save_params -> file -> load_params -> ViT.apply on the GPU -> oracle, on the tiny
+    model (fp32 mode, 1e-4) and on ViT-B/16 at depth 2 (fp16 operands, 2e-2)."""
+    from vit_flax_b200 import load_params, save_params
+    for cfg, batch, precision in ((TINY, 3, "fp32"), (dict(C2, depth=2), 2, "fp16")):
+        variables = perturb_params(init_params(seed=21, **cfg), seed=22)
+        path = tmp_path / f"vit_{cfg['dim']}{ext}"
+        save_params(variables, path)
+        loaded = load_params(path)
+        img = images_for(cfg, batch, seed=23)
+        got = ViT(**cfg).apply(loaded, img, precision=precision)
+        want = oracle_logits(variables, img, cfg)
+        assert np.abs(got - want).max() < TOL[precision]
+        clear_cache()
+
+
+def test_checkpoint_stored_in_bf16_loads_widened():
+    """A checkpoint whose leaves were stored as bfloat16 (a common way to ship weights): load_params widens to fp32,
+    and the forward equals the forward on the bf16-rounded tree handed over in memory, bit for bit."""
+    import ml_dtypes
+    from vit_flax_b200 import load_params
+    from vit_flax_b200.checkpoint import msgpack_serialize
+    from vit_flax_b200.params import flatten_params
+    from vit_flax_b200.checkpoint import _unflatten
+    cfg = dict(C2, depth=2)
+    variables = perturb_params(init_params(seed=31, **cfg), seed=32)
+    flat16 = {k: np.asarray(v).astype(ml_dtypes.bfloat16) for k, v in flatten_params(variables).items()}
+    blob = msgpack_serialize({"params": _unflatten(flat16)})
+    loaded = load_params(blob)
+    rounded = {"params": _unflatten({k: v.astype(np.float32) for k, v in flat16.items()})}
+    img = images_for(cfg, 2, seed=33)
+    v = ViT(**cfg)
+    got = v.apply(loaded, img).copy()
+    np.testing.assert_array_equal(got, v.apply(rounded, img))
+    assert np.abs(got - oracle_logits(rounded, img, cfg)).max() < TOL["fp16"]
+
+
+def test_inline_params_dicts_are_not_confused_by_recycled_ids():
+    """``v.apply({'params': p_i}, x)`` twice with different weights must use each call's weights."""
+    v = ViT(**TINY)
+    img = images_for(TINY, 2, seed=1)
+    p1 = perturb_params(init_params(seed=41, **TINY), seed=42)["params"]
+    p2 = perturb_params(init_params(seed=43, **TINY), seed=44)["params"]
+    y1 = v.apply({"params": p1}, img, precision="fp32").copy()
+    y2 = v.apply({"params": p2}, img, precision="fp32").copy()
+    assert np.abs(y1 - oracle_logits({"params": p1}, img, TINY)).max() < 1e-4
+    assert np.abs(y2 - oracle_logits({"params": p2}, img, TINY)).max() < 1e-4
+    p2["Dense_1"]["bias"] += 1.0                                  # in-place edit: seen by the content probe
+    y3 = v.apply({"params": p2}, img, precision="fp32")
+    assert np.abs((y3 - y2) - 1.0).max() < 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """Function attributes (dynamic shared memory opt-in) are per device: an engine on cuda:1 created after cuda:0 has
+    configured every kernel must still launch (gemm_tc.cu launch_cg / PerDevice)."""
+    cfg = dict(C2, depth=1)
+    variables = perturb_params(init_params(seed=51, **cfg), seed=52)
+    img = images_for(cfg, 2, seed=53)
+    want = oracle_logits(variables, img, cfg)
+    for dev in (0, 1):
+        got = ViT(**cfg).apply(variables, img, device=dev)
+        assert np.abs(got - want).max() < TOL["fp16"], f"device {dev}"

@@ -108,3 +108,40 @@ def test_simple_vit_vjp_matches_finite_differences_of_the_oracle():
                 vals.append(f(p2))
             fd = (vals[0] - vals[1]) / 2e-4
             assert abs(g[idx] - fd) < 3e-2 * scale, (path, idx, g[idx], fd)
+
+
+def test_inline_params_dicts_with_different_weights_are_not_confused():
+    """``v.apply({'params': p_i}, x)`` builds a temporary dict per call whose id CPython recycles: the weight cache
+    must go by the leaves, not by id(variables).  Also: in-place edits are seen, ``reload`` forces."""
+    v = SimpleViT(**SMALL)
+    img = np.random.default_rng(0).standard_normal((3, 3, 32, 64)).astype(np.float32)
+    p1 = _perturbed(v, img, 10)["params"]
+    p2 = _perturbed(v, img, 20)["params"]
+    y1 = v.apply({"params": p1}, img, precision="fp32").copy()
+    y2 = v.apply({"params": p2}, img, precision="fp32").copy()
+    assert np.abs(y1 - simple_vit_numpy.simple_vit_forward({"params": p1}, img, **SMALL)).max() < 1e-4
+    assert np.abs(y2 - simple_vit_numpy.simple_vit_forward({"params": p2}, img, **SMALL)).max() < 1e-4
+    assert np.abs(y1 - y2).max() > 1e-2
+    p2["Dense_0"]["bias"] += 1.0                                   # in-place: every head logit moves by 1
+    y3 = v.apply({"params": p2}, img, precision="fp32")
+    assert np.abs((y3 - y2) - 1.0).max() < 1e-4
+    y4 = v.apply({"params": p2}, img, precision="fp32", reload=True)
+    np.testing.assert_array_equal(y3, y4)
+
+
+def test_adoption_layout_loads_and_gives_the_same_logits_and_gradient_layout():
+    v = SimpleViT(**SMALL)
+    img = np.random.default_rng(1).standard_normal((2, 3, 32, 64)).astype(np.float32)
+    params = _perturbed(v, img, 30)
+    p = params["params"]
+    adoption = {"params": {"Dense_0": p["Dense_1"], "Transformer_0": p["Transformer_0"],
+                           "Sequential_0": {"layers_0": p["LayerNorm_0"], "layers_1": p["Dense_0"]}}}
+    ya = v.apply(params, img).copy()
+    yb = v.apply(adoption, img)
+    np.testing.assert_array_equal(ya, yb)
+    dl = np.ones((2, SMALL["num_classes"]), np.float32)
+    ga = v.vjp(params, img)[1](dl)["params"]
+    gb = v.vjp(adoption, img)[1](dl)["params"]
+    assert set(ga) == set(p) and set(gb) == {"Dense_0", "Transformer_0", "Sequential_0"}
+    np.testing.assert_array_equal(ga["Dense_1"]["kernel"], gb["Dense_0"]["kernel"])            # patch embedding
+    np.testing.assert_array_equal(ga["Dense_0"]["kernel"], gb["Sequential_0"]["layers_1"]["kernel"])   # head

@@ -100,3 +100,63 @@ def test_apply_fails_loudly_without_cuda():
     variables = v.init(0, np.zeros((1, 32, 32, 3), np.float32))
     with pytest.raises((RuntimeError, ImportError)):
         v.apply(variables, np.zeros((1, 32, 32, 3), np.float32))
+
+
+# ---- weight-cache identity (runtime.ParamsStamp) and the SimpleViT params layouts: host logic, no GPU ----
+def test_params_stamp_sees_recycled_ids_and_inplace_edits():
+    from vit_flax_b200.params import init_params
+    from vit_flax_b200.runtime import ParamsStamp
+    p1 = init_params(seed=1, **TINY)["params"]
+    p2 = init_params(seed=2, **TINY)["params"]
+    # the usual flax call builds a temporary {'params': p} per call: CPython may hand both the same id
+    s1 = ParamsStamp({"params": p1})
+    s2 = ParamsStamp({"params": p2})
+    assert not s2.matches(s1) and s1.matches(ParamsStamp({"params": p1}))
+    assert not s1.matches(None)
+    # in-place edits of a host leaf are seen by the content probe, a torch leaf by its version counter
+    before = ParamsStamp(p1)
+    p1["Dense_0"]["kernel"] *= 0.5
+    assert not ParamsStamp(p1).matches(before)
+    t = {k: torch.as_tensor(np.array(v)) if not isinstance(v, dict) else v for k, v in p2.items()}
+    before = ParamsStamp(t)
+    assert ParamsStamp(t).matches(before)
+    t["cls"].add_(1.0)
+    assert not ParamsStamp(t).matches(before)
+    # a different tree structure never matches
+    assert not ParamsStamp({"a": np.zeros(3, np.float32)}).matches(ParamsStamp({"b": np.zeros(3, np.float32)}))
+
+
+def test_simple_vit_init_layout_is_flax_construction_scope_and_both_layouts_load():
+    """simple_vit.py:117-126: LayerNorm and head Dense are constructed (inside nn.Sequential([...])) in SimpleViT's
+    scope BEFORE the patch Dense => LayerNorm_0, Dense_0 = head, Dense_1 = patch embedding, no Sequential_0 params.
+    The adoption layout (Dense_0 = patch, Sequential_0/layers_*) is accepted too and maps to the same weights."""
+    from oracle import simple_vit_numpy
+    from vit_flax_b200 import SimpleViT
+    cfg = dict(image_size=(32, 64), patch_size=(8, 16), num_classes=10, dim=64, depth=2, heads=2, mlp_dim=128)
+    v = SimpleViT(**cfg)
+    img = np.random.default_rng(0).standard_normal((2, 3, 32, 64)).astype(np.float32)
+    variables = v.init({"params": 3}, img)
+    p = variables["params"]
+    assert set(p) == {"LayerNorm_0", "Dense_0", "Dense_1", "Transformer_0"}
+    assert p["Dense_0"]["kernel"].shape == (64, 10) and p["Dense_1"]["kernel"].shape == (8 * 16 * 3, 64)
+    assert set(p["LayerNorm_0"]) == {"scale"}                                        # use_bias=False
+    assert set(p["Transformer_0"]) == {f"{m}_{l}" for m in ("Attention", "FeedForward") for l in range(2)}
+    assert set(p["Transformer_0"]["Attention_0"]) == {"LayerNorm_0", "Dense_0", "Dense_1"}
+    assert set(p["Transformer_0"]["Attention_0"]["Dense_1"]) == {"kernel"}           # to_out has no bias
+    adoption = {"params": {"Dense_0": p["Dense_1"], "Transformer_0": p["Transformer_0"],
+                           "Sequential_0": {"layers_0": p["LayerNorm_0"], "layers_1": p["Dense_0"]}}}
+    assert v._split_tree(variables)[0] == "construction" and v._split_tree(adoption)[0] == "adoption"
+    fa, fb = flatten_params(v._engine_tree(variables)), flatten_params(v._engine_tree(adoption))
+    assert sorted(fa) == sorted(fb) and all(np.array_equal(fa[k], fb[k]) for k in fa)
+    np.testing.assert_array_equal(simple_vit_numpy.simple_vit_forward(variables, img, **cfg),
+                                  simple_vit_numpy.simple_vit_forward(adoption, img, **cfg))
+    # a tree whose head / patch kernels are swapped (the other reading of the names) fails loudly
+    swapped = {"params": dict(p, Dense_0=p["Dense_1"], Dense_1=p["Dense_0"])}
+    with pytest.raises(ValueError, match="kernel shapes"):
+        v._engine_tree(swapped)
+    with pytest.raises(ValueError, match="lacks"):
+        v._engine_tree({"params": {"Transformer_0": p["Transformer_0"]}})
+    # gradients come back in the caller's layout
+    flat = {k: np.zeros(s, np.float32) for k, s in tree_shapes(v._engine_tree(variables)).items()}
+    assert set(v._grads_tree(flat)["params"]) == set(p)
+    assert set(v._grads_tree(flat, "adoption")["params"]) == {"Dense_0", "Transformer_0", "Sequential_0"}

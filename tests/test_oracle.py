@@ -203,3 +203,37 @@ def test_vjp_oracle_matches_finite_differences():
             for k in path:
                 ref = ref[k]
             assert abs(fd - ref[idx]) < 1e-6 * max(1.0, abs(fd)), (pool, path, fd, ref[idx])
+
+
+def _round_kernels(tree, dt):
+    """Every Dense kernel rounded to the 16-bit type `dt` and back (biases / LayerNorm affine / cls / pos stay fp32,
+    as they do on the tensor-core path)."""
+    if isinstance(tree, dict):
+        return {k: (v.to(dt).to(torch.float32) if k == "kernel" else _round_kernels(v, dt)) for k, v in tree.items()}
+    return tree
+
+
+def test_bf16_operand_floor_on_vit_b16():
+    """BASELINE.json's north star asks for bf16 logits within max-abs 2e-2 of the fp32 reference.  On the
+    metric's own config (ViT-B/16, reference initialisers => unit-variance logits) that bound is not
+    reachable by ANY bf16-operand implementation: rounding the Dense KERNELS ALONE to bf16 -- exact fp32
+    arithmetic everywhere else -- already moves the logits by ~2.2e-2, and rounding every tensor-core operand
+    (what a bf16 GEMM path must do) by ~3e-2.  The error is spread evenly over patch / qkv / out / ff1 / ff2 /
+    head (no single GEMM to special-case).  fp16 operands (same tcgen05 rate, 3 more significand bits) stay
+    8x below the bound, which is why fp16 is the shipped default and bf16 is held to this derived floor
+    (tests/test_gpu_forward.py: error <= max(2e-2, 1.25 x this emulated error), and within 2e-2 of the
+    same-rounding emulation)."""
+    variables = perturb_params(init_params(seed=1, **C2), seed=2)
+    img = images_for(C2, 8, seed=0)
+    pt = vit_torch.tree_to_torch(variables)
+    want = vit_torch.vit_forward(pt, img, **C2).numpy()
+    err = {}
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        w_only = vit_torch.vit_forward(_round_kernels(pt, dt), img, **C2).numpy()
+        full = vit_torch.vit_forward(pt, img, operand_dtype=dt, **C2).numpy()
+        err[name] = (float(np.abs(w_only - want).max()), float(np.abs(full - want).max()))
+    print(f"[bf16 floor] ViT-B/16, 8 images: weights-only / every-operand rounding: bf16 {err['bf16']}, fp16 {err['fp16']}")
+    assert 0.9 < want.std() < 1.1                 # unit-variance logits: the absolute tolerance is a relative one
+    assert err["bf16"][0] > 1.8e-2                # weights alone (measured 2.19e-2)
+    assert err["bf16"][1] > 2e-2                  # every operand (measured 3.03e-2): the north-star bound is out of reach
+    assert err["fp16"][1] < 6e-3                  # fp16 operands (measured 3.2e-3)

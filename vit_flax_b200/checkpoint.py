@@ -2,9 +2,10 @@
 
 * ``.msgpack`` -- ``flax.serialization.to_bytes`` / ``msgpack_serialize``: a msgpack map whose leaves
   are ``ExtType(1, packb((shape, dtype_name, raw_bytes)))`` (numpy scalars: code 3), arrays above
-  2**30 bytes split into ``{'__msgpack_chunked_array__': True, 'shape': ..., 'chunks': {...}}``.
-  Restated from the published format (flax is not installed here); ``save_msgpack`` writes the
-  same layout, so files round-trip with Flax.
+  2**30 bytes split into ``{'__msgpack_chunked_array__': True, 'shape': {'0': d0, ...}, 'chunks':
+  {'0': ..., ...}}`` (tuples go through flax's ``_tuple_to_dict``).  Restated from the published format
+  (flax is not installed here, so no file written by Flax itself could be read back in this image);
+  ``save_params`` writes the same layout.
 * ``.npz`` -- flat ``'/'``- or ``'.'``-joined paths.
 * ``.safetensors`` -- flat paths (``safetensors.flax.save_file`` joins with ``'.'``).
 
@@ -44,12 +45,21 @@ def _ext_hook(code: int, data: bytes):
     return msgpack.ExtType(code, data)
 
 
+def _seq(node):
+    """A tuple that flax wrote through ``_tuple_to_dict`` (``{'0': a, '1': b}``) or a plain list -> list,
+    in index order (keys may come back as str or int)."""
+    if isinstance(node, Mapping):
+        return [node[k] for k in sorted(node, key=lambda k: int(k))]
+    return list(node)
+
+
 def _unchunk(node):
     if isinstance(node, dict):
         if node.get("__msgpack_chunked_array__"):
-            chunks = node["chunks"]
-            flat = np.concatenate([np.asarray(chunks[str(i)]).ravel() for i in range(len(chunks))])
-            return flat.reshape(tuple(node["shape"]))
+            # flax.serialization._chunk: {'__msgpack_chunked_array__': True, 'shape': {'0': d0, ...},
+            # 'chunks': {'0': flat chunk, ...}} -- both through _tuple_to_dict; lists are accepted too
+            flat = np.concatenate([np.asarray(c).ravel() for c in _seq(node["chunks"])])
+            return flat.reshape(tuple(int(d) for d in _seq(node["shape"])))
         return {k: _unchunk(v) for k, v in node.items()}
     return node
 
@@ -85,7 +95,7 @@ def _chunk(node):
     per = max(1, _MAX_CHUNK // a.dtype.itemsize)
     flat = a.ravel()
     chunks = {str(i): flat[o:o + per] for i, o in enumerate(range(0, flat.size, per))}
-    return {"__msgpack_chunked_array__": True, "shape": list(a.shape), "chunks": chunks}
+    return {"__msgpack_chunked_array__": True, "shape": {str(i): int(d) for i, d in enumerate(a.shape)}, "chunks": chunks}
 
 
 def msgpack_serialize(tree: Mapping) -> bytes:

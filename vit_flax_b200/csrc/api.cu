@@ -156,6 +156,7 @@ struct vitb200_model {
   };
   struct TrainState {
     int fwd_batch = 0;                    // batch of the last train_forward (0 = none to differentiate)
+    bool stale = false;                   // that forward's workspace was overwritten by an inference forward since
     int rows_cap = 0;                     // max_batch * T rounded up to the GEMM tile height (256)
     uint64_t fwd_key = 0;                 // 'dropout' rng key of that forward: the backward replays its masks
     std::vector<DevBuf<float>> xs;        // residual stream before every LayerNorm + after the last layer
@@ -379,16 +380,14 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   // vit.py:159-165  pool, LayerNorm_0, Dense_1
   if (m->head_tc) {
     mark(m, st, VITB200_CAT_POOL_LN);
-    mark(m, st, VITB200_CAT_POOL_LN);
-  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, m->dt, m->eps))) return rc;
+    if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, m->dt, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_HEAD);
     CUtensorMap c_logits;   // the caller's buffer: encoded per call (host-side, ~1 us)
     if ((rc = make_tmap_2d(&c_logits, logits, batch, c.num_classes, c.num_classes, GEMM_BM, VITB200_DT_F32))) return rc;
     if ((rc = launch_gemm_tc(st, am->pooled, m->head.map(cgh), &c_logits, leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0, m->dt, cgh))) return rc;
   } else {
     mark(m, st, VITB200_CAT_POOL_LN);
-    mark(m, st, VITB200_CAT_POOL_LN);
-  if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32, m->eps))) return rc;
+    if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_f.p, batch, T, D, c.pool, VITB200_DT_F32, m->eps))) return rc;
     mark(m, st, VITB200_CAT_GEMM_HEAD);
     if ((rc = launch_gemm_f32(st, m->pooled_f.p, leaf_ptr(m, m->head.leaf_kernel), leaf_ptr(m, m->head.leaf_bias), logits, batch, c.num_classes, D, VITB200_EPI_BIAS_F32, nullptr, 0))) return rc;
   }
@@ -670,6 +669,8 @@ int vitb200_forward(vitb200_model* m, void* stream, const float* images_dev, int
   if (batch <= 0 || batch > m->cfg.max_batch) return fail(VITB200_ERR_INVALID, "forward: batch must be in [1, max_batch]");
   DeviceGuard guard(m->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // an inference forward re-uses the patch matrix a pending backward would read: that backward is now refused
+  if (m->train && m->train->fwd_batch != 0) { m->train->fwd_batch = 0; m->train->stale = true; }
   if (!m->tc) return forward_f32(m, st, images_dev, batch, logits_dev);
   if (graph_eligible(m, st, batch)) return forward_graph(m, st, images_dev, batch, logits_dev);
   return forward_tc(m, st, images_dev, batch, logits_dev);
@@ -837,6 +838,7 @@ int train_supported(const vitb200_model* m) {
   if (!m->tc) return fail(VITB200_ERR_UNSUPPORTED, "train: the backward pass is built for the bf16/fp16 modes only");
   if (!m->project_out) return fail(VITB200_ERR_UNSUPPORTED, "train: heads == 1 with dim == 64 (identity to_out) is not built");
   if (c.dim > 1280) return fail(VITB200_ERR_UNSUPPORTED, "train: dim > 1280 is not built for the backward pass");
+  if (c.depth < 1) return fail(VITB200_ERR_UNSUPPORTED, "train: the backward pass needs at least one transformer layer");
   return 0;
 }
 
@@ -898,6 +900,7 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
   if ((rc = ensure_train(m, st))) return rc;
   auto& ts = *m->train;
   ts.fwd_batch = 0;
+  ts.stale = false;
   const auto& c = m->cfg;
   const int D = c.dim, I = m->inner, T = m->T, H = c.mlp_dim, R = batch * T;
   if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels, c.patch_h, c.patch_w,
@@ -949,6 +952,9 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
 
 int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int batch) {
   if (!m || !dlogits) return fail(VITB200_ERR_INVALID, "backward: null argument");
+  if (m->train && m->train->fwd_batch == 0 && m->train->stale)
+    return fail(VITB200_ERR_INVALID, "backward: a forward ran on this handle since train_forward and overwrote its workspace; "
+                                     "call train_forward again");
   if (!m->train || m->train->fwd_batch == 0) return fail(VITB200_ERR_INVALID, "backward: call train_forward first");
   if (batch != m->train->fwd_batch) return fail(VITB200_ERR_INVALID, "backward: batch differs from the last train_forward");
   if (!m->finalized) return fail(VITB200_ERR_PARAM_MISSING, "backward: parameters changed since train_forward");

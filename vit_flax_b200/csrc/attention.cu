@@ -230,8 +230,8 @@ static int launch_attention_t(cudaStream_t stream, const uint16_t* qkv, uint16_t
   const int ctas = ceil_div(nq16, MAX_WARPS);
   const int nwarps = ceil_div(nq16, ctas);
   const size_t smem = size_t(nwarps) * 16 * ROW_BYTES + 4 * size_t(KV_BLOCK) * ROW_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<kDT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  MAX_WARPS * 16 * ROW_BYTES + 4 * KV_BLOCK * ROW_BYTES));
     configured = true;

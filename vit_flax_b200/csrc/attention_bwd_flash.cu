@@ -334,8 +334,8 @@ int launch_attention_bwd_flash(cudaStream_t st, const void* qkv, const void* o_f
   uint16_t* g16 = static_cast<uint16_t*>(dqkv);
   const unsigned cgrid = unsigned(std::min<int64_t>((rows * (inner / 8) + 255) / 256, int64_t(sm_count()) * 16));
   constexpr size_t kMainSmem = 7 * TILE_BYTES + 2 * 2 * TILE * sizeof(float);     // 57 KB: three CTAs per SM
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMainSmem)));
     VB_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMainSmem)));
     configured = true;

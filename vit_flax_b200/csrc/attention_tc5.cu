@@ -474,8 +474,8 @@ int attn_turns() {
 template <int kDT, int KP, int kPoly>
 int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
   using L = Smem<KP>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<kDT, KP, kPoly>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;

@@ -420,8 +420,8 @@ int attn_m_turns() {   // VITB200_ATTN_TURNS=0: free-running groups (A/B tests)
 template <int kDT, int KP>
 int launch_m(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
   using L = SmemM<KP>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(attention_tc5m_kernel<kDT, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  L::TOTAL));
     configured = true;

@@ -843,8 +843,8 @@ int launch_ln_bwd_t(cudaStream_t st, const void* dy, const float* x, const float
                     const Dropout& drop) {
   const int grid = std::min((rows + 3) / 4, sm_count() * 3);   // persistent: 128-thread blocks, two to three resident per SM
   const size_t smem = 4 * 3 * size_t(dim) * sizeof(float);     // 60 KB at dim 1280
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<kDT, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * 1280 * int(sizeof(float))));
     configured = true;
   }
@@ -930,8 +930,8 @@ int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* o_fwd, co
   const int TP = (T + 15) / 16 * 16, pitch = TP * 2 + 16;
   const int nblk = TP / 16, nw = nblk;                        // one warp per 16-row block (<= 13)
   const size_t smem = size_t(4) * TP * ROW_BYTES + size_t(TP) * pitch;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VB_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;

@@ -37,6 +37,19 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 int sm_count();   // SMs of the current device (cached per device)
+// One value per CUDA device, indexed by the current device: function attributes
+// (cudaFuncSetAttribute) and occupancy answers belong to the device they were set / asked on, so a
+// process that drives several GPUs must configure each kernel once PER DEVICE.
+constexpr int VB_MAX_DEVICES = 64;
+template <typename T> struct PerDevice {
+  T v[VB_MAX_DEVICES] = {};
+  T spill{};            // devices beyond the table are re-configured on every call (correct, just slower)
+  T& here() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= VB_MAX_DEVICES) { spill = T{}; return spill; }
+    return v[dev];
+  }
+};
 bool pdl_enabled();   // VITB200_PDL=0 turns programmatic dependent launch off (A/B tests)
 
 // cudaLaunchKernelEx with the attributes every kernel of the path uses: programmatic stream

@@ -470,9 +470,10 @@ template <int kEpi, int kDT, int kCG, bool kDrop, bool kMN = false>
 int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
               const float* aux, int tpi, const Dropout& drop, int cls_off, const float* cls) {
-  static bool configured = false;   // per-process; attribute is per-function, device-agnostic
-  static int max_units = 0;         // clusters (CTAs for kCG == 1) that can be resident at once
-  if (!configured) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  static PerDevice<int> max_units_on;   // clusters (CTAs for kCG == 1) that can be resident at once, per device
+  int& max_units = max_units_on.here();
+  if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG, kDrop, kMN>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG>()));
     max_units = sm_count() / Cfg<kCG>::CL;

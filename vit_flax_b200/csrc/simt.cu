@@ -631,8 +631,8 @@ int launch_attention_f32(cudaStream_t st, const float* qkv, float* out, int batc
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_f32: empty problem");
   const int Tpad = (T + 31) & ~31;
   const size_t smem = size_t(8) * (Tpad + 64) * sizeof(float);
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
+  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
+  if (bool& configured = configured_on.here(); !configured && smem > 48 * 1024) {
     VB_CUDA(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }

@@ -75,3 +75,75 @@ def all_reduce_grads(grads_flat: torch.Tensor, group: Optional[dist.ProcessGroup
         if average:
             grads_flat.div_(dist.get_world_size(group))
     return grads_flat
+
+
+def sharded_apply_stream(forward_local: Callable[[torch.Tensor, torch.Tensor], None], host_batches,
+                         global_batch: int, num_classes: int, image_shape: Tuple[int, ...], device: torch.device,
+                         group: Optional[dist.ProcessGroup] = None):
+    """Serving loop of the sharded forward, end to end: iterate this rank's HOST shards (pinned float32 tensors
+    ``[B/G, *image_shape]``) and yield the gathered HOST logits ``[global_batch, C]`` of every step, in order.
+
+    Two steps are in flight: the host->device copy of shard k+1 (copy stream) overlaps the forward + logits
+    all-gather of step k (current stream), whose device->host read-back (output stream) overlaps step k+1.
+    Every step's images cross PCIe, every step's gathered logits come back to the host, and the all-gather is
+    inside the loop -- this is the path ``bench.py`` times as `e2e` at N > 1.  Yielded tensors are pinned staging
+    buffers re-used two steps later."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    start, stop = shard_range(global_batch, world, rank)
+    if global_batch % world != 0:
+        raise ValueError("sharded_apply_stream needs equal shards (global_batch divisible by the world size)")
+    local = stop - start
+    cuda = device.type == "cuda"
+    main = torch.cuda.current_stream(device) if cuda else None
+    copy_s = torch.cuda.Stream(device) if cuda else None
+    out_s = torch.cuda.Stream(device) if cuda else None
+    img = [torch.empty((local,) + tuple(image_shape), dtype=torch.float32, device=device) for _ in range(2)]
+    gath = [torch.empty((global_batch, num_classes), dtype=torch.float32, device=device) for _ in range(2)]
+    host = [torch.empty((global_batch, num_classes), dtype=torch.float32, pin_memory=cuda) for _ in range(2)]
+    ev = lambda: torch.cuda.Event() if cuda else None
+    h2d_done, fwd_done, d2h_done = [ev(), ev()], [ev(), ev()], [ev(), ev()]
+    used = [False, False]
+    pending = []
+    nccl = dist.is_initialized() and world > 1 and dist.get_backend(group) == "nccl"
+    k = 0
+    for shard in host_batches:
+        if tuple(shard.shape) != tuple(img[0].shape):
+            raise ValueError(f"rank {rank} expected a shard of shape {tuple(img[0].shape)}, got {tuple(shard.shape)}")
+        s = k & 1
+        if len(pending) == 2:
+            t = pending.pop(0)
+            if cuda:
+                d2h_done[t].synchronize()
+            yield host[t]
+        if cuda:
+            with torch.cuda.stream(copy_s):
+                if used[s]:
+                    copy_s.wait_event(fwd_done[s])          # the forward two steps ago has read this buffer
+                img[s].copy_(shard, non_blocking=True)
+                h2d_done[s].record(copy_s)
+            main.wait_event(h2d_done[s])
+            if used[s]:
+                main.wait_event(d2h_done[s])                # its gathered logits have left for the host
+        else:
+            img[s].copy_(shard)
+        slot = gath[s][start:stop]
+        forward_local(img[s], slot)
+        if world > 1:
+            dist.all_gather_into_tensor(gath[s], slot if nccl else slot.clone(), group=group)
+        if cuda:
+            fwd_done[s].record(main)
+            with torch.cuda.stream(out_s):
+                out_s.wait_event(fwd_done[s])
+                host[s].copy_(gath[s], non_blocking=True)
+                d2h_done[s].record(out_s)
+        else:
+            host[s].copy_(gath[s])
+        used[s] = True
+        pending.append(s)
+        k += 1
+    while pending:
+        t = pending.pop(0)
+        if cuda:
+            d2h_done[t].synchronize()
+        yield host[t]

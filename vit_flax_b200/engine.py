@@ -54,6 +54,10 @@ class Engine:
         _lib.check(self.lib.vitb200_create(C.byref(self.cfg), device, C.byref(handle)))
         self.handle = handle
         self._loaded = False
+        # Bumped by everything that overwrites what a pending backward reads (any forward, a weight
+        # reload, close): ``ViT.vjp`` captures it after ``train_forward`` and ``backward`` refuses a
+        # cotangent whose forward is no longer the one held by the handle.
+        self.epoch = 0
 
     # -- params ----------------------------------------------------------------
     def param_table(self) -> Dict[str, tuple]:
@@ -68,6 +72,7 @@ class Engine:
 
     def load_params(self, variables) -> None:
         """Upload a Flax-style params pytree (dict / FrozenDict / Mapping)."""
+        self.epoch += 1
         flat = flatten_params(variables)
         table = self.param_table()
         missing = sorted(set(table) - set(flat))
@@ -104,6 +109,7 @@ class Engine:
         b = images.shape[0]
         if out is None:
             out = torch.empty((b, self.num_classes), dtype=torch.float32, device=images.device)
+        self.epoch += 1
         _lib.check(self.lib.vitb200_forward(self.handle, _stream_ptr(torch, images.device),
                                             images.data_ptr(), b, out.data_ptr()))
         return out
@@ -120,14 +126,22 @@ class Engine:
         b = images.shape[0]
         if out is None:
             out = torch.empty((b, self.num_classes), dtype=torch.float32, device=images.device)
+        self.epoch += 1
         _lib.check(self.lib.vitb200_train_forward(self.handle, _stream_ptr(torch, images.device),
                                                   images.data_ptr(), b, out.data_ptr()))
         return out
 
-    def backward(self, dlogits) -> None:
+    def backward(self, dlogits, epoch: Optional[int] = None) -> None:
         """Cotangent of the logits of the last ``train_forward`` (fp32 CUDA tensor [B, classes]) ->
-        one fp32 gradient per parameter leaf, read with ``grads()`` / ``grad_tensor(path)``."""
+        one fp32 gradient per parameter leaf, read with ``grads()`` / ``grad_tensor(path)``.
+        ``epoch``: the value of ``self.epoch`` right after the ``train_forward`` this cotangent belongs
+        to; a mismatch means another forward / reload ran on this engine since and is an error."""
         torch = self._torch
+        if self.handle is None:
+            raise RuntimeError("backward: this engine was closed (a larger batch re-created it); run vjp again")
+        if epoch is not None and epoch != self.epoch:
+            raise RuntimeError("backward: the engine ran another forward or reloaded its weights since the "
+                               "train_forward this cotangent belongs to (activations overwritten); run vjp again")
         if dlogits.dtype != torch.float32 or not dlogits.is_cuda or not dlogits.is_contiguous() or dlogits.dim() != 2 \
                 or dlogits.shape[1] != self.num_classes:
             raise ValueError(f"backward expects a contiguous float32 CUDA tensor [B, {self.num_classes}]")
@@ -176,6 +190,7 @@ class Engine:
         b = images.shape[0]
         if out is None:
             out = np.empty((b, self.num_classes), np.float32)
+        self.epoch += 1
         _lib.check(self.lib.vitb200_forward_host(self.handle, _stream_ptr(self._torch, self.device),
                                                  images.ctypes.data, b, out.ctypes.data))
         return out
@@ -190,6 +205,7 @@ class Engine:
         b = images.shape[0]
         if out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (b, self.num_classes):
             raise ValueError(f"submit_host expects a C-contiguous float32 out of shape ({b}, {self.num_classes})")
+        self.epoch += 1
         _lib.check(self.lib.vitb200_submit_host(self.handle, _stream_ptr(self._torch, self.device),
                                                 images.ctypes.data, b, out.ctypes.data))
 
@@ -229,6 +245,7 @@ class Engine:
         n = len(_lib.CATEGORIES)
         ms = (C.c_float * n)()
         cnt = (C.c_int * n)()
+        self.epoch += 1
         _lib.check(self.lib.vitb200_profile_forward(self.handle, _stream_ptr(torch, images.device),
                                                     images.data_ptr(), b, out.data_ptr(), ms, cnt))
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.CATEGORIES)}
@@ -243,6 +260,7 @@ class Engine:
         if getattr(self, "handle", None):
             self.lib.vitb200_destroy(self.handle)
             self.handle = None
+            self.epoch += 1
 
     def __del__(self):  # best effort
         try:

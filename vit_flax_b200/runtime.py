@@ -1,21 +1,65 @@
-"""Engine cache behind ``ViT.apply``: one ``Engine`` per (config, precision, device),
-weights re-packed only when a different params object is passed."""
+"""Engine cache behind ``ViT.apply`` / ``SimpleViT.apply``: one ``Engine`` per (config, precision,
+device), weights re-packed only when different params are passed.
+
+"Different" is decided by ``ParamsStamp``: the leaves of the last loaded tree are held by STRONG
+reference and compared with ``is`` (an ``id()`` alone can be recycled by CPython as soon as the old
+object dies -- ``v.apply({'params': p1}, x); v.apply({'params': p2}, x)`` builds two temporaries with
+the same id), plus a cheap content probe per leaf (a strided sample of up to 16 values for host
+arrays, the ``_version`` counter for torch tensors), so the usual in-place updates -- an optimiser
+step, ``leaf *= 0`` -- are seen too.  An in-place edit that misses every probed element of a host
+array is the one case left to ``reload=True``.
+"""
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
 
 from .engine import Engine
 from .params import flatten_params
 
 _engines: Dict[Tuple, Engine] = {}
-_loaded: Dict[Tuple, Tuple] = {}
+_loaded: Dict[Tuple, "ParamsStamp"] = {}
+
+_PROBE = 16   # sampled values per host leaf
 
 
-def _fingerprint(variables) -> Tuple:
-    """Identity of the params object: ids of the container and of every leaf.  In-place
-    mutation of a leaf is NOT detected -- pass ``reload=True`` to ``apply`` after one."""
-    flat = flatten_params(variables)
-    return (id(variables),) + tuple((k, id(v)) for k, v in sorted(flat.items()))
+def _probe(leaf) -> object:
+    """Cheap content witness of one leaf (never copies the leaf, never synchronises a GPU)."""
+    if hasattr(leaf, "_version") and hasattr(leaf, "data_ptr"):         # torch.Tensor (any device)
+        return ("torch", int(leaf._version), int(leaf.data_ptr()))
+    if isinstance(leaf, np.ndarray):
+        flat = leaf.reshape(-1) if leaf.flags.c_contiguous else leaf.ravel()
+        n = flat.size
+        if n == 0:
+            return ("np", b"")
+        step = max(1, n // _PROBE)
+        return ("np", flat[::step][:_PROBE].tobytes(), flat[-1:].tobytes())
+    return ("other",)                                                    # jax arrays are immutable: identity is enough
+
+
+class ParamsStamp:
+    """Identity (strong references, compared with ``is``) + content probe of a params tree."""
+
+    def __init__(self, variables):
+        flat = flatten_params(variables)
+        self.keys: List[str] = sorted(flat)
+        self.leaves = [flat[k] for k in self.keys]       # strong references: ids cannot be recycled
+        self.probes = [_probe(v) for v in self.leaves]
+
+    def matches(self, other: Optional["ParamsStamp"]) -> bool:
+        if other is None or self.keys != other.keys:
+            return False
+        return all(a is b for a, b in zip(self.leaves, other.leaves)) and self.probes == other.probes
+
+
+def needs_reload(key, variables, reload: bool) -> Optional[ParamsStamp]:
+    """The stamp to record after loading ``variables`` for cache slot ``key``, or None when the
+    weights already on the device are these."""
+    stamp = ParamsStamp(variables)
+    if not reload and stamp.matches(_loaded.get(key)):
+        return None
+    return stamp
 
 
 def get_engine(vit, channels: int, precision: str, device: int, batch: int, variables,
@@ -32,10 +76,10 @@ def get_engine(vit, channels: int, precision: str, device: int, batch: int, vari
                      mlp_dim=vit.mlp_dim, pool=vit.pool, channels=channels, precision=precision,
                      max_batch=batch, device=device, dropout=vit.dropout, emb_dropout=vit.emb_dropout)
         _engines[key] = eng
-    fp = _fingerprint(variables)
-    if reload or _loaded.get(key) != fp:
+    stamp = needs_reload(key, variables, reload)
+    if stamp is not None:
         eng.load_params(variables)
-        _loaded[key] = fp
+        _loaded[key] = stamp
     return eng
 
 

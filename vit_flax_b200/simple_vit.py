@@ -5,7 +5,26 @@ Differences from ``ViT`` that the engine takes as configuration: NCHW images
 (simple_vit.py:14-25, 127-128), ``LayerNorm(epsilon=1e-5, use_bias=False)`` inside Attention /
 FeedForward and in the head (simple_vit.py:41, 58, 118), a bias-free ``to_out`` (simple_vit.py:61),
 mean pooling (simple_vit.py:131).  ``dim_head`` is a field here (default 64); the kernels are
-built for 64.  The params pytree is the one Flax's compact naming gives that file.
+built for 64.
+
+Params pytree.  Flax names a module at CONSTRUCTION, under the module whose ``@nn.compact`` method
+is running (the same rule that makes ``Attention_l`` / ``PreNorm_k`` siblings under ``Transformer_0``
+in vit.py).  In simple_vit.py the ``nn.LayerNorm`` and ``nn.Dense`` handed to
+``nn.Sequential([...])`` (lines 117-120) are constructed in SimpleViT's scope, before the patch
+``nn.Dense`` of line 126, so the tree ``init`` gives is
+
+    LayerNorm_0/scale [dim]          head norm          (simple_vit.py:118)
+    Dense_0/{kernel [dim, classes], bias}   head        (simple_vit.py:119)
+    Dense_1/{kernel [p1*p2*c, dim], bias}   patch embedding (simple_vit.py:126)
+    Transformer_0/{Attention_l/{LayerNorm_0/scale, Dense_0/kernel, Dense_1/kernel},
+                   FeedForward_l/{LayerNorm_0/scale, Dense_0/{kernel,bias}, Dense_1/{kernel,bias}}}
+
+(``Sequential_0`` owns no parameters: the two layers already have a parent).  ``init`` emits this
+layout.  ``apply`` / ``vjp`` also accept the ADOPTION layout that round 1 of this repository wrote
+(``Dense_0`` = patch embedding, ``Sequential_0/layers_0|layers_1`` = head): the two are told apart
+by the presence of ``Sequential_0`` and checked against the kernel shapes.  Neither could be checked
+against a real Flax ``init`` here (jax/flax are not installable in this image): the construction-scope
+layout is derived from Flax's naming rule, not executed.
 """
 from __future__ import annotations
 
@@ -56,9 +75,10 @@ class SimpleViT:
 
     # ------------------------------------------------------------------ params
     def init(self, rngs: Any, x: Any) -> Dict[str, Dict]:
-        """``{'params': tree}`` with Flax's names for simple_vit.py: Dense_0 (patch embedding),
-        Transformer_0/{Attention_l/{LayerNorm_0/scale, Dense_0/kernel, Dense_1/kernel},
-        FeedForward_l/{LayerNorm_0/scale, Dense_0, Dense_1}}, Sequential_0/{layers_0/scale, layers_1}."""
+        """``{'params': tree}`` with the names Flax gives simple_vit.py (module docstring): LayerNorm_0 and
+        Dense_0 are the head, Dense_1 the patch embedding, Transformer_0/{Attention_l, FeedForward_l}.
+        Values are not bit-equal to a Flax ``init`` (that needs JAX's threefry stream); the distributions
+        (lecun_normal / zeros / ones) are the reference's."""
         self._validate(np.shape(x))
         _, _, ph, pw, _ = self._geometry()
         key = rngs.get("params") if hasattr(rngs, "get") else rngs
@@ -72,6 +92,7 @@ class SimpleViT:
                 d["bias"] = np.zeros((o,), np.float32)
             return d
 
+        patch = dense(k0, self.dim)
         t = {}
         for l in range(self.depth):
             t[f"Attention_{l}"] = {"LayerNorm_0": {"scale": np.ones((self.dim,), np.float32)},
@@ -79,18 +100,39 @@ class SimpleViT:
                                    "Dense_1": dense(inner, self.dim, False)}
             t[f"FeedForward_{l}"] = {"LayerNorm_0": {"scale": np.ones((self.dim,), np.float32)},
                                      "Dense_0": dense(self.dim, self.mlp_dim), "Dense_1": dense(self.mlp_dim, self.dim)}
-        return {"params": {"Dense_0": dense(k0, self.dim), "Transformer_0": t,
-                           "Sequential_0": {"layers_0": {"scale": np.ones((self.dim,), np.float32)},
-                                            "layers_1": dense(self.dim, self.num_classes)}}}
+        return {"params": {"LayerNorm_0": {"scale": np.ones((self.dim,), np.float32)},
+                           "Dense_0": dense(self.dim, self.num_classes),
+                           "Dense_1": patch, "Transformer_0": t}}
+
+    def _split_tree(self, variables):
+        """``(layout, patch_dense, transformer, head_norm, head_dense)`` of either accepted layout
+        (module docstring); kernel shapes are checked so a tree of the other layout fails loudly."""
+        _, _, ph, pw, _ = self._geometry()
+        p = variables["params"] if "params" in variables else variables
+        k0 = ph * pw * self.channels
+        if "Sequential_0" in p:
+            layout = "adoption"
+            patch, norm, head = p["Dense_0"], p["Sequential_0"]["layers_0"], p["Sequential_0"]["layers_1"]
+        else:
+            layout = "construction"
+            missing = [k for k in ("LayerNorm_0", "Dense_0", "Dense_1", "Transformer_0") if k not in p]
+            if missing:
+                raise ValueError(f"SimpleViT params tree lacks {missing}; expected LayerNorm_0 / Dense_0 (head) / "
+                                 "Dense_1 (patch) / Transformer_0, or the Sequential_0 layout")
+            patch, norm, head = p["Dense_1"], p["LayerNorm_0"], p["Dense_0"]
+        want = {"patch": (k0, self.dim), "head": (self.dim, self.num_classes)}
+        got = {"patch": tuple(np.shape(patch["kernel"])), "head": tuple(np.shape(head["kernel"]))}
+        if got != want:
+            raise ValueError(f"SimpleViT params ({layout} layout): kernel shapes {got} do not match the config {want}")
+        return layout, patch, p["Transformer_0"], norm, head
 
     def _engine_tree(self, variables) -> Dict[str, Any]:
         """Re-express the SimpleViT pytree in the leaf names the engine registers (those of vit.py):
         absent biases become zeros, the sin/cos table takes the place of pos_embedding."""
         ih, iw, ph, pw, n = self._geometry()
-        p = variables["params"] if "params" in variables else variables
+        _, patch, tp, norm, head = self._split_tree(variables)
         z = lambda k: np.zeros((k,), np.float32)
         f = leaf_to_numpy
-        tp = p["Transformer_0"]
         t = {}
         for l in range(self.depth):
             a, ff = tp[f"Attention_{l}"], tp[f"FeedForward_{l}"]
@@ -100,18 +142,18 @@ class SimpleViT:
             t[f"PreNorm_{2 * l + 1}"] = {"LayerNorm_0": {"scale": f(ff["LayerNorm_0"]["scale"]), "bias": z(self.dim)}}
             t[f"FeedForward_{l}"] = {"Dense_0": {k: f(v) for k, v in ff["Dense_0"].items()},
                                      "Dense_1": {k: f(v) for k, v in ff["Dense_1"].items()}}
-        head = p["Sequential_0"]
         return {"params": {
             "pos_embedding": posemb_sincos_2d(ih // ph, iw // pw, self.dim)[None],
             "cls": np.zeros((1, 1, self.dim), np.float32),
-            "Dense_0": {k: f(v) for k, v in p["Dense_0"].items()},
+            "Dense_0": {k: f(v) for k, v in patch.items()},
             "Transformer_0": t,
-            "LayerNorm_0": {"scale": f(head["layers_0"]["scale"]), "bias": z(self.dim)},
-            "Dense_1": {k: f(v) for k, v in head["layers_1"].items()}}}
+            "LayerNorm_0": {"scale": f(norm["scale"]), "bias": z(self.dim)},
+            "Dense_1": {k: f(v) for k, v in head.items()}}}
 
-    def _engine(self, variables, img, precision, device, max_batch):
+    def _engine(self, variables, img, precision, device, max_batch, reload=False):
         from . import vit as _vit
         from .engine import Engine
+        from .runtime import ParamsStamp
         is_cuda = hasattr(img, "is_cuda") and bool(img.is_cuda)
         self._validate(tuple(img.shape) if hasattr(img, "shape") else np.shape(img))
         batch = int(img.shape[0])
@@ -128,15 +170,19 @@ class SimpleViT:
                          channels=self.channels, precision=precision or _vit._DEFAULT_PRECISION,
                          max_batch=max_batch or batch, device=device, nchw=True, cls_token=False, ln_eps=1e-5)
             loaded = None
-        if loaded != id(variables):
+        # identity by strong reference + content probe (runtime.ParamsStamp): an id() alone is recycled by
+        # CPython for the temporary dict of ``v.apply({'params': p}, x)``
+        stamp = ParamsStamp(variables)
+        if reload or not stamp.matches(loaded):
             eng.load_params(self._engine_tree(variables))
-            loaded = id(variables)
+            loaded = stamp
         _ENGINES[key] = (eng, loaded)
         return eng
 
-    def _grads_tree(self, flat: Dict[str, np.ndarray]) -> Dict[str, Any]:
-        """Engine gradients (vit.py leaf names) -> the SimpleViT pytree; the gradients of leaves SimpleViT does
-        not have (zero biases, the fixed sin/cos table, the unused cls) are dropped."""
+    def _grads_tree(self, flat: Dict[str, np.ndarray], layout: str = "construction") -> Dict[str, Any]:
+        """Engine gradients (vit.py leaf names) -> the SimpleViT pytree in the layout the caller's params
+        came in; the gradients of leaves SimpleViT does not have (zero biases, the fixed sin/cos table, the
+        unused cls) are dropped."""
         t = {}
         for l in range(self.depth):
             pre = "Transformer_0/"
@@ -146,10 +192,12 @@ class SimpleViT:
             t[f"FeedForward_{l}"] = {"LayerNorm_0": {"scale": flat[pre + f"PreNorm_{2 * l + 1}/LayerNorm_0/scale"]},
                                      "Dense_0": {k: flat[pre + f"FeedForward_{l}/Dense_0/{k}"] for k in ("kernel", "bias")},
                                      "Dense_1": {k: flat[pre + f"FeedForward_{l}/Dense_1/{k}"] for k in ("kernel", "bias")}}
-        return {"params": {"Dense_0": {k: flat[f"Dense_0/{k}"] for k in ("kernel", "bias")},
-                           "Transformer_0": t,
-                           "Sequential_0": {"layers_0": {"scale": flat["LayerNorm_0/scale"]},
-                                            "layers_1": {k: flat[f"Dense_1/{k}"] for k in ("kernel", "bias")}}}}
+        patch = {k: flat[f"Dense_0/{k}"] for k in ("kernel", "bias")}
+        norm = {"scale": flat["LayerNorm_0/scale"]}
+        head = {k: flat[f"Dense_1/{k}"] for k in ("kernel", "bias")}
+        if layout == "adoption":
+            return {"params": {"Dense_0": patch, "Transformer_0": t, "Sequential_0": {"layers_0": norm, "layers_1": head}}}
+        return {"params": {"LayerNorm_0": norm, "Dense_0": head, "Dense_1": patch, "Transformer_0": t}}
 
     def vjp(self, variables: Any, img: Any, *, precision: Optional[str] = None, device: Optional[int] = None,
             max_batch: Optional[int] = None):
@@ -158,10 +206,12 @@ class SimpleViT:
         import torch
         is_cuda = hasattr(img, "is_cuda") and bool(img.is_cuda)
         eng = self._engine(variables, img, precision, device, max_batch)
+        layout = self._split_tree(variables)[0]
         batch = int(img.shape[0])
         x = img if is_cuda else torch.as_tensor(np.asarray(img, dtype=np.float32), device=eng.device)
         x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
         logits = eng.train_forward(x)
+        epoch = eng.epoch      # any later forward / reload on this engine invalidates vjp_fn
 
         def vjp_fn(dlogits):
             d = dlogits if hasattr(dlogits, "is_cuda") else torch.as_tensor(np.asarray(dlogits, dtype=np.float32))
@@ -170,17 +220,18 @@ class SimpleViT:
                 raise ValueError(f"vjp_fn expects a cotangent of shape ({batch}, {self.num_classes})")
             peak = float(d.abs().max())
             scale = 1.0 if peak == 0.0 or not np.isfinite(peak) else float(2.0 ** -np.round(np.log2(peak)))
-            eng.backward(d * scale if scale != 1.0 else d)
-            return self._grads_tree({k: g / np.float32(scale) for k, g in eng.grads().items()})
+            eng.backward(d * scale if scale != 1.0 else d, epoch=epoch)
+            return self._grads_tree({k: g / np.float32(scale) for k, g in eng.grads().items()}, layout)
 
         return (logits if is_cuda else logits.cpu().numpy()), vjp_fn
 
     # ------------------------------------------------------------------- apply
     def apply(self, variables: Any, img: Any, rngs: Any = None, *, precision: Optional[str] = None,
-              device: Optional[int] = None, max_batch: Optional[int] = None):
-        """``v.apply(params, img)`` -> logits ``[B, num_classes]`` float32; ``img`` is NCHW."""
+              device: Optional[int] = None, max_batch: Optional[int] = None, reload: bool = False):
+        """``v.apply(params, img)`` -> logits ``[B, num_classes]`` float32; ``img`` is NCHW.  ``reload=True``
+        forces the weights to be re-packed (after an in-place edit the content probe did not see)."""
         is_cuda = hasattr(img, "is_cuda") and bool(img.is_cuda)
-        eng = self._engine(variables, img, precision, device, max_batch)
+        eng = self._engine(variables, img, precision, device, max_batch, reload)
         if is_cuda:
             import torch
             x = img if (img.dtype == torch.float32 and img.is_contiguous()) else img.float().contiguous()

@@ -158,6 +158,7 @@ class ViT:
         if key is not None:
             eng.set_dropout_key(key)           # the backward replays the masks of this key
         logits = eng.train_forward(xin)
+        epoch = eng.epoch      # any later forward / reload on this engine invalidates vjp_fn
 
         def vjp_fn(dlogits):
             d = dlogits if hasattr(dlogits, "is_cuda") else torch.as_tensor(np.asarray(dlogits, dtype=np.float32))
@@ -166,7 +167,7 @@ class ViT:
                 raise ValueError(f"vjp_fn expects a cotangent of shape ({batch}, {self.num_classes})")
             peak = float(d.abs().max())
             scale = 1.0 if peak == 0.0 or not np.isfinite(peak) else float(2.0 ** -np.round(np.log2(peak)))
-            eng.backward(d * scale if scale != 1.0 else d)
+            eng.backward(d * scale if scale != 1.0 else d, epoch=epoch)
             from .checkpoint import _unflatten
             return {"params": _unflatten({k: g / np.float32(scale) for k, g in eng.grads().items()})}
 
