@@ -302,7 +302,8 @@ def run_b200(args) -> None:
     # ---- both 16-bit operand formats under the SAME protocol; `args.dtype` is the headline ----
     other = "fp16" if args.dtype == "bf16" else "bf16"
     engines, runs = {}, {}
-    for dt in (args.dtype, other):
+    formats = (args.dtype,) if args.quick else (args.dtype, other)
+    for dt in formats:
         engines[dt] = Engine(precision=dt, max_batch=B, device=local, **cfg)
         engines[dt].load_params(variables)
         runs[dt] = timed_forward(engines[dt], args.steps, args.warmup, sample_clocks=(dt == args.dtype))
@@ -338,7 +339,7 @@ def run_b200(args) -> None:
     # step k).  N > 1: dist.sharded_apply_stream, the same pipeline around the sharded forward WITH its logits
     # all-gather; every rank reads the gathered [global_batch, classes] logits back to its host.
     vit = ViT(**cfg)
-    host_imgs = [torch.empty((B, S, S, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_imgs = [torch.empty((B, S, S, 3), dtype=torch.float32).pin_memory() for _ in range(1 if args.quick else 2)]
     for h in host_imgs:
         h.copy_(images)
     host_np = [h.numpy() for h in host_imgs]
@@ -346,27 +347,29 @@ def run_b200(args) -> None:
 
     def e2e_iter(n):
         if world == 1:
-            yield from vit.apply_stream(variables, (host_np[i & 1] for i in range(n)), precision=args.dtype,
+            yield from vit.apply_stream(variables, (host_np[i % len(host_np)] for i in range(n)), precision=args.dtype,
                                         device=local, max_batch=B)
         else:
-            for y in sharded_apply_stream(lambda x, out: eng.forward(x, out=out), (host_imgs[i & 1] for i in range(n)),
+            for y in sharded_apply_stream(lambda x, out: eng.forward(x, out=out), (host_imgs[i % len(host_imgs)] for i in range(n)),
                                           global_batch, classes, (S, S, 3), dev):
                 yield y.numpy()
 
     checksum = 0.0
-    for y in e2e_iter(3):
-        checksum += float(y[0, 0])
-    barrier()
-    t0 = time.perf_counter()
-    for y in e2e_iter(e2e_steps):
-        checksum += float(y[0, 0])                       # the host reads every step's result
-    torch.cuda.synchronize()
-    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = global_batch / e2e_t.item()
+    e2e_value = None
+    if not args.quick:
+        for y in e2e_iter(3):
+            checksum += float(y[0, 0])
+        barrier()
+        t0 = time.perf_counter()
+        for y in e2e_iter(e2e_steps):
+            checksum += float(y[0, 0])                       # the host reads every step's result
+        torch.cuda.synchronize()
+        e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_value = global_batch / e2e_t.item()
     e2e_sync_value = None
-    if world == 1:   # one blocking call per step (H2D, forward, D2H, sync -- nothing overlaps)
+    if world == 1 and not args.quick:   # one blocking call per step (H2D, forward, D2H, sync -- nothing overlaps)
         for _ in range(2):
             vit.apply(variables, host_np[0], precision=args.dtype, device=local, max_batch=B)
         t0 = time.perf_counter()
@@ -378,7 +381,7 @@ def run_b200(args) -> None:
 
     # ---- the training step (train_forward + backward, no optimiser), for the record ----
     train_line = None
-    if rank == 0 and world == 1 and not args.no_train and args.config == "c2":
+    if rank == 0 and world == 1 and not args.no_train and not args.quick and args.config == "c2":
         tr = engines["fp16"]
         dl = torch.randn((B, classes), dtype=torch.float32, device=dev) / B
         lt = torch.empty((B, classes), dtype=torch.float32, device=dev)
@@ -412,16 +415,18 @@ def run_b200(args) -> None:
         from oracle import vit_torch
         import torch as _t
         _t.set_num_threads(os.cpu_count() or 1)
-        k = min(args.parity_images, B)
+        k = min(8 if args.quick else args.parity_images, B)
         k_emu = min(64, k)
         pt = vit_torch.tree_to_torch(variables)
         img_cpu = images[:k].cpu().numpy()
         want = vit_torch.vit_forward(pt, img_cpu, **cfg).numpy()
-        emu = vit_torch.vit_forward(pt, img_cpu[:k_emu], operand_dtype=_t.bfloat16, **cfg).numpy()
+        # the oracle rounding bf16 operands where the GPU path does (LayerNorm folded into the GEMMs unless VITB200_LN_FOLD=0)
+        ln_fold = os.environ.get("VITB200_LN_FOLD", "1") != "0"
+        emu = vit_torch.vit_forward(pt, img_cpu[:k_emu], operand_dtype=_t.bfloat16, ln_fold=ln_fold, **cfg).numpy()
         bf16_floor = float(np.abs(emu - want[:k_emu]).max())
         srt = np.sort(want, axis=1)
         margin = srt[:, -1] - srt[:, -2]                     # oracle top-1 margin per image
-        for dt in (args.dtype, other):
+        for dt in formats:
             got = runs[dt]["logits"][start:start + k].cpu().numpy()
             err = float(np.abs(got - want).max())
             bound = 2e-2 if dt == "fp16" else max(2e-2, 1.25 * bf16_floor)
@@ -440,13 +445,13 @@ def run_b200(args) -> None:
                                       "test_bf16_operand_floor_on_vit_b16); bound = max(2e-2, 1.25 x emulated bf16 error)")
         parity["note"] = ("random-init weights: top-1 margins are ~exponential with mean 0.27, so raw agreement measures "
                           "luck at margins below the error (SURVEY.md H3); 2048-image figures: profiles/r02_parity.md")
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             cpu = cpu_reference(cfg, steps=12, warmup=1, sample_images=args.cpu_images)   # ~10 s of CPU work
 
     if rank == 0:
         total_tflops = fl["total"] * value / 1e12
         by_dtype = {}
-        for dt in (args.dtype, other):
+        for dt in formats:
             r = runs[dt]
             v = global_batch / (r["ms_per_step"] * 1e-3)
             by_dtype[dt] = {"value": v, "unit": "images/s", "ms_per_step": r["ms_per_step"], "steps": args.steps,
@@ -532,6 +537,8 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=64, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step (forward + backward) record")
+    ap.add_argument("--quick", action="store_true", help="headline format only, no e2e / train / CPU legs, parity on 8 images "
+                                                          "(the strong-scaling runs of profiles/r02_scaling.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

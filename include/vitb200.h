@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VITB200_ABI_VERSION 3
+#define VITB200_ABI_VERSION 4
 
 /* error codes */
 #define VITB200_OK                 0
@@ -187,6 +187,16 @@ int vitb200_grad_device(vitb200_model* m, const char* path, float** dev_out);
                                         * C_16[r + off] = gelu_tanh(pre), off = tokens_per_image >= M, a multiple of
                                         * 256 (training forward: FF Dense_0 without a separate GELU pass)        */
 
+/* LayerNorm fold (PreNorm, vit.py:31): LN(x) W = rstd (x W') - rstd mean c + d,  W' = diag(gamma) W, c = 1^T W',
+ * d = beta^T W (+ bias).  The two GEMMs that PRODUCE the residual stream also emit what the next LayerNorm needs, the
+ * two that CONSUME a LayerNorm apply it in their epilogue: no stand-alone LayerNorm kernel in between.  Only through
+ * vitb200_gemm_tc_ln.                                                                                                */
+#define VITB200_EPI_RESID_LN        8  /* C_f32 = C_f32 + acc + bias (x_old read by TMA, added in the SM, stored back);
+                                        * x16[M,N] = 16-bit copy of C; stats[M, slots] = per-row partial (sum, sum sq)   */
+#define VITB200_EPI_TOKENS_LN       9  /* EPI_TOKENS_F32 + the same x16 / stats outputs (patch embedding, vit.py:147-153) */
+#define VITB200_EPI_LN_STORE_16     10 /* C_16 = rstd*acc - rstd*mean*c + d        (to_qkv after PreNorm, vit.py:31,68)    */
+#define VITB200_EPI_LN_GELU_16      11 /* C_16 = gelu_tanh(rstd*acc - rstd*mean*c + d)  (FeedForward Dense_0, vit.py:48-49) */
+
 /* tcgen05 GEMM: acc[M,N] = A[M,K] (16-bit row-major) x Wt[N,K]^T (16-bit row-major, i.e. the
  * transposed Flax kernel), fp32 accumulation in TMEM.  dtype = VITB200_DT_BF16 | _F16.
  * K % 8 == 0, N % 8 == 0.  `aux` = pos_embedding [T, N] fp32 and `tokens_per_image` = T-1 for
@@ -209,6 +219,20 @@ int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const fl
                            void* C, int M, int N, int K, int epilogue,
                            const float* aux, int tokens_per_image, const float* cls, int dtype,
                            float rate, uint64_t key, uint32_t site);
+/* The LayerNorm-fold epilogues (8..11).  Producers (8, 9): `x16` [M,N] 16-bit and `stats` [M, stats_slots] float pairs
+ * are OUTPUTS, stats_slots = 2 * ceil(N / tile columns) (tile columns: 256, or 64 when M <= 256 and N > 256 -- ask
+ * vitb200_gemm_tc_ln_slots).  Consumers (10, 11): `stats` / `stats_slots` are those of the GEMM that produced A's rows
+ * (its N == this K), `ln_c` [N] the column sums c, `bias` the vector d [N] (vitb200_fold_layernorm makes W', c, d),
+ * `ln_eps` the LayerNorm epsilon; A is the producer's x16.  No dropout variants.                                        */
+int vitb200_gemm_tc_ln(void* stream, const void* A, const void* Wt, const float* bias,
+                       void* C, int M, int N, int K, int epilogue,
+                       const float* aux, int tokens_per_image, const float* cls, int dtype,
+                       void* x16, float* stats, int stats_slots, const float* ln_c, float ln_eps);
+int vitb200_gemm_tc_ln_slots(int M, int N);
+/* W fp32 [K,N] (Flax kernel), gamma / beta [K] (LayerNorm scale / bias), bias [N] or NULL ->
+ * Wt 16-bit [N,Kpad] = (diag(gamma) W)^T, c [N] = column sums of the ROUNDED W', d [N] = beta^T W + bias            */
+int vitb200_fold_layernorm(void* stream, const float* W, const float* gamma, const float* beta, const float* bias,
+                           void* Wt, float* c, float* d, int K, int N, int Kpad, int dtype);
 /* SIMT fp32 GEMM (validation mode): acc = A[M,K] x W[K,N] (Flax layout).
  * The two "_16" epilogues write fp32 here.                                  */
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias,

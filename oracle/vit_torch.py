@@ -52,9 +52,31 @@ def _drop(x, drop, site):
     return torch.where(keep, x * inv, torch.zeros((), dtype=x.dtype))
 
 
-def _attention(x, p, heads, dim, dt=None, drop=None, site=0):
+def _ln_dense(x, lnp, dense, dt=None, fold=False):
+    """``Dense(LayerNorm(x))`` (PreNorm then the first Dense of its fn, vit.py:31 + 48 / 68).  With 16-bit operand
+    emulation, ``fold`` selects WHERE the tensor-core path rounds: False = LayerNorm output and kernel (the stand-alone
+    LayerNorm kernel); True = the raw x and diag(gamma) W, LayerNorm applied after the product as
+    rstd (x16 W'16) - rstd mean c + d with c = 1^T W'16, d = beta^T W + bias (csrc/gemm_tc.cu, LayerNorm fold)."""
+    W, bias = dense["kernel"], dense.get("bias")
+    if dt is None or not fold:
+        y = _r(_ln(x, lnp), dt) @ _r(W, dt)
+        return y if bias is None else y + bias
+    mean = x.mean(-1, keepdim=True)
+    var = (x * x).mean(-1, keepdim=True) - mean * mean                     # flax: E[x^2] - E[x]^2
+    rstd = torch.rsqrt(torch.clamp(var, min=0.0) + 1e-6)
+    Wp = _r(lnp["scale"][:, None] * W, dt)
+    d = lnp["bias"] @ W
+    if bias is not None:
+        d = d + bias
+    return rstd * (_r(x, dt) @ Wp) - rstd * mean * Wp.sum(0) + d
+
+
+def _attention(x, p, heads, dim, dt=None, drop=None, site=0, pre=None):
     b, n, _ = x.shape
-    qkv = _r(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt), dt)               # vit.py:68
+    if pre is not None:      # x is the un-normalised stream, `pre` = (LayerNorm params, fold?)
+        qkv = _r(_ln_dense(x, pre[0], p["Dense_0"], dt, pre[1]), dt)
+    else:
+        qkv = _r(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt), dt)           # vit.py:68
     q, k, v = qkv.chunk(3, dim=-1)                                         # vit.py:69
     q, k, v = (t.view(b, n, heads, DIM_HEAD).transpose(1, 2) for t in (q, k, v))  # vit.py:71
     if dt is None:
@@ -70,16 +92,21 @@ def _attention(x, p, heads, dim, dt=None, drop=None, site=0):
     return o
 
 
-def _ff(x, p, dt=None, drop=None, site=0):
-    h = F.gelu(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt) + p["Dense_0"]["bias"], approximate="tanh")  # vit.py:48-49
+def _ff(x, p, dt=None, drop=None, site=0, pre=None):
+    if pre is not None:
+        h = F.gelu(_ln_dense(x, pre[0], p["Dense_0"], dt, pre[1]), approximate="tanh")
+    else:
+        h = F.gelu(_r(x, dt) @ _r(p["Dense_0"]["kernel"], dt) + p["Dense_0"]["bias"], approximate="tanh")  # vit.py:48-49
     h = _drop(h, drop, site)                                                                           # vit.py:50
     return _drop(_r(h, dt) @ _r(p["Dense_1"]["kernel"], dt) + p["Dense_1"]["bias"], drop, site + 1)    # vit.py:51-52
 
 
 def _vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, depth,
-                heads, mlp_dim, pool="cls", operand_dtype=None, dropout=0.0, emb_dropout=0.0, dropout_key=None):
+                heads, mlp_dim, pool="cls", operand_dtype=None, dropout=0.0, emb_dropout=0.0, dropout_key=None,
+                ln_fold=False):
     """``params_t``: the ``params`` sub-tree already converted by ``tree_to_torch``.
-    ``operand_dtype`` (torch.bfloat16 / torch.float16 / None): emulate 16-bit GEMM operands."""
+    ``operand_dtype`` (torch.bfloat16 / torch.float16 / None): emulate 16-bit GEMM operands; ``ln_fold``: round where the
+    LayerNorm-folding forward rounds (``_ln_dense``) -- the default inference path of libvitb200 at dropout 0."""
     dt = operand_dtype
     p = params_t["params"] if "params" in params_t else params_t
     ph, pw = (patch_size, patch_size) if not isinstance(patch_size, tuple) else patch_size
@@ -95,6 +122,10 @@ def _vit_forward(params_t, images, *, image_size, patch_size, num_classes, dim, 
     drop = (dropout, dropout_key) if dropout else None
     tp = p["Transformer_0"]
     for l in range(depth):                                                 # vit.py:108-110
+        if dt is not None and ln_fold:
+            x = _attention(x, tp[f"Attention_{l}"], heads, dim, dt, drop, 1 + 3 * l, pre=(tp[f"PreNorm_{2 * l}"]["LayerNorm_0"], True)) + x
+            x = _ff(x, tp[f"FeedForward_{l}"], dt, drop, 2 + 3 * l, pre=(tp[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"], True)) + x
+            continue
         x = _attention(_ln(x, tp[f"PreNorm_{2 * l}"]["LayerNorm_0"]), tp[f"Attention_{l}"], heads, dim, dt, drop, 1 + 3 * l) + x
         x = _ff(_ln(x, tp[f"PreNorm_{2 * l + 1}"]["LayerNorm_0"]), tp[f"FeedForward_{l}"], dt, drop, 2 + 3 * l) + x
     x = x.mean(dim=1) if pool == "mean" else x[:, 0]                       # vit.py:159

@@ -31,6 +31,15 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float seed)
       if (OP == 10) { uint32_t u = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
       if (OP == 11) { uint32_t u = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
       if (OP == 12) { uint32_t u = __float_as_uint(a[i]); float f; asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(f) : "r"(u)); a[i] = f + 1.0f; }
+      if (OP == 13) { uint32_t u = __float_as_uint(a[i]); asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u); }
+      if (OP == 14) { uint32_t u = __float_as_uint(a[i]); asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(u) : "r"(0x3c003c00u)); a[i] = __uint_as_float(u); }
+      if (OP == 15) {   // the softmax inner step in fp16: pack two fp32 exponents (F2FP), one MUFU for both
+        uint32_t r; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r & 0x3fffffffu); }
+      if (OP == 16) {   // f16x2 -> two fp32 (for the fp32 row sum)
+        uint32_t u = __float_as_uint(a[i]); float f0, f1;
+        asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(f0), "=f"(f1) : "r"(u));
+        a[i] = f0 + f1; }
       if (OP == 9) { uint32_t u = __float_as_uint(a[i]); asm volatile("shl.b32 %0, %0, 3;" : "+r"(u)); asm volatile("add.u32 %0, %0, %1;" : "+r"(u) : "r"(__float_as_uint(seed))); a[i] = __uint_as_float(u); }
     }
   }
@@ -69,5 +78,9 @@ int main() {
   run<10>("ex2.approx.ftz.f16x2", 2);
   run<11>("ex2.approx.ftz.bf16x2", 2);
   run<12>("cvt.f32.f16 + add", 1);
+  run<13>("tanh.approx.f16x2", 2);
+  run<14>("fma.rn.f16x2", 2);
+  run<15>("cvt.f16x2.f32 + ex2.f16x2", 2);
+  run<16>("2x cvt.f32.f16 + add", 2);
   return 0;
 }

@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(lib_built):
     raw = C.CDLL(str(_lib.LIB_PATH))
     for s in declared_symbols():
         assert hasattr(raw, s), f"{s} declared in include/vitb200.h but not exported"
-    assert lib_built.vitb200_abi_version() == _lib.ABI_VERSION == 3
+    assert lib_built.vitb200_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_config_struct_layout():

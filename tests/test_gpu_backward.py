@@ -244,8 +244,9 @@ def test_backward_with_dropout_replays_the_forward_masks(precision, tol):
     eng.load_params(variables)
     eng.set_dropout_key(key)
     x = torch.as_tensor(img, device="cuda")
+    inference = eng.forward(x).cpu().numpy()     # BEFORE train_forward: a forward in between voids the kept activations
     logits = eng.train_forward(x).cpu().numpy()
-    assert np.abs(logits - eng.forward(x).cpu().numpy()).max() < 2e-2          # the same masks as the inference-path dropout
+    assert np.abs(logits - inference).max() < 2e-2                             # the same masks as the inference-path dropout
     eng.set_dropout_key(key + 1)                                               # backward must use the FORWARD's key
     eng.backward(torch.as_tensor(dl, device="cuda"))
     want_logits, want = vit_torch.vit_vjp(variables, img, dl, dropout=rate, emb_dropout=emb_rate, dropout_key=key, **cfg)
@@ -362,8 +363,8 @@ def test_vjp_fn_refuses_a_stale_forward():
     assert any(np.abs(g4[k] - g1[k]).max() > 0 for k in g1)
     _, f5 = v.vjp(variables, img)
     g5 = flatten_params(f5(dl))
-    for k in g1:
-        np.testing.assert_array_equal(g1[k], g5[k])
+    for k in g1:     # same inputs again: the same gradients (split-K partial sums meet in any order: not bit-equal)
+        np.testing.assert_allclose(g1[k], g5[k], rtol=0, atol=1e-3 * max(1e-6, float(np.abs(g1[k]).max())))
     # the C ABI refuses on its own when an inference forward ran in between
     from vit_flax_b200._lib import VitB200Error
     eng = Engine(precision="fp16", max_batch=3, **cfg)

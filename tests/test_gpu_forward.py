@@ -7,12 +7,16 @@ rounding every tensor-core operand by 3e-2 (tests/test_oracle.py::test_bf16_oper
 a CPU test of the oracle alone).  bf16 runs are therefore held to a bound DERIVED from the oracle on
 the same inputs instead of a blanket constant:
 
-    |gpu - fp32 oracle| <= max(2e-2, 1.25 x |bf16-emulating oracle - fp32 oracle|)   and
-    |gpu - bf16-emulating oracle| <= 2e-2
+    floor = |bf16-emulating oracle - fp32 oracle|        (the oracle rounding where the GPU path rounds)
+    |gpu - fp32 oracle|           <= max(2e-2, 1.25 x floor)      and
+    |gpu - bf16-emulating oracle| <= max(2e-2, floor)
 
 i.e. the north-star tolerance wherever the operand format can meet it, otherwise at most 25 % above
-the format's own rounding floor, and always within the north-star tolerance of the reference
-computed with the same operand rounding.
+the format's own rounding floor; and the GPU result is at least as close to the reference computed
+with the same operand rounding as that reference is to exact arithmetic (two correct bf16
+evaluations that merely round at different points -- LayerNorm output vs. raw x, or another
+accumulation order flipping one-ulp roundings -- differ by up to ~1.1 x floor: measured on the CPU
+oracle alone, 3.4e-2 between its two rounding placements at floor 3.0e-2).
 Top-1 agreement is checked on images whose oracle top-1 margin exceeds twice the error bound
 (on random-init weights the raw metric measures luck, not kernels; the 2048-image
 figures, raw and margin-filtered, are in profiles/r02_parity.md and bench.py's `parity`)."""
@@ -32,7 +36,7 @@ pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 2e-2}   # BASELINE.json north star; bf16: see bf16_bound()
 # 16-bit run vs the oracle with the SAME operand rounding: what is left is accumulation order and
 # one-ulp rounding flips (measured on ViT-B/16 depth 12: fp16 2.3e-3, bf16 1.8e-2).
-TOL_VS_EMULATED = {"fp16": 1e-2, "bf16": 2e-2}
+TOL_VS_EMULATED = {"fp16": 1e-2, "bf16": 2e-2}     # bf16: max(this, floor), see the module docstring
 TORCH_DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
 
 
@@ -42,9 +46,11 @@ def bf16_bound(emulated, want):
     return max(TOL["bf16"], 1.25 * float(np.abs(emulated - want).max()))
 
 
-def oracle_logits(variables, images, cfg, pool="cls", operand_dtype=None):
+def oracle_logits(variables, images, cfg, pool="cls", operand_dtype=None, ln_fold=True):
+    """fp32 oracle, or (operand_dtype given) the oracle rounding 16-bit operands where the GPU path does: by default
+    where the LayerNorm-folding forward rounds (raw x and gamma*W), ln_fold=False where the LayerNorm kernel path does."""
     return vit_torch.vit_forward(vit_torch.tree_to_torch(variables), images, pool=pool,
-                                 operand_dtype=operand_dtype, **cfg).numpy()
+                                 operand_dtype=operand_dtype, ln_fold=ln_fold, **cfg).numpy()
 
 
 @pytest.fixture(autouse=True)
@@ -117,7 +123,8 @@ def _check_16bit(cfg, batch, depth=None, pool="cls", seed=0, precision="fp16"):
     print(f"[parity] {precision} depth={cfg['depth']} batch={batch}: max abs logit error {err:.5f} (bound {tol:.5f}; "
           f"same-rounding oracle is {np.abs(emu - want).max():.5f} from fp32, gpu is {err_emu:.5f} from it)")
     assert err < tol, f"{precision}: max abs logit error {err} (bound {tol})"
-    assert err_emu < TOL_VS_EMULATED[precision], f"{precision}: {err_emu} away from the same-rounding oracle"
+    tol_emu = TOL_VS_EMULATED[precision] if precision == "fp16" else max(TOL_VS_EMULATED["bf16"], float(np.abs(emu - want).max()))
+    assert err_emu < tol_emu, f"{precision}: {err_emu} away from the same-rounding oracle (bound {tol_emu})"
     srt = np.sort(want, axis=1)
     confident = (srt[:, -1] - srt[:, -2]) > 2 * tol
     assert np.array_equal(got.argmax(1)[confident], want.argmax(1)[confident])
@@ -379,3 +386,32 @@ def test_second_device_in_the_same_process():
     for dev in (0, 1):
         got = ViT(**cfg).apply(variables, img, device=dev)
         assert np.abs(got - want).max() < TOL["fp16"], f"device {dev}"
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_layernorm_fold_and_layernorm_kernel_paths_agree(precision, monkeypatch):
+    """The default forward folds every PreNorm LayerNorm into the GEMMs around it (4 + 5L launches, gemm_tc.cu header);
+    VITB200_LN_FOLD=0 keeps the stand-alone LayerNorm kernel (4 + 7L).  Both against the oracle and against each other,
+    at a batch served by CTA-pair tiles and at batch 1 (64-column tiles, 24 statistics slots per row)."""
+    cfg = dict(C2, depth=3)
+    variables = perturb_params(init_params(seed=61, **cfg), seed=62)
+    for batch in (6, 1):
+        img = images_for(cfg, batch, seed=63)
+        x = torch.as_tensor(img, device="cuda")
+        want = oracle_logits(variables, img, cfg)
+        out = {}
+        for fold in ("1", "0"):
+            monkeypatch.setenv("VITB200_LN_FOLD", fold)
+            eng = Engine(precision=precision, max_batch=batch, **cfg)
+            eng.load_params(variables)
+            n0 = launch_count()
+            out[fold] = eng.forward(x).cpu().numpy()
+            launches = launch_count() - n0
+            eng.close()
+            # batch 1 replays a captured graph on its second call; the first call launches directly
+            assert launches == (4 + 5 * 3 if fold == "1" else 4 + 7 * 3), (fold, launches)
+        for fold in ("1", "0"):
+            emu = oracle_logits(variables, img, cfg, "cls", TORCH_DT[precision], ln_fold=(fold == "1"))
+            tol = TOL[precision] if precision == "fp16" else bf16_bound(emu, want)
+            assert np.abs(out[fold] - want).max() < tol, (fold, batch)
+        assert np.abs(out["1"] - out["0"]).max() < (1e-2 if precision == "fp16" else 5e-2)

@@ -436,3 +436,112 @@ def test_gemm_tc_random_shapes(lib, monkeypatch):
         err = (out.double() - want).abs().max().item()
         tol = 3e-4 if out.dtype == torch.float32 else 8 * ulp + 2e-3
         assert err < tol, (case, M, N, K, epi, err)
+
+
+# ---- LayerNorm folded into the GEMMs around it (gemm_tc.cu header) ----
+LN_SHAPES = [
+    # (M rows, D = LayerNorm dim, N = consumer columns, Kp = producer K)
+    (300, 264, 136, 72),        # ragged everything: partial n-tiles, partial slabs, rows past M in the last tile
+    (197, 768, 2304, 768),      # one image of ViT-B/16: 64-column tiles (M <= 256): 24 statistics slots
+    (1576, 768, 3072, 768),     # batch 8: CTA pairs, 6 slots
+    (12608, 1280, 320, 1024),   # ViT-H width: 5 n-tiles of the producer, many waves of RESID_LN slab loads
+]
+
+
+@pytest.mark.parametrize("M,D,N,Kp", LN_SHAPES)
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+@pytest.mark.parametrize("cta_group", ["auto", "1", "2", "64"])
+def test_gemm_tc_layernorm_fold(lib, M, D, N, Kp, fmt, cta_group, monkeypatch):
+    """x_new = x_old + o Wo + bo (RESID_LN: also x16 and the row statistics), then y = LN(x_new) W1 + b1 through
+    LN_STORE_16 / gelu(...) through LN_GELU_16 on the folded weights -- against float64 on the same rounded operands,
+    and against the plain LayerNorm -> Dense it replaces (vit.py:31,48,68)."""
+    if cta_group != "auto":
+        if M > 4000:
+            pytest.skip("large case runs in the production mode only")
+        monkeypatch.setenv("VITB200_GEMM_CTA_GROUP", cta_group)
+    dt, tdt, ulp = DT16[fmt]
+    rng = np.random.default_rng(M + D + N)
+    eps = 1e-6
+    o = dev(rng.standard_normal((M, Kp)), tdt)
+    Wo = dev(rng.standard_normal((D, Kp)) / np.sqrt(Kp), tdt)               # packed [N = D, K = Kp]
+    bo = dev(rng.standard_normal(D) * 0.5)
+    x_old = dev(rng.standard_normal((M, D)) * 1.5 + rng.standard_normal((M, 1)) * 0.7)   # rows with a non-zero mean
+    slots = lib.vitb200_gemm_tc_ln_slots(M, D)
+    x = x_old.clone()
+    x16 = torch.full((M, D), float("nan"), dtype=tdt, device="cuda")
+    stats = torch.full((M, slots, 2), float("nan"), device="cuda")
+    _lib.check(lib.vitb200_gemm_tc_ln(stream(), o.data_ptr(), Wo.data_ptr(), bo.data_ptr(), x.data_ptr(), M, D, Kp,
+                                      _lib.EPI_RESID_LN, None, 0, None, dt, x16.data_ptr(), stats.data_ptr(), slots, None, 0.0))
+    torch.cuda.synchronize()
+    want_x = x_old.double() + o.double() @ Wo.double().t() + bo.double()
+    assert (x.double() - want_x).abs().max().item() < 2e-4
+    assert torch.equal(x16, x.to(tdt)), "x16 must be the rounded fp32 output, bit for bit"
+    s = stats.double().sum(1)
+    assert (s[:, 0] - x.double().sum(1)).abs().max().item() < 1e-2
+    assert ((s[:, 1] - (x.double() ** 2).sum(1)).abs() / (x.double() ** 2).sum(1)).max().item() < 1e-5
+
+    # weight side of the fold
+    W1 = (rng.standard_normal((D, N)) / np.sqrt(D)).astype(np.float32)      # flax kernel [in, out]
+    gamma = (1.0 + 0.3 * rng.standard_normal(D)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(D)).astype(np.float32)
+    b1 = (0.5 * rng.standard_normal(N)).astype(np.float32)
+    Kpad = (D + 63) // 64 * 64
+    Wt = torch.full((N, Kpad), float("nan"), dtype=tdt, device="cuda")
+    c = torch.empty(N, device="cuda")
+    d = torch.empty(N, device="cuda")
+    W1_d, gamma_d, beta_d, b1_d = dev(W1), dev(gamma), dev(beta), dev(b1)     # keep the device copies alive across the call
+    _lib.check(lib.vitb200_fold_layernorm(stream(), W1_d.data_ptr(), gamma_d.data_ptr(), beta_d.data_ptr(),
+                                          b1_d.data_ptr(), Wt.data_ptr(), c.data_ptr(), d.data_ptr(), D, N, Kpad, dt))
+    torch.cuda.synchronize()
+    Wp = torch.as_tensor((gamma[:, None] * W1).astype(np.float32)).to(tdt)  # fp32 product, one rounding -- like the kernel
+    assert torch.equal(Wt[:, :D].cpu(), Wp.t().contiguous()) and (Wt[:, D:] == 0).all()
+    assert (c.cpu().double() - Wp.double().sum(0)).abs().max().item() < 1e-4
+    assert (d.cpu().double() - (torch.as_tensor(beta).double() @ torch.as_tensor(W1).double() + torch.as_tensor(b1).double())).abs().max().item() < 1e-5
+
+    # consumers: A = x16 [M, D] (row pitch D), weights padded to Kpad only when D % 64 != 0 -> pack to pitch D here
+    Wt_d = Wt[:, :D].contiguous()
+    xd = x.double()
+    mean = xd.mean(1, keepdim=True)
+    var = (xd * xd).mean(1, keepdim=True) - mean * mean
+    rstd = 1.0 / torch.sqrt(var + eps)
+    same_rounding = rstd * (x16.double() @ Wt_d.double().t()) - rstd * mean * c.double() + d.double()
+    plain = ((xd - mean) * rstd * torch.as_tensor(gamma).double().cuda() + torch.as_tensor(beta).double().cuda()) @ \
+        torch.as_tensor(W1).double().cuda() + torch.as_tensor(b1).double().cuda()
+    for epi, f in ((_lib.EPI_LN_STORE_16, lambda t: t), (_lib.EPI_LN_GELU_16, lambda t: torch.nn.functional.gelu(t, approximate="tanh"))):
+        y = torch.full((M, N), float("nan"), dtype=tdt, device="cuda")
+        _lib.check(lib.vitb200_gemm_tc_ln(stream(), x16.data_ptr(), Wt_d.data_ptr(), d.data_ptr(), y.data_ptr(), M, N, D, epi,
+                                          None, 0, None, dt, None, stats.data_ptr(), slots, c.data_ptr(), eps))
+        torch.cuda.synchronize()
+        err = (y.double() - f(same_rounding)).abs()
+        assert err.max().item() < 8 * ulp + 2e-3, f"epi {epi}: {err.max().item()} from the same-rounding reference"
+        assert err.mean().item() < ulp + 2e-4
+        # and it IS LayerNorm -> Dense: what is left against exact arithmetic is the 16-bit rounding of x and gamma W
+        assert (y.double() - f(plain)).abs().max().item() < (0.25 if fmt == "bf16" else 0.04)
+
+
+def test_gemm_tc_tokens_layernorm_outputs(lib):
+    """TOKENS_LN = EPI_TOKENS_F32 (vit.py:147-153) + the 16-bit copy and row statistics the first PreNorm needs."""
+    B, T, K, D = 5, 17, 192, 328
+    dt, tdt, _ = DT16["fp16"]
+    rng = np.random.default_rng(11)
+    A = dev(rng.standard_normal((B * T, K)), tdt)
+    A.view(B, T, K)[:, 0] = 0                                              # class-token slot rows of the patch matrix
+    Wt = dev(rng.standard_normal((D, K)) / np.sqrt(K), tdt)
+    bias, cls = dev(rng.standard_normal(D)), dev(rng.standard_normal(D))
+    pos = dev(rng.standard_normal((T, D)))
+    M = B * T
+    slots = lib.vitb200_gemm_tc_ln_slots(M, D)
+    x = torch.full((M, D), float("nan"), device="cuda")
+    x16 = torch.full((M, D), float("nan"), dtype=tdt, device="cuda")
+    stats = torch.full((M, slots, 2), float("nan"), device="cuda")
+    _lib.check(lib.vitb200_gemm_tc_ln(stream(), A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), x.data_ptr(), M, D, K,
+                                      _lib.EPI_TOKENS_LN, pos.data_ptr(), T, cls.data_ptr(), dt, x16.data_ptr(), stats.data_ptr(),
+                                      slots, None, 0.0))
+    torch.cuda.synchronize()
+    want = (A.double() @ Wt.double().t()).view(B, T, D) + bias.double() + pos.double()
+    want[:, 0] = cls.double() + pos.double()[0]
+    assert (x.view(B, T, D).double() - want).abs().max().item() < 2e-4
+    assert torch.equal(x16, x.to(tdt))
+    s = stats.double().sum(1)
+    assert (s[:, 0] - x.double().sum(1)).abs().max().item() < 1e-2
+    assert ((s[:, 1] - (x.double() ** 2).sum(1)).abs() / (x.double() ** 2).sum(1)).max().item() < 1e-5

@@ -11,7 +11,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libvitb200.so"
 
 # error codes / enums (keep in sync with include/vitb200.h)
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_NCHW, FLAG_NO_CLS = 1, 2
 OK = 0
 PREC_BF16, PREC_FP32, PREC_FP16 = 0, 1, 2
@@ -21,6 +21,7 @@ POOL_CLS, POOL_MEAN = 0, 1
 CATEGORIES = ["patchify", "gemm_patch", "cls_rows", "layernorm", "gemm_qkv", "attention", "gemm_out",
               "gemm_ff1", "gemm_ff2", "pool_ln", "gemm_head"]
 EPI_STORE_16, EPI_BIAS_GELU_16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32, EPI_TOKENS_F32, EPI_BIAS_16, EPI_BIAS_PRE_GELU_16 = range(8)
+EPI_RESID_LN, EPI_TOKENS_LN, EPI_LN_STORE_16, EPI_LN_GELU_16 = range(8, 12)
 
 
 class Config(C.Structure):
@@ -75,6 +76,9 @@ SIGNATURES = {
     "vitb200_gemm_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i]),
     "vitb200_gemm_tc_dropout": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _i, C.c_float, C.c_uint64, C.c_uint32]),
     "vitb200_gemm_tc_tokens": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _fp, _i, C.c_float, C.c_uint64, C.c_uint32]),
+    "vitb200_gemm_tc_ln": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _fp, _i, _vp, _fp, _i, _fp, C.c_float]),
+    "vitb200_gemm_tc_ln_slots": (_i, [_i, _i]),
+    "vitb200_fold_layernorm": (_i, [_vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _i]),
     "vitb200_gemm_f32": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i]),
     "vitb200_layernorm": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i]),
     "vitb200_attention_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),

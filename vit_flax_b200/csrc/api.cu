@@ -1,6 +1,8 @@
 // api.cu -- the C ABI of include/vitb200.h: model handle, parameter registry
 // (the Flax pytree of vit.py, looked up by path), weight packing, the forward
 // schedule of ViT.__call__ (vit.py:127-167) and the per-kernel entry points.
+#include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -37,6 +39,13 @@ struct DenseW {
   CUtensorMap tm2{};                      // box 128 x 64 over wt (CTA pair per tile)
   CUtensorMap tm4{};                      // box 64 x 64 over wt (cluster of two pairs, multicast)
   const CUtensorMap& map(int mode) const { return (mode == 4 || mode == 64) ? tm4 : (mode == 2 ? tm2 : tm); }
+  // LayerNorm fold (the Dense behind a PreNorm: to_qkv, FeedForward Dense_0): W' = diag(gamma) W packed like wt,
+  // c = column sums of the rounded W', d = beta^T W (+ bias)   (gemm_tc.cu header)
+  uint16_t* wt_ln = nullptr;
+  float* ln_c = nullptr;
+  float* ln_d = nullptr;
+  CUtensorMap tm_ln{}, tm2_ln{}, tm4_ln{};
+  const CUtensorMap& map_ln(int mode) const { return (mode == 4 || mode == 64) ? tm4_ln : (mode == 2 ? tm2_ln : tm_ln); }
 };
 
 struct Layer {
@@ -94,6 +103,7 @@ struct vitb200_model {
   int dt = VITB200_DT_BF16; // operand type of the tensor-core path
   bool finalized = false;
   bool head_tc = false;
+  bool fold = false;          // LayerNorm folded into the GEMMs around it (inference forward, dropout rates 0)
   uint64_t dropout_key = 0;   // 'dropout' rng stream (vitb200_set_dropout_key)
 
   // the Dropout instance `site` of this model (rate 0 => off)
@@ -120,6 +130,8 @@ struct vitb200_model {
   DevBuf<float> x;                                   // residual stream [B*T, D] fp32 (both modes)
   DevBuf<uint16_t> patches_h, xn_h, qkv_h, o_h, hid_h, pooled_h;
   DevBuf<float> patches_f, xn_f, qkv_f, o_f, hid_f, pooled_f;
+  DevBuf<float> stats_a, stats_b;                    // LayerNorm fold: per-row partial (sum, sum sq) of x for LN1 / LN2
+  int stats_slots_cap = 0;                           // float pairs per row the two buffers hold
   DevBuf<float> img_stage, logit_stage;              // forward_host staging
   // submit_host / wait_host: two jobs in flight (H2D of job k+1 overlaps the forward of job k)
   struct HostJob {
@@ -173,7 +185,11 @@ struct vitb200_model {
     auto free_dense = [](DenseW& d) {
       if (d.wt) cudaFree(d.wt);
       if (d.wf) cudaFree(d.wf);
-      d.wt = d.wf = nullptr;
+      if (d.wt_ln) cudaFree(d.wt_ln);
+      if (d.ln_c) cudaFree(d.ln_c);
+      if (d.ln_d) cudaFree(d.ln_d);
+      d.wt = d.wf = d.wt_ln = nullptr;
+      d.ln_c = d.ln_d = nullptr;
     };
     free_dense(patch);
     free_dense(head);
@@ -262,6 +278,10 @@ int alloc_workspace(vitb200_model* m) {
     if ((rc = m->qkv_h.alloc(R * 3 * m->inner))) return rc;
     if ((rc = m->o_h.alloc(R * m->inner))) return rc;
     if ((rc = m->hid_h.alloc(R * c.mlp_dim))) return rc;
+    if (m->fold) {   // slots: 2 per n-tile of a [R, dim] GEMM; the 64-column tiles of small batches need the most
+      m->stats_slots_cap = 2 * ceil_div(c.dim, 64);
+      if ((rc = m->stats_a.alloc(R * 2 * size_t(m->stats_slots_cap))) || (rc = m->stats_b.alloc(R * 2 * size_t(m->stats_slots_cap)))) return rc;
+    }
     if (m->head_tc) { if ((rc = m->pooled_h.alloc(B * c.dim))) return rc; }
     else { if ((rc = m->pooled_f.alloc(B * c.dim))) return rc; }
   } else {
@@ -312,6 +332,21 @@ int pack_dense(vitb200_model* m, DenseW& d, cudaStream_t st) {
 
 inline const float* leaf_ptr(const vitb200_model* m, int idx) { return idx >= 0 ? m->leaves[idx].dev : nullptr; }
 
+// The Dense that follows a PreNorm, with that LayerNorm folded in (gemm_tc.cu header)
+int fold_dense(vitb200_model* m, DenseW& d, int ln_scale, int ln_bias, float* scratch, cudaStream_t st) {
+  if (d.wt_ln == nullptr) {
+    VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.wt_ln), size_t(d.N) * d.Kpad * sizeof(uint16_t)));
+    VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.ln_c), size_t(d.N) * sizeof(float)));
+    VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.ln_d), size_t(d.N) * sizeof(float)));
+  }
+  int rc = launch_fold_layernorm(st, m->leaves[d.leaf_kernel].dev, leaf_ptr(m, ln_scale), leaf_ptr(m, ln_bias),
+                                 leaf_ptr(m, d.leaf_bias), d.wt_ln, d.ln_c, d.ln_d, d.K, d.N, d.Kpad, m->dt, scratch);
+  if (rc) return rc;
+  if ((rc = make_tmap_2d(&d.tm_ln, d.wt_ln, d.N, d.Kpad, d.Kpad, GEMM_BN, m->dt))) return rc;
+  if ((rc = make_tmap_2d(&d.tm2_ln, d.wt_ln, d.N, d.Kpad, d.Kpad, GEMM_BN / 2, m->dt))) return rc;
+  return make_tmap_2d(&d.tm4_ln, d.wt_ln, d.N, d.Kpad, d.Kpad, GEMM_BN / 4, m->dt);
+}
+
 // profiling marks: one event BEFORE each launch (+ one at the end); launches are back to back
 // on one stream, so the gap between consecutive marks is that launch's duration.
 inline void mark(vitb200_model* m, cudaStream_t st, int cat) {
@@ -331,8 +366,65 @@ __global__ void add_f32_into_f32_kernel(const float* __restrict__ a, float* __re
   if (i < n) x[i] += a[i];
 }
 
+int forward_head(vitb200_model* m, cudaStream_t st, const ActMaps* am, int batch, float* logits);
+
+// ---- the forward schedule with every PreNorm LayerNorm folded into the GEMMs around it: 4 + 5L launches ----
+// patchify | patch GEMM (TOKENS_LN: x, x16, stats_a) | per layer: to_qkv (LN_STORE_16 on x16 / stats_a) | attention |
+// to_out (RESID_LN: x, x16, stats_b) | FF Dense_0 (LN_GELU_16 on x16 / stats_b) | FF Dense_1 (RESID_LN -> stats_a; plain
+// RESID in the last layer) | pool + LayerNorm | head.  x16 lives in the buffer the LayerNorm kernel used to write.
+int forward_tc_fold(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
+  const auto& c = m->cfg;
+  const int D = c.dim, I = m->inner, T = m->T;
+  const int R = batch * T;
+  const ActMaps* am;
+  int rc;
+  if ((rc = get_act_maps(m, batch, &am))) return rc;
+  const int cg_qkv = gemm_tc_tile_mode(R, 3 * I), cg_d = gemm_tc_tile_mode(R, D), cg_ff1 = gemm_tc_tile_mode(R, c.mlp_dim);
+  LnFold out_a, out_b, in_a, in_b;                 // producers write x16 + stats, consumers read stats + c
+  out_a.x16 = out_b.x16 = m->xn_h.p;
+  out_a.stats = in_a.stats = reinterpret_cast<float2*>(m->stats_a.p);
+  out_b.stats = in_b.stats = reinterpret_cast<float2*>(m->stats_b.p);
+  out_a.slots = out_b.slots = in_a.slots = in_b.slots = 2 * ceil_div(D, cg_d == 64 ? 64 : GEMM_BN);
+  in_a.eps = in_b.eps = m->eps;
+  mark(m, st, VITB200_CAT_PATCHIFY);
+  if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
+                            c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
+  mark(m, st, VITB200_CAT_GEMM_PATCH);
+  if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cg_d), &am->c_x, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+                           R, D, m->K0pad, VITB200_EPI_TOKENS_LN, leaf_ptr(m, m->leaf_pos), T, m->dt, cg_d,
+                           Dropout(), m->cls_off, leaf_ptr(m, m->leaf_cls), out_a))) return rc;
+  for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
+    Layer& L = m->layers[l];
+    // Residual(PreNorm(Attention))  vit.py:31,39,62-87
+    mark(m, st, VITB200_CAT_GEMM_QKV);
+    in_a.c = L.qkv.ln_c;
+    if ((rc = launch_gemm_tc(st, am->xn, L.qkv.map_ln(cg_qkv), &am->c_qkv, L.qkv.ln_d, m->qkv_h.p, R, 3 * I, D,
+                             VITB200_EPI_LN_STORE_16, nullptr, 0, m->dt, cg_qkv, Dropout(), m->cls_off, nullptr, in_a))) return rc;
+    mark(m, st, VITB200_CAT_ATTENTION);
+    if ((rc = launch_attention_tc(st, m->qkv_h.p, m->o_h.p, batch, T, c.heads, m->dt))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_OUT);
+    if ((rc = launch_gemm_tc(st, am->o, L.out.map(cg_d), &am->c_x, leaf_ptr(m, L.out.leaf_bias), m->x.p, R, D, I,
+                             VITB200_EPI_RESID_LN, nullptr, 0, m->dt, cg_d, Dropout(), m->cls_off, nullptr, out_b))) return rc;
+    // Residual(PreNorm(FeedForward))  vit.py:31,39,47-53
+    mark(m, st, VITB200_CAT_GEMM_FF1);
+    in_b.c = L.ff1.ln_c;
+    if ((rc = launch_gemm_tc(st, am->xn, L.ff1.map_ln(cg_ff1), &am->c_hid, L.ff1.ln_d, m->hid_h.p, R, c.mlp_dim, D,
+                             VITB200_EPI_LN_GELU_16, nullptr, 0, m->dt, cg_ff1, Dropout(), m->cls_off, nullptr, in_b))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_FF2);
+    if (l + 1 < c.depth) {
+      if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg_d), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim,
+                               VITB200_EPI_RESID_LN, nullptr, 0, m->dt, cg_d, Dropout(), m->cls_off, nullptr, out_a))) return rc;
+    } else {   // nothing normalises the last layer's output row by row: pool + head LayerNorm read x itself
+      if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg_d), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim,
+                               VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg_d))) return rc;
+    }
+  }
+  return forward_head(m, st, am, batch, logits);
+}
+
 // ---- the forward schedule, bf16 / tcgen05 flavour ---------------------------
 int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch, float* logits) {
+  if (m->fold) return forward_tc_fold(m, st, images, batch, logits);
   const auto& c = m->cfg;
   const int D = c.dim, I = m->inner, T = m->T;
   const int R = batch * T;
@@ -340,7 +432,7 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   int rc;
   if ((rc = get_act_maps(m, batch, &am))) return rc;
   // tile mode per GEMM shape (pairs for anything that fills the machine, small tiles otherwise)
-  const int cgp = gemm_tc_tile_mode(R, D), cgh = gemm_tc_tile_mode(batch, c.num_classes);
+  const int cgp = gemm_tc_tile_mode(R, D);
   const int cg_qkv = gemm_tc_tile_mode(R, 3 * I), cg_d = gemm_tc_tile_mode(R, D), cg_ff1 = gemm_tc_tile_mode(R, c.mlp_dim);
   // vit.py:146  patchify (+ fp32->16-bit cast, zero pad to K0pad) into the token layout: row b*T+cls+t
   mark(m, st, VITB200_CAT_PATCHIFY);
@@ -377,7 +469,15 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
     mark(m, st, VITB200_CAT_GEMM_FF2);
     if ((rc = launch_gemm_tc(st, am->h, L.ff2.map(cg_d), &am->c_x, leaf_ptr(m, L.ff2.leaf_bias), m->x.p, R, D, c.mlp_dim, VITB200_EPI_BIAS_RESID_F32, nullptr, 0, m->dt, cg_d, m->drop(c.dropout, 3 + 3 * l)))) return rc;
   }
-  // vit.py:159-165  pool, LayerNorm_0, Dense_1
+  return forward_head(m, st, am, batch, logits);
+}
+
+// vit.py:159-165  pool, LayerNorm_0, Dense_1
+int forward_head(vitb200_model* m, cudaStream_t st, const ActMaps* am, int batch, float* logits) {
+  const auto& c = m->cfg;
+  const int D = c.dim, T = m->T;
+  const int cgh = gemm_tc_tile_mode(batch, c.num_classes);
+  int rc;
   if (m->head_tc) {
     mark(m, st, VITB200_CAT_POOL_LN);
     if ((rc = launch_pool_layernorm(st, m->x.p, leaf_ptr(m, m->leaf_head_scale), leaf_ptr(m, m->leaf_head_bias), m->pooled_h.p, batch, T, D, c.pool, m->dt, m->eps))) return rc;
@@ -512,6 +612,10 @@ int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out) {
   m->inner = DIM_HEAD * c.heads;
   m->project_out = !(c.heads == 1 && DIM_HEAD == c.dim);             // vit.py:65
   m->head_tc = m->tc && (c.num_classes % 8 == 0);
+  {  // LayerNorm fold: on by default for the dropout-free inference forward; VITB200_LN_FOLD=0 keeps the LayerNorm kernel (A/B)
+    const char* e = getenv("VITB200_LN_FOLD");
+    m->fold = m->tc && m->project_out && c.depth > 0 && c.dropout == 0.f && c.emb_dropout == 0.f && !(e && e[0] == '0');
+  }
   if (m->tc && (c.dim % 8 != 0 || c.mlp_dim % 8 != 0))
     return fail(VITB200_ERR_UNSUPPORTED, "create: bf16/fp16 modes need dim and mlp_dim to be multiples of 8");
   if (!m->tc && m->K0pad != m->K0)
@@ -580,6 +684,15 @@ int vitb200_finalize_params(vitb200_model* m, void* stream) {
       if ((rc = pack_dense(m, L.ff2, st))) return rc;
     }
     if (m->head_tc && (rc = pack_dense(m, m->head, st))) return rc;
+    if (m->fold) {
+      DevBuf<float> scratch;
+      if ((rc = scratch.alloc(size_t(m->cfg.dim) * std::max(3 * m->inner, m->cfg.mlp_dim)))) return rc;
+      for (auto& L : m->layers) {
+        if ((rc = fold_dense(m, L.qkv, L.ln1_scale, L.ln1_bias, scratch.p, st))) return rc;
+        if ((rc = fold_dense(m, L.ff1, L.ln2_scale, L.ln2_bias, scratch.p, st))) return rc;
+      }
+      VB_CUDA(cudaStreamSynchronize(st));      // scratch is freed on return
+    }
   }
   VB_CUDA(cudaStreamSynchronize(st));
   // graphs captured before a reload hold the old tensor maps and leaf pointers
@@ -1093,6 +1206,49 @@ int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const fl
   if (!direct && (rc = make_tmap_2d(&tc, C, c_rows, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
   return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, direct ? nullptr : &tc, bias, C, M, N, K, epilogue,
                         aux, tokens_per_image, dtype, cg, drop, 1, cls);
+}
+
+int vitb200_gemm_tc_ln_slots(int M, int N) {
+  if (M <= 0 || N <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc_ln_slots: empty problem");
+  return 2 * ceil_div(N, gemm_tc_tile_mode(M, N) == 64 ? 64 : GEMM_BN);
+}
+
+int vitb200_gemm_tc_ln(void* stream, const void* A, const void* Wt, const float* bias, void* C, int M, int N, int K,
+                       int epilogue, const float* aux, int tokens_per_image, const float* cls, int dtype,
+                       void* x16, float* stats, int stats_slots, const float* ln_c, float ln_eps) {
+  if (epilogue < VITB200_EPI_RESID_LN || epilogue > VITB200_EPI_LN_GELU_16)
+    return fail(VITB200_ERR_INVALID, "gemm_tc_ln: epilogue must be one of the LayerNorm-fold epilogues (8..11)");
+  if (!A || !Wt || !C || !bias || !stats) return fail(VITB200_ERR_INVALID, "gemm_tc_ln: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 8) != 0 || (K % 8) != 0)
+    return fail(VITB200_ERR_INVALID, "gemm_tc_ln: M, N, K must be positive, N and K multiples of 8");
+  if (dtype != VITB200_DT_BF16 && dtype != VITB200_DT_F16) return fail(VITB200_ERR_INVALID, "gemm_tc_ln: dtype must be bf16 or fp16");
+  const bool out16 = epilogue == VITB200_EPI_LN_STORE_16 || epilogue == VITB200_EPI_LN_GELU_16;
+  const int cg = gemm_tc_tile_mode(M, N);
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, A, M, K, K, GEMM_BM, dtype))) return rc;
+  if ((rc = make_tmap_2d(&tb, Wt, N, K, K, cg == 64 ? 64 : GEMM_BN / cg, dtype))) return rc;
+  if ((rc = make_tmap_2d(&tc, C, M, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
+  LnFold ln;
+  ln.x16 = x16;
+  ln.stats = reinterpret_cast<float2*>(stats);
+  ln.slots = stats_slots;
+  ln.c = ln_c;
+  ln.eps = ln_eps > 0.f ? ln_eps : 1e-6f;
+  return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, &tc, bias, C, M, N, K, epilogue, aux, tokens_per_image,
+                        dtype, cg, Dropout(), 1, cls, ln);
+}
+
+int vitb200_fold_layernorm(void* stream, const float* W, const float* gamma, const float* beta, const float* bias,
+                           void* Wt, float* c, float* d, int K, int N, int Kpad, int dtype) {
+  if (!W || !gamma || !beta || !Wt || !c || !d) return fail(VITB200_ERR_INVALID, "fold_layernorm: null pointer");
+  if (K <= 0 || N <= 0 || Kpad < K) return fail(VITB200_ERR_INVALID, "fold_layernorm: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* scratch = nullptr;
+  VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), size_t(K) * N * sizeof(float), st));
+  const int rc = launch_fold_layernorm(st, W, gamma, beta, bias, Wt, c, d, K, N, Kpad, dtype, scratch);
+  cudaFreeAsync(scratch, st);
+  return rc;
 }
 
 int vitb200_gemm_f32(void* stream, const float* A, const float* W, const float* bias, float* C, int M, int N,

@@ -102,7 +102,13 @@ constexpr int GEMM_BK = 64;
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tokens_per_image, int dtype, int cta_group,
-                   const Dropout& drop = Dropout(), int cls_off = 1, const float* cls = nullptr);
+                   const Dropout& drop = Dropout(), int cls_off = 1, const float* cls = nullptr,
+                   const LnFold& ln = LnFold());
+// LayerNorm fold (gemm_tc.cu header): W' = diag(gamma) W packed to 16-bit [N, Kpad], c[n] = sum_k W'_16[n, k] (of the
+// ROUNDED values, so that rstd mean c cancels the mean part of x16 W'_16 exactly), d[n] = sum_k beta[k] W[k, n] (+ bias[n]).
+// `scratch`: K * N floats.
+int launch_fold_layernorm(cudaStream_t stream, const float* W, const float* gamma, const float* beta, const float* bias,
+                          void* Wt, float* c, float* d, int K, int N, int Kpad, int dtype, float* scratch);
 // Weight gradient C[M, N] += X[K, M]^T dY[K, N] (fp32 C, TMA reduce-add, split-K `splits`): tmX / tmdY are maps
 // over the ROW-MAJOR activations with 64-row x 64-column boxes (MN-major operands, no transposed copies)
 int launch_gemm_tc_wgrad(cudaStream_t stream, const CUtensorMap& tmX, const CUtensorMap& tmdY, const CUtensorMap& tmC,

@@ -24,6 +24,17 @@
 // tile i overlaps the MMAs of tile i+1; two slab buffers per epilogue group so a slab drains while
 // the next is filled.  Dropout (template kDrop) is applied in the epilogues that have an
 // nn.Dropout behind them in the reference (ptx.cuh: dropout4).
+//
+// LayerNorm fold (PreNorm, vit.py:31): LN(x) W = rstd (x W') - rstd mean c + d with
+// W' = diag(gamma) W, c = 1^T W', d = beta^T W (+ bias).  The GEMMs that PRODUCE the residual stream
+// (TOKENS_LN, RESID_LN) also emit a 16-bit copy of the raw x and per-row partial sums (sum, sum of
+// squares -- Flax's E[x^2] - E[x]^2 variance) of the fp32 values; the GEMMs that CONSUME a LayerNorm
+// (LN_STORE_16 = to_qkv, LN_GELU_16 = FeedForward Dense_0) read the raw 16-bit x as A and apply the
+// row statistics in their epilogue.  No stand-alone LayerNorm kernel runs between them.  RESID_LN has
+// to see x_old in the SM (the plain RESID epilogue adds in L2 and never does): the epilogue groups pull
+// the 128x32 fp32 slabs of x by TMA two slabs ahead into a ring of three buffers, add in place and
+// TMA-store them back.  Statistics partials go to one slot per (n-tile, epilogue group) and are summed
+// in slot order by the consumer: no atomics, bit-reproducible.
 #include <cstdlib>
 
 #include "common.h"
@@ -58,9 +69,15 @@ template <int kCG> struct Cfg {
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;   // 384
 constexpr int SLAB_BYTES = BM * 128;            // 128 rows x 128 B = 16 KB
-constexpr int NUM_SLABS = 4;                    // 2 per epilogue group
-template <int kCG> constexpr int smem_bytes() {
-  return Cfg<kCG>::STAGES * Cfg<kCG>::STAGE_BYTES + NUM_SLABS * SLAB_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// slab buffers per epilogue group: 2 (one drains while the next is filled); RESID_LN: a ring of 3 (x_old
+// loads run two slabs ahead), paid for with one smem stage
+template <int kEpi> __host__ __device__ constexpr int slabs_per_group() { return kEpi == VITB200_EPI_RESID_LN ? 3 : 2; }
+template <int kCG, int kEpi> __host__ __device__ constexpr int num_stages() {
+  return Cfg<kCG>::STAGES - (kEpi == VITB200_EPI_RESID_LN ? 1 : 0);
+}
+template <int kCG, int kEpi = VITB200_EPI_STORE_16> constexpr int smem_bytes() {
+  return num_stages<kCG, kEpi>() * Cfg<kCG>::STAGE_BYTES + 2 * slabs_per_group<kEpi>() * SLAB_BYTES + 1024 /*align*/ +
+         256 /*barriers*/;
 }
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
@@ -68,6 +85,22 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * x * fmaf(k1 * x, x, 1.0f);
   return 0.5f * x * (1.0f + tanh_approx(u));
+}
+
+// The same on two values at a time (fp32x2: one issue slot for two lanes of FFMA / FMUL -- the GELU epilogue of
+// FeedForward Dense_0 is the most instruction-heavy one and sits next to the MMA time of its K = dim tiles):
+// u = x (k0 + k0 k1 x^2), gelu = hx + hx tanh(u) with hx = 0.5 x.
+__device__ __forceinline__ unsigned long long gelu_tanh_fast2(unsigned long long x2) {
+  const unsigned long long kA = pack_f32x2(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const unsigned long long kB = pack_f32x2(0.7978845608028654f, 0.7978845608028654f);
+  const unsigned long long half2 = pack_f32x2(0.5f, 0.5f);
+  const unsigned long long t2 = mul_f32x2(x2, x2);
+  const unsigned long long u2 = mul_f32x2(fma_f32x2(t2, kA, kB), x2);
+  float u0, u1;
+  unpack_f32x2(u2, u0, u1);
+  const unsigned long long th2 = pack_f32x2(tanh_approx(u0), tanh_approx(u1));
+  const unsigned long long hx2 = mul_f32x2(x2, half2);
+  return fma_f32x2(th2, hx2, hx2);
 }
 
 // kMN (weight gradients, dW = X^T dY): both operands are read MN-major straight from the row-major
@@ -82,14 +115,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, void* __restrict__ Cout,
                int M, int N, int K, const float* __restrict__ aux, int tpi, int dbg, Dropout drop, int cls_off,
-               const float* __restrict__ cls) {
+               const float* __restrict__ cls, LnFold ln) {
   constexpr bool kOut16 = (kEpi == VITB200_EPI_STORE_16 || kEpi == VITB200_EPI_BIAS_GELU_16 || kEpi == VITB200_EPI_BIAS_16 ||
-                           kEpi == VITB200_EPI_BIAS_PRE_GELU_16);
+                           kEpi == VITB200_EPI_BIAS_PRE_GELU_16 || kEpi == VITB200_EPI_LN_STORE_16 ||
+                           kEpi == VITB200_EPI_LN_GELU_16);
+  constexpr bool kLnIn = (kEpi == VITB200_EPI_LN_STORE_16 || kEpi == VITB200_EPI_LN_GELU_16);   // A = raw x, LayerNorm applied here
+  constexpr bool kLnOut = (kEpi == VITB200_EPI_RESID_LN || kEpi == VITB200_EPI_TOKENS_LN);      // also emits x16 + row statistics
+  constexpr bool kLoadX = (kEpi == VITB200_EPI_RESID_LN);                                       // x_old comes in by TMA
+  constexpr bool kTokens = (kEpi == VITB200_EPI_TOKENS_F32 || kEpi == VITB200_EPI_TOKENS_LN);
+  constexpr int SPG = slabs_per_group<kEpi>();
   constexpr bool kDual = (kEpi == VITB200_EPI_BIAS_PRE_GELU_16);   // two outputs per slab: pre-activation and GELU
   constexpr bool kDirect = (kEpi == VITB200_EPI_PATCH_F32);   // row-remapped output: plain stores
   constexpr int SLAB_COLS = kOut16 ? 64 : 32;                 // 128 B of output per row
   constexpr int SLABS_PER_TILE = Cfg<kCG>::BN_ / SLAB_COLS;
-  constexpr int STAGES = Cfg<kCG>::STAGES, B_BYTES = Cfg<kCG>::B_BYTES;
+  constexpr int STAGES = num_stages<kCG, kEpi>(), B_BYTES = Cfg<kCG>::B_BYTES;
   constexpr int STAGE_BYTES = Cfg<kCG>::STAGE_BYTES, TILE_M = Cfg<kCG>::TILE_M;
   constexpr int MMA_CG = Cfg<kCG>::MMA_CG, PAIRS = Cfg<kCG>::PAIRS, CL = Cfg<kCG>::CL;
   constexpr int BN = Cfg<kCG>::BN_, TMEM_COLS = Cfg<kCG>::TMEM_COLS;   // shadow the 256-column default
@@ -106,13 +145,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * A_BYTES;
   const uint32_t sSlab = smem_base + STAGES * STAGE_BYTES;
-  const uint32_t bars = sSlab + NUM_SLABS * SLAB_BYTES;
-  // barrier layout: full[STAGES] empty[STAGES] tfull[2] tempty[2] | tmem ptr
+  const uint32_t bars = sSlab + 2 * SPG * SLAB_BYTES;
+  // barrier layout: full[STAGES] empty[STAGES] tfull[2] tempty[2] | tmem ptr | xfull[2 groups][3] (RESID_LN)
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  auto xfull_bar = [&](int g, int b) { return bars + 8u * (2 * STAGES + 5 + g * 3 + b); };
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -142,6 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), NUM_EPI_WARPS * MMA_CG);   // pair: epilogue warps of both CTAs
     }
+    if constexpr (kLoadX)
+      for (int i = 0; i < 6; ++i) mbar_init(xfull_bar(i / 3, i % 3), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<MMA_CG>(tmem_slot, TMEM_COLS);
@@ -267,10 +309,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
+    // RESID_LN: the group's leader streams the x_old slabs in, two ahead of the slab being updated (ring of 3)
+    int ld_tile = tile0, ld_s = grp, ld_issued = 0, x_used = 0;
+    auto issue_x_load = [&]() {
+      while (ld_tile < num_tiles) {
+        if (ld_s < SLABS_PER_TILE && (ld_tile % n_tiles) * BN + ld_s * SLAB_COLS < N) break;
+        ld_tile += tile_step;
+        ld_s = grp;
+      }
+      if (ld_tile >= num_tiles) return;
+      const int lm = ld_tile / n_tiles, lnb = ld_tile % n_tiles;      // RESID_LN never splits K: tile = m_blk * n_tiles + n_blk
+      const int b = ld_issued % 3;
+      mbar_arrive_expect_tx(xfull_bar(grp, b), SLAB_BYTES);
+      tma_load_2d(sSlab + uint32_t(grp * SPG + b) * SLAB_BYTES, &tmC, xfull_bar(grp, b), lnb * BN + ld_s * SLAB_COLS,
+                  (lm * PAIRS + int(pair)) * TILE_M + int(rank) * BM);
+      ++ld_issued;
+      ld_s += 2;
+    };
+    if constexpr (kLoadX) {
+      if (leader) { issue_x_load(); issue_x_load(); }
+    }
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int sp = tile / mn_tiles, t2 = tile - sp * mn_tiles;
       const int m_blk = t2 / n_tiles, n_blk = t2 % n_tiles;
       const int m_row0 = (m_blk * PAIRS + int(pair)) * TILE_M + int(rank) * BM;   // first output row of this CTA
+      // LayerNorm of this thread's row of A (consumers): mean and rstd from the producer's partial sums, summed in
+      // slot order (bit-reproducible); variance = E[x^2] - E[x]^2 like flax.linen.LayerNorm
+      float ln_rstd = 0.f, ln_rm = 0.f;
+      if constexpr (kLnIn) {
+        if (m_row0 + lrow < M) {
+          const float2* sp2 = ln.stats + int64_t(m_row0 + lrow) * ln.slots;
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < ln.slots; ++i) { const float2 v = __ldg(sp2 + i); s1 += v.x; s2 += v.y; }
+          const float inv_d = 1.0f / float(K);
+          const float mean = s1 * inv_d;
+          ln_rstd = rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.f) + ln.eps);
+          ln_rm = ln_rstd * mean;
+        }
+      }
+      float st1 = 0.f, st2 = 0.f;       // producers: this thread's partial row sums over the group's slabs of the tile
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
@@ -324,11 +401,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int s = grp; s < SLABS_PER_TILE; s += 2) {
           const int n0 = n_blk * BN + s * SLAB_COLS;
           if (n0 >= N || (dbg & 4)) break;             // uniform over the group
-          const uint32_t slab = sSlab + uint32_t(grp * 2 + buf) * SLAB_BYTES;
-          // the slab buffer used two slabs ago must have been read out by its TMA store (dual output: both
-          // buffers of the group are filled per slab, so every earlier store must have been read out)
-          if (leader) { if constexpr (kDual) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
-          named_bar_sync(1 + grp, 128);
+          const uint32_t slab = sSlab + uint32_t(grp * SPG + (kLoadX ? x_used % 3 : buf)) * SLAB_BYTES;
+          if constexpr (kLoadX) {
+            // the slab's x_old values have landed in the buffer (loaded two slabs ago, after the store that last
+            // used the buffer had been read out)
+            mbar_wait(xfull_bar(grp, x_used % 3), uint32_t(x_used / 3) & 1u);
+          } else {
+            // the slab buffer used two slabs ago must have been read out by its TMA store (dual output: both
+            // buffers of the group are filled per slab, so every earlier store must have been read out)
+            if (leader) { if constexpr (kDual) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
+            named_bar_sync(1 + grp, 128);
+          }
           const uint32_t srow = slab + uint32_t(lrow) * 128u;
           const int sw = lrow & 7;
           // dual output: the GELU values go to the group's other slab buffer and leave `tpi` rows further down
@@ -373,6 +456,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                pack2<kDT>(v[4], v[5]), pack2<kDT>(v[6], v[7]));
                   continue;
                 }
+                if constexpr (kLnIn) {
+                  // LayerNorm folded into the weights: y = rstd acc - rstd mean c + d  (d = beta W + bias), then GELU for FF
+                  const int nb = n0 + half * 32 + j * 8;
+                  float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, d0 = c0, d1 = c0;
+                  if (nb < N) {
+                    c0 = __ldg(reinterpret_cast<const float4*>(ln.c + nb));
+                    c1 = __ldg(reinterpret_cast<const float4*>(ln.c + nb + 4));
+                    d0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
+                    d1 = __ldg(reinterpret_cast<const float4*>(bias + nb + 4));
+                  }
+                  const unsigned long long rs2 = pack_f32x2(ln_rstd, ln_rstd), nrm2 = pack_f32x2(-ln_rm, -ln_rm);
+                  const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                  const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                  for (int e = 0; e < 8; e += 2) {
+                    unsigned long long y2 = fma_f32x2(rs2, pack_f32x2(v[e], v[e + 1]),
+                                                      fma_f32x2(nrm2, pack_f32x2(cc[e], cc[e + 1]), pack_f32x2(dd[e], dd[e + 1])));
+                    if constexpr (kEpi == VITB200_EPI_LN_GELU_16) y2 = gelu_tanh_fast2(y2);
+                    unpack_f32x2(y2, v[e], v[e + 1]);
+                  }
+                }
                 if constexpr (kEpi == VITB200_EPI_BIAS_GELU_16) {
                   const int nb = n0 + half * 32 + j * 8;
                   float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
@@ -380,10 +484,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                     b0 = __ldg(reinterpret_cast<const float4*>(bias + nb));
                     b1 = __ldg(reinterpret_cast<const float4*>(bias + nb + 4));
                   }
-                  v[0] = gelu_tanh_fast(v[0] + b0.x); v[1] = gelu_tanh_fast(v[1] + b0.y);
-                  v[2] = gelu_tanh_fast(v[2] + b0.z); v[3] = gelu_tanh_fast(v[3] + b0.w);
-                  v[4] = gelu_tanh_fast(v[4] + b1.x); v[5] = gelu_tanh_fast(v[5] + b1.y);
-                  v[6] = gelu_tanh_fast(v[6] + b1.z); v[7] = gelu_tanh_fast(v[7] + b1.w);
+                  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                  for (int e = 0; e < 8; e += 2)
+                    unpack_f32x2(gelu_tanh_fast2(add_f32x2(pack_f32x2(v[e], v[e + 1]), pack_f32x2(bb[e], bb[e + 1]))), v[e], v[e + 1]);
                   if constexpr (kDrop) {   // FeedForward's first Dropout (vit.py:50), on the hidden activations
                     const int64_t e0 = int64_t(m_row0 + lrow) * N + nb;
                     dropout4(drop, e0, v[0], v[1], v[2], v[3]);
@@ -400,9 +504,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             tmem_ld_32x32b_x32(t_row + uint32_t(s * SLAB_COLS), r);
             // TOKENS: output row = token row b*T + t; t = 0 is the class-token row when cls is given
             // (vit.py:151-153: concat([cls, x]) + pos_embedding), every other row a patch row
-            const int tok = kEpi == VITB200_EPI_TOKENS_F32 ? (m_row0 + lrow) % tpi : 0;
-            const bool cls_row = kEpi == VITB200_EPI_TOKENS_F32 && cls != nullptr && tok == 0;
+            const int tok = kTokens ? (m_row0 + lrow) % tpi : 0;
+            const bool cls_row = kTokens && cls != nullptr && tok == 0;
             const float* pos_row = aux + int64_t(tok) * N;
+            uint16_t* x16_row = kLnOut ? static_cast<uint16_t*>(ln.x16) + int64_t(m_row0 + lrow) * N : nullptr;
+            const bool row_ok = m_row0 + lrow < M;
+            uint32_t h0 = 0, h1 = 0;                   // 16-bit pairs of the previous 4-column chunk
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {              // 4 fp32 columns -> one 16-byte chunk
@@ -411,7 +518,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
               if (nb < N && sp == 0 && bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>((cls_row ? cls : bias) + nb));
               float o0 = __uint_as_float(r[j * 4 + 0]), o1 = __uint_as_float(r[j * 4 + 1]);
               float o2 = __uint_as_float(r[j * 4 + 2]), o3 = __uint_as_float(r[j * 4 + 3]);
-              if constexpr (kEpi == VITB200_EPI_TOKENS_F32) {
+              if constexpr (kTokens) {
                 if (cls_row) o0 = o1 = o2 = o3 = 0.f;   // the slot row of the patch matrix holds no data
                 if (nb < N) {
                   const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos_row + nb));
@@ -419,12 +526,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                 }
               }
               o0 += b4.x; o1 += b4.y; o2 += b4.z; o3 += b4.w;
-              if constexpr (kDrop && kEpi == VITB200_EPI_TOKENS_F32)      // emb dropout (vit.py:155)
+              if constexpr (kDrop && kTokens)      // emb dropout (vit.py:155)
                 dropout4(drop, int64_t(m_row0 + lrow) * N + nb, o0, o1, o2, o3);
               if constexpr (kDrop && kEpi == VITB200_EPI_BIAS_RESID_F32)   // Dropout after to_out / FF Dense_1
                 dropout4(drop, int64_t(m_row0 + lrow) * N + nb, o0, o1, o2, o3);   // (vit.py:52,83), before the residual add
+              if constexpr (kLoadX) {               // the Residual add (vit.py:39) happens here, on the slab TMA brought in
+                const float4 xo = ld_shared_v4f(srow + (uint32_t(j ^ sw) << 4));
+                o0 += xo.x; o1 += xo.y; o2 += xo.z; o3 += xo.w;
+              }
               st_shared_v4(srow + (uint32_t(j ^ sw) << 4), __float_as_uint(o0), __float_as_uint(o1),
                            __float_as_uint(o2), __float_as_uint(o3));
+              if constexpr (kLnOut) {
+                // what the next LayerNorm needs: the row's sum and sum of squares (fp32 values, columns >= N are zero) and
+                // the 16-bit copy of the raw row, the A operand of the GEMM that follows it
+                st1 += (o0 + o1) + (o2 + o3);
+                st2 = fmaf(o0, o0, fmaf(o1, o1, fmaf(o2, o2, fmaf(o3, o3, st2))));
+                if ((j & 1) == 0) {
+                  h0 = pack2<kDT>(o0, o1); h1 = pack2<kDT>(o2, o3);
+                } else if (row_ok && nb - 4 < N) {
+                  *reinterpret_cast<uint4*>(x16_row + nb - 4) = make_uint4(h0, h1, pack2<kDT>(o0, o1), pack2<kDT>(o2, o3));
+                }
+              }
             }
           }
           fence_proxy_async_smem();                    // generic-proxy smem writes -> async proxy
@@ -437,7 +559,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             if constexpr (kDual) tma_store_2d(&tmC, sSlab + uint32_t(grp * 2 + (buf ^ 1)) * SLAB_BYTES, n0, m_row0 + tpi);
             tma_store_commit();
           }
+          if constexpr (kLoadX) {
+            // the buffer of the PREVIOUS slab is free once its store has been read out: refill it with the slab two ahead
+            if (leader) { tma_store_wait_read<1>(); issue_x_load(); }
+            ++x_used;
+          }
           buf ^= 1;
+        }
+        if constexpr (kLnOut) {
+          if (m_row0 + lrow < M && sp == 0)
+            ln.stats[int64_t(m_row0 + lrow) * ln.slots + n_blk * 2 + grp] = make_float2(st1, st2);
         }
       }
       tc_fence_before();
@@ -469,19 +600,19 @@ int gemm_dbg() {   // VITB200_GEMM_DBG bit 0: no TMA loads, bit 1: no output sto
 template <int kEpi, int kDT, int kCG, bool kDrop, bool kMN = false>
 int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
               const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
-              const float* aux, int tpi, const Dropout& drop, int cls_off, const float* cls) {
+              const float* aux, int tpi, const Dropout& drop, int cls_off, const float* cls, const LnFold& ln = LnFold()) {
   static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
   static PerDevice<int> max_units_on;   // clusters (CTAs for kCG == 1) that can be resident at once, per device
   int& max_units = max_units_on.here();
   if (bool& configured = configured_on.here(); !configured) {
     VB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kEpi, kDT, kCG, kDrop, kMN>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG>()));
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kCG, kEpi>()));
     max_units = sm_count() / Cfg<kCG>::CL;
     if (Cfg<kCG>::CL > 2) {   // clusters of 4 do not tile every GPC: ask how many fit (33 on a 148-SM B200)
       int n = 0;
       cudaLaunchConfig_t cfg{};
       cfg.blockDim = dim3(NUM_THREADS);
-      cfg.dynamicSmemBytes = smem_bytes<kCG>();
+      cfg.dynamicSmemBytes = smem_bytes<kCG, kEpi>();
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = Cfg<kCG>::CL;
@@ -500,10 +631,22 @@ int launch_cg(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tm
   const int splits = (kEpi == VITB200_EPI_BIAS_RESID_F32 && tpi > 1) ? tpi : 1;
   const int tiles = ceil_div(ceil_div(M, Cfg<kCG>::TILE_M), Cfg<kCG>::PAIRS) * ceil_div(N, Cfg<kCG>::BN_) * splits;
   const int units = tiles < max_units ? tiles : max_units;
-  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop, kMN>, dim3(units * Cfg<kCG>::CL), dim3(NUM_THREADS), smem_bytes<kCG>(),
-                        stream, Cfg<kCG>::CL, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off, cls));
+  VB_CUDA(launch_kernel(gemm_tc_kernel<kEpi, kDT, kCG, kDrop, kMN>, dim3(units * Cfg<kCG>::CL), dim3(NUM_THREADS), smem_bytes<kCG, kEpi>(),
+                        stream, Cfg<kCG>::CL, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, gemm_dbg(), drop, cls_off, cls, ln));
   VB_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
+}
+
+// the LayerNorm-fold epilogues: tile modes 1, 2 and 64, no dropout variants (the forward keeps the stand-alone
+// LayerNorm kernel when a dropout rate is > 0)
+template <int kEpi, int kDT>
+int launch_ln(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+              const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
+              const float* aux, int tpi, int cta_group, int cls_off, const float* cls, const LnFold& ln) {
+  if (cta_group == 64) return launch_cg<kEpi, kDT, 64, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, Dropout(), cls_off, cls, ln);
+  if (cta_group == 1) return launch_cg<kEpi, kDT, 1, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, Dropout(), cls_off, cls, ln);
+  if (cta_group == 2) return launch_cg<kEpi, kDT, 2, false>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, Dropout(), cls_off, cls, ln);
+  return fail(VITB200_ERR_UNSUPPORTED, "gemm_tc: the LayerNorm-fold epilogues are built for tile modes 1, 2 and 64");
 }
 
 template <int kEpi, int kDT>
@@ -533,7 +676,26 @@ template <int kDT>
 int dispatch_epi(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const CUtensorMap& tmC, const float* bias, void* C, int M, int N, int K,
                  int epilogue, const float* aux, int tpi, int cta_group, const Dropout& drop, int cls_off,
-                 const float* cls) {
+                 const float* cls, const LnFold& ln) {
+  if (epilogue >= VITB200_EPI_RESID_LN && epilogue <= VITB200_EPI_LN_GELU_16) {
+    if (drop.threshold != 0) return fail(VITB200_ERR_UNSUPPORTED, "gemm_tc: the LayerNorm-fold epilogues have no dropout variant");
+    if (ln.stats == nullptr || ln.slots <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: LayerNorm-fold epilogue without a statistics buffer");
+    const bool producer = epilogue == VITB200_EPI_RESID_LN || epilogue == VITB200_EPI_TOKENS_LN;
+    if (producer && (ln.x16 == nullptr || ln.slots != 2 * ceil_div(N, cta_group == 64 ? 64 : GEMM_BN)))
+      return fail(VITB200_ERR_INVALID, "gemm_tc: RESID_LN / TOKENS_LN need x16 and 2 * n_tiles statistics slots");
+    if (!producer && ln.c == nullptr) return fail(VITB200_ERR_INVALID, "gemm_tc: LN_STORE / LN_GELU need the column sums c");
+    switch (epilogue) {
+      case VITB200_EPI_RESID_LN:
+        return launch_ln<VITB200_EPI_RESID_LN, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, 0, cta_group, cls_off, cls, ln);
+      case VITB200_EPI_TOKENS_LN:
+        if (aux == nullptr || tpi <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: TOKENS_LN needs pos_embedding and tokens per image");
+        return launch_ln<VITB200_EPI_TOKENS_LN, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, cls_off, cls, ln);
+      case VITB200_EPI_LN_STORE_16:
+        return launch_ln<VITB200_EPI_LN_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, 0, cta_group, cls_off, cls, ln);
+      default:
+        return launch_ln<VITB200_EPI_LN_GELU_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, 0, cta_group, cls_off, cls, ln);
+    }
+  }
   switch (epilogue) {
     case VITB200_EPI_STORE_16:
       return launch_one<VITB200_EPI_STORE_16, kDT>(stream, tmA, tmB, tmC, bias, C, M, N, K, aux, tpi, cta_group, drop, cls_off, cls);
@@ -603,7 +765,7 @@ int launch_gemm_tc_wgrad(cudaStream_t stream, const CUtensorMap& tmX, const CUte
 int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap* tmC, const float* bias, void* C, int M, int N, int K,
                    int epilogue, const float* aux, int tpi, int dtype, int cta_group, const Dropout& drop,
-                   int cls_off, const float* cls) {
+                   int cls_off, const float* cls, const LnFold& ln) {
   if (cta_group != 1 && cta_group != 2 && cta_group != 4 && cta_group != 64)
     return fail(VITB200_ERR_INVALID, "gemm_tc: tile mode must be 1, 2, 4 or 64");
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm_tc: empty problem");
@@ -621,11 +783,12 @@ int launch_gemm_tc(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMa
     tpi = sp;
   }
   const CUtensorMap& c = tmC ? *tmC : tmA;   // PATCH never touches it
-  const float* cls_p = (cls_off == 1 && (epilogue == VITB200_EPI_PATCH_F32 || epilogue == VITB200_EPI_TOKENS_F32)) ? cls : nullptr;
+  const float* cls_p = (cls_off == 1 && (epilogue == VITB200_EPI_PATCH_F32 || epilogue == VITB200_EPI_TOKENS_F32 ||
+                                         epilogue == VITB200_EPI_TOKENS_LN)) ? cls : nullptr;
   if (dtype == DT_BF16)
-    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off, cls_p);
+    return dispatch_epi<DT_BF16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off, cls_p, ln);
   if (dtype == DT_F16)
-    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off, cls_p);
+    return dispatch_epi<DT_F16>(stream, tmA, tmB, c, bias, C, M, N, K, epilogue, aux, tpi, cta_group, drop, cls_off, cls_p, ln);
   return fail(VITB200_ERR_INVALID, "gemm_tc: dtype must be bf16 or fp16");
 }
 

@@ -179,6 +179,11 @@ __device__ __forceinline__ void tma_store_wait() {        // <= N groups not yet
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -441,6 +446,11 @@ __device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, un
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
   unsigned long long d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -483,6 +493,17 @@ __device__ __forceinline__ void dropout4(const Dropout& d, long long elem, float
   c = r.z < d.threshold ? 0.f : c * d.inv_keep;
   e = r.w < d.threshold ? 0.f : e * d.inv_keep;
 }
+
+// LayerNorm folded into the GEMMs around it (gemm_tc.cu header).  Producers (RESID_LN, TOKENS_LN) write `x16`
+// ([M, N] 16-bit copy of their fp32 output) and `stats` ([M, slots] partial (sum, sum of squares) of each output row,
+// slot = 2 * n_tile + epilogue group); consumers (LN_STORE_16, LN_GELU_16) read `stats` of their A rows and `c`.
+struct LnFold {
+  void* x16 = nullptr;
+  float2* stats = nullptr;
+  const float* c = nullptr;
+  int slots = 0;
+  float eps = 1e-6f;
+};
 
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;

@@ -387,6 +387,33 @@ pack_weight_kernel(const float* __restrict__ W, uint16_t* __restrict__ Wt, int K
   }
 }
 
+// ------------------------------------------------ LayerNorm fold, weight side
+// (gemm_tc.cu header)  Ws[k, n] = gamma[k] W[k, n]; d[n] = sum_k beta[k] W[k, n] (+ bias[n]); c[n] = sum_k of the
+// 16-bit ROUNDED packed row Wt[n, :].  Run once per weight load, not on the forward path.
+__global__ void __launch_bounds__(256)
+fold_scale_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ bias, float* __restrict__ Ws, float* __restrict__ d, int K, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;     // one column per thread: coalesced over n for every k
+  if (n >= N) return;
+  float acc = bias ? bias[n] : 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float w = W[int64_t(k) * N + n];
+    Ws[int64_t(k) * N + n] = gamma[k] * w;
+    acc = fmaf(beta[k], w, acc);
+  }
+  d[n] = acc;
+}
+template <int kDT>
+__global__ void __launch_bounds__(256)
+fold_rowsum16_kernel(const uint16_t* __restrict__ Wt, float* __restrict__ c, int N, int Kpad) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // one warp per packed row
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = lane; k < Kpad; k += 32) acc += to_f32<kDT>(Wt[int64_t(n) * Kpad + k]);
+  acc = warp_sum(acc);
+  if (lane == 0) c[n] = acc;
+}
+
 // ------------------------------------------------------ fp32 SIMT GEMM (mode)
 __device__ __forceinline__ float gelu_tanh_exact(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
@@ -606,6 +633,20 @@ int launch_pack_weight(cudaStream_t st, const float* W, void* Wt, int K, int N, 
   if (dtype == DT_BF16) pack_weight_kernel<DT_BF16><<<grid, 256, 0, st>>>(W, static_cast<uint16_t*>(Wt), K, N, Kpad);
   else pack_weight_kernel<DT_F16><<<grid, 256, 0, st>>>(W, static_cast<uint16_t*>(Wt), K, N, Kpad);
   VB_LAUNCH_CHECK("pack_weight_kernel");
+  return 0;
+}
+
+int launch_fold_layernorm(cudaStream_t st, const float* W, const float* gamma, const float* beta, const float* bias,
+                          void* Wt, float* c, float* d, int K, int N, int Kpad, int dtype, float* scratch) {
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(VITB200_ERR_INVALID, "fold_layernorm: dtype must be bf16 or fp16");
+  if (K <= 0 || N <= 0 || Kpad < K) return fail(VITB200_ERR_INVALID, "fold_layernorm: bad shape");
+  fold_scale_kernel<<<ceil_div(N, 256), 256, 0, st>>>(W, gamma, beta, bias, scratch, d, K, N);
+  VB_LAUNCH_CHECK("fold_scale_kernel");
+  int rc = launch_pack_weight(st, scratch, Wt, K, N, Kpad, dtype);
+  if (rc) return rc;
+  if (dtype == DT_BF16) fold_rowsum16_kernel<DT_BF16><<<ceil_div(N, 8), 256, 0, st>>>(static_cast<const uint16_t*>(Wt), c, N, Kpad);
+  else fold_rowsum16_kernel<DT_F16><<<ceil_div(N, 8), 256, 0, st>>>(static_cast<const uint16_t*>(Wt), c, N, Kpad);
+  VB_LAUNCH_CHECK("fold_rowsum16_kernel");
   return 0;
 }
 
