@@ -219,7 +219,7 @@ def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
     from vit_flax_b200 import ViT, init_params, perturb_params
-    from vit_flax_b200.dist import shard_range, sharded_apply_stream, sharded_logits
+    from vit_flax_b200.dist import counts_range, rebalance, shard_range, sharded_apply_stream, sharded_logits
     from vit_flax_b200.engine import Engine, launch_count
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,20 +238,29 @@ def run_b200(args) -> None:
     S, classes = cfg["image_size"], cfg["num_classes"]
     if B * world != global_batch:
         raise SystemExit(f"global batch {global_batch} is not divisible by {world} ranks")
-    start, stop = shard_range(global_batch, world, rank)
     variables = perturb_params(init_params(seed=1, **cfg), seed=2)
-
-    # synthetic N(0,1) images, seeded by global image index so every N sees the same images
-    g = torch.Generator(device=dev)
-    images = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)
-    for i in range(B):
-        g.manual_seed(1000 + start + i)
-        images[i].normal_(generator=g)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- shards (N > 1): equal to begin with; `balance()` below re-divides the global batch from lockstep measurements ----
+    counts = None if world == 1 else [B] * world
+    cap = B if world == 1 or args.no_balance else B + max(8, B // 8)       # engine capacity: room for a faster rank
+    g = torch.Generator(device=dev)
+    state = {}
+
+    def make_images():
+        """synthetic N(0,1) images of this rank's shard, seeded by GLOBAL image index so every N sees the same images"""
+        start, stop = counts_range(counts, rank) if counts else shard_range(global_batch, world, rank)
+        images = torch.empty((stop - start, S, S, 3), dtype=torch.float32, device=dev)
+        for i in range(stop - start):
+            g.manual_seed(1000 + start + i)
+            images[i].normal_(generator=g)
+        state.update(start=start, stop=stop, images=images)
+
+    make_images()
 
     def timed_forward(eng, steps, warmup, sample_clocks):
         """W warm-up + K timed steps of the sharded forward through dist.sharded_logits (forward into the rank's slot
@@ -267,7 +276,7 @@ def run_b200(args) -> None:
 
         out = None
         for _ in range(max(3, warmup)):
-            out = sharded_logits(fwd_local, images, global_batch, classes)
+            out = sharded_logits(fwd_local, state["images"], global_batch, classes, counts=counts)
         barrier()
         sampler = ClockSampler(local) if sample_clocks and rank == 0 else None
         if sampler:
@@ -279,7 +288,7 @@ def run_b200(args) -> None:
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         marks[0].record()
         for i in range(steps):
-            out = sharded_logits(fwd_local, images, global_batch, classes)
+            out = sharded_logits(fwd_local, state["images"], global_batch, classes, counts=counts)
             marks[i + 1].record()
         barrier()
         launches = launch_count() - n0
@@ -293,8 +302,11 @@ def run_b200(args) -> None:
             dist.all_gather(every, ms)
             all_ms = [float(t.item()) for t in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            # the gather's own time on this rank: head GEMM end -> step end (includes waiting for the slowest rank)
-            gather_ms = statistics.median(gather_ev[i].elapsed_time(marks[i + 1]) for i in range(steps))
+            # the gather's own time per rank: head GEMM end -> step end (includes waiting for the slowest rank)
+            gm = torch.tensor([statistics.median(gather_ev[i].elapsed_time(marks[i + 1]) for i in range(steps))], device=dev)
+            every = [torch.zeros_like(gm) for _ in range(world)]
+            dist.all_gather(every, gm)
+            gather_ms = [round(float(t.item()), 4) for t in every]
         clocks = sampler.stop() if sampler else None
         return {"ms_per_step": ms.item(), "per_rank_ms": all_ms, "per_step": per_step, "launches": int(launches),
                 "clocks": clocks, "logits": out, "gather_ms": gather_ms}
@@ -303,10 +315,24 @@ def run_b200(args) -> None:
     other = "fp16" if args.dtype == "bf16" else "bf16"
     engines, runs = {}, {}
     formats = (args.dtype,) if args.quick else (args.dtype, other)
+    balance_log = []
     for dt in formats:
-        engines[dt] = Engine(precision=dt, max_batch=B, device=local, **cfg)
+        engines[dt] = Engine(precision=dt, max_batch=cap, device=local, **cfg)
         engines[dt].load_params(variables)
+        if world > 1 and not args.no_balance and dt == args.dtype:
+            # speed-balanced shards: the GPUs of a box run a few percent apart under the power cap and every step ends in
+            # a collective, so equal shards run at the pace of the slowest.  Two rounds of: 10 lockstep steps -> per-rank
+            # time spent waiting in the gather -> dist.rebalance (shards in proportion to each rank's own rate).
+            for _ in range(2):
+                r = timed_forward(engines[dt], 10, 5, sample_clocks=False)
+                new = rebalance(counts, r["ms_per_step"], r["gather_ms"], cap=cap)
+                balance_log.append({"shards": list(counts), "ms_per_step": round(r["ms_per_step"], 4), "gather_wait_ms": r["gather_ms"]})
+                if new != counts:
+                    counts = new
+                    make_images()
         runs[dt] = timed_forward(engines[dt], args.steps, args.warmup, sample_clocks=(dt == args.dtype))
+    images, start, stop = state["images"], state["start"], state["stop"]
+    B_local = stop - start
     eng, main = engines[args.dtype], runs[args.dtype]
     ms_per_step = main["ms_per_step"]
     value = global_batch / (ms_per_step * 1e-3)
@@ -314,7 +340,7 @@ def run_b200(args) -> None:
     # ---- per-kernel pass (CUDA event before every launch, same stream, same inputs) ----
     prof = {}
     reps = 3
-    scratch = torch.empty((B, classes), dtype=torch.float32, device=dev)
+    scratch = torch.empty((B_local, classes), dtype=torch.float32, device=dev)
     for _ in range(reps):
         for k, (m, c) in eng.profile_forward(images, out=scratch).items():
             pm, pc = prof.get(k, (0.0, 0))
@@ -323,7 +349,7 @@ def run_b200(args) -> None:
     gemm_cats = ["gemm_patch", "gemm_qkv", "gemm_out", "gemm_ff1", "gemm_ff2", "gemm_head"]
     gemm_ms = sum(prof[c][0] for c in gemm_cats)
     gemm_launches = sum(prof[c][1] for c in gemm_cats)
-    gemm_flops = sum(fl[c] for c in gemm_cats) * B
+    gemm_flops = sum(fl[c] for c in gemm_cats) * B_local
     peaks = measured_peaks()
     step_ms_prof = sum(m for m, _ in prof.values())
     # The per-launch pass runs a few forwards with an event before every launch: it measures each
@@ -339,7 +365,7 @@ def run_b200(args) -> None:
     # step k).  N > 1: dist.sharded_apply_stream, the same pipeline around the sharded forward WITH its logits
     # all-gather; every rank reads the gathered [global_batch, classes] logits back to its host.
     vit = ViT(**cfg)
-    host_imgs = [torch.empty((B, S, S, 3), dtype=torch.float32).pin_memory() for _ in range(1 if args.quick else 2)]
+    host_imgs = [torch.empty((B_local, S, S, 3), dtype=torch.float32).pin_memory() for _ in range(1 if args.quick else 2)]
     for h in host_imgs:
         h.copy_(images)
     host_np = [h.numpy() for h in host_imgs]
@@ -348,10 +374,10 @@ def run_b200(args) -> None:
     def e2e_iter(n):
         if world == 1:
             yield from vit.apply_stream(variables, (host_np[i % len(host_np)] for i in range(n)), precision=args.dtype,
-                                        device=local, max_batch=B)
+                                        device=local, max_batch=B_local)
         else:
             for y in sharded_apply_stream(lambda x, out: eng.forward(x, out=out), (host_imgs[i % len(host_imgs)] for i in range(n)),
-                                          global_batch, classes, (S, S, 3), dev):
+                                          global_batch, classes, (S, S, 3), dev, counts=counts):
                 yield y.numpy()
 
     checksum = 0.0
@@ -415,7 +441,7 @@ def run_b200(args) -> None:
         from oracle import vit_torch
         import torch as _t
         _t.set_num_threads(os.cpu_count() or 1)
-        k = min(8 if args.quick else args.parity_images, B)
+        k = min(8 if args.quick else args.parity_images, B_local)
         k_emu = min(64, k)
         pt = vit_torch.tree_to_torch(variables)
         img_cpu = images[:k].cpu().numpy()
@@ -488,7 +514,7 @@ def run_b200(args) -> None:
                 "algorithmic_flops_per_step": gemm_flops,
                 "per_launch": {"flops": gemm_flops / max(1, gemm_launches),
                                "ms": gemm_ms_in_region / max(1, gemm_launches)},
-                "by_epilogue_isolated_tflops": {c: fl[c] * B / (prof[c][0] * 1e-3) / 1e12 for c in gemm_cats
+                "by_epilogue_isolated_tflops": {c: fl[c] * B_local / (prof[c][0] * 1e-3) / 1e12 for c in gemm_cats
                                                 if prof[c][0] > 0},
                 "traffic_note": "dram bytes of ONE FF1 launch (ncu --set full, profiles/); algorithmic 392 MB",
             },
@@ -508,7 +534,12 @@ def run_b200(args) -> None:
         }
         if world > 1:
             line["multi_gpu"] = {"per_rank_ms_per_step": [round(x, 4) for x in main["per_rank_ms"]],
-                                 "rank0_gather_ms_median": main["gather_ms"],
+                                 "per_rank_gather_wait_ms_median": main["gather_ms"],
+                                 "shard_sizes": counts,
+                                 "sharding": ("equal shards" if args.no_balance else
+                                              "speed-balanced from lockstep measurements (dist.rebalance): 2 rounds of 10 steps "
+                                              "before the warm-up"),
+                                 "balance_rounds": balance_log,
                                  "api": "vit_flax_b200.dist.sharded_logits (forward into the rank's slot + in-place all-gather)",
                                  "note": "per-rank = each rank's own event time for the same K steps; every step ends in the "
                                          "all-gather, so ranks run in lockstep with the slowest (power-capped) GPU"}
@@ -537,6 +568,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=64, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step (forward + backward) record")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: equal shards instead of speed-balanced ones")
     ap.add_argument("--quick", action="store_true", help="headline format only, no e2e / train / CPU legs, parity on 8 images "
                                                           "(the strong-scaling runs of profiles/r02_scaling.md)")
     args = ap.parse_args()

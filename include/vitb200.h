@@ -219,6 +219,15 @@ int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const fl
                            void* C, int M, int N, int K, int epilogue,
                            const float* aux, int tokens_per_image, const float* cls, int dtype,
                            float rate, uint64_t key, uint32_t site);
+/* The patch embedding as ONE kernel (vit.py:146-153; csrc/patch_tc.cu): im2col-mode TMA over NHWC fp32 images (no patch
+ * matrix in memory) + tcgen05 GEMM + bias + pos_embedding + class-token rows.  W: the Flax kernel [ph*pw*C, dim] fp32
+ * (packed inside; the model path packs once), pos [T, dim], cls [dim] or NULL (no class token: T = Np), x [batch*T, dim]
+ * fp32 out.  x16 / stats (both or neither): the LayerNorm-fold outputs, stats [batch*T, 2*ceil(dim/256)] float pairs.
+ * Needs pw*C <= 64 and pw*C*4 a multiple of 16 bytes (every /16 patch size); else VITB200_ERR_UNSUPPORTED.            */
+int vitb200_patch_embed_im2col(void* stream, const float* images, const float* W, const float* bias,
+                               const float* pos, const float* cls, float* x, int batch, int H, int W_px, int C,
+                               int ph, int pw, int dim, int dtype, void* x16, float* stats);
+
 /* The LayerNorm-fold epilogues (8..11).  Producers (8, 9): `x16` [M,N] 16-bit and `stats` [M, stats_slots] float pairs
  * are OUTPUTS, stats_slots = 2 * ceil(N / tile columns) (tile columns: 256, or 64 when M <= 256 and N > 256 -- ask
  * vitb200_gemm_tc_ln_slots).  Consumers (10, 11): `stats` / `stats_slots` are those of the GEMM that produced A's rows

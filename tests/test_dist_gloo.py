@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vit_flax_b200.dist import shard_range, sharded_apply_stream, sharded_logits
+from vit_flax_b200.dist import balanced_counts, counts_range, rebalance, shard_range, sharded_apply_stream, sharded_logits
 
 
 def test_shard_range_partitions_the_batch():
@@ -21,6 +21,24 @@ def test_shard_range_partitions_the_batch():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(8, 2, 2)
+
+
+def test_balanced_counts():
+    assert balanced_counts(2048, [1.0] * 8) == [256] * 8
+    c = balanced_counts(512, [1.0, 0.96])                       # a GPU 4 % slower gets 4 % fewer images
+    assert sum(c) == 512 and c == [261, 251]
+    c = balanced_counts(2048, [100, 101, 99, 100, 97, 103, 100, 100])
+    assert sum(c) == 2048 and max(c) - min(c) <= 16 and c[5] == max(c) and c[4] == min(c)
+    assert balanced_counts(7, [1, 1, 1]) == [3, 2, 2]           # leftovers by largest remainder, ties to the lower rank
+    assert [counts_range([3, 2, 2], r) for r in range(3)] == [(0, 3), (3, 5), (5, 7)]
+    with pytest.raises(ValueError):
+        balanced_counts(8, [1.0, 0.0])
+    # lockstep measurement -> new shards: rank 0 idles 0.4 ms of a 10 ms step, i.e. it is 4 % faster
+    c = rebalance([256, 256], 10.0, [0.42, 0.02])
+    assert sum(c) == 512 and c[0] > c[1] and c == [261, 251]
+    assert rebalance(c, 9.8, [0.02, 0.02]) == c                 # balanced: stays put
+    assert rebalance([256] * 4, 10.0, [0.0, 3.0, 0.0, 0.0]) == [231, 331, 231, 231]
+    assert rebalance([256] * 4, 10.0, [0.0, 3.0, 0.0, 0.0], cap=260) == [255, 260, 255, 254]   # capped rank pinned, rest re-divided
 
 
 def _free_port():
@@ -43,6 +61,11 @@ def _worker(rank, world, port, global_batch, q):
 
         got = sharded_logits(forward_local, full[s:e], global_batch, classes)
         ok = torch.allclose(got, full @ w)
+        # explicit, uneven shard sizes (speed-balanced sharding): padded gather + one compaction
+        counts = [global_batch - global_batch // 3, global_batch // 3]
+        s2, e2 = counts_range(counts, rank)
+        got2 = sharded_logits(forward_local, full[s2:e2], global_batch, classes, counts=counts)
+        ok = ok and torch.allclose(got2, full @ w) and tuple(got2.shape) == (global_batch, classes)
         if global_batch % world == 0:
             # the serving loop (host shards in, gathered host logits out, two steps in flight): 5 steps, each with
             # its own inputs, must come back in order
@@ -50,6 +73,10 @@ def _worker(rank, world, port, global_batch, q):
             outs = [y.clone() for y in sharded_apply_stream(forward_local, iter(steps), global_batch, classes, (12,),
                                                             torch.device("cpu"))]
             ok = ok and len(outs) == 5 and all(torch.allclose(y, (full * (i + 1)) @ w) for i, y in enumerate(outs))
+            steps = [full[s2:e2] * (i + 1) for i in range(4)]      # the same loop over speed-balanced (uneven) shards
+            outs = [y.clone() for y in sharded_apply_stream(forward_local, iter(steps), global_batch, classes, (12,),
+                                                            torch.device("cpu"), counts=counts)]
+            ok = ok and len(outs) == 4 and all(torch.allclose(y, (full * (i + 1)) @ w) for i, y in enumerate(outs))
         q.put((rank, ok, tuple(got.shape)))
     finally:
         dist.destroy_process_group()

@@ -415,3 +415,30 @@ def test_layernorm_fold_and_layernorm_kernel_paths_agree(precision, monkeypatch)
             tol = TOL[precision] if precision == "fp16" else bf16_bound(emu, want)
             assert np.abs(out[fold] - want).max() < tol, (fold, batch)
         assert np.abs(out["1"] - out["0"]).max() < (1e-2 if precision == "fp16" else 5e-2)
+
+
+def test_im2col_patch_embedding_and_patchify_paths_agree(monkeypatch):
+    """VITB200_IM2COL=1 embeds patches with ONE kernel (im2col-mode TMA + GEMM + cls / pos, csrc/patch_tc.cu); the default
+    is patchify + the TOKENS GEMM, which is faster on B200 (profiles/r02_patch_embed.md).  Same arithmetic on the same
+    rounded operands (another accumulation order), with and without the LayerNorm fold, at several batch sizes incl. one
+    whose tiles straddle images."""
+    cfg = dict(C2, depth=2)
+    variables = perturb_params(init_params(seed=71, **cfg), seed=72)
+    for batch in (1, 3, 7):
+        img = images_for(cfg, batch, seed=73)
+        x = torch.as_tensor(img, device="cuda")
+        want = oracle_logits(variables, img, cfg)
+        out = {}
+        for fold in ("1", "0"):
+            for i2c in ("1", "0"):
+                monkeypatch.setenv("VITB200_LN_FOLD", fold)
+                monkeypatch.setenv("VITB200_IM2COL", i2c)
+                eng = Engine(precision="fp16", max_batch=batch, **cfg)
+                eng.load_params(variables)
+                n0 = launch_count()
+                out[fold, i2c] = eng.forward(x).cpu().numpy()
+                launches = launch_count() - n0
+                eng.close()
+                assert launches == 4 + (5 if fold == "1" else 7) * 2 - (1 if i2c == "1" else 0), (fold, i2c, launches)
+                assert np.abs(out[fold, i2c] - want).max() < TOL["fp16"]
+        assert np.abs(out["1", "1"] - out["1", "0"]).max() < 5e-3 and np.abs(out["0", "1"] - out["0", "0"]).max() < 5e-3

@@ -545,3 +545,50 @@ def test_gemm_tc_tokens_layernorm_outputs(lib):
     s = stats.double().sum(1)
     assert (s[:, 0] - x.double().sum(1)).abs().max().item() < 1e-2
     assert ((s[:, 1] - (x.double() ** 2).sum(1)).abs() / (x.double() ** 2).sum(1)).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,H,W,ph,pw,D,with_cls,with_ln", [
+    (3, 32, 48, 8, 8, 264, True, True),          # several patch rows per tile, tiles crossing images, ragged D
+    (5, 224, 224, 16, 16, 768, True, True),      # ViT-B/16 geometry: 980 patches = 7.66 tiles of 128
+    (2, 224, 224, 16, 16, 768, False, False),    # SimpleViT-style token layout (no class token), plain outputs
+    (1, 64, 32, 16, 4, 64, True, False),         # pw*C = 12 floats = 48 bytes
+])
+def test_patch_embed_im2col(lib, B, H, W, ph, pw, D, with_cls, with_ln, fmt):
+    """vit.py:146-153 as one kernel: im2col-mode TMA straight from the NHWC fp32 images, GEMM on the rounded pixels and
+    kernel, + bias + pos_embedding, class-token rows, and (fold) the 16-bit copy and row statistics of x."""
+    dt, tdt, _ = DT16[fmt]
+    C = 3
+    rng = np.random.default_rng(B * H + D)
+    img = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    Wk = (rng.standard_normal((ph * pw * C, D)) / np.sqrt(ph * pw * C)).astype(np.float32)
+    bias = rng.standard_normal(D).astype(np.float32)
+    gh, gw = H // ph, W // pw
+    Np = gh * gw
+    T = Np + (1 if with_cls else 0)
+    pos = rng.standard_normal((T, D)).astype(np.float32)
+    cls = rng.standard_normal(D).astype(np.float32)
+    img_d, W_d, bias_d, pos_d, cls_d = dev(img), dev(Wk), dev(bias), dev(pos), dev(cls)
+    x = torch.full((B * T, D), float("nan"), device="cuda")
+    slots = 2 * ((D + 255) // 256)
+    x16 = torch.full((B * T, D), float("nan"), dtype=tdt, device="cuda") if with_ln else None
+    stats = torch.full((B * T, slots, 2), float("nan"), device="cuda") if with_ln else None
+    _lib.check(lib.vitb200_patch_embed_im2col(stream(), img_d.data_ptr(), W_d.data_ptr(), bias_d.data_ptr(), pos_d.data_ptr(),
+                                              cls_d.data_ptr() if with_cls else None, x.data_ptr(), B, H, W, C, ph, pw, D, dt,
+                                              x16.data_ptr() if with_ln else None, stats.data_ptr() if with_ln else None))
+    torch.cuda.synchronize()
+    patches = vit_numpy.patchify(img, ph, pw)                                   # [B, Np, ph*pw*C], (p1 p2 c) order
+    a = torch.as_tensor(patches).to(tdt).double()
+    w = torch.as_tensor(Wk).to(tdt).double()
+    want = a @ w + torch.as_tensor(bias).double()
+    off = 1 if with_cls else 0
+    want = want + torch.as_tensor(pos).double()[off:]
+    got = x.view(B, T, D).cpu().double()
+    assert (got[:, off:] - want).abs().max().item() < 2e-4
+    if with_cls:
+        assert (got[:, 0] - (torch.as_tensor(cls).double() + torch.as_tensor(pos).double()[0])).abs().max().item() < 1e-6
+    if with_ln:
+        assert torch.equal(x16, x.to(tdt))
+        s = stats.double().sum(1)
+        assert (s[:, 0] - x.double().sum(1)).abs().max().item() < 1e-2
+        assert ((s[:, 1] - (x.double() ** 2).sum(1)).abs() / (x.double() ** 2).sum(1)).max().item() < 1e-5

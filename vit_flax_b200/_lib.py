@@ -78,6 +78,7 @@ SIGNATURES = {
     "vitb200_gemm_tc_tokens": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _fp, _i, C.c_float, C.c_uint64, C.c_uint32]),
     "vitb200_gemm_tc_ln": (_i, [_vp, _vp, _vp, _fp, _vp, _i, _i, _i, _i, _fp, _i, _fp, _i, _vp, _fp, _i, _fp, C.c_float]),
     "vitb200_gemm_tc_ln_slots": (_i, [_i, _i]),
+    "vitb200_patch_embed_im2col": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _fp]),
     "vitb200_fold_layernorm": (_i, [_vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _i]),
     "vitb200_gemm_f32": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _i]),
     "vitb200_layernorm": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i]),

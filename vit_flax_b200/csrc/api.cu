@@ -104,6 +104,10 @@ struct vitb200_model {
   bool finalized = false;
   bool head_tc = false;
   bool fold = false;          // LayerNorm folded into the GEMMs around it (inference forward, dropout rates 0)
+  bool im2col = false;        // patch embedding as one im2col-TMA + tcgen05 kernel (patch_tc.cu), else patchify + TOKENS GEMM
+  uint16_t* patch_wt_i2c = nullptr;   // Wt' [dim, ph*64] for that kernel
+  CUtensorMap patch_tm_i2c{};
+  std::map<std::pair<const float*, int>, CUtensorMap> img_maps;   // im2col maps by (images pointer, batch)
   uint64_t dropout_key = 0;   // 'dropout' rng stream (vitb200_set_dropout_key)
 
   // the Dropout instance `site` of this model (rate 0 => off)
@@ -193,6 +197,7 @@ struct vitb200_model {
     };
     free_dense(patch);
     free_dense(head);
+    if (patch_wt_i2c) cudaFree(patch_wt_i2c);
     for (auto& L : layers) { free_dense(L.qkv); free_dense(L.out); free_dense(L.ff1); free_dense(L.ff2); }
     for (auto& g : graphs)
       for (auto& e : g.second.entries)
@@ -368,6 +373,24 @@ __global__ void add_f32_into_f32_kernel(const float* __restrict__ a, float* __re
 
 int forward_head(vitb200_model* m, cudaStream_t st, const ActMaps* am, int batch, float* logits);
 
+// vit.py:146-153 as one kernel (patch_tc.cu): im2col TMA over the caller's images + GEMM + cls / pos placement; `ln` non-null
+// adds the LayerNorm-fold outputs.  The im2col map depends on the images pointer: kept per (pointer, batch), a handful.
+int patch_embed_im2col(vitb200_model* m, cudaStream_t st, const float* images, int batch, const LnFold* ln) {
+  const auto& c = m->cfg;
+  auto key = std::make_pair(images, batch);
+  auto it = m->img_maps.find(key);
+  if (it == m->img_maps.end()) {
+    if (m->img_maps.size() >= 64) m->img_maps.clear();
+    CUtensorMap tm;
+    int rc = make_tmap_im2col_patches(&tm, images, batch, c.image_h, c.image_w, c.channels, c.patch_h, c.patch_w, 128);
+    if (rc) return rc;
+    it = m->img_maps.emplace(key, tm).first;
+  }
+  return launch_patch_embed_im2col(st, it->second, m->patch_tm_i2c, leaf_ptr(m, m->patch.leaf_bias), leaf_ptr(m, m->leaf_pos),
+                                   leaf_ptr(m, m->leaf_cls), m->x.p, batch, m->Np, c.image_w / c.patch_w, c.patch_h, c.patch_w,
+                                   c.channels, c.dim, m->cls_off, m->dt, ln);
+}
+
 // ---- the forward schedule with every PreNorm LayerNorm folded into the GEMMs around it: 4 + 5L launches ----
 // patchify | patch GEMM (TOKENS_LN: x, x16, stats_a) | per layer: to_qkv (LN_STORE_16 on x16 / stats_a) | attention |
 // to_out (RESID_LN: x, x16, stats_b) | FF Dense_0 (LN_GELU_16 on x16 / stats_b) | FF Dense_1 (RESID_LN -> stats_a; plain
@@ -386,13 +409,19 @@ int forward_tc_fold(vitb200_model* m, cudaStream_t st, const float* images, int 
   out_b.stats = in_b.stats = reinterpret_cast<float2*>(m->stats_b.p);
   out_a.slots = out_b.slots = in_a.slots = in_b.slots = 2 * ceil_div(D, cg_d == 64 ? 64 : GEMM_BN);
   in_a.eps = in_b.eps = m->eps;
-  mark(m, st, VITB200_CAT_PATCHIFY);
-  if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
-                            c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
-  mark(m, st, VITB200_CAT_GEMM_PATCH);
-  if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cg_d), &am->c_x, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
-                           R, D, m->K0pad, VITB200_EPI_TOKENS_LN, leaf_ptr(m, m->leaf_pos), T, m->dt, cg_d,
-                           Dropout(), m->cls_off, leaf_ptr(m, m->leaf_cls), out_a))) return rc;
+  // the im2col kernel's statistics slots are 2 per 256-column tile: usable whenever the other producers use the same count
+  if (m->im2col && out_a.slots % (2 * ceil_div(D, GEMM_BN)) == 0 && (reinterpret_cast<uintptr_t>(images) & 15) == 0) {
+    mark(m, st, VITB200_CAT_GEMM_PATCH);
+    if ((rc = patch_embed_im2col(m, st, images, batch, &out_a))) return rc;
+  } else {
+    mark(m, st, VITB200_CAT_PATCHIFY);
+    if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
+                              c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
+    mark(m, st, VITB200_CAT_GEMM_PATCH);
+    if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cg_d), &am->c_x, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+                             R, D, m->K0pad, VITB200_EPI_TOKENS_LN, leaf_ptr(m, m->leaf_pos), T, m->dt, cg_d,
+                             Dropout(), m->cls_off, leaf_ptr(m, m->leaf_cls), out_a))) return rc;
+  }
   for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
     Layer& L = m->layers[l];
     // Residual(PreNorm(Attention))  vit.py:31,39,62-87
@@ -434,16 +463,21 @@ int forward_tc(vitb200_model* m, cudaStream_t st, const float* images, int batch
   // tile mode per GEMM shape (pairs for anything that fills the machine, small tiles otherwise)
   const int cgp = gemm_tc_tile_mode(R, D);
   const int cg_qkv = gemm_tc_tile_mode(R, 3 * I), cg_d = gemm_tc_tile_mode(R, D), cg_ff1 = gemm_tc_tile_mode(R, c.mlp_dim);
-  // vit.py:146  patchify (+ fp32->16-bit cast, zero pad to K0pad) into the token layout: row b*T+cls+t
-  mark(m, st, VITB200_CAT_PATCHIFY);
-  if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
-                            c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
-  // vit.py:147-153  Dense_0 + bias + pos_embedding[t] over all B*T token rows; the class-token row of
-  // every image (t = 0) is cls + pos_embedding[0], written by the same epilogue
-  mark(m, st, VITB200_CAT_GEMM_PATCH);
-  if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), &am->c_x, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
-                             R, D, m->K0pad, VITB200_EPI_TOKENS_F32, leaf_ptr(m, m->leaf_pos), T, m->dt, cgp,
-                             m->drop(c.emb_dropout, 0), m->cls_off, leaf_ptr(m, m->leaf_cls)))) return rc;
+  if (m->im2col && (reinterpret_cast<uintptr_t>(images) & 15) == 0) {
+    mark(m, st, VITB200_CAT_GEMM_PATCH);
+    if ((rc = patch_embed_im2col(m, st, images, batch, nullptr))) return rc;
+  } else {
+    // vit.py:146  patchify (+ fp32->16-bit cast, zero pad to K0pad) into the token layout: row b*T+cls+t
+    mark(m, st, VITB200_CAT_PATCHIFY);
+    if ((rc = launch_patchify(st, images, m->patches_h.p, batch, c.image_h, c.image_w, c.channels,
+                              c.patch_h, c.patch_w, m->K0pad, m->dt, m->nchw, m->cls_off))) return rc;
+    // vit.py:147-153  Dense_0 + bias + pos_embedding[t] over all B*T token rows; the class-token row of
+    // every image (t = 0) is cls + pos_embedding[0], written by the same epilogue
+    mark(m, st, VITB200_CAT_GEMM_PATCH);
+    if ((rc = launch_gemm_tc(st, am->patches, m->patch.map(cgp), &am->c_x, leaf_ptr(m, m->patch.leaf_bias), m->x.p,
+                               R, D, m->K0pad, VITB200_EPI_TOKENS_F32, leaf_ptr(m, m->leaf_pos), T, m->dt, cgp,
+                               m->drop(c.emb_dropout, 0), m->cls_off, leaf_ptr(m, m->leaf_cls)))) return rc;
+  }
   for (int l = 0; l < c.depth; ++l) {   // vit.py:108-110
     Layer& L = m->layers[l];
     // Residual(PreNorm(Attention))  vit.py:31,39,62-87
@@ -612,6 +646,14 @@ int vitb200_create(const vitb200_config* cfg, int device, vitb200_model** out) {
   m->inner = DIM_HEAD * c.heads;
   m->project_out = !(c.heads == 1 && DIM_HEAD == c.dim);             // vit.py:65
   m->head_tc = m->tc && (c.num_classes % 8 == 0);
+  {  // Fused im2col patch embedding (patch_tc.cu): NHWC images whose patch rows are whole 16-byte-aligned TMA runs (every
+     // /16 config).  OPT-IN (VITB200_IM2COL=1): measured on B200 at ViT-B/16 batch 256 it takes 0.29 ms against 0.06 +
+     // 0.15 ms for patchify + the TOKENS GEMM -- an im2col-mode load is one 192-byte request per (patch, patch row), 2.4 M
+     // requests per n-tile pass, and the TMA unit is the bottleneck (profiles/r02_patch_embed.md).
+    const char* e = getenv("VITB200_IM2COL");
+    m->im2col = m->tc && !m->nchw && c.emb_dropout == 0.f && c.patch_h <= 16 &&
+                patch_im2col_supported(c.patch_w, c.channels, c.dim) && (e && e[0] == '1');
+  }
   {  // LayerNorm fold: on by default for the dropout-free inference forward; VITB200_LN_FOLD=0 keeps the LayerNorm kernel (A/B)
     const char* e = getenv("VITB200_LN_FOLD");
     m->fold = m->tc && m->project_out && c.depth > 0 && c.dropout == 0.f && c.emb_dropout == 0.f && !(e && e[0] == '0');
@@ -684,6 +726,13 @@ int vitb200_finalize_params(vitb200_model* m, void* stream) {
       if ((rc = pack_dense(m, L.ff2, st))) return rc;
     }
     if (m->head_tc && (rc = pack_dense(m, m->head, st))) return rc;
+    if (m->im2col) {
+      const auto& c = m->cfg;
+      const int run = c.patch_w * c.channels, kp = c.patch_h * 64;
+      if (!m->patch_wt_i2c) VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->patch_wt_i2c), size_t(c.dim) * kp * sizeof(uint16_t)));
+      if ((rc = launch_pack_weight_im2col(st, m->leaves[m->patch.leaf_kernel].dev, m->patch_wt_i2c, c.dim, c.patch_h, run, m->dt))) return rc;
+      if ((rc = make_tmap_2d(&m->patch_tm_i2c, m->patch_wt_i2c, c.dim, kp, kp, GEMM_BN, m->dt))) return rc;
+    }
     if (m->fold) {
       DevBuf<float> scratch;
       if ((rc = scratch.alloc(size_t(m->cfg.dim) * std::max(3 * m->inner, m->cfg.mlp_dim)))) return rc;
@@ -1206,6 +1255,34 @@ int vitb200_gemm_tc_tokens(void* stream, const void* A, const void* Wt, const fl
   if (!direct && (rc = make_tmap_2d(&tc, C, c_rows, N, N, GEMM_BM, out16 ? dtype : VITB200_DT_F32))) return rc;
   return launch_gemm_tc(static_cast<cudaStream_t>(stream), ta, tb, direct ? nullptr : &tc, bias, C, M, N, K, epilogue,
                         aux, tokens_per_image, dtype, cg, drop, 1, cls);
+}
+
+int vitb200_patch_embed_im2col(void* stream, const float* images, const float* W, const float* bias, const float* pos,
+                               const float* cls, float* x, int batch, int H, int Wd, int C, int ph, int pw, int dim, int dtype,
+                               void* x16, float* stats) {
+  if (!images || !W || !bias || !pos || !x) return fail(VITB200_ERR_INVALID, "patch_embed_im2col: null pointer");
+  if (batch <= 0 || H <= 0 || Wd <= 0 || C <= 0 || ph <= 0 || pw <= 0 || H % ph || Wd % pw)
+    return fail(VITB200_ERR_INVALID, "patch_embed_im2col: bad geometry");
+  if (!patch_im2col_supported(pw, C, dim))
+    return fail(VITB200_ERR_UNSUPPORTED, "patch_embed_im2col: needs pw*C <= 64 floats, a multiple of 16 bytes");
+  if ((x16 == nullptr) != (stats == nullptr)) return fail(VITB200_ERR_INVALID, "patch_embed_im2col: x16 and stats go together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int run = pw * C, kp = ph * 64, gw = Wd / pw, Np = (H / ph) * gw;
+  uint16_t* wt = nullptr;
+  VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wt), size_t(dim) * kp * sizeof(uint16_t), st));
+  CUtensorMap tmi, tmw;
+  int rc = launch_pack_weight_im2col(st, W, wt, dim, ph, run, dtype);
+  if (!rc) rc = make_tmap_2d(&tmw, wt, dim, kp, kp, GEMM_BN, dtype);
+  if (!rc) rc = make_tmap_im2col_patches(&tmi, images, batch, H, Wd, C, ph, pw, 128);
+  LnFold ln;
+  ln.x16 = x16;
+  ln.stats = reinterpret_cast<float2*>(stats);
+  ln.slots = 2 * ceil_div(dim, GEMM_BN);
+  if (!rc && ph > 16) rc = fail(VITB200_ERR_UNSUPPORTED, "patch_embed_im2col: patch height above 16");
+  if (!rc) rc = launch_patch_embed_im2col(st, tmi, tmw, bias, pos, cls, x, batch, Np, gw, ph, pw, C, dim, cls ? 1 : 0, dtype,
+                                          x16 ? &ln : nullptr);
+  cudaFreeAsync(wt, st);
+  return rc;
 }
 
 int vitb200_gemm_tc_ln_slots(int M, int N) {

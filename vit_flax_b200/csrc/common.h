@@ -91,6 +91,9 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols,
 int make_tmap_3d_16(CUtensorMap* out, const void* base, int64_t batch, int64_t rows, int64_t cols,
                     int64_t ld, int box_rows, int dt);
 
+int make_tmap_im2col_patches(CUtensorMap* out, const float* images, int64_t batch, int H, int W, int C, int ph, int pw,
+                             int pixels);
+
 // ---- kernels (host launchers; all enqueue on `stream`, return 0 / <0) -----
 constexpr int GEMM_BM = 128;   // tcgen05 tile rows (A box rows)
 constexpr int GEMM_BN = 256;   // tcgen05 tile cols (Wt box rows)
@@ -145,6 +148,14 @@ int launch_pool_layernorm(cudaStream_t stream, const float* x, const float* scal
                           int out_dtype, float eps = 1e-6f);
 int launch_pack_weight(cudaStream_t stream, const float* W, void* Wt, int K, int N, int Kpad,
                        int dtype);
+// ---- fused patch embedding (patch_tc.cu): im2col TMA + tcgen05 GEMM + cls / pos placement (+ LayerNorm-fold outputs) ----
+bool patch_im2col_supported(int pw, int channels, int dim);
+// W fp32 [ph*pw*C, D] -> Wt' 16-bit [D, ph*64] (k-block p1 = image row p1 of the patch, padded to 64 columns)
+int launch_pack_weight_im2col(cudaStream_t stream, const float* W, void* Wt, int D, int ph, int run, int dtype);
+// tmImg: make_tmap_im2col_patches(images, ..., 128 pixels); tmW: 2-D map over Wt' [D, ph*64] with a 256-row box
+int launch_patch_embed_im2col(cudaStream_t stream, const CUtensorMap& tmImg, const CUtensorMap& tmW, const float* bias,
+                              const float* pos, const float* cls, float* x, int batch, int Np, int gw, int ph, int pw,
+                              int channels, int D, int cls_off, int dtype, const LnFold* ln);
 
 // ---- backward pass (backward.cu); 16-bit buffers are of type `dtype` (VITB200_DT_BF16 / _F16) ----
 int launch_cast16(cudaStream_t stream, const float* x, void* y, int64_t n, int dtype);

@@ -167,6 +167,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// im2col-mode load of an NDHWC tensor (cuTensorMapEncodeIm2col, rank 5): `pixelsPerColumn` output pixels starting at base
+// pixel (w, h, d, n), walked along W, then H, then D, then N inside the map's bounding box of filter origins,
+// `channelsPerPixel` channels from c each; the filter tap (w_off, h_off, d_off) is added to every pixel.  Lands as a dense
+// [pixels, channels] tile.
+__device__ __forceinline__ void tma_load_im2col_5d(uint32_t dst, const void* tmap, uint32_t bar, int32_t c, int32_t w,
+                                                   int32_t h, int32_t d, int32_t n, uint16_t w_off, uint16_t h_off,
+                                                   uint16_t d_off) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], {%8, %9, %10};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "h"(w_off),
+        "h"(h_off), "h"(d_off)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {   // <= N groups may still be reading smem

@@ -19,6 +19,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_encode_once;
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn g_encode_im2col = nullptr;
+std::once_flag g_encode_im2col_once;
 }  // namespace
 
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -110,6 +115,41 @@ int make_tmap_3d_16(CUtensorMap* out, const void* base, int64_t batch, int64_t r
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult " + std::to_string(int(r)));
+  return 0;
+}
+
+// The patch rearrange of vit.py:146 as an im2col-mode TMA map (patch_tc.cu header).  NHWC fp32 images [batch, H, W, C] are
+// described as the 5-D "NDHWC" tensor [batch, gh, ph, gw, pw*C]: depth = the patch row hh, height = the row p1 inside a
+// patch, width = the patch column ww, channels = the pw*C contiguous floats of one patch row.  The filter is ph x 1 x 1
+// (all of H, nothing else), so the box of filter origins is {w in [0, gw), h = 0, d in [0, gh)} and consecutive "pixels"
+// are consecutive patches (ww fastest, then hh, then the image).  One load = `pixels` patches x pw*C floats of patch row
+// h_off, dense.  (A 4-D map with an H traversal stride of ph is the obvious form, but TMA traversal strides stop at 8.)
+int make_tmap_im2col_patches(CUtensorMap* out, const float* images, int64_t batch, int H, int W, int C, int ph, int pw,
+                             int pixels) {
+  std::call_once(g_encode_im2col_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  });
+  if (!g_encode_im2col) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeIm2col entry point unavailable");
+  const int run = pw * C;
+  if ((reinterpret_cast<uintptr_t>(images) & 15) != 0 || (run * 4) % 16 != 0 || run > 256 || pixels < 1 || pixels > 1024 ||
+      ph < 1 || ph > 16 || pw < 1 || H % ph != 0 || W % pw != 0)
+    return fail(VITB200_ERR_INVALID, "im2col patch map: unsupported geometry (pw*C*4 a multiple of 16 bytes, ph <= 16)");
+  const int gw = W / pw, gh = H / ph;
+  cuuint64_t gdim[5] = {cuuint64_t(run), cuuint64_t(gw), cuuint64_t(ph), cuuint64_t(gh), cuuint64_t(batch)};
+  cuuint64_t gstride[4] = {cuuint64_t(run) * 4, cuuint64_t(W) * C * 4, cuuint64_t(ph) * W * C * 4, cuuint64_t(H) * W * C * 4};
+  int lower[3] = {0, 0, 0};               // {W, H, D}
+  int upper[3] = {0, -(ph - 1), 0};       // the filter covers all ph rows of H: its only origin is h = 0
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  CUresult r = g_encode_im2col(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(images), gdim, gstride, lower,
+                               upper, cuuint32_t(run), cuuint32_t(pixels), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult " + std::to_string(int(r)));
   return 0;
 }
 

@@ -10,7 +10,7 @@ staging copy.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -25,17 +25,83 @@ def shard_range(global_batch: int, world_size: int, rank: int) -> Tuple[int, int
     return start, start + base + (1 if rank < rem else 0)
 
 
+def balanced_counts(global_batch: int, rates: Sequence[float]) -> List[int]:
+    """Shard sizes proportional to each rank's measured rate (images/s of its own forward), summing to
+    ``global_batch``.  The GPUs of one box do not run at the same speed under the 1000 W power cap (a few percent
+    apart), and every step ends in a collective: with equal shards all ranks run at the pace of the slowest.  Largest
+    remainders get the leftover images; ties go to the lower rank, so every rank computes the same list."""
+    if global_batch < 0 or not rates or any(not (r > 0) for r in rates):
+        raise ValueError("balanced_counts needs positive rates")
+    total = float(sum(rates))
+    exact = [global_batch * r / total for r in rates]
+    counts = [int(e) for e in exact]
+    order = sorted(range(len(rates)), key=lambda i: (-(exact[i] - counts[i]), i))
+    for i in order[: global_batch - sum(counts)]:
+        counts[i] += 1
+    return counts
+
+
+def rebalance(counts: Sequence[int], step_ms: float, waits_ms: Sequence[float], cap: Optional[int] = None) -> List[int]:
+    """New shard sizes from one lockstep measurement: every step ends in the logits all-gather, so all ranks take
+    ``step_ms`` per step and rank r spends ``waits_ms[r]`` of it inside the gather waiting for the slowest rank.  Its own
+    forward therefore takes ``step_ms - waits_ms[r]`` for ``counts[r]`` images; the global batch is re-divided in
+    proportion to those rates (``balanced_counts``).  Measured in the running loop itself, i.e. in the thermal / power
+    state that matters (a separate calibration burst is not: profiles/r02_scaling.md).  ``cap`` bounds a shard."""
+    if len(counts) != len(waits_ms) or step_ms <= 0:
+        raise ValueError("rebalance needs one wait per rank and a positive step time")
+    rates = [max(1, c) / max(step_ms - w, 0.25 * step_ms) for c, w in zip(counts, waits_ms)]
+    total = int(sum(counts))
+    new = balanced_counts(total, rates)
+    if cap is not None:
+        if cap * len(counts) < total:
+            raise ValueError("cap too small for the global batch")
+        capped = set()
+        while any(c > cap for i, c in enumerate(new) if i not in capped):   # pin the ranks at the cap, re-divide the rest
+            capped |= {i for i, c in enumerate(new) if c >= cap}
+            free = [i for i in range(len(counts)) if i not in capped]
+            rest = balanced_counts(total - cap * len(capped), [rates[i] for i in free]) if free else []
+            new = [cap] * len(counts)
+            for i, c in zip(free, rest):
+                new[i] = c
+    return new
+
+
+def counts_range(counts: Sequence[int], rank: int) -> Tuple[int, int]:
+    """Contiguous shard ``[start, stop)`` of ``rank`` for explicit shard sizes."""
+    start = int(sum(counts[:rank]))
+    return start, start + int(counts[rank])
+
+
+_compact_index = {}
+
+
+def _compaction_index(counts: Tuple[int, ...], per: int, device) -> torch.Tensor:
+    """Row r of the compact [sum(counts), C] logits <- row of the padded [world * per, C] gather buffer."""
+    key = (counts, per, str(device))
+    idx = _compact_index.get(key)
+    if idx is None:
+        idx = torch.cat([torch.arange(n, dtype=torch.int64) + r * per for r, n in enumerate(counts)]).to(device)
+        _compact_index[key] = idx
+    return idx
+
+
 def sharded_logits(forward_local: Callable[[torch.Tensor, torch.Tensor], None],
                    images_local: torch.Tensor, global_batch: int, num_classes: int,
-                   group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+                   group: Optional[dist.ProcessGroup] = None, counts: Optional[Sequence[int]] = None) -> torch.Tensor:
     """Run ``forward_local(images_local, out_slot)`` and all-gather to ``[global_batch, C]``.
 
     ``forward_local`` must write fp32 logits for its shard into ``out_slot`` (a view of
     the gather buffer).  Equal shards use the in-place ``all_gather_into_tensor``;
-    ragged shards fall back to padded slots."""
+    ragged shards (``counts`` given -- see ``balanced_counts`` -- or a batch the world size does not divide) gather
+    padded slots and compact them with one index_select."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    start, stop = shard_range(global_batch, world, rank)
+    if counts is not None:
+        if len(counts) != world or sum(counts) != global_batch:
+            raise ValueError("counts must hold one shard size per rank and sum to global_batch")
+        start, stop = counts_range(counts, rank)
+    else:
+        start, stop = shard_range(global_batch, world, rank)
     if images_local.shape[0] != stop - start:
         raise ValueError(f"rank {rank} expected {stop - start} images, got {images_local.shape[0]}")
     dev = images_local.device
@@ -43,6 +109,14 @@ def sharded_logits(forward_local: Callable[[torch.Tensor, torch.Tensor], None],
         out = torch.empty((global_batch, num_classes), dtype=torch.float32, device=dev)
         forward_local(images_local, out)
         return out
+    if counts is not None and len(set(counts)) > 1:
+        per = max(counts)
+        padded = torch.empty((world, per, num_classes), dtype=torch.float32, device=dev)
+        if stop > start:
+            forward_local(images_local, padded[rank, : stop - start])
+        send = padded[rank] if dist.get_backend(group) == "nccl" else padded[rank].clone()
+        dist.all_gather_into_tensor(padded.view(world * per, num_classes), send, group=group)
+        return padded.view(world * per, num_classes).index_select(0, _compaction_index(tuple(int(c) for c in counts), per, dev))
     if global_batch % world == 0:
         out = torch.empty((global_batch, num_classes), dtype=torch.float32, device=dev)
         slot = out[start:stop]
@@ -79,7 +153,7 @@ def all_reduce_grads(grads_flat: torch.Tensor, group: Optional[dist.ProcessGroup
 
 def sharded_apply_stream(forward_local: Callable[[torch.Tensor, torch.Tensor], None], host_batches,
                          global_batch: int, num_classes: int, image_shape: Tuple[int, ...], device: torch.device,
-                         group: Optional[dist.ProcessGroup] = None):
+                         group: Optional[dist.ProcessGroup] = None, counts: Optional[Sequence[int]] = None):
     """Serving loop of the sharded forward, end to end: iterate this rank's HOST shards (pinned float32 tensors
     ``[B/G, *image_shape]``) and yield the gathered HOST logits ``[global_batch, C]`` of every step, in order.
 
@@ -90,16 +164,26 @@ def sharded_apply_stream(forward_local: Callable[[torch.Tensor, torch.Tensor], N
     buffers re-used two steps later."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    start, stop = shard_range(global_batch, world, rank)
-    if global_batch % world != 0:
-        raise ValueError("sharded_apply_stream needs equal shards (global_batch divisible by the world size)")
+    uneven = counts is not None and len(set(counts)) > 1
+    if counts is not None:
+        if len(counts) != world or sum(counts) != global_batch:
+            raise ValueError("counts must hold one shard size per rank and sum to global_batch")
+        start, stop = counts_range(counts, rank)
+    else:
+        start, stop = shard_range(global_batch, world, rank)
+        if global_batch % world != 0:
+            raise ValueError("sharded_apply_stream needs equal shards or explicit counts")
     local = stop - start
+    per = max(counts) if uneven else local
+    index = _compaction_index(tuple(int(c) for c in counts), per, device) if uneven else None
     cuda = device.type == "cuda"
     main = torch.cuda.current_stream(device) if cuda else None
     copy_s = torch.cuda.Stream(device) if cuda else None
     out_s = torch.cuda.Stream(device) if cuda else None
     img = [torch.empty((local,) + tuple(image_shape), dtype=torch.float32, device=device) for _ in range(2)]
-    gath = [torch.empty((global_batch, num_classes), dtype=torch.float32, device=device) for _ in range(2)]
+    gath = [torch.empty((world * per if uneven else global_batch, num_classes), dtype=torch.float32, device=device)
+            for _ in range(2)]
+    compact = [torch.empty((global_batch, num_classes), dtype=torch.float32, device=device) for _ in range(2)] if uneven else gath
     host = [torch.empty((global_batch, num_classes), dtype=torch.float32, pin_memory=cuda) for _ in range(2)]
     ev = lambda: torch.cuda.Event() if cuda else None
     h2d_done, fwd_done, d2h_done = [ev(), ev()], [ev(), ev()], [ev(), ev()]
@@ -127,18 +211,24 @@ def sharded_apply_stream(forward_local: Callable[[torch.Tensor, torch.Tensor], N
                 main.wait_event(d2h_done[s])                # its gathered logits have left for the host
         else:
             img[s].copy_(shard)
-        slot = gath[s][start:stop]
-        forward_local(img[s], slot)
-        if world > 1:
-            dist.all_gather_into_tensor(gath[s], slot if nccl else slot.clone(), group=group)
+        if uneven:      # padded slots of `per` rows, compacted on the device before the read-back
+            forward_local(img[s], gath[s][rank * per: rank * per + local])
+            send = gath[s][rank * per: (rank + 1) * per]
+            dist.all_gather_into_tensor(gath[s], send if nccl else send.clone(), group=group)
+            torch.index_select(gath[s], 0, index, out=compact[s])
+        else:
+            slot = gath[s][start:stop]
+            forward_local(img[s], slot)
+            if world > 1:
+                dist.all_gather_into_tensor(gath[s], slot if nccl else slot.clone(), group=group)
         if cuda:
             fwd_done[s].record(main)
             with torch.cuda.stream(out_s):
                 out_s.wait_event(fwd_done[s])
-                host[s].copy_(gath[s], non_blocking=True)
+                host[s].copy_(compact[s], non_blocking=True)
                 d2h_done[s].record(out_s)
         else:
-            host[s].copy_(gath[s])
+            host[s].copy_(compact[s])
         used[s] = True
         pending.append(s)
         k += 1
