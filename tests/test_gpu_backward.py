@@ -49,15 +49,16 @@ def rel_err(got, want):
 @pytest.mark.parametrize("batch,T,heads", [(2, 197, 3), (1, 208, 1), (3, 64, 2), (2, 17, 2), (1, 100, 1), (40, 197, 12),
                                            (2, 257, 2), (1, 1025, 1), (3, 300, 2), (2, 209, 1)])
 @pytest.mark.parametrize("fmt", ["fp16", "bf16"])
-@pytest.mark.parametrize("impl", ["auto", "flash"])
+@pytest.mark.parametrize("impl", ["auto", "flash", "hmma"])
 def test_attention_bwd(lib, batch, T, heads, fmt, impl, monkeypatch):
-    """Adjoint of vit.py:69-79 per (image, head): dq, dk, dv from (q, k, v, d_out), all 16-bit.  auto = the
-    shared-memory-resident kernel up to T = 208 and the streamed (flash-style) kernels beyond; flash forces the
-    latter at every shape, so both implementations are checked wherever both exist."""
-    if impl == "flash":
+    """Adjoint of vit.py:69-79 per (image, head): dq, dk, dv from (q, k, v, d_out), all 16-bit.  auto = the tcgen05
+    kernel (attention_bwd_tc5.cu; the row log-sum-exp it needs comes from the statistics kernel here, from the forward
+    in the model path) up to T = 208 and the streamed (flash-style) kernels beyond; flash forces the latter at every
+    shape, hmma the first shared-memory-resident mma.sync kernel: all implementations are checked wherever they exist."""
+    if impl in ("flash", "hmma"):
         if T > 208:
             pytest.skip("auto already runs the streamed kernels here")
-        monkeypatch.setenv("VITB200_ATTN_BWD", "flash")
+        monkeypatch.setenv("VITB200_ATTN_BWD", impl)
     else:
         monkeypatch.delenv("VITB200_ATTN_BWD", raising=False)
     dt, tdt = DT16[fmt]

@@ -168,6 +168,7 @@ struct vitb200_model {
   // training (train_forward / backward): activations kept per layer, gradient workspace, leaf gradients
   struct TrainLayer {
     DevBuf<uint16_t> xn1, qkv, o, xn2, pre;   // pre: [2 * rows_cap, mlp] -- FF pre-activation, then its GELU (hid)
+    DevBuf<float> lse;                        // attention row log-sum-exp [batch*heads, T] (T <= 208: the tcgen05 adjoint)
     uint16_t* hid = nullptr;
   };
   struct TrainState {
@@ -1018,6 +1019,7 @@ int ensure_train(vitb200_model* m, cudaStream_t st) {
   for (auto& L : ts->layers) {
     if ((rc = L.xn1.alloc(R * D)) || (rc = L.qkv.alloc(R * 3 * I)) || (rc = L.o.alloc(R * I)) ||
         (rc = L.xn2.alloc(R * D)) || (rc = L.pre.alloc(2 * size_t(ts->rows_cap) * H))) return rc;
+    if (attention_tc5_supports(m->T) && (rc = L.lse.alloc(B * size_t(c.heads) * m->T))) return rc;
     L.hid = L.pre.p + size_t(ts->rows_cap) * H;
   }
   if ((rc = ts->dx.alloc(R * D)) || (rc = ts->pooled_ln.alloc(B * D)) || (rc = ts->dpl.alloc(B * D))) return rc;
@@ -1079,7 +1081,7 @@ int vitb200_train_forward(vitb200_model* m, void* stream, const float* images, i
     // x1 = x0 + to_out(attention(to_qkv(LN1(x0))));  x0 stays behind as the saved LayerNorm input
     if ((rc = launch_layernorm(st, x0, leaf_ptr(m, L.ln1_scale), leaf_ptr(m, L.ln1_bias), S.xn1.p, R, D, m->dt, m->eps, x1))) return rc;
     if ((rc = gemm16(m, st, S.xn1.p, R, D, L.qkv.wt, L.qkv.Kpad, 3 * I, S.qkv.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
-    if ((rc = launch_attention_tc(st, S.qkv.p, S.o.p, batch, T, c.heads, m->dt))) return rc;
+    if ((rc = launch_attention_tc(st, S.qkv.p, S.o.p, batch, T, c.heads, m->dt, S.lse.p))) return rc;
     if ((rc = gemm16(m, st, S.o.p, R, I, L.out.wt, L.out.Kpad, D, x1, R, VITB200_EPI_BIAS_RESID_F32, leaf_ptr(m, L.out.leaf_bias),
                      nullptr, 0, nullptr, m->drop(c.dropout, 1 + 3 * l)))) return rc;
     // x2 = x1 + ff2(gelu(ff1(LN2(x1)))), the pre-activation kept for gelu'
@@ -1157,7 +1159,7 @@ int vitb200_backward(vitb200_model* m, void* stream, const float* dlogits, int b
     // ---- x1 = x0 + to_out(attention(to_qkv(LN1(x0))))   (vit.py:39,62-87) ----
     if ((rc = gemm16(m, st, ts.dy16.p, R, D, L.out.wf, D, I, ts.do16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.o.p, I, ts.dy16.p, D, R, grad_ptr(m, L.out.leaf_kernel), I))) return rc;
-    if ((rc = launch_attention_bwd(st, S.qkv.p, S.o.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt, ts.attn_ws.p))) return rc;
+    if ((rc = launch_attention_bwd(st, S.qkv.p, S.o.p, ts.do16.p, ts.dqkv16.p, batch, T, c.heads, dt, ts.attn_ws.p, S.lse.p))) return rc;
     if ((rc = gemm16(m, st, ts.dqkv16.p, R, 3 * I, L.qkv.wf, 3 * I, D, ts.dxn16.p, R, VITB200_EPI_STORE_16, nullptr))) return rc;
     if ((rc = wgrad(m, st, S.xn1.p, D, ts.dqkv16.p, 3 * I, R, grad_ptr(m, L.qkv.leaf_kernel), D))) return rc;
     // its dx is the cotangent of the previous layer's FF Dense_1 output (layer 0: of the token embedding, handled below)

@@ -243,7 +243,7 @@ static int launch_attention_t(cudaStream_t stream, const uint16_t* qkv, uint16_t
 }
 
 int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads,
-                        int dtype) {
+                        int dtype, float* lse) {
   if (batch <= 0 || T <= 0 || heads <= 0)
     return fail(VITB200_ERR_INVALID, "attention_tc: empty problem");
   // VITB200_ATTENTION=hmma forces the mma.sync generation (A/B tests); default: the tcgen05
@@ -251,7 +251,8 @@ int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int bat
   const char* force = getenv("VITB200_ATTENTION");
   const bool want_hmma = force && force[0] == 'h';
   if (!want_hmma && attention_tc5_supports(T))
-    return launch_attention_tc5(stream, qkv, out, batch, T, heads, dtype);
+    return launch_attention_tc5(stream, qkv, out, batch, T, heads, dtype, lse);
+  if (lse != nullptr) return fail(VITB200_ERR_UNSUPPORTED, "attention_tc: the row log-sum-exp output needs the T <= 208 tcgen05 kernel");
   if (!want_hmma) return launch_attention_tc5m(stream, qkv, out, batch, T, heads, dtype);
   if (int64_t(batch) * heads > 65535)
     return fail(VITB200_ERR_INVALID, "attention_tc: batch*heads exceeds grid.y limit; chunk the batch");

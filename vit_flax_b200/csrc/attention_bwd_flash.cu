@@ -310,6 +310,21 @@ dq_convert_kernel(const float* __restrict__ dq_acc, uint16_t* __restrict__ dqkv,
 
 }  // namespace
 
+int launch_attention_bwd_stats(cudaStream_t st, const void* qkv, const void* o_fwd, const void* d_out, float* lse2, float* dsum,
+                               int batch, int T, int heads, int dtype) {
+  if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd_stats: empty problem");
+  if (int64_t(batch) * heads > 65535) return fail(VITB200_ERR_INVALID, "attention_bwd_stats: batch * heads exceeds grid.y");
+  const dim3 grid(unsigned((T + TILE - 1) / TILE), unsigned(batch * heads));
+  const uint16_t* q16 = static_cast<const uint16_t*>(qkv);
+  const uint16_t* o16 = static_cast<const uint16_t*>(o_fwd);
+  const uint16_t* d16 = static_cast<const uint16_t*>(d_out);
+  if (dtype == DT_F16) attn_bwd_stats_kernel<DT_F16><<<grid, 128, 0, st>>>(q16, o16, d16, lse2, dsum, T, heads);
+  else if (dtype == DT_BF16) attn_bwd_stats_kernel<DT_BF16><<<grid, 128, 0, st>>>(q16, o16, d16, lse2, dsum, T, heads);
+  else return fail(VITB200_ERR_INVALID, "attention_bwd_stats: dtype must be bf16 or fp16");
+  VB_LAUNCH_CHECK("attn_bwd_stats_kernel");
+  return 0;
+}
+
 size_t attention_bwd_flash_workspace_floats(int batch, int T, int heads) {
   // lse2 + D per (image, head, token), fp32 dQ accumulator [batch * T, heads * 64]
   return 2 * size_t(round_up(int64_t(batch) * heads * T, 64)) + size_t(batch) * T * heads * DH;

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT, 1)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I], box 128 rows
                      const __grid_constant__ CUtensorMap tmKV,   // qkv [B,T,3I], box KP rows
                      const __grid_constant__ CUtensorMap tmO,    // out [B,T,I],  box 128 rows
-                     int T, int heads, int nqt, int items, int turns) {
+                     int T, int heads, int nqt, int items, int turns, float* __restrict__ lse_out) {
   using L = Smem<KP>;
   // TMEM columns: slot s holds S (fp32, KP columns) then P (16-bit pairs, KP/2 columns) of the
   // item in flight on it; one O accumulator (64 columns) is shared by both slots.
@@ -382,6 +382,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
         float l0, l1;
         unpack_f32x2(add_f32x2(la, lb), l0, l1);
         inv_sh[(i & 3) * 128 + row] = 1.0f / (l0 + l1);   // for the epilogue warps (ordered by p_ready)
+        // training: the row's log-sum-exp in the log2 domain, lse2 = log2 sum_j exp2(s_ij sl2), which lets the adjoint
+        // (attention_bwd_tc5.cu) rebuild P block by block without a row maximum
+        if (lse_out != nullptr && qt * QT + row < T) lse_out[int64_t(bh) * T + qt * QT + row] = __log2f(l0 + l1) - mneg;
         tmem_st_wait();
         if (turns == 1 && lane == 0) mbar_arrive(xu_done);
       } else if (turns) {
@@ -472,7 +475,7 @@ int attn_turns() {
 }
 
 template <int kDT, int KP, int kPoly>
-int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
+int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
   using L = Smem<KP>;
   static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
   if (bool& configured = configured_on.here(); !configured) {
@@ -492,7 +495,7 @@ int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
   const int items = int(items64);
   const int grid = items < sm_count() ? items : sm_count();
   VB_CUDA(launch_kernel(attention_tc5_kernel<kDT, KP, kPoly>, dim3(grid), dim3(NT), L::TOTAL, stream, 1,
-                        tq, tkv, to, T, heads, nqt, items, attn_turns()));
+                        tq, tkv, to, T, heads, nqt, items, attn_turns(), lse));
   VB_LAUNCH_CHECK("attention_tc5_kernel");
   return 0;
 }
@@ -508,18 +511,18 @@ int poly_quarters() {
 }
 
 template <int kDT, int kPoly>
-int launch_poly(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
-  if (T <= 64) return launch_kp<kDT, 64, kPoly>(stream, qkv, out, batch, T, heads);
-  if (T <= 128) return launch_kp<kDT, 128, kPoly>(stream, qkv, out, batch, T, heads);
-  return launch_kp<kDT, 208, kPoly>(stream, qkv, out, batch, T, heads);
+int launch_poly(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
+  if (T <= 64) return launch_kp<kDT, 64, kPoly>(stream, qkv, out, batch, T, heads, lse);
+  if (T <= 128) return launch_kp<kDT, 128, kPoly>(stream, qkv, out, batch, T, heads, lse);
+  return launch_kp<kDT, 208, kPoly>(stream, qkv, out, batch, T, heads, lse);
 }
 
 template <int kDT>
-int launch_dt(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
+int launch_dt(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
   switch (poly_quarters()) {
-    case 0: return launch_poly<kDT, 0>(stream, qkv, out, batch, T, heads);
-    case 2: return launch_poly<kDT, 2>(stream, qkv, out, batch, T, heads);
-    default: return launch_poly<kDT, 1>(stream, qkv, out, batch, T, heads);
+    case 0: return launch_poly<kDT, 0>(stream, qkv, out, batch, T, heads, lse);
+    case 2: return launch_poly<kDT, 2>(stream, qkv, out, batch, T, heads, lse);
+    default: return launch_poly<kDT, 1>(stream, qkv, out, batch, T, heads, lse);
   }
 }
 
@@ -536,11 +539,11 @@ namespace vb {
 bool attention_tc5_supports(int T) { return T >= 1 && T <= 208; }
 
 int launch_attention_tc5(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads,
-                         int dtype) {
+                         int dtype, float* lse) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention: empty problem");
   if (!attention_tc5_supports(T)) return fail(VITB200_ERR_UNSUPPORTED, "attention_tc5: T > 208");
-  if (dtype == DT_BF16) return launch_dt<DT_BF16>(stream, qkv, out, batch, T, heads);
-  if (dtype == DT_F16) return launch_dt<DT_F16>(stream, qkv, out, batch, T, heads);
+  if (dtype == DT_BF16) return launch_dt<DT_BF16>(stream, qkv, out, batch, T, heads, lse);
+  if (dtype == DT_F16) return launch_dt<DT_F16>(stream, qkv, out, batch, T, heads, lse);
   return fail(VITB200_ERR_INVALID, "attention: dtype must be bf16 or fp16");
 }
 

@@ -907,18 +907,33 @@ int launch_token_grads(cudaStream_t st, const float* dx, float* dpos, float* dcl
 
 int attention_bwd_max_tokens() { return ABW_MAX_T; }
 
-// 0 = the shared-memory-resident kernel when T <= 208 and the streamed one beyond (default), 1 = always streamed
-// (VITB200_ATTN_BWD=flash, A/B tests)
+// Default: the tcgen05 kernel (attention_bwd_tc5.cu) when T <= 208 and the streamed kernels beyond.  VITB200_ATTN_BWD=flash
+// forces the streamed ones everywhere, =hmma the first, shared-memory-resident mma.sync kernel (A/B tests).
 static int attn_bwd_force_flash() {
   const char* e = getenv("VITB200_ATTN_BWD");
   return e && e[0] == 'f';
+}
+static int attn_bwd_force_hmma() {
+  const char* e = getenv("VITB200_ATTN_BWD");
+  return e && e[0] == 'h';
 }
 
 bool attention_bwd_needs_workspace(int T) { return T > ABW_MAX_T || attn_bwd_force_flash(); }
 
 int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv, int batch, int T,
-                         int heads, int dtype, float* workspace) {
+                         int heads, int dtype, float* workspace, const float* lse2) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
+  if (!attention_bwd_needs_workspace(T) && !attn_bwd_force_hmma() && attention_bwd_tc5_supports(T)) {
+    if (lse2 != nullptr) return launch_attention_bwd_tc5(st, qkv, o_fwd, d_out, dqkv, lse2, batch, T, heads, dtype);
+    // no log-sum-exp from the forward (the per-kernel entry point): the streamed statistics kernel makes it first
+    const size_t n = size_t(round_up(int64_t(batch) * heads * T, 64));
+    float* ws = nullptr;
+    VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * n * sizeof(float), st));
+    int rc = launch_attention_bwd_stats(st, qkv, o_fwd, d_out, ws, ws + n, batch, T, heads, dtype);
+    if (!rc) rc = launch_attention_bwd_tc5(st, qkv, o_fwd, d_out, dqkv, ws, batch, T, heads, dtype);
+    cudaFreeAsync(ws, st);
+    return rc;
+  }
   if (attention_bwd_needs_workspace(T)) {
     if (workspace != nullptr) return launch_attention_bwd_flash(st, qkv, o_fwd, d_out, dqkv, workspace, batch, T, heads, dtype);
     float* ws = nullptr;                     // per-kernel entry point: stream-ordered scratch

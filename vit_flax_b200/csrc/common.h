@@ -129,11 +129,12 @@ int launch_gemm_f32(cudaStream_t stream, const float* A, const float* W, const f
 int launch_layernorm(cudaStream_t stream, const float* x, const float* scale, const float* bias,
                      void* y, int rows, int dim, int out_dtype, float eps = 1e-6f, float* copy = nullptr);
 // `copy` (training): the kernel also writes x to `copy`, the residual buffer the following GEMM adds into
+// `lse` (optional, T <= 208 only): [batch*heads, T] fp32, the row log-sum-exp in the log2 domain, kept for the adjoint
 int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
-                        int heads, int dtype);
+                        int heads, int dtype, float* lse = nullptr);
 bool attention_tc5_supports(int T);
 int launch_attention_tc5(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
-                         int heads, int dtype);
+                         int heads, int dtype, float* lse = nullptr);
 // tcgen05 kernel for T > 208: streamed key blocks, online softmax (attention_tc5m.cu)
 int launch_attention_tc5m(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
                           int heads, int dtype);
@@ -190,7 +191,15 @@ int attention_bwd_max_tokens();
 // streamed kernels of attention_bwd_flash.cu, which need `workspace` (attention_bwd_flash_workspace_floats floats;
 // null = stream-ordered scratch allocated per call)
 int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
-                         int batch, int T, int heads, int dtype, float* workspace = nullptr);
+                         int batch, int T, int heads, int dtype, float* workspace = nullptr, const float* lse2 = nullptr);
+// `lse2` (the forward's row log-sum-exp, launch_attention_tc's `lse`): with it and T <= 208 the adjoint runs on tcgen05
+// (attention_bwd_tc5.cu); without it the per-kernel entry point computes it first (statistics kernel, stream-ordered scratch)
+bool attention_bwd_tc5_supports(int T);
+int launch_attention_bwd_tc5(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
+                             const float* lse2, int batch, int T, int heads, int dtype);
+// lse2 [batch*heads, T] (and dsum, same shape) by the streamed statistics kernel of attention_bwd_flash.cu
+int launch_attention_bwd_stats(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, float* lse2,
+                               float* dsum, int batch, int T, int heads, int dtype);
 bool attention_bwd_needs_workspace(int T);
 size_t attention_bwd_flash_workspace_floats(int batch, int T, int heads);
 int launch_attention_bwd_flash(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
