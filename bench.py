@@ -247,7 +247,7 @@ def run_b200(args) -> None:
 
     # ---- shards (N > 1): equal to begin with; `balance()` below re-divides the global batch from lockstep measurements ----
     counts = None if world == 1 else [B] * world
-    cap = B if world == 1 or args.no_balance else B + max(8, B // 8)       # engine capacity: room for a faster rank
+    cap = B if world == 1 or not args.balance else B + max(8, B // 8)       # engine capacity: room for a faster rank
     g = torch.Generator(device=dev)
     state = {}
 
@@ -319,7 +319,7 @@ def run_b200(args) -> None:
     for dt in formats:
         engines[dt] = Engine(precision=dt, max_batch=cap, device=local, **cfg)
         engines[dt].load_params(variables)
-        if world > 1 and not args.no_balance and dt == args.dtype:
+        if world > 1 and args.balance and dt == args.dtype:
             # speed-balanced shards: the GPUs of a box run a few percent apart under the power cap and every step ends in
             # a collective, so equal shards run at the pace of the slowest.  Two rounds of: 10 lockstep steps -> per-rank
             # time spent waiting in the gather -> dist.rebalance (shards in proportion to each rank's own rate).
@@ -536,7 +536,7 @@ def run_b200(args) -> None:
             line["multi_gpu"] = {"per_rank_ms_per_step": [round(x, 4) for x in main["per_rank_ms"]],
                                  "per_rank_gather_wait_ms_median": main["gather_ms"],
                                  "shard_sizes": counts,
-                                 "sharding": ("equal shards" if args.no_balance else
+                                 "sharding": ("equal shards" if not args.balance else
                                               "speed-balanced from lockstep measurements (dist.rebalance): 2 rounds of 10 steps "
                                               "before the warm-up"),
                                  "balance_rounds": balance_log,
@@ -568,7 +568,10 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=64, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step (forward + backward) record")
-    ap.add_argument("--no-balance", action="store_true", help="N > 1: equal shards instead of speed-balanced ones")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: re-divide the global batch from lockstep measurements (dist.rebalance).  Off by default: at "
+                         "batch 256 the 591 GEMM tiles of ViT-B/16 are exactly 8 waves of 74 CTA pairs, and moving three images "
+                         "to a faster GPU costs it a ninth wave (profiles/r02_scaling.md)")
     ap.add_argument("--quick", action="store_true", help="headline format only, no e2e / train / CPU legs, parity on 8 images "
                                                           "(the strong-scaling runs of profiles/r02_scaling.md)")
     args = ap.parse_args()
