@@ -19,11 +19,17 @@
 //   dV_k += P^T dO_q,  dK_k += dS^T Q_q   accumulate over the query tiles in TMEM (64 columns each)
 //   dQ_q += dS K_k                        accumulates over the key tiles in TMEM (64 columns per query tile)
 //
+// S and dP of a block are computed in two 64-key halves with their own barriers: the halves ARE the double buffer -- the
+// math warps work on one half (and release it as soon as it is in registers) while the other, or the next block's, is
+// computed; the MMA thread issues the next block's halves ahead of this block's dV / dK / dQ, and the dS tile is
+// double-buffered, so neither side waits for the other's long phase.
 // TMEM: S 128 + dP 128 + dV 64 + dK 64 + dQ 2 x 64 = 512 columns.  The softmax is NOT recomputed from scratch: the row
 // log-sum-exp comes from the forward kernel (attention_tc5 writes it when asked), so no pass needs a row maximum and the
 // blocks are independent.  Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 math (thread = query row; the two
 // warps of a lane quarter split the block's key columns), 12..15 epilogue (dK / dV per key tile, dQ per item -> 16-bit
 // rows of dqkv).  Bound: the XU pipe -- one ex2 and two fp32->16-bit packs per score, 16 cycles per score pair per SMSP.
+#include <type_traits>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -38,7 +44,7 @@ constexpr int IN_BYTES = ROWS_MAX * 128;     // 26 KB per operand
 constexpr int ATOM_BYTES = BT * 128;         // 128 rows x 64 keys of 16 bits
 constexpr int OFF_Q = 0, OFF_K = IN_BYTES, OFF_V = 2 * IN_BYTES, OFF_DO = 3 * IN_BYTES;
 constexpr int OFF_P = 4 * IN_BYTES, OFF_DS = OFF_P + 2 * ATOM_BYTES;
-constexpr int OFF_BAR = OFF_DS + 2 * ATOM_BYTES;
+constexpr int OFF_BAR = OFF_DS + 4 * ATOM_BYTES;      // two dS tiles (consecutive blocks alternate), one P tile
 constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
 constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;   // TMEM columns
 
@@ -53,10 +59,11 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base + OFF_Q, sK = base + OFF_K, sV = base + OFF_V, sDO = base + OFF_DO;
   const uint32_t sP = base + OFF_P, sDS = base + OFF_DS, bars = base + OFF_BAR;
-  const uint32_t in_full = bars, in_empty = bars + 8, sdp_ready = bars + 16, sdp_free = bars + 24, p_ready = bars + 32,
-                 p_free = bars + 40, ds_ready = bars + 48, ds_free = bars + 56, dkv_ready = bars + 64, dkv_free = bars + 72,
-                 dq_ready = bars + 80, dq_free = bars + 88, tmem_slot = bars + 96;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + 96);
+  const uint32_t in_full = bars, in_empty = bars + 8, pds_ready = bars + 16, p_free = bars + 24,
+                 ds_free0 = bars + 32 /* [2] */, dkv_ready = bars + 48, dkv_free = bars + 56, dq_ready = bars + 64,
+                 dq_free = bars + 72, sdp_ready0 = bars + 80 /* [2]: per 64-key half of a block */,
+                 sdp_free0 = bars + 96 /* [2] */, tmem_slot = bars + 112;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = heads * DH;
@@ -67,9 +74,10 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmDO); }
   if (warp == 1 && lane == 0) {
     mbar_init(in_full, 1);   mbar_init(in_empty, 1);
-    mbar_init(sdp_ready, 1); mbar_init(sdp_free, 8);
-    mbar_init(p_ready, 8);   mbar_init(p_free, 1);
-    mbar_init(ds_ready, 8);  mbar_init(ds_free, 1);
+    mbar_init(sdp_ready0, 1); mbar_init(sdp_ready0 + 8, 1);
+    mbar_init(sdp_free0, 8);  mbar_init(sdp_free0 + 8, 8);
+    mbar_init(pds_ready, 8); mbar_init(p_free, 1);
+    mbar_init(ds_free0, 1);  mbar_init(ds_free0 + 8, 1);
     mbar_init(dkv_ready, 1); mbar_init(dkv_free, 4);
     mbar_init(dq_ready, 1);  mbar_init(dq_free, 4);
     fence_barrier_init();
@@ -102,50 +110,61 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
     if (lane == 0) {
       constexpr int fmt = kDT == DT_F16 ? 0 : 1;
       const uint32_t d_s = tmem_base + COL_S, d_dp = tmem_base + COL_DP, d_dv = tmem_base + COL_DV, d_dk = tmem_base + COL_DK;
+      constexpr uint32_t idesc_t = umma_idesc_16(BT, DH, fmt, 1, 1);          // A and B MN-major: dV, dK
+      constexpr uint32_t idesc_q = umma_idesc_16(BT, DH, fmt, 1, 0);          // A K-major, B MN-major: dQ
+      // S = Q_q K_k^T and dP = dO_q V_k^T of block (kt, qt), in two 64-key halves with their own barriers: the halves are
+      // the double buffer -- the math warps work on one while the other is computed, with no extra TMEM
+      auto issue_half = [&](int kt, int qt, int hf, uint32_t bph) {
+        const int nkh = max(0, min(64, ext(kt) - 64 * hf));                   // keys of this half: 64, 16 (T = 197 tail) or 0
+        mbar_wait(sdp_free0 + 8u * hf, bph ^ 1u);
+        if (nkh > 0) {
+          const uint32_t k0 = sK + kt * ATOM_BYTES + hf * 8192, v0 = sV + kt * ATOM_BYTES + hf * 8192;
+          const uint32_t q0 = sQ + qt * ATOM_BYTES, do0 = sDO + qt * ATOM_BYTES;
+          const uint32_t idesc_s = umma_idesc_16(BT, nkh, fmt, 0, 0);         // [128 q] x [nkh keys], both K-major
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16_ss<1>(d_s + 64 * hf, umma_desc_k_sw128(q0 + k * 32), umma_desc_k_sw128(k0 + k * 32), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16_ss<1>(d_dp + 64 * hf, umma_desc_k_sw128(do0 + k * 32), umma_desc_k_sw128(v0 + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(sdp_ready0 + 8u * hf);
+      };
       int it = 0, blk = 0, kti = 0;
+      const int nb = ntile * ntile;                        // blocks per item, key tile outermost
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         mbar_wait(in_full, uint32_t(it & 1));
-        for (int kt = 0; kt < ntile; ++kt, ++kti) {
-          const int nk = ext(kt);
-          const uint32_t k0 = sK + kt * ATOM_BYTES, v0 = sV + kt * ATOM_BYTES;
-          const uint32_t idesc_s = umma_idesc_16(BT, nk, fmt, 0, 0);           // [128 q] x [nk keys], both K-major
-          for (int qt = 0; qt < ntile; ++qt, ++blk) {
-            const int nq = ext(qt);
-            const uint32_t q0 = sQ + qt * ATOM_BYTES, do0 = sDO + qt * ATOM_BYTES;
-            const uint32_t bph = uint32_t(blk & 1);
-            // ---- S = Q_q K_k^T and dP = dO_q V_k^T, once the math warps have read the previous block's ----
-            mbar_wait(sdp_free, bph ^ 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k)
-              umma_bf16_ss<1>(d_s, umma_desc_k_sw128(q0 + k * 32), umma_desc_k_sw128(k0 + k * 32), idesc_s, k != 0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k)
-              umma_bf16_ss<1>(d_dp, umma_desc_k_sw128(do0 + k * 32), umma_desc_k_sw128(v0 + k * 32), idesc_s, k != 0 ? 1u : 0u);
-            umma_commit(sdp_ready);
-            // ---- dV_k += P^T dO_q : A = the P tile read MN-major (M = key, K = query), B = dO_q MN-major ----
-            constexpr uint32_t idesc_t = umma_idesc_16(BT, DH, fmt, 1, 1);
-            mbar_wait(p_ready, bph);
-            if (qt == 0) mbar_wait(dkv_free, uint32_t(kti & 1) ^ 1u);         // the previous key tile's dK / dV were drained
-            tc_fence_after();
-            for (int kk = 0; kk < nq / 16; ++kk)
-              umma_bf16_ss<1>(d_dv, umma_desc_mn_sw128_wide(sP + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(do0 + kk * 2048),
-                              idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
-            umma_commit(p_free);
-            // ---- dK_k += dS^T Q_q (same shape) and dQ_q += dS K_k (A = the dS tile read K-major) ----
-            constexpr uint32_t idesc_q = umma_idesc_16(BT, DH, fmt, 1, 0);
-            mbar_wait(ds_ready, bph);
-            if (kt == 0 && qt == 0) mbar_wait(dq_free, uint32_t(it & 1) ^ 1u);   // the previous item's dQ was drained
-            tc_fence_after();
-            for (int kk = 0; kk < nq / 16; ++kk)
-              umma_bf16_ss<1>(d_dk, umma_desc_mn_sw128_wide(sDS + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(q0 + kk * 2048),
-                              idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
-            for (int kk = 0; kk < nk / 16; ++kk)
-              umma_bf16_ss<1>(tmem_base + COL_DQ + qt * DH, umma_desc_k_sw128(sDS + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32),
-                              umma_desc_mn_sw128(k0 + kk * 2048), idesc_q, (kt != 0 || kk != 0) ? 1u : 0u);
-            umma_commit(ds_free);
-            if (qt == ntile - 1) umma_commit(dkv_ready);
-          }
+        issue_half(0, 0, 0, uint32_t(blk & 1));
+        issue_half(0, 0, 1, uint32_t(blk & 1));
+        for (int j = 0; j < nb; ++j, ++blk) {
+          const int kt = j / ntile, qt = j - kt * ntile;
+          const int nk = ext(kt), nq = ext(qt);
+          const uint32_t k0 = sK + kt * ATOM_BYTES, q0 = sQ + qt * ATOM_BYTES, do0 = sDO + qt * ATOM_BYTES;
+          const uint32_t bph = uint32_t(blk & 1);
+          const uint32_t ds_tile = sDS + uint32_t(blk & 1) * 2 * ATOM_BYTES;
+          // the next block's first half as soon as this block's has been read, its second half right after this block's math
+          if (j + 1 < nb) issue_half((j + 1) / ntile, (j + 1) % ntile, 0, bph ^ 1u);
+          mbar_wait(pds_ready, bph);                       // P and dS of this block are in shared memory
+          if (j + 1 < nb) issue_half((j + 1) / ntile, (j + 1) % ntile, 1, bph ^ 1u);
+          // ---- dV_k += P^T dO_q : A = the P tile read MN-major (M = key, K = query), B = dO_q MN-major ----
+          if (qt == 0) { mbar_wait(dkv_free, uint32_t(kti & 1) ^ 1u); }       // the previous key tile's dK / dV were drained
+          tc_fence_after();
+          for (int kk = 0; kk < nq / 16; ++kk)
+            umma_bf16_ss<1>(d_dv, umma_desc_mn_sw128_wide(sP + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(do0 + kk * 2048),
+                            idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
+          umma_commit(p_free);
+          // ---- dK_k += dS^T Q_q (same shape as dV) and dQ_q += dS K_k (A = the dS tile read K-major) ----
+          if (j == 0) mbar_wait(dq_free, uint32_t(it & 1) ^ 1u);              // the previous item's dQ was drained
+          tc_fence_after();
+          for (int kk = 0; kk < nq / 16; ++kk)
+            umma_bf16_ss<1>(d_dk, umma_desc_mn_sw128_wide(ds_tile + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(q0 + kk * 2048),
+                            idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < nk / 16; ++kk)
+            umma_bf16_ss<1>(tmem_base + COL_DQ + qt * DH, umma_desc_k_sw128(ds_tile + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32),
+                            umma_desc_mn_sw128(k0 + kk * 2048), idesc_q, (kt != 0 || kk != 0) ? 1u : 0u);
+          umma_commit(ds_free0 + 8u * uint32_t(blk & 1));
+          if (qt == ntile - 1) { umma_commit(dkv_ready); ++kti; }
         }
         umma_commit(dq_ready);
         umma_commit(in_empty);
@@ -190,37 +209,80 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
       }
       for (int kt = 0; kt < ntile; ++kt) {
         const int nk = ext(kt);
-        const int c_lo = half == 0 ? 0 : (nk / 2 + 7) & ~7, c_hi = half == 0 ? (nk / 2 + 7) & ~7 : nk;   // this warp's key columns
         for (int qt = 0; qt < ntile; ++qt, ++blk) {
           const uint32_t bph = uint32_t(blk & 1);
           const int qrow = qt * BT + r;
           const bool row_ok = qrow < T;
-          const float lse = L[qt], Dq = Dv[qt];
-          mbar_wait(sdp_ready, bph);
-          mbar_wait(p_free, bph ^ 1u);                     // the previous block's dV MMAs have read the P tile
-          mbar_wait(ds_free, bph ^ 1u);                    // ... and its dK / dQ MMAs the dS tile
-          tc_fence_after();
-#pragma unroll 1
-          for (int c0 = c_lo; c0 < c_hi; c0 += 8) {        // 8 key columns -> one 16-byte chunk of each tile
-            uint32_t s8[8], d8[8];
-            tmem_ld_32x32b_x8(t_lane + COL_S + c0, s8);
-            tmem_ld_32x32b_x8(t_lane + COL_DP + c0, d8);
-            tmem_ld_wait();
-            float p[8], ds[8];
+          const float lse = L[qt], Dq8 = Dv[qt] * 0.125f;
+          const uint32_t ds_tile = sDS + uint32_t(blk & 1) * 2 * ATOM_BYTES;
+          bool tiles_free = false;                         // waited for lazily: the first exponentials overlap the MMAs
+          for (int hf = 0; hf < 2; ++hf) {                 // the block's two 64-key halves (TMEM double buffer)
+            const int nkh = max(0, min(64, nk - 64 * hf));
+            const int wcols = nkh / 2;                     // this warp's share of the half: 32, 8 (T = 197 tail) or 0
+            const int cw = 64 * hf + half * wcols;         // first of this warp's columns
+            mbar_wait(sdp_ready0 + 8u * hf, bph);
+            tc_fence_after();
+            // the block has no key or row past T (warp-uniform): no masking selects in the inner loop
+            const bool full = __all_sync(0xffffffffu, row_ok) && kt * BT + 64 * hf + nkh <= T;
+            // NN (32 or 8) key columns: scores and dP out of TMEM (the half is released at once), P and dS into the smem tiles
+            auto chunk = [&](auto nn_tag, int c0, bool release) {
+              constexpr int NN = decltype(nn_tag)::value;
+              uint32_t sv[NN], dv[NN];
+              if constexpr (NN == 32) {
+                tmem_ld_32x32b_x32p(t_lane + COL_S + c0, sv);
+                tmem_ld_32x32b_x32p(t_lane + COL_DP + c0, dv);
+              } else {
+                tmem_ld_32x32b_x8(t_lane + COL_S + c0, sv);
+                tmem_ld_32x32b_x8(t_lane + COL_DP + c0, dv);
+              }
+              tmem_ld_wait();
+              if (release) {                               // the warp's last values of this half are in registers:
+                tc_fence_before();                         // the next block's half may be computed
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sdp_free0 + 8u * hf);
+              }
+              uint32_t pk[NN / 2], dk[NN / 2];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const bool ok = row_ok && (kt * BT + c0 + e) < T;
-              p[e] = ok ? ex2_approx(fmaf(__uint_as_float(s8[e]), sl2, -lse)) : 0.f;
-              ds[e] = ok ? p[e] * (__uint_as_float(d8[e]) - Dq) * 0.125f : 0.f;   // (rows / keys past T hold arbitrary bits)
+              for (int e = 0; e < NN; e += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(sv[e]), sl2, -lse));
+                float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), sl2, -lse));
+                if (!full) {                               // rows / keys past T hold arbitrary bits
+                  if (!(row_ok && kt * BT + c0 + e < T)) p0 = 0.f;
+                  if (!(row_ok && kt * BT + c0 + e + 1 < T)) p1 = 0.f;
+                }
+                float d0 = p0 * fmaf(__uint_as_float(dv[e]), 0.125f, -Dq8);          // dS = P o (dP - D) / 8
+                float d1 = p1 * fmaf(__uint_as_float(dv[e + 1]), 0.125f, -Dq8);
+                if (!full) {
+                  if (p0 == 0.f) d0 = 0.f;
+                  if (p1 == 0.f) d1 = 0.f;
+                }
+                pk[e >> 1] = pack2<kDT>(p0, p1);
+                dk[e >> 1] = pack2<kDT>(d0, d1);
+              }
+              if (!tiles_free) {
+                mbar_wait(p_free, bph ^ 1u);               // the previous block's dV MMAs have read the P tile
+                mbar_wait(ds_free0 + 8u * uint32_t(blk & 1), (uint32_t(blk >> 1) & 1u) ^ 1u);   // dK / dQ of two blocks ago this dS tile
+                tiles_free = true;
+              }
+#pragma unroll
+              for (int g = 0; g < NN / 8; ++g) {           // 8 key columns -> one 16-byte chunk of each tile
+                const int c = c0 + g * 8;
+                const uint32_t off = uint32_t(c >> 6) * ATOM_BYTES + uint32_t(r) * 128u + (uint32_t(((c & 63) >> 3) ^ (r & 7)) << 4);
+                st_shared_v4(sP + off, pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                st_shared_v4(ds_tile + off, dk[g * 4 + 0], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+              }
+            };
+            if (wcols == 32) chunk(std::integral_constant<int, 32>{}, cw, true);
+            else if (wcols > 0) {                          // 8, 16 or 24 columns (short sequences, the T = 197 tail)
+              for (int c = 0; c < wcols; c += 8) chunk(std::integral_constant<int, 8>{}, cw + c, c + 8 >= wcols);
+            } else {                                       // the half is empty
+              __syncwarp();
+              if (lane == 0) mbar_arrive(sdp_free0 + 8u * hf);
             }
-            const uint32_t off = uint32_t(c0 >> 6) * ATOM_BYTES + uint32_t(r) * 128u + (uint32_t(((c0 & 63) >> 3) ^ (r & 7)) << 4);
-            st_shared_v4(sP + off, pack2<kDT>(p[0], p[1]), pack2<kDT>(p[2], p[3]), pack2<kDT>(p[4], p[5]), pack2<kDT>(p[6], p[7]));
-            st_shared_v4(sDS + off, pack2<kDT>(ds[0], ds[1]), pack2<kDT>(ds[2], ds[3]), pack2<kDT>(ds[4], ds[5]), pack2<kDT>(ds[6], ds[7]));
           }
-          tc_fence_before();
           fence_proxy_async_smem();                        // generic-proxy tile writes -> the MMAs' async-proxy reads
           __syncwarp();
-          if (lane == 0) { mbar_arrive(sdp_free); mbar_arrive(p_ready); mbar_arrive(ds_ready); }
+          if (lane == 0) mbar_arrive(pds_ready);
         }
       }
     }
