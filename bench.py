@@ -199,9 +199,7 @@ def run_reference(args) -> None:
     # caller's K / W (the arm's protocol) and says how many sample steps were actually timed
     timed, warm = max(1, min(args.steps, 30)), max(1, min(args.warmup, 3))
     cb = cpu_reference(wl["cfg"], timed, warm, args.cpu_images)
-    cfg_block = config_block(wl, world, args.dtype)
-    cfg_block["reference_sample"] = (f"{args.cpu_images} images per CPU step, {timed} timed steps after {warm} warm-up "
-                                     "(CPU port of the reference on the host cores; rank 0 only)")
+    cfg_block = config_block(wl, world, args.dtype)        # identical to our arm's `config`
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": cb["ms_per_step"],
@@ -210,6 +208,8 @@ def run_reference(args) -> None:
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_sample": (f"{args.cpu_images} images per CPU step, {timed} timed steps after {warm} warm-up "
+                             "(CPU port of the reference on the host cores; rank 0 only)"),
     }
     print(json.dumps(line), flush=True)
 
@@ -517,6 +517,9 @@ def run_b200(args) -> None:
                 "by_epilogue_isolated_tflops": {c: fl[c] * B_local / (prof[c][0] * 1e-3) / 1e12 for c in gemm_cats
                                                 if prof[c][0] > 0},
                 "traffic_note": "dram bytes of ONE FF1 launch (ncu --set full, profiles/); algorithmic 392 MB",
+                "note": ("the GEMM launches now also carry the PreNorm LayerNorms (x16 copy, row statistics, x_old read in the "
+                         "residual epilogues: DESIGN.md 'LayerNorm fold'), so their share of the step rose and their FLOP rate "
+                         "fell against round 1 while the step got shorter; only GEMM FLOPs are counted"),
             },
             "kernels_ms": {k: round(v[0], 4) for k, v in prof.items()},
             "e2e": {"value": e2e_value, "unit": "images/s",
