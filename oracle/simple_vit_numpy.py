@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- numpy restatement of ``vit_flax/simple_vit.py`` (PARITY UNPINNED, see
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of ``vit_flax/simple_vit.py`` (parity: tests/golden/ref_simple_vit.npz, the output of simple_vit.py itself over oracle/flax_shim; see
 oracle/__init__.py: jax/flax are absent and the reference has no tests).  Reuses the building blocks
 of vit_numpy.py; cites the lines of simple_vit.py it follows."""
 from __future__ import annotations

@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of ``vit_flax/vit.py``.
 
-PARITY UNPINNED (see ``oracle/__init__.py``): jax/flax are absent, the reference
-has no tests or golden vectors for this path.  Every function cites the
-reference lines it restates; library semantics (flax.linen 0.5 / jax 0.3.13,
-README.md:837,847) are the published ones:
+PARITY (see ``oracle/__init__.py``): checked against tests/golden/ref_vit.npz, the outputs of
+vit.py itself executed over oracle/flax_shim (jax/flax are absent; the reference has no tests
+or golden vectors of its own).  Every function cites the reference lines it restates; library
+semantics (flax.linen 0.5 / jax 0.3.13, README.md:837,847) are the published ones:
 
 * ``nn.Dense``      y = x @ kernel (+ bias), kernel ``[in, out]``
 * ``nn.LayerNorm``  last axis, eps 1e-6, var = max(0, E[x^2] - E[x]^2)

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- torch-CPU float32 twin of ``vit_flax/vit.py``.
 
-PARITY UNPINNED (see ``oracle/__init__.py``).  Written independently of
+PARITY: held to the reference run in tests/golden/ref_vit.npz (see ``oracle/__init__.py``).  Written independently of
 ``vit_numpy.py`` (torch library ops instead of hand-written formulas) so the
 two restatements cross-check each other; also the timed CPU baseline
 (``bench.py`` ``cpu_baseline`` / ``--impl reference``) because its GEMMs run on

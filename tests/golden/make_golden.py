@@ -1,10 +1,10 @@
 """Regenerate the committed golden vectors:  python tests/golden/make_golden.py
 
-PARITY UNPINNED: the reference (vit_flax/vit.py) cannot be imported here (no
-jax/flax), so these vectors come from the float64 oracle (oracle/vit_numpy.py),
-cross-checked against the independent torch restatement before being written.
-They pin the ORACLE (and the param initialiser) against drift; they are not
-outputs of the reference itself.
+These vectors come from the float64 oracle (oracle/vit_numpy.py), cross-checked
+against the independent torch restatement before being written: they pin the
+ORACLE (and the param initialiser) against drift.  The outputs of the reference
+itself on the same inputs are in ref_vit.npz (make_reference_golden.py), and
+tests/test_reference_run.py checks that the two agree.
 """
 import sys
 from pathlib import Path

@@ -924,13 +924,18 @@ int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* o_fwd, co
                          int heads, int dtype, float* workspace, const float* lse2) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
   if (!attention_bwd_needs_workspace(T) && !attn_bwd_force_hmma() && attention_bwd_tc5_supports(T)) {
-    if (lse2 != nullptr) return launch_attention_bwd_tc5(st, qkv, o_fwd, d_out, dqkv, lse2, batch, T, heads, dtype);
-    // no log-sum-exp from the forward (the per-kernel entry point): the streamed statistics kernel makes it first
     const size_t n = size_t(round_up(int64_t(batch) * heads * T, 64));
+    if (lse2 != nullptr && workspace != nullptr) {   // model path: lse2 from the forward, D by one HBM-bound pass
+      int rc = launch_attention_bwd_rowdot(st, d_out, o_fwd, workspace, batch, T, heads, dtype);
+      if (rc) return rc;
+      return launch_attention_bwd_tc5(st, qkv, d_out, dqkv, lse2, workspace, batch, T, heads, dtype);
+    }
+    // per-kernel entry point: no log-sum-exp from the forward -- the streamed statistics kernel makes it (and D) first
     float* ws = nullptr;
     VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * n * sizeof(float), st));
-    int rc = launch_attention_bwd_stats(st, qkv, o_fwd, d_out, ws, ws + n, batch, T, heads, dtype);
-    if (!rc) rc = launch_attention_bwd_tc5(st, qkv, o_fwd, d_out, dqkv, ws, batch, T, heads, dtype);
+    int rc = lse2 ? launch_attention_bwd_rowdot(st, d_out, o_fwd, ws + n, batch, T, heads, dtype)
+                  : launch_attention_bwd_stats(st, qkv, o_fwd, d_out, ws, ws + n, batch, T, heads, dtype);
+    if (!rc) rc = launch_attention_bwd_tc5(st, qkv, d_out, dqkv, lse2 ? lse2 : ws, ws + n, batch, T, heads, dtype);
     cudaFreeAsync(ws, st);
     return rc;
   }

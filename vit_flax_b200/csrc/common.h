@@ -195,8 +195,11 @@ int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* o_fwd
 // `lse2` (the forward's row log-sum-exp, launch_attention_tc's `lse`): with it and T <= 208 the adjoint runs on tcgen05
 // (attention_bwd_tc5.cu); without it the per-kernel entry point computes it first (statistics kernel, stream-ordered scratch)
 bool attention_bwd_tc5_supports(int T);
-int launch_attention_bwd_tc5(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
-                             const float* lse2, int batch, int T, int heads, int dtype);
+int launch_attention_bwd_tc5(cudaStream_t stream, const void* qkv, const void* d_out, void* dqkv, const float* lse2,
+                             const float* dsum, int batch, int T, int heads, int dtype);
+// dsum [batch*heads, T] = rowsum(dO o O) per (image, head, token): the D of the softmax adjoint
+int launch_attention_bwd_rowdot(cudaStream_t stream, const void* d_out, const void* o_fwd, float* dsum, int batch, int T,
+                                int heads, int dtype);
 // lse2 [batch*heads, T] (and dsum, same shape) by the streamed statistics kernel of attention_bwd_flash.cu
 int launch_attention_bwd_stats(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, float* lse2,
                                float* dsum, int batch, int T, int heads, int dtype);
