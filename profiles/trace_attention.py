@@ -27,9 +27,12 @@ tr = np.zeros((12, 64), np.int64)
 lib.vitb200_debug_attention_trace.argtypes = [C.c_void_p, C.c_int]
 assert lib.vitb200_debug_attention_trace(tr.ctypes.data, tr.size) == 0
 names = ["qk_load", "v_load", "S_issue", "PV_issue", "sm_begin", "s_ready", "pass1_end", "p_ready", "epi_begin",
-         "k_seen", "stored", "q_seen"]
+         "p2_begin", "stored", "p2_end"]
 t0 = tr[0, 0]
 print("item " + " ".join(f"{n:>9s}" for n in names))
 for i in range(0, 30):
     print(f"{i:4d} " + " ".join(f"{int(tr[e, i] - t0):9d}" for e in range(12)))
 print("per-item period (cycles):", (tr[7, 30] - tr[7, 10]) / 20.0)
+d = lambda a, b: float(np.mean([tr[b, i] - tr[a, i] for i in range(8, 32)]))
+print(f"means over items 8..31: S_issue->s_ready {d(2, 5):.0f}  s_ready->pass1_end {d(5, 6):.0f}  pass1_end->p2_begin {d(6, 9):.0f}  "
+      f"p2_begin->p2_end {d(9, 11):.0f}  p2_end->p_ready {d(11, 7):.0f}  PV_issue->p_ready {d(3, 7):.0f}  p_ready->stored {d(7, 10):.0f}")

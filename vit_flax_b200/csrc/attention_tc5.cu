@@ -11,8 +11,11 @@
 //                    ring); Q has a 4-deep ring, so loads run one to two items ahead of the MMAs.
 //   warps 1, 3     : tcgen05.mma issuers, one per TMEM slot (lane 0 each, blocking mbarrier waits):
 //                      S = Q K^T  (M=128, N=KP, K=64; SS operands)
-//                      O = P V    (M=128, N=64,  K=KP; P from TMEM, V MN-major)
-//                    S(i+2) is queued right behind PV(i): MMAs of one thread execute in order.
+//                      O = P V    (M=128, N=64,  K=KP; P from TMEM, V MN-major), issued in PARTS of 64 keys
+//                      as the softmax group publishes them (p_part barriers): the product runs UNDER the
+//                      exponentials instead of behind them, so a slot is busy from S(i) to the end of pass 2
+//                      plus one short tail, and S(i+2) -- queued right behind the last part, MMAs of one
+//                      thread execute in order -- is ready long before the group's next turn.
 //   warp 2         : TMEM allocator: two slots of KP columns (S fp32, then P as 16-bit pairs over
 //                    the first KP/2 columns) + one 64-column O accumulator shared by both slots.
 //   warps 4..7     : softmax group 0 -- items 0, 2, 4, ... of this CTA (slot 0)
@@ -23,14 +26,20 @@
 // Pass 1 streams the score row out of TMEM for the max, pass 2 streams it again (TMEM reads are
 // cheap), exponentiates, sums in fp32 and writes P back over S with tcgen05.st; 1/rowsum goes to
 // the epilogue warps through shared memory.
-// Bound (measured, profiles/r01_attention.md): the XU pipe -- ex2 (8 cycles per warp instruction and
-// SMSP) AND the fp32 -> 16-bit pack F2FP (4 cycles) share it: 20 cycles per pair of scores.  The
-// exponential phases of consecutive items take turns (mbarrier hand-off): left alone the two
-// groups fall into step -- both exponentiate, then both wait for their MMAs -- which idles the XU
-// for the length of everything else.  A polynomial ex2 on the FMA pipe (kPoly quarters of the
-// pairs; Cody-Waite + degree-3 minimax, rel. error 7.5e-5) is built in but off by default: on
-// B200 FFMA2 issues at 2.25 cycles per warp instruction, so the 5 FFMA2 + 3 FADD2 + 2 IMAD it
-// costs per pair outweigh the 16 XU cycles it saves.
+// What bounds it (measured; profiles/r01_attention.md, profiles/r02_attention.md).  XU work -- ex2 at 8 cycles per
+// warp instruction and SMSP plus the fp32 -> 16-bit pack F2FP at 4: 20 cycles per pair of scores -- is 2.08 k cycles
+// per item; the tensor side is 0.64 k (S: four dependent UTCHMMA of N = 208) + 0.73 k (P V: thirteen of N = 64, paced by
+// the ~50-cycle issue cost of one tcgen05.mma, not by the pipe: profiles/microbench/mma_chain.cu); the kernel runs at
+// ~3.2 k cycles per item because a TMEM slot goes round a LATENCY loop -- S 0.6-1.1 k, pass 1 0.7 k, pass 2 2.6 k (a
+// single warp issues in order and ptxas batches a chunk's MUFUs apart from its FFMA2 / FADD2 / F2FP work), store drain
+// 0.4 k, last P V part + next S issue 0.5-1.0 k -- and 512 TMEM columns hold two slots, no more.  The exponential phases
+// of the two groups are offset per SMSP (xu_done[q]: warp q hands over to warp q of the other group one chunk before
+// it finishes; free-running or earlier hand-offs measure the same within 2 %, strict alternation is 12 % slower).
+// Round-2 experiments that did NOT pay and were removed: all eight softmax warps on every item with the key columns
+// split between the two warps of a lane quarter (no phase overlap between items: 118 us against 84); the bf16 pack on
+// the integer pipe (add 0x8000 + PRMT: 97 against 88 us -- the softmax warps are short of issue slots, not of XU
+// cycles); hand-ordered volatile-asm interleaving of MUFU and FMA work (ptxas reschedules it to the same SASS); round
+// 1's polynomial ex2 on the FMA pipe.
 // Warps whose 32 query rows are all >= T (the last quarter of the 69-row tail tile at T = 197)
 // skip their softmax: rows of an MMA are independent and those rows are never stored.
 // The [B,h,T,T] score tensor of vit.py:73-75 never reaches HBM.
@@ -67,41 +76,17 @@ struct Smem {
   static constexpr int OFF_K = OFF_Q + QS * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KS * KV_BYTES;
   static constexpr int OFF_O = OFF_V + KS * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_O + 2 * O_BYTES;        // 2 staging buffers; then 32 mbarrier slots
-  static constexpr int OFF_INV = OFF_BAR + 256;              // float [4][128]: 1/rowsum, by item parity mod 4
+  static constexpr int OFF_BAR = OFF_O + 2 * O_BYTES;        // 2 staging buffers; then 64 mbarrier slots
+  static constexpr int OFF_INV = OFF_BAR + 512;              // float [4][128]: 1/rowsum, by item parity mod 4
   static constexpr int TOTAL = OFF_INV + 4 * 128 * 4 + 1024 /*align slack*/;
   static_assert(KV_BYTES % 1024 == 0, "K/V stage must keep 1024-byte alignment");
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-// 2^x for x <= 0 on the FMA/ALU pipes, two lanes at a time.  x = n + f, n = round(x), f in
-// [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial; 2^n is added into the exponent field.
-__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, float& p1) {
-  const float MAGIC = 12582912.f;   // 1.5 * 2^23: (x + MAGIC) holds round(x) in its low mantissa bits
-  float x0, x1;
-  unpack_f32x2(x2, x0, x1);
-  x0 = fmaxf(x0, -125.f);
-  x1 = fmaxf(x1, -125.f);
-  const unsigned long long xc = pack_f32x2(x0, x1);
-  const unsigned long long t2 = add_f32x2(xc, pack_f32x2(MAGIC, MAGIC));
-  const unsigned long long n2 = add_f32x2(t2, pack_f32x2(-MAGIC, -MAGIC));
-  const unsigned long long f2 = fma_f32x2(n2, pack_f32x2(-1.f, -1.f), xc);
-  unsigned long long p2 = fma_f32x2(pack_f32x2(0.0551716648f, 0.0551716648f), f2,
-                                    pack_f32x2(0.2426111251f, 0.2426111251f));
-  p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677f, 0.6932609677f));
-  p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999280572f, 0.9999280572f));
-  float t0, t1, q0, q1;
-  unpack_f32x2(t2, t0, t1);
-  unpack_f32x2(p2, q0, q1);
-  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
-  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
-}
-
 // NN (32 or 16) score columns of this thread's row, already in registers:
-// p = exp2(s*sl2 + mneg) -> fp32 partial sums (la/lb) -> 16-bit P pairs.  kPoly of every 4 pairs
-// go through the polynomial; kMask: the chunk may reach past T (keys >= T are zero-filled K rows:
-// score 0, not -inf, so they are forced to -inf here).
-template <int kDT, int NN, int kPoly, bool kMask>
+// p = exp2(s*sl2 + mneg) -> fp32 partial sums (la/lb) -> 16-bit P pairs.  kMask: the chunk may reach
+// past T (keys >= T are zero-filled K rows: score 0, not -inf, so they are forced to -inf here).
+template <int kDT, int NN, bool kMask>
 __device__ __forceinline__ void softmax_chunk(uint32_t* r, uint32_t* pp, int c0, int T,
                                               unsigned long long sl2x2, unsigned long long mnegx2,
                                               unsigned long long& la, unsigned long long& lb) {
@@ -114,22 +99,16 @@ __device__ __forceinline__ void softmax_chunk(uint32_t* r, uint32_t* pp, int c0,
   for (int j = 0; j < NN / 2; ++j) {
     const unsigned long long a2 =
         fma_f32x2(pack_f32x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), sl2x2, mnegx2);
-    float p0, p1;
-    if ((j & 3) < kPoly) {
-      exp2_poly2(a2, p0, p1);
-    } else {
-      float a0, a1;
-      unpack_f32x2(a2, a0, a1);
-      p0 = ex2_approx(a0);
-      p1 = ex2_approx(a1);
-    }
+    float a0, a1;
+    unpack_f32x2(a2, a0, a1);
+    const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
     if (j & 1) lb = add_f32x2(lb, pack_f32x2(p0, p1));
     else la = add_f32x2(la, pack_f32x2(p0, p1));
     pp[j] = pack2<kDT>(p0, p1);
   }
 }
 
-template <int kDT, int KP, int kPoly>
+template <int kDT, int KP>
 __global__ void __launch_bounds__(NT, 1)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I], box 128 rows
                      const __grid_constant__ CUtensorMap tmKV,   // qkv [B,T,3I], box KP rows
@@ -153,16 +132,17 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
   auto k_empty = [&](int s) { return bars + 8u * (12 + s); };
   auto v_empty = [&](int s) { return bars + 8u * (14 + s); };
   auto s_ready = [&](int s) { return bars + 8u * (16 + s); };  // [2 TMEM slots]
-  auto p_ready = [&](int s) { return bars + 8u * (18 + s); };
   auto o_ready = [&](int s) { return bars + 8u * (20 + s); };
   const uint32_t o_free = bars + 8u * 22;
-  const uint32_t xu_done = bars + 8u * 23;                     // exponential phases take turns (see below)
+  auto p_part = [&](int s, int g) { return bars + 8u * (32 + 4 * s + g); };   // [2 slots][<= 4 parts of 64 keys]
+  auto xu_done = [&](int q) { return bars + 8u * (40 + q); };  // [4 SMSPs]: exponential phases take turns (see below)
   const uint32_t tmem_slot = bars + 8u * 24;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + L::OFF_BAR + 8 * 24);
   float* inv_sh = reinterpret_cast<float*>(gbase + L::OFF_INV);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = heads * DH;
+  if (turns < 0) turns = KP / 32 - 1 > 0 ? KP / 32 - 1 : 1;
   const int64_t first = int64_t(blockIdx.x) * items / gridDim.x;
   const int64_t last = int64_t(blockIdx.x + 1) * items / gridDim.x;
   const int n = int(last - first);
@@ -183,11 +163,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
       mbar_init(k_empty(s), nqt);                      // one arrival per q tile of the (image, head): the
       mbar_init(v_empty(s), nqt);                      // two issuers release a K/V entry independently
       mbar_init(s_ready(s), 1);
-      mbar_init(p_ready(s), 4);
+      for (int g = 0; g < 4; ++g) mbar_init(p_part(s, g), 4);
       mbar_init(o_ready(s), 1);
     }
     mbar_init(o_free, 4);
-    mbar_init(xu_done, 4);
+    for (int q = 0; q < 4; ++q) mbar_init(xu_done(q), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
@@ -243,6 +223,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
       constexpr int fmt = kDT == DT_F16 ? 0 : 1;
       constexpr uint32_t idesc_s = umma_idesc_16(QT, KP, fmt, 0);   // B = K, K-major
       constexpr uint32_t idesc_o = umma_idesc_16(QT, DH, fmt, 1);   // B = V, MN-major
+      constexpr int NPARTS = KP >= 128 ? KP / 64 : 1;               // parts of 64 keys (the last takes the remainder)
       const int s = warp == 1 ? 0 : 1;
       const uint32_t d_s = tmem_base + s * SLOT_COLS, d_o = tmem_base + O_COL;
       const int first_lo = int(first % nqt);             // q tile of item 0
@@ -279,15 +260,23 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
         int es, missing; uint32_t eph;
         meta(i, es, eph, missing);
         const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(p_ready(s), ph);
-        mbar_wait(v_full(es), eph);
-        mbar_wait(o_free, uint32_t(i & 1) ^ 1u);
-        TRACE(3, i);
-        tc_fence_after();
         const uint32_t v0 = sV + es * L::KV_BYTES;
+        // O = P V in parts of 64 keys, each issued as soon as the softmax group has published it
 #pragma unroll
-        for (int kk = 0; kk < KP / 16; ++kk)
-          umma_bf16_ts(d_o, d_s + kk * 8, umma_desc_mn_sw128(v0 + kk * 2048), idesc_o, kk != 0 ? 1u : 0u);
+        for (int g = 0; g < NPARTS; ++g) {
+          mbar_wait(p_part(s, g), ph);
+          if (g == 0) {
+            mbar_wait(v_full(es), eph);
+            mbar_wait(o_free, uint32_t(i & 1) ^ 1u);
+            TRACE(3, i);
+          }
+          tc_fence_after();
+          constexpr int KSTEPS = KP / 16;
+          const int k_end = g == NPARTS - 1 ? KSTEPS : 4 * g + 4;
+#pragma unroll
+          for (int kk = 4 * g; kk < k_end; ++kk)
+            umma_bf16_ts(d_o, d_s + kk * 8, umma_desc_mn_sw128(v0 + kk * 2048), idesc_o, kk != 0 ? 1u : 0u);
+        }
         umma_commit(v_empty(es));
         for (int j = 0; j < missing; ++j) mbar_arrive(v_empty(es));
         umma_commit(o_ready(s));
@@ -307,13 +296,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
     constexpr int NFULL = KP / 32, TAIL = KP % 32;
     constexpr int KMIN = KP == 208 ? 128 : (KP == 128 ? 64 : 0);   // launch_poly: T > KMIN
     static_assert(TAIL == 0 || TAIL == 16, "key block = n*32 (+16)");
-    constexpr int HANDOFF = NFULL >= 3 ? NFULL - 2 : NFULL - 1;   // chunk after which the next item may start its exponentials
+    constexpr int NPARTS = KP >= 128 ? KP / 64 : 1;       // P is published in parts of 2 chunks = 64 keys (issuer: same constant)
+    static_assert(NPARTS <= 4 && 2 * NPARTS <= NFULL, "parts are pairs of 32-key chunks");
 
     for (int i = grp; i < n; i += 2) {
       const uint32_t ph = (i >> 1) & 1;
       const int64_t item = first + i;
       const int bh = int(item / nqt), qt = int(item - int64_t(bh) * nqt);
-      const int b = bh / heads, h = bh - b * heads;
       const bool active = qt * QT + q * 32 < T;          // warp-uniform: any valid query row here?
       if (q == 0 && lane == 0) TRACE(4, i);
       mbar_wait(s_ready(grp), ph);
@@ -352,55 +341,68 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
             mx = fmaxf(mx, fmaxf(__uint_as_float(rc[j]), __uint_as_float(rc[j + 1])));
         }
         if (q == 0 && lane == 0) TRACE(6, i);
-        // The exponential phases of consecutive items take turns on the MUFU: left alone the two
-        // groups fall into step (both exponentiate, then both wait), which idles the pipe that
-        // bounds this kernel for the length of everything else.
-        if (turns) mbar_wait(xu_done, uint32_t(i & 1) ^ 1u);
         // ---- pass 2: p = exp2((s - max) * scale * log2e), un-normalised; row sum in fp32; P -> TMEM
         // P chunk c (16 columns of 16-bit pairs) lands on S columns [16c, 16c+16), all read already.
         const float mneg = -mx * sl2;
         const unsigned long long sl2x2 = pack_f32x2(sl2, sl2), mnegx2 = pack_f32x2(mneg, mneg);
         unsigned long long la = pack_f32x2(0.f, 0.f), lb = la;
-        tmem_ld_32x32b_x32p(t_slot, r[0]);
+        tmem_ld_32x32b_x32p(t_slot, r[0]);               // the first chunk is in registers before the turn begins
         tmem_ld_wait();
+        // The exponential phases of consecutive items take turns on the MUFU of each SMSP (this warp and warp q of
+        // the other group share a scheduler): left alone the two groups fall into step (both exponentiate, then both
+        // wait), which idles the pipe that bounds this kernel for the length of everything else.
+        if (turns) mbar_wait(xu_done(q), uint32_t(i & 1) ^ 1u);
+        if (q == 0 && lane == 0) TRACE(9, i);
 #pragma unroll
         for (int c = 0; c < NFULL; ++c) {
           if (c + 1 < NFULL) tmem_ld_32x32b_x32p(t_slot + (c + 1) * 32, r[(c + 1) & 1]);
           else if (TAIL) tmem_ld_32x32b_x16(t_slot + (c + 1) * 32, r[(c + 1) & 1]);
           uint32_t pp[16];
-          if (c * 32 + 32 > KMIN && c * 32 + 32 > T) softmax_chunk<kDT, 32, 0, true>(r[c & 1], pp, c * 32, T, sl2x2, mnegx2, la, lb);
-          else softmax_chunk<kDT, 32, kPoly, false>(r[c & 1], pp, c * 32, T, sl2x2, mnegx2, la, lb);
+          if (c * 32 + 32 > KMIN && c * 32 + 32 > T) softmax_chunk<kDT, 32, true>(r[c & 1], pp, c * 32, T, sl2x2, mnegx2, la, lb);
+          else softmax_chunk<kDT, 32, false>(r[c & 1], pp, c * 32, T, sl2x2, mnegx2, la, lb);
           if (c + 1 < NFULL || TAIL) tmem_ld_wait();    // chunk c+1 is in registers: its S columns may go
+          if (c >= 2 && (c & 1) == 0 && c / 2 - 1 < NPARTS - 1) {
+            // publish part c/2 - 1 (chunks c-2, c-1): their stores were issued a chunk of exponentials ago, so the
+            // wait does not stall; the issuer starts that part of P V while this row goes on
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_part(grp, c / 2 - 1));
+          }
           tmem_st_32x32b_x16(t_slot + c * 16, pp);
-          if (c == HANDOFF && turns == 2) { __syncwarp(); if (lane == 0) mbar_arrive(xu_done); }
+          if (c + 1 == turns) { __syncwarp(); if (lane == 0) mbar_arrive(xu_done(q)); }   // the other group's warp on this SMSP may start
         }
         if constexpr (TAIL != 0) {
           uint32_t pp[8];
-          softmax_chunk<kDT, 16, 0, true>(r[NFULL & 1], pp, NFULL * 32, T, sl2x2, mnegx2, la, lb);
+          softmax_chunk<kDT, 16, true>(r[NFULL & 1], pp, NFULL * 32, T, sl2x2, mnegx2, la, lb);
           tmem_st_32x32b_x8(t_slot + NFULL * 16, pp);
         }
+        if (turns > NFULL) { __syncwarp(); if (lane == 0) mbar_arrive(xu_done(q)); }   // strict alternation
+        if (q == 0 && lane == 0) TRACE(11, i);
         float l0, l1;
         unpack_f32x2(add_f32x2(la, lb), l0, l1);
-        inv_sh[(i & 3) * 128 + row] = 1.0f / (l0 + l1);   // for the epilogue warps (ordered by p_ready)
+        inv_sh[(i & 3) * 128 + row] = 1.0f / (l0 + l1);   // for the epilogue warps (ordered by the last p_part)
         // training: the row's log-sum-exp in the log2 domain, lse2 = log2 sum_j exp2(s_ij sl2), which lets the adjoint
         // (attention_bwd_tc5.cu) rebuild P block by block without a row maximum
         if (lse_out != nullptr && qt * QT + row < T) lse_out[int64_t(bh) * T + qt * QT + row] = __log2f(l0 + l1) - mneg;
         tmem_st_wait();
-        if (turns == 1 && lane == 0) mbar_arrive(xu_done);
-      } else if (turns) {
-        mbar_wait(xu_done, uint32_t(i & 1) ^ 1u);
-        if (lane == 0) mbar_arrive(xu_done);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_part(grp, NPARTS - 1));   // the last part: chunks 2 (NPARTS - 1) .. and the tail
+      } else {
+        // no valid query row in this warp (last quarter of the 69-row tail tile): keep the hand-offs moving
+        if (turns) {
+          mbar_wait(xu_done(q), uint32_t(i & 1) ^ 1u);
+          if (lane == 0) mbar_arrive(xu_done(q));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int g = 0; g < NPARTS; ++g) mbar_arrive(p_part(grp, g));
+        }
       }
-      // A parity wait tells "phase t-1 done" from "not done" only if phase t-2 is known to be done.
-      // Phase i (this group's turn) is complete once all four warps of the group have arrived:
-      // the group barrier below makes that true before any of them tests for the partner's turn
-      // i+1 -- otherwise a fast warp would take the still-open phase i for it and run ahead.
-      if (turns) named_bar_sync(2 + grp, 128);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready(grp));
       if (q == 0 && lane == 0) TRACE(7, i);
-
     }
   } else if (warp >= 12) {
     // ===================== epilogue: O / rowsum -> 16-bit -> swizzled smem -> TMA store ==========
@@ -417,7 +419,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
       const bool active = qt * QT + q * 32 < T;
       const uint32_t sOi = sO + uint32_t(i & 1) * O_BYTES;
       if (leader) TRACE(8, i);
-      mbar_wait(o_ready(s), ph);                         // PV(i) done; it was issued after p_ready(i),
+      mbar_wait(o_ready(s), ph);                         // PV(i) done; its last part was issued after p_part(i),
                                                          // which ordered the group's 1/rowsum writes
       tc_fence_after();
       uint32_t o[64];
@@ -463,24 +465,26 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
   }
 }
 
-// how the two softmax groups share the MUFU: 0 = free-running, 1 = exponential phases strictly
-// alternate, 2 = alternate with the hand-off two chunks before the end (VITB200_ATTN_TURNS)
+// How the two softmax groups share the XU of each SMSP (VITB200_ATTN_TURNS): 0 = free-running; h in 1..6 = a warp lets
+// its partner (warp q of the other group, next item) start pass 2 once it has finished its own chunk h - 1 of 32 keys,
+// so the two exponential phases overlap from there on; 7 = strict alternation (hand-off after the last exponential).
+// Measured at ViT-B/16 batch 256 (profiles/r02_attention.md): 0..3 85-86 us, 4 and 5 84 us, 6 and 7 95 us; the default
+// is the chunk before the last full one (5 at 208 keys).
 int attn_turns() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VITB200_ATTN_TURNS");
-    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+    v = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1;   // default: hand-off one chunk before the last
   }
   return v;
 }
 
-template <int kDT, int KP, int kPoly>
+template <int kDT, int KP>
 int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
   using L = Smem<KP>;
   static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
   if (bool& configured = configured_on.here(); !configured) {
-    VB_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<kDT, KP, kPoly>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    VB_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<kDT, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   const int inner = heads * DH;
@@ -494,36 +498,17 @@ int launch_kp(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
   if (items64 > 0x7fffffff) return fail(VITB200_ERR_INVALID, "attention: too many work items");
   const int items = int(items64);
   const int grid = items < sm_count() ? items : sm_count();
-  VB_CUDA(launch_kernel(attention_tc5_kernel<kDT, KP, kPoly>, dim3(grid), dim3(NT), L::TOTAL, stream, 1,
+  VB_CUDA(launch_kernel(attention_tc5_kernel<kDT, KP>, dim3(grid), dim3(NT), L::TOTAL, stream, 1,
                         tq, tkv, to, T, heads, nqt, items, attn_turns(), lse));
   VB_LAUNCH_CHECK("attention_tc5_kernel");
   return 0;
 }
 
-// share of the ex2 evaluated on the FMA pipe, in quarters (0..2); VITB200_ATTN_POLY overrides
-int poly_quarters() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VITB200_ATTN_POLY");
-    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
-  }
-  return v;
-}
-
-template <int kDT, int kPoly>
-int launch_poly(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
-  if (T <= 64) return launch_kp<kDT, 64, kPoly>(stream, qkv, out, batch, T, heads, lse);
-  if (T <= 128) return launch_kp<kDT, 128, kPoly>(stream, qkv, out, batch, T, heads, lse);
-  return launch_kp<kDT, 208, kPoly>(stream, qkv, out, batch, T, heads, lse);
-}
-
 template <int kDT>
 int launch_dt(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
-  switch (poly_quarters()) {
-    case 0: return launch_poly<kDT, 0>(stream, qkv, out, batch, T, heads, lse);
-    case 2: return launch_poly<kDT, 2>(stream, qkv, out, batch, T, heads, lse);
-    default: return launch_poly<kDT, 1>(stream, qkv, out, batch, T, heads, lse);
-  }
+  if (T <= 64) return launch_kp<kDT, 64>(stream, qkv, out, batch, T, heads, lse);      // KMIN: T > 0 / 64 / 128
+  if (T <= 128) return launch_kp<kDT, 128>(stream, qkv, out, batch, T, heads, lse);
+  return launch_kp<kDT, 208>(stream, qkv, out, batch, T, heads, lse);
 }
 
 }  // namespace
