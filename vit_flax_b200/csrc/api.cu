@@ -168,7 +168,7 @@ struct vitb200_model {
   // training (train_forward / backward): activations kept per layer, gradient workspace, leaf gradients
   struct TrainLayer {
     DevBuf<uint16_t> xn1, qkv, o, xn2, pre;   // pre: [2 * rows_cap, mlp] -- FF pre-activation, then its GELU (hid)
-    DevBuf<float> lse;                        // attention row log-sum-exp [batch*heads, T] (T <= 208: the tcgen05 adjoint)
+    DevBuf<float> lse;                        // attention row log-sum-exp [batch*heads, T] (for the tcgen05 adjoint)
     uint16_t* hid = nullptr;
   };
   struct TrainState {
@@ -1019,7 +1019,7 @@ int ensure_train(vitb200_model* m, cudaStream_t st) {
   for (auto& L : ts->layers) {
     if ((rc = L.xn1.alloc(R * D)) || (rc = L.qkv.alloc(R * 3 * I)) || (rc = L.o.alloc(R * I)) ||
         (rc = L.xn2.alloc(R * D)) || (rc = L.pre.alloc(2 * size_t(ts->rows_cap) * H))) return rc;
-    if (attention_tc5_supports(m->T) && (rc = L.lse.alloc(B * size_t(c.heads) * m->T))) return rc;
+    if ((rc = L.lse.alloc(B * size_t(c.heads) * m->T))) return rc;
     L.hid = L.pre.p + size_t(ts->rows_cap) * H;
   }
   if ((rc = ts->dx.alloc(R * D)) || (rc = ts->pooled_ln.alloc(B * D)) || (rc = ts->dpl.alloc(B * D))) return rc;

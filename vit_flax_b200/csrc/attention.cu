@@ -252,8 +252,8 @@ int launch_attention_tc(cudaStream_t stream, const void* qkv, void* out, int bat
   const bool want_hmma = force && force[0] == 'h';
   if (!want_hmma && attention_tc5_supports(T))
     return launch_attention_tc5(stream, qkv, out, batch, T, heads, dtype, lse);
-  if (lse != nullptr) return fail(VITB200_ERR_UNSUPPORTED, "attention_tc: the row log-sum-exp output needs the T <= 208 tcgen05 kernel");
-  if (!want_hmma) return launch_attention_tc5m(stream, qkv, out, batch, T, heads, dtype);
+  if (!want_hmma) return launch_attention_tc5m(stream, qkv, out, batch, T, heads, dtype, lse);
+  if (lse != nullptr) return fail(VITB200_ERR_UNSUPPORTED, "attention_tc: the row log-sum-exp output needs a tcgen05 kernel");
   if (int64_t(batch) * heads > 65535)
     return fail(VITB200_ERR_INVALID, "attention_tc: batch*heads exceeds grid.y limit; chunk the batch");
   if (dtype == DT_BF16)

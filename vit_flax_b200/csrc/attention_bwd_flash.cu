@@ -325,6 +325,16 @@ int launch_attention_bwd_stats(cudaStream_t st, const void* qkv, const void* o_f
   return 0;
 }
 
+// fp32 dQ accumulator [rows, inner] -> the q third of dqkv (16-bit); shared with the streamed tcgen05 adjoint
+int launch_dq_convert(cudaStream_t st, const float* dq_acc, void* dqkv, int64_t rows, int inner, int dtype) {
+  const unsigned cgrid = unsigned(std::min<int64_t>((rows * (inner / 8) + 255) / 256, int64_t(sm_count()) * 16));
+  if (dtype == DT_F16) dq_convert_kernel<DT_F16><<<cgrid, 256, 0, st>>>(dq_acc, static_cast<uint16_t*>(dqkv), rows, inner);
+  else if (dtype == DT_BF16) dq_convert_kernel<DT_BF16><<<cgrid, 256, 0, st>>>(dq_acc, static_cast<uint16_t*>(dqkv), rows, inner);
+  else return fail(VITB200_ERR_INVALID, "attention_bwd: dtype must be bf16 or fp16");
+  VB_LAUNCH_CHECK("dq_convert_kernel");
+  return 0;
+}
+
 size_t attention_bwd_flash_workspace_floats(int batch, int T, int heads) {
   // lse2 + D per (image, head, token), fp32 dQ accumulator [batch * T, heads * 64]
   return 2 * size_t(round_up(int64_t(batch) * heads * T, 64)) + size_t(batch) * T * heads * DH;

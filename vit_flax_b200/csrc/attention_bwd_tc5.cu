@@ -19,6 +19,12 @@
 //   dV_k += P^T dO_q,  dK_k += dS^T Q_q   accumulate over the query tiles in TMEM (64 columns each)
 //   dQ_q += dS K_k                        accumulates over the key tiles in TMEM (64 columns per query tile)
 //
+// Two modes of the same kernel.  RESIDENT (T <= 208, kStream = false): the unit of work is an (image, head), its blocks
+// run key tile outermost, and dQ of both query tiles accumulates over the key tiles in TMEM (2 x 64 columns) and leaves
+// once per item.  STREAMED (any T, kStream = true): the unit is an (image, head, key tile) -- its blocks are the query
+// tiles -- so dK / dV still accumulate in TMEM, while the block's dQ contribution (a fresh 64-column accumulator, two of
+// them alternating) is added into an fp32 buffer [B T, heads 64] with 16-byte vector reductions (red.global.add.v4.f32)
+// by the epilogue warps and converted to 16 bits by a last pass; ViT-H/14 (257 tokens) and 512-px inputs (1025) run it.
 // Operands: the four 128-row tiles a block needs (Q_q, dO_q, K_k, V_k: 64 KB, TMA boxes cut out of the to_qkv output /
 // the cotangent, rows past T zero-filled) stream through a two-deep ring, loaded a block ahead -- also across items.
 // TMEM: S 128 + dP 128 + dV 64 + dK 64 + dQ 2 x 64 = 512 columns.  The softmax is NOT recomputed from scratch: the row
@@ -39,7 +45,7 @@ namespace {
 constexpr int DH = 64;
 constexpr int BT = 128;                      // block edge (UMMA M)
 constexpr int NTHR = 512;
-constexpr int ROWS_MAX = 208;                // longest sequence (S and dP of a block pair with dV, dK, dQ in 512 TMEM columns)
+constexpr int ROWS_MAX = 208;                // longest RESIDENT sequence (dQ of at most two query tiles stays in TMEM)
 constexpr int ATOM_BYTES = BT * 128;         // 128 rows x 64 columns of 16 bits: one operand tile, one 64-key atom of P / dS
 constexpr int SET_BYTES = 4 * ATOM_BYTES;    // Q_q, dO_q, K_k, V_k of one block
 constexpr int OFF_P = 2 * SET_BYTES, OFF_DS = OFF_P + 2 * ATOM_BYTES;
@@ -47,20 +53,20 @@ constexpr int OFF_BAR = OFF_DS + 4 * ATOM_BYTES;      // two dS tiles (consecuti
 constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
 constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;   // TMEM columns
 
-template <int kDT>
+template <int kDT, bool kStream>
 __global__ void __launch_bounds__(NTHR, 1)
 attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B, T, 3I], box 128 rows x 64
                          const __grid_constant__ CUtensorMap tmDO,    // d_out [B, T, I], box 128 rows x 64
                          const float* __restrict__ lse2, const float* __restrict__ dsum,
-                         uint16_t* __restrict__ dqkv, int T, int heads, int items) {
+                         uint16_t* __restrict__ dqkv, float* __restrict__ dq_acc, int T, int heads, int items) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sP = base + OFF_P, sDS = base + OFF_DS, bars = base + OFF_BAR;
   const uint32_t set_full0 = bars /* [2] */, set_empty0 = bars + 16 /* [2] */, pds_ready = bars + 32, p_free = bars + 40,
-                 ds_free0 = bars + 48 /* [2] */, dkv_ready = bars + 64, dkv_free = bars + 72, dq_ready = bars + 80,
-                 dq_free = bars + 88, sdp_ready0 = bars + 96 /* [2]: per 64-key half of a block */,
-                 sdp_free0 = bars + 112 /* [2] */, tmem_slot = bars + 128;
+                 ds_free0 = bars + 48 /* [2] */, dkv_ready = bars + 64, dkv_free = bars + 72,
+                 sdp_ready0 = bars + 96 /* [2]: per 64-key half of a block */, sdp_free0 = bars + 112 /* [2] */,
+                 tmem_slot = bars + 128, dq_ready0 = bars + 144 /* [2]: resident mode uses [0] */, dq_free0 = bars + 160 /* [2] */;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + 128);
   // operand tiles of the block in ring slot s
   auto sQ = [&](int s) { return base + uint32_t(s) * SET_BYTES; };
@@ -71,12 +77,24 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = heads * DH;
   const int TP = (T + 15) & ~15;                             // rows the MMAs see (zero-filled past T by TMA)
-  const int ntile = (T + BT - 1) / BT;                       // key tiles == query tiles (1 or 2)
-  const int nb = ntile * ntile;                              // blocks per item, key tile outermost
+  const int ntile = (T + BT - 1) / BT;                       // key tiles == query tiles (resident: 1 or 2)
   auto ext = [&](int t) { return min(BT, TP - t * BT); };    // valid (padded) rows of tile t: 128, or 80 at T = 197
-  const int my_items = blockIdx.x < items ? (items - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
-  const int G = my_items * nb;                               // this CTA's flat block sequence: g -> (item g / nb, block g % nb)
-  auto item_of = [&](int g) { return int(blockIdx.x) + (g / nb) * int(gridDim.x); };
+  // unit of work: resident = an (image, head), ntile^2 blocks, key tile outermost; streamed = an (image, head, key tile),
+  // ntile blocks (its query tiles).  A CTA takes units blockIdx.x, blockIdx.x + gridDim.x, ... and walks their blocks as
+  // ONE flat sequence g -> (unit g / nb, block g % nb).
+  const int nb = kStream ? ntile : ntile * ntile;
+  const int units = kStream ? items * ntile : items;
+  const int my_units = int(blockIdx.x) < units ? (units - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+  const int G = my_units * nb;
+  struct Blk { int item, kt, qt, j; };
+  auto block_of = [&](int g) {
+    const int u = int(blockIdx.x) + (g / nb) * int(gridDim.x), j = g % nb;
+    Blk b;
+    b.j = j;
+    if (kStream) { b.item = u / ntile; b.kt = u - b.item * ntile; b.qt = j; }
+    else { b.item = u; b.kt = j / ntile; b.qt = j - b.kt * ntile; }
+    return b;
+  };
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmDO); }
   if (warp == 1 && lane == 0) {
@@ -87,7 +105,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
     }
     mbar_init(pds_ready, 8); mbar_init(p_free, 1);
     mbar_init(dkv_ready, 1); mbar_init(dkv_free, 4);
-    mbar_init(dq_ready, 1);  mbar_init(dq_free, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(dq_ready0 + 8 * i, 1); mbar_init(dq_free0 + 8 * i, 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
@@ -102,8 +120,9 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
     // ===================== TMA producer: the four operand tiles of every block, one block ahead =====================
     if (lane == 0) {
       for (int g = 0; g < G; ++g) {
-        const int item = item_of(g), j = g % nb, kt = j / ntile, qt = j - kt * ntile;
-        const int b = item / heads, h = item - b * heads, s = g & 1;
+        const Blk bk = block_of(g);
+        const int kt = bk.kt, qt = bk.qt;
+        const int b = bk.item / heads, h = bk.item - b * heads, s = g & 1;
         mbar_wait(set_empty0 + 8u * s, (uint32_t(g >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(set_full0 + 8u * s, SET_BYTES);
         tma_load_3d(sQ(s), &tmQKV, set_full0 + 8u * s, h * DH, qt * BT, b);
@@ -122,7 +141,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
       constexpr uint32_t idesc_q = umma_idesc_16(BT, DH, fmt, 1, 0);          // A K-major, B MN-major: dQ
       // half hf (64 keys) of S = Q_q K_k^T and dP = dO_q V_k^T of block g, once the math warps have read the previous block's
       auto issue_half = [&](int g, int hf) {
-        const int kt = (g % nb) / ntile, s = g & 1;
+        const int kt = block_of(g).kt, s = g & 1;
         const uint32_t bph = uint32_t(g & 1);
         const int nkh = max(0, min(64, ext(kt) - 64 * hf));                   // keys of this half: 64, 16 (T = 197 tail) or 0
         mbar_wait(sdp_free0 + 8u * hf, bph ^ 1u);
@@ -147,7 +166,8 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
         issue_half(0, 1);
       }
       for (int g = 0; g < G; ++g) {
-        const int it = g / nb, j = g - it * nb, kt = j / ntile, qt = j - kt * ntile, s = g & 1;
+        const Blk bk = block_of(g);
+        const int it = g / nb, j = bk.j, kt = bk.kt, qt = bk.qt, s = g & 1;
         const int nk = ext(kt), nq = ext(qt);
         const uint32_t bph = uint32_t(g & 1);
         const uint32_t ds_tile = sDS + uint32_t(g & 1) * 2 * ATOM_BYTES;
@@ -162,7 +182,12 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
         //      MN-major;  dQ_q += dS K_k : A = the dS tile read K-major, B = K_k MN-major.  Three independent accumulators:
         //      their k-steps are interleaved so that they overlap in the tensor pipeline.
         if (qt == 0) { mbar_wait(dkv_free, uint32_t(kti & 1) ^ 1u); }         // the previous key tile's dK / dV were drained
-        if (j == 0) mbar_wait(dq_free, uint32_t(it & 1) ^ 1u);                // the previous item's dQ was drained
+        // dQ: resident = one accumulator per query tile, kept over the item's key tiles; streamed = a fresh accumulator per
+        // block, two alternating, drained by the epilogue warps a block later
+        const uint32_t d_dq = tmem_base + COL_DQ + uint32_t(kStream ? (g & 1) : qt) * DH;
+        if (kStream) mbar_wait(dq_free0 + 8u * uint32_t(g & 1), (uint32_t(g >> 1) & 1u) ^ 1u);
+        else if (j == 0) mbar_wait(dq_free0, uint32_t(it & 1) ^ 1u);          // the previous item's dQ was drained
+        const bool dq_fresh = kStream || kt == 0;
         tc_fence_after();
         for (int kk = 0; kk < 8; ++kk) {
           if (kk < nq / 16) {
@@ -172,14 +197,15 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
                             idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
           }
           if (kk < nk / 16)
-            umma_bf16_ss<1>(tmem_base + COL_DQ + qt * DH, umma_desc_k_sw128(ds_tile + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32),
-                            umma_desc_mn_sw128(sK(s) + kk * 2048), idesc_q, (kt != 0 || kk != 0) ? 1u : 0u);
+            umma_bf16_ss<1>(d_dq, umma_desc_k_sw128(ds_tile + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32),
+                            umma_desc_mn_sw128(sK(s) + kk * 2048), idesc_q, (!dq_fresh || kk != 0) ? 1u : 0u);
         }
         umma_commit(p_free);
         umma_commit(ds_free0 + 8u * uint32_t(g & 1));
         umma_commit(set_empty0 + 8u * uint32_t(s));        // the block's operand tiles may be overwritten
         if (qt == ntile - 1) { umma_commit(dkv_ready); ++kti; }
-        if (j == nb - 1) umma_commit(dq_ready);
+        if (kStream) umma_commit(dq_ready0 + 8u * uint32_t(g & 1));
+        else if (j == nb - 1) umma_commit(dq_ready0);
       }
     }
     __syncwarp();
@@ -189,31 +215,28 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
     const int r = q * 32 + lane;                           // row inside the query tile == TMEM lane
     const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
     const float sl2 = 0.125f * 1.4426950408889634f;
-    // per row: lse2 from the forward and D = sum_d dO O; the NEXT item's are loaded while this one is worked on
-    float Ln[2] = {0.f, 0.f}, Dn[2] = {0.f, 0.f}, L[2] = {0.f, 0.f}, Dv[2] = {0.f, 0.f};
-    auto load_stats = [&](int item) {
-#pragma unroll
-      for (int qt = 0; qt < 2; ++qt) {
-        const int qrow = qt * BT + r;
-        const bool ok = qt < ntile && qrow < T;
-        Ln[qt] = ok ? __ldg(lse2 + (int64_t(item) * T + qrow)) : 0.f;
-        Dn[qt] = ok ? __ldg(dsum + (int64_t(item) * T + qrow)) : 0.f;
-      }
+    // per row: lse2 from the forward and D = sum_d dO O of the block's query tile; the NEXT block's are loaded while
+    // this one is worked on
+    float Ln = 0.f, Dn = 0.f;
+    auto load_stats = [&](int g) {
+      const Blk nx = block_of(g);
+      const int qrow = nx.qt * BT + r;
+      const bool ok = qrow < T;
+      Ln = ok ? __ldg(lse2 + (int64_t(nx.item) * T + qrow)) : 0.f;
+      Dn = ok ? __ldg(dsum + (int64_t(nx.item) * T + qrow)) : 0.f;
     };
-    if (G > 0) load_stats(item_of(0));
+    if (G > 0) load_stats(0);
     for (int blk = 0; blk < G; ++blk) {
-      const int it = blk / nb, j = blk - it * nb, kt = j / ntile, qt = j - kt * ntile;
-      if (j == 0) {
-        L[0] = Ln[0]; L[1] = Ln[1]; Dv[0] = Dn[0]; Dv[1] = Dn[1];
-        if (blk + nb < G) load_stats(item_of(blk + nb));
-      }
+      const Blk bk = block_of(blk);
+      const int kt = bk.kt, qt = bk.qt;
+      const float lse = Ln, Dq8 = Dn * 0.125f;
+      if (blk + 1 < G) load_stats(blk + 1);
       {
         const int nk = ext(kt);
         {
           const uint32_t bph = uint32_t(blk & 1);
           const int qrow = qt * BT + r;
           const bool row_ok = qrow < T;
-          const float lse = L[qt], Dq8 = Dv[qt] * 0.125f;
           const uint32_t ds_tile = sDS + uint32_t(blk & 1) * 2 * ATOM_BYTES;
           bool tiles_free = false;                         // waited for lazily: the first exponentials overlap the MMAs
           for (int hf = 0; hf < 2; ++hf) {                 // the block's two 64-key halves (TMEM double buffer)
@@ -305,30 +328,61 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
                                                         pack2<kDT>(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
       }
     };
-    int kti = 0;
-    for (int it = 0; it < my_items; ++it) {
-      const int item = int(blockIdx.x) + it * int(gridDim.x);
+    // dK / dV of a finished key tile -> 16-bit rows of dqkv
+    auto drain_dkv = [&](int item, int kt, int kti) {
       const int b = item / heads, h = item - b * heads;
       uint16_t* rowbase = dqkv + int64_t(b) * T * ld + h * DH;
-      for (int kt = 0; kt < ntile; ++kt, ++kti) {
-        const int key = kt * BT + r;
-        mbar_wait(dkv_ready, uint32_t(kti & 1));
-        tc_fence_after();
-        store_row(COL_DK, key < T ? rowbase + int64_t(key) * ld + inner : nullptr);
-        store_row(COL_DV, key < T ? rowbase + int64_t(key) * ld + 2 * inner : nullptr);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dkv_free);
-      }
-      mbar_wait(dq_ready, uint32_t(it & 1));
+      const int key = kt * BT + r;
+      mbar_wait(dkv_ready, uint32_t(kti & 1));
       tc_fence_after();
-      for (int qt = 0; qt < ntile; ++qt) {
-        const int qrow = qt * BT + r;
-        store_row(COL_DQ + qt * DH, qrow < T ? rowbase + int64_t(qrow) * ld : nullptr);
-      }
+      store_row(COL_DK, key < T ? rowbase + int64_t(key) * ld + inner : nullptr);
+      store_row(COL_DV, key < T ? rowbase + int64_t(key) * ld + 2 * inner : nullptr);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dq_free);
+      if (lane == 0) mbar_arrive(dkv_free);
+    };
+    if constexpr (kStream) {
+      // one dQ contribution per block: 64 fp32 columns of this lane's query row are ADDED into dq_acc [B T, heads 64]
+      int kti = 0;
+      for (int g = 0; g < G; ++g) {
+        const Blk bk = block_of(g);
+        const int b = bk.item / heads, h = bk.item - b * heads;
+        const int qrow = bk.qt * BT + r;
+        mbar_wait(dq_ready0 + 8u * uint32_t(g & 1), uint32_t(g >> 1) & 1u);
+        tc_fence_after();
+        uint32_t v[64];
+        tmem_ld_32x32b_x32p(t_lane + COL_DQ + uint32_t(g & 1) * DH, v);
+        tmem_ld_32x32b_x32p(t_lane + COL_DQ + uint32_t(g & 1) * DH + 32, v + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_free0 + 8u * uint32_t(g & 1));
+        if (qrow < T) {
+          float* dst = dq_acc + (int64_t(b) * T + qrow) * inner + h * DH;
+#pragma unroll
+          for (int c = 0; c < 64; c += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(__uint_as_float(v[c])),
+                         "f"(__uint_as_float(v[c + 1])), "f"(__uint_as_float(v[c + 2])), "f"(__uint_as_float(v[c + 3])) : "memory");
+        }
+        if (bk.qt == ntile - 1) { drain_dkv(bk.item, bk.kt, kti); ++kti; }
+      }
+    } else {
+      int kti = 0;
+      for (int it = 0; it < my_units; ++it) {
+        const int item = int(blockIdx.x) + it * int(gridDim.x);
+        const int b = item / heads, h = item - b * heads;
+        uint16_t* rowbase = dqkv + int64_t(b) * T * ld + h * DH;
+        for (int kt = 0; kt < ntile; ++kt, ++kti) drain_dkv(item, kt, kti);
+        mbar_wait(dq_ready0, uint32_t(it & 1));
+        tc_fence_after();
+        for (int qt = 0; qt < ntile; ++qt) {
+          const int qrow = qt * BT + r;
+          store_row(COL_DQ + qt * DH, qrow < T ? rowbase + int64_t(qrow) * ld : nullptr);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_free0);
+      }
     }
   }
 
@@ -368,12 +422,12 @@ attn_bwd_rowdot_kernel(const uint16_t* __restrict__ d_out, const uint16_t* __res
   }
 }
 
-template <int kDT>
-int launch_t(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, const float* lse2, const float* dsum, int batch,
-             int T, int heads) {
+template <int kDT, bool kStream>
+int launch_t(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, const float* lse2, const float* dsum,
+             float* dq_acc, int batch, int T, int heads) {
   static PerDevice<bool> configured_on;
   if (bool& configured = configured_on.here(); !configured) {
-    VB_CUDA(cudaFuncSetAttribute(attention_bwd_tc5_kernel<kDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    VB_CUDA(cudaFuncSetAttribute(attention_bwd_tc5_kernel<kDT, kStream>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured = true;
   }
   const int inner = heads * DH;
@@ -382,9 +436,10 @@ int launch_t(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, co
   if ((rc = make_tmap_3d_16(&tq, qkv, batch, T, 3 * inner, 3 * inner, BT, kDT))) return rc;
   if ((rc = make_tmap_3d_16(&tdo, d_out, batch, T, inner, inner, BT, kDT))) return rc;
   const int items = batch * heads;
-  const int grid = items < sm_count() ? items : sm_count();
-  VB_CUDA(launch_kernel(attention_bwd_tc5_kernel<kDT>, dim3(grid), dim3(NTHR), SMEM_TOTAL, st, 1, tq, tdo, lse2, dsum,
-                        static_cast<uint16_t*>(dqkv), T, heads, items));
+  const int64_t units = kStream ? int64_t(items) * ((T + BT - 1) / BT) : items;
+  const int grid = int(units < sm_count() ? units : sm_count());
+  VB_CUDA(launch_kernel(attention_bwd_tc5_kernel<kDT, kStream>, dim3(grid), dim3(NTHR), SMEM_TOTAL, st, 1, tq, tdo, lse2, dsum,
+                        static_cast<uint16_t*>(dqkv), dq_acc, T, heads, items));
   VB_LAUNCH_CHECK("attention_bwd_tc5_kernel");
   return 0;
 }
@@ -410,11 +465,28 @@ int launch_attention_bwd_rowdot(cudaStream_t st, const void* d_out, const void* 
 int launch_attention_bwd_tc5(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, const float* lse2,
                              const float* dsum, int batch, int T, int heads, int dtype) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
-  if (!attention_bwd_tc5_supports(T)) return fail(VITB200_ERR_UNSUPPORTED, "attention_bwd_tc5: T > 208");
+  if (!attention_bwd_tc5_supports(T)) return fail(VITB200_ERR_UNSUPPORTED, "attention_bwd_tc5: T > 208 needs the streamed form");
   if (lse2 == nullptr || dsum == nullptr) return fail(VITB200_ERR_INVALID, "attention_bwd_tc5: needs the forward's row log-sum-exp and D");
-  if (dtype == DT_BF16) return launch_t<DT_BF16>(st, qkv, d_out, dqkv, lse2, dsum, batch, T, heads);
-  if (dtype == DT_F16) return launch_t<DT_F16>(st, qkv, d_out, dqkv, lse2, dsum, batch, T, heads);
+  if (dtype == DT_BF16) return launch_t<DT_BF16, false>(st, qkv, d_out, dqkv, lse2, dsum, nullptr, batch, T, heads);
+  if (dtype == DT_F16) return launch_t<DT_F16, false>(st, qkv, d_out, dqkv, lse2, dsum, nullptr, batch, T, heads);
   return fail(VITB200_ERR_INVALID, "attention_bwd: dtype must be bf16 or fp16");
+}
+
+// any T: dK / dV from TMEM per (image, head, key tile), dQ summed into dq_acc (fp32 [batch * T, heads * 64], zeroed here)
+// and converted into the q third of dqkv by a last pass
+int launch_attention_bwd_tc5_stream(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, const float* lse2,
+                                    const float* dsum, float* dq_acc, int batch, int T, int heads, int dtype) {
+  if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
+  if (lse2 == nullptr || dsum == nullptr || dq_acc == nullptr)
+    return fail(VITB200_ERR_INVALID, "attention_bwd_tc5: the streamed form needs lse2, D and the fp32 dQ buffer");
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(VITB200_ERR_INVALID, "attention_bwd: dtype must be bf16 or fp16");
+  const int64_t rows = int64_t(batch) * T;
+  const int inner = heads * DH;
+  VB_CUDA(cudaMemsetAsync(dq_acc, 0, size_t(rows) * inner * sizeof(float), st));
+  int rc = dtype == DT_BF16 ? launch_t<DT_BF16, true>(st, qkv, d_out, dqkv, lse2, dsum, dq_acc, batch, T, heads)
+                            : launch_t<DT_F16, true>(st, qkv, d_out, dqkv, lse2, dsum, dq_acc, batch, T, heads);
+  if (rc) return rc;
+  return launch_dq_convert(st, dq_acc, dqkv, rows, inner, dtype);
 }
 
 }  // namespace vb

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NT, 1)
 attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I], box 128 rows
                       const __grid_constant__ CUtensorMap tmKV,   // qkv [B,T,3I], box KP rows
                       const __grid_constant__ CUtensorMap tmO,    // out [B,T,I],  box 128 rows
-                      int T, int heads, int nqt, int nkb, int items, int turns) {
+                      int T, int heads, int nqt, int nkb, int items, int turns, float* __restrict__ lse_out) {
   using L = SmemM<KP>;
   constexpr uint32_t O_COL = 2 * KP;
   extern __shared__ uint8_t smem_raw[];
@@ -333,7 +333,11 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
           float l0, l1;
           unpack_f32x2(add_f32x2(la, lb), l0, l1);
           l += l0 + l1;
-          if (j == nkb - 1) inv_sh[(i & 3) * 128 + row] = 1.0f / l;   // for the epilogue warps
+          if (j == nkb - 1) {
+            inv_sh[(i & 3) * 128 + row] = 1.0f / l;   // for the epilogue warps
+            // training: the row's log-sum-exp in the log2 domain (m is the running max of the raw scores), for the adjoint
+            if (lse_out != nullptr && qt * QT + row < T) lse_out[int64_t(bh) * T + qt * QT + row] = m * sl2 + __log2f(l);
+          }
           tmem_st_wait();
         } else if (turns) {
           wait_turn(xu_done, turn);
@@ -418,7 +422,7 @@ int attn_m_turns() {   // VITB200_ATTN_TURNS=0: free-running groups (A/B tests)
 }
 
 template <int kDT, int KP>
-int launch_m(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
+int launch_m(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
   using L = SmemM<KP>;
   static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
   if (bool& configured = configured_on.here(); !configured) {
@@ -438,25 +442,25 @@ int launch_m(cudaStream_t stream, const void* qkv, void* out, int batch, int T, 
   const int items = int(items64);
   const int grid = items < sm_count() ? items : sm_count();
   VB_CUDA(launch_kernel(attention_tc5m_kernel<kDT, KP>, dim3(grid), dim3(NT), L::TOTAL, stream, 1,
-                        tq, tkv, to, T, heads, nqt, nkb, items, attn_m_turns()));
+                        tq, tkv, to, T, heads, nqt, nkb, items, attn_m_turns(), lse));
   VB_LAUNCH_CHECK("attention_tc5m_kernel");
   return 0;
 }
 
 template <int kDT>
-int launch_m_dt(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads) {
+int launch_m_dt(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads, float* lse) {
   // two blocks of 144 cover T <= 288 (ViT-H/14: 257) with less padding than two of 192
-  if (T <= 288) return launch_m<kDT, 144>(stream, qkv, out, batch, T, heads);
-  return launch_m<kDT, 192>(stream, qkv, out, batch, T, heads);
+  if (T <= 288) return launch_m<kDT, 144>(stream, qkv, out, batch, T, heads, lse);
+  return launch_m<kDT, 192>(stream, qkv, out, batch, T, heads, lse);
 }
 
 }  // namespace
 
 int launch_attention_tc5m(cudaStream_t stream, const void* qkv, void* out, int batch, int T, int heads,
-                          int dtype) {
+                          int dtype, float* lse) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention: empty problem");
-  if (dtype == DT_BF16) return launch_m_dt<DT_BF16>(stream, qkv, out, batch, T, heads);
-  if (dtype == DT_F16) return launch_m_dt<DT_F16>(stream, qkv, out, batch, T, heads);
+  if (dtype == DT_BF16) return launch_m_dt<DT_BF16>(stream, qkv, out, batch, T, heads, lse);
+  if (dtype == DT_F16) return launch_m_dt<DT_F16>(stream, qkv, out, batch, T, heads, lse);
   return fail(VITB200_ERR_INVALID, "attention: dtype must be bf16 or fp16");
 }
 

@@ -907,8 +907,9 @@ int launch_token_grads(cudaStream_t st, const float* dx, float* dpos, float* dcl
 
 int attention_bwd_max_tokens() { return ABW_MAX_T; }
 
-// Default: the tcgen05 kernel (attention_bwd_tc5.cu) when T <= 208 and the streamed kernels beyond.  VITB200_ATTN_BWD=flash
-// forces the streamed ones everywhere, =hmma the first, shared-memory-resident mma.sync kernel (A/B tests).
+// Default: the tcgen05 kernel (attention_bwd_tc5.cu), resident form when T <= 208 and streamed form beyond.
+// VITB200_ATTN_BWD=flash forces the streamed mma.sync kernels everywhere, =hmma the first, shared-memory-resident mma.sync
+// kernel (A/B tests).
 static int attn_bwd_force_flash() {
   const char* e = getenv("VITB200_ATTN_BWD");
   return e && e[0] == 'f';
@@ -940,11 +941,24 @@ int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* o_fwd, co
     return rc;
   }
   if (attention_bwd_needs_workspace(T)) {
-    if (workspace != nullptr) return launch_attention_bwd_flash(st, qkv, o_fwd, d_out, dqkv, workspace, batch, T, heads, dtype);
-    float* ws = nullptr;                     // per-kernel entry point: stream-ordered scratch
-    VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), attention_bwd_flash_workspace_floats(batch, T, heads) * sizeof(float), st));
-    const int rc = launch_attention_bwd_flash(st, qkv, o_fwd, d_out, dqkv, ws, batch, T, heads, dtype);
-    cudaFreeAsync(ws, st);
+    // beyond 208 tokens: the tcgen05 kernel in its streamed form (dQ summed in an fp32 buffer); VITB200_ATTN_BWD=flash
+    // keeps the mma.sync kernels of attention_bwd_flash.cu (A/B tests).  Workspace layout of both: lse2 | D | dq_acc.
+    float* ws = workspace;
+    if (ws == nullptr)                       // per-kernel entry point: stream-ordered scratch
+      VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), attention_bwd_flash_workspace_floats(batch, T, heads) * sizeof(float), st));
+    int rc;
+    if (attn_bwd_force_flash()) {
+      rc = launch_attention_bwd_flash(st, qkv, o_fwd, d_out, dqkv, ws, batch, T, heads, dtype);
+    } else {
+      const size_t n = size_t(round_up(int64_t(batch) * heads * T, 64));
+      float* dsum = ws + n;
+      float* dq_acc = ws + 2 * n;
+      // the row log-sum-exp: from the forward when it kept it (train_forward), else from the statistics kernel (with D)
+      rc = lse2 ? launch_attention_bwd_rowdot(st, d_out, o_fwd, dsum, batch, T, heads, dtype)
+                : launch_attention_bwd_stats(st, qkv, o_fwd, d_out, ws, dsum, batch, T, heads, dtype);
+      if (!rc) rc = launch_attention_bwd_tc5_stream(st, qkv, d_out, dqkv, lse2 ? lse2 : ws, dsum, dq_acc, batch, T, heads, dtype);
+    }
+    if (workspace == nullptr) cudaFreeAsync(ws, st);
     return rc;
   }
   const int TP = (T + 15) / 16 * 16, pitch = TP * 2 + 16;

@@ -137,7 +137,7 @@ int launch_attention_tc5(cudaStream_t stream, const void* qkv, void* out, int ba
                          int heads, int dtype, float* lse = nullptr);
 // tcgen05 kernel for T > 208: streamed key blocks, online softmax (attention_tc5m.cu)
 int launch_attention_tc5m(cudaStream_t stream, const void* qkv, void* out, int batch, int T,
-                          int heads, int dtype);
+                          int heads, int dtype, float* lse = nullptr);
 int launch_attention_f32(cudaStream_t stream, const float* qkv, float* out, int batch, int T,
                          int heads);
 int launch_patchify(cudaStream_t stream, const float* images, void* patches, int batch, int H,
@@ -197,6 +197,11 @@ int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* o_fwd
 bool attention_bwd_tc5_supports(int T);
 int launch_attention_bwd_tc5(cudaStream_t stream, const void* qkv, const void* d_out, void* dqkv, const float* lse2,
                              const float* dsum, int batch, int T, int heads, int dtype);
+// the same kernel for any T (attention_bwd_tc5.cu, streamed mode): dQ contributions are summed in dq_acc (fp32
+// [batch * T, heads * 64]) and converted into dqkv at the end
+int launch_attention_bwd_tc5_stream(cudaStream_t stream, const void* qkv, const void* d_out, void* dqkv, const float* lse2,
+                                    const float* dsum, float* dq_acc, int batch, int T, int heads, int dtype);
+int launch_dq_convert(cudaStream_t stream, const float* dq_acc, void* dqkv, int64_t rows, int inner, int dtype);
 // dsum [batch*heads, T] = rowsum(dO o O) per (image, head, token): the D of the softmax adjoint
 int launch_attention_bwd_rowdot(cudaStream_t stream, const void* d_out, const void* o_fwd, float* dsum, int batch, int T,
                                 int heads, int dtype);
