@@ -34,6 +34,7 @@
 // split a half's key columns), 12..15 epilogue (dK / dV per key tile, dQ per item -> 16-bit rows of dqkv).
 // Bound: the XU pipe -- one ex2 and two fp32->16-bit packs per score, 16 cycles per score pair per SMSP.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.h"
@@ -177,30 +178,36 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
           issue_half(g + 1, 0);
         }
         mbar_wait(pds_ready, bph);                         // P and dS of this block are in shared memory
-        if (g + 1 < G) issue_half(g + 1, 1);
-        // ---- dV_k += P^T dO_q, dK_k += dS^T Q_q : A = the P / dS tile read MN-major (M = key, K = query), B = dO_q / Q_q
-        //      MN-major;  dQ_q += dS K_k : A = the dS tile read K-major, B = K_k MN-major.  Three independent accumulators:
-        //      their k-steps are interleaved so that they overlap in the tensor pipeline.
+        // Order of issue (one tcgen05.mma costs the issuing thread ~50 cycles whatever its size --
+        // profiles/microbench/mma_chain.cu -- so a block's 40 are ~2 k cycles): dV first, so that the single P tile is
+        // released to the next block's math warps early; then the next block's second half of S / dP; dK and dQ last (the
+        // dS tile is double-buffered).  Measured against "everything after the next block's halves": the same step time
+        // (24.3 ms of backward at ViT-B/16 batch 256 either way, gpurun_out/r03c_train.log) -- the P tile is not what the
+        // math warps wait for.
+        // ---- dV_k += P^T dO_q : A = the P tile read MN-major (M = key, K = query), B = dO_q MN-major ----
         if (qt == 0) { mbar_wait(dkv_free, uint32_t(kti & 1) ^ 1u); }         // the previous key tile's dK / dV were drained
-        // dQ: resident = one accumulator per query tile, kept over the item's key tiles; streamed = a fresh accumulator per
-        // block, two alternating, drained by the epilogue warps a block later
+        tc_fence_after();
+        for (int kk = 0; kk < nq / 16; ++kk)
+          umma_bf16_ss<1>(d_dv, umma_desc_mn_sw128_wide(sP + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(sDO(s) + kk * 2048),
+                          idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
+        umma_commit(p_free);
+        if (g + 1 < G) issue_half(g + 1, 1);
+        // ---- dK_k += dS^T Q_q (A = the dS tile read MN-major) and dQ_q += dS K_k (A = the dS tile read K-major, B = K_k
+        //      MN-major).  dQ: resident = one accumulator per query tile, kept over the item's key tiles; streamed = a fresh
+        //      accumulator per block, two alternating, drained by the epilogue warps a block later
         const uint32_t d_dq = tmem_base + COL_DQ + uint32_t(kStream ? (g & 1) : qt) * DH;
         if (kStream) mbar_wait(dq_free0 + 8u * uint32_t(g & 1), (uint32_t(g >> 1) & 1u) ^ 1u);
         else if (j == 0) mbar_wait(dq_free0, uint32_t(it & 1) ^ 1u);          // the previous item's dQ was drained
         const bool dq_fresh = kStream || kt == 0;
         tc_fence_after();
         for (int kk = 0; kk < 8; ++kk) {
-          if (kk < nq / 16) {
-            umma_bf16_ss<1>(d_dv, umma_desc_mn_sw128_wide(sP + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(sDO(s) + kk * 2048),
-                            idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
+          if (kk < nq / 16)
             umma_bf16_ss<1>(d_dk, umma_desc_mn_sw128_wide(ds_tile + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(sQ(s) + kk * 2048),
                             idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
-          }
           if (kk < nk / 16)
             umma_bf16_ss<1>(d_dq, umma_desc_k_sw128(ds_tile + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32),
                             umma_desc_mn_sw128(sK(s) + kk * 2048), idesc_q, (!dq_fresh || kk != 0) ? 1u : 0u);
         }
-        umma_commit(p_free);
         umma_commit(ds_free0 + 8u * uint32_t(g & 1));
         umma_commit(set_empty0 + 8u * uint32_t(s));        // the block's operand tiles may be overwritten
         if (qt == ntile - 1) { umma_commit(dkv_ready); ++kti; }
