@@ -17,7 +17,7 @@ struct Case {
   int N, L, accs, ts, ld_warps;
 };
 
-template <int N, int L, int ACCS, bool TS>
+template <int N, int L, int ACCS, int TS>
 __global__ void __launch_bounds__(512, 1) k(Case c, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -47,7 +47,13 @@ __global__ void __launch_bounds__(512, 1) k(Case c, long long* out) {
         const int a = i % ACCS;
         const uint32_t d = tmem_base + 256 + a * 64;             // accumulators at columns 256.. (N <= 64 when ACCS > 1)
         const uint32_t acc = i >= ACCS ? 1u : 0u;
-        if (TS) umma_bf16_ts(d, tmem_base + (i % 13) * 8, umma_desc_mn_sw128(sB + (i % 13) * 2048), idesc_mn, acc);
+        // TS: 0 = both operands K-major from smem (Q K^T), 1 = A from TMEM, B MN-major (forward P V), 2 = A MN-major two
+        // atoms wide + B MN-major (adjoint dV = P^T dO, dK = dS^T Q), 3 = A K-major + B MN-major (adjoint dQ = dS K)
+        if (TS == 1) umma_bf16_ts(d, tmem_base + (i % 13) * 8, umma_desc_mn_sw128(sB + (i % 13) * 2048), idesc_mn, acc);
+        else if (TS == 2) umma_bf16_ss<1>(d, umma_desc_mn_sw128_wide(sB + (i & 7) * 2048, 16384), umma_desc_mn_sw128(sA + (i & 7) * 2048),
+                                          umma_idesc_16(128, N, 1, 1, 1), acc);
+        else if (TS == 3) umma_bf16_ss<1>(d, umma_desc_k_sw128(sB + (i >> 2 & 1) * 16384 + (i & 3) * 32), umma_desc_mn_sw128(sA + (i & 7) * 2048),
+                                          idesc_mn, acc);
         else umma_bf16_ss<1>(d, umma_desc_k_sw128(sA + (i & 3) * 32), umma_desc_k_sw128(sB + (i & 3) * 32), idesc_k, acc);
       }
       umma_commit(done);
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(512, 1) k(Case c, long long* out) {
   } else if (warp >= 4 && warp < 4 + c.ld_warps) {
     // background warps, like the softmax passes.  c.ts >> 4 selects what they do: 0 = tcgen05.ld over columns [0, 192)
     // of their lane quarter; 1 = ld + tcgen05.st (columns 192..207); 2 = MUFU only (no TMEM); 3 = ld + MUFU + st
-    const int mode = c.ts >> 4;
+    const int mode = c.ts >> 4;   // (the low four bits are the operand form)
     uint32_t r[32];
     float acc = 0.f;
     const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
@@ -90,11 +96,11 @@ __global__ void __launch_bounds__(512, 1) k(Case c, long long* out) {
   if (warp == 2) { tc_fence_after(); tmem_dealloc<1>(tmem_base, 512); }
 }
 
-template <int N, int L, int ACCS, bool TS>
+template <int N, int L, int ACCS, int TS>
 void run(long long* out, int ld_warps) {
   const int smem = 16384 + 32768 + 1024 + 1024;
   cudaFuncSetAttribute(k<N, L, ACCS, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  Case c{N, L, ACCS, int(TS) | ((ld_warps >> 8) << 4), ld_warps & 255};
+  Case c{N, L, ACCS, (TS & 15) | ((ld_warps >> 8) << 4), ld_warps & 255};
   ld_warps = c.ld_warps;
   k<N, L, ACCS, TS><<<148, 512, smem>>>(c, out);
   if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); exit(1); }
@@ -107,35 +113,42 @@ int main() {
   long long* out;
   cudaMalloc(&out, 64);
   printf("%5s %4s %5s %3s %9s | %8s %8s %10s\n", "N", "L", "accs", "TS", "ld_warps", "issue", "done", "done/L");
-  run<16, 16, 1, false>(out, 0);
-  run<64, 16, 1, false>(out, 0);
-  run<128, 16, 1, false>(out, 0);
-  run<208, 16, 1, false>(out, 0);
-  run<256, 16, 1, false>(out, 0);
-  run<208, 4, 1, false>(out, 0);
-  run<208, 1, 1, false>(out, 0);
-  run<64, 1, 1, true>(out, 0);
-  run<64, 4, 1, true>(out, 0);
-  run<64, 13, 1, true>(out, 0);
-  run<64, 16, 1, true>(out, 0);
-  run<32, 16, 1, true>(out, 0);
-  run<64, 16, 2, true>(out, 0);
-  run<64, 16, 4, true>(out, 0);
-  run<64, 16, 2, false>(out, 0);
-  run<64, 32, 1, true>(out, 0);
+  run<16, 16, 1, 0>(out, 0);
+  run<64, 16, 1, 0>(out, 0);
+  run<128, 16, 1, 0>(out, 0);
+  run<208, 16, 1, 0>(out, 0);
+  run<256, 16, 1, 0>(out, 0);
+  run<208, 4, 1, 0>(out, 0);
+  run<208, 1, 1, 0>(out, 0);
+  run<64, 1, 1, 1>(out, 0);
+  run<64, 4, 1, 1>(out, 0);
+  run<64, 13, 1, 1>(out, 0);
+  run<64, 16, 1, 1>(out, 0);
+  run<32, 16, 1, 1>(out, 0);
+  run<64, 16, 2, 1>(out, 0);
+  run<64, 16, 4, 1>(out, 0);
+  run<64, 16, 2, 0>(out, 0);
+  run<64, 32, 1, 1>(out, 0);
+  printf("adjoint shapes: A MN-major wide + B MN-major (TS=2), A K-major + B MN-major (TS=3), 8 and 24 in a row\n");
+  run<64, 8, 1, 0>(out, 0);
+  run<64, 8, 1, 2>(out, 0);
+  run<64, 8, 1, 3>(out, 0);
+  run<64, 24, 1, 2>(out, 0);
+  run<64, 24, 3, 2>(out, 0);
+  run<64, 8, 1, 2>(out, 8 | (3 << 8));
   printf("background warps (ld_warps): tcgen05.ld\n");
-  run<64, 13, 1, true>(out, 4);
-  run<64, 13, 1, true>(out, 8);
-  run<208, 4, 1, false>(out, 8);
+  run<64, 13, 1, 1>(out, 4);
+  run<64, 13, 1, 1>(out, 8);
+  run<208, 4, 1, 0>(out, 8);
   printf("background: ld + st\n");
-  run<64, 13, 1, true>(out, 8 | (1 << 8));
-  run<208, 4, 1, false>(out, 8 | (1 << 8));
+  run<64, 13, 1, 1>(out, 8 | (1 << 8));
+  run<208, 4, 1, 0>(out, 8 | (1 << 8));
   printf("background: MUFU only\n");
-  run<64, 13, 1, true>(out, 8 | (2 << 8));
-  run<208, 4, 1, false>(out, 8 | (2 << 8));
+  run<64, 13, 1, 1>(out, 8 | (2 << 8));
+  run<208, 4, 1, 0>(out, 8 | (2 << 8));
   printf("background: ld + MUFU + st\n");
-  run<64, 13, 1, true>(out, 4 | (3 << 8));
-  run<64, 13, 1, true>(out, 8 | (3 << 8));
-  run<208, 4, 1, false>(out, 8 | (3 << 8));
+  run<64, 13, 1, 1>(out, 4 | (3 << 8));
+  run<64, 13, 1, 1>(out, 8 | (3 << 8));
+  run<208, 4, 1, 0>(out, 8 | (3 << 8));
   return 0;
 }

@@ -41,6 +41,15 @@
 #include "ptx.cuh"
 
 namespace vb {
+
+#ifdef VITB200_TRACE
+// debug timeline of CTA 0: g_trace_bwd[event][block] = clock64 at the event (profiles/trace_attention_bwd.py)
+__device__ long long g_trace_bwd[12][64];
+#define TRACEB(ev, i) do { if (blockIdx.x == 0 && (i) < 64) g_trace_bwd[ev][i] = clock64(); } while (0)
+#else
+#define TRACEB(ev, i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int DH = 64;
@@ -48,8 +57,9 @@ constexpr int BT = 128;                      // block edge (UMMA M)
 constexpr int NTHR = 512;
 constexpr int ROWS_MAX = 208;                // longest RESIDENT sequence (dQ of at most two query tiles stays in TMEM)
 constexpr int ATOM_BYTES = BT * 128;         // 128 rows x 64 columns of 16 bits: one operand tile, one 64-key atom of P / dS
-constexpr int SET_BYTES = 4 * ATOM_BYTES;    // Q_q, dO_q, K_k, V_k of one block
-constexpr int OFF_P = 2 * SET_BYTES, OFF_DS = OFF_P + 2 * ATOM_BYTES;
+constexpr int PAIR_BYTES = 2 * ATOM_BYTES;   // (K_k, V_k) or (Q_q, dO_q): two operand tiles that are loaded and released together
+constexpr int OFF_KV = 0, OFF_QDO = 2 * PAIR_BYTES;   // two slots of each
+constexpr int OFF_P = 4 * PAIR_BYTES, OFF_DS = OFF_P + 2 * ATOM_BYTES;
 constexpr int OFF_BAR = OFF_DS + 4 * ATOM_BYTES;      // two dS tiles (consecutive blocks alternate), one P tile
 constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
 constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;   // TMEM columns
@@ -64,16 +74,17 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sP = base + OFF_P, sDS = base + OFF_DS, bars = base + OFF_BAR;
-  const uint32_t set_full0 = bars /* [2] */, set_empty0 = bars + 16 /* [2] */, pds_ready = bars + 32, p_free = bars + 40,
+  const uint32_t kv_full0 = bars /* [2] */, kv_empty0 = bars + 16 /* [2] */, pds_ready = bars + 32, p_free = bars + 40,
                  ds_free0 = bars + 48 /* [2] */, dkv_ready = bars + 64, dkv_free = bars + 72,
                  sdp_ready0 = bars + 96 /* [2]: per 64-key half of a block */, sdp_free0 = bars + 112 /* [2] */,
-                 tmem_slot = bars + 128, dq_ready0 = bars + 144 /* [2]: resident mode uses [0] */, dq_free0 = bars + 160 /* [2] */;
+                 tmem_slot = bars + 128, dq_ready0 = bars + 144 /* [2]: resident mode uses [0] */, dq_free0 = bars + 160 /* [2] */,
+                 qdo_full0 = bars + 176 /* [2] */, qdo_empty0 = bars + 192 /* [2] */;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + 128);
-  // operand tiles of the block in ring slot s
-  auto sQ = [&](int s) { return base + uint32_t(s) * SET_BYTES; };
-  auto sDO = [&](int s) { return base + uint32_t(s) * SET_BYTES + ATOM_BYTES; };
-  auto sK = [&](int s) { return base + uint32_t(s) * SET_BYTES + 2 * ATOM_BYTES; };
-  auto sV = [&](int s) { return base + uint32_t(s) * SET_BYTES + 3 * ATOM_BYTES; };
+  // operand tiles: (K, V) pair slot s, (Q, dO) pair slot s
+  auto sK = [&](int s) { return base + OFF_KV + uint32_t(s) * PAIR_BYTES; };
+  auto sV = [&](int s) { return base + OFF_KV + uint32_t(s) * PAIR_BYTES + ATOM_BYTES; };
+  auto sQ = [&](int s) { return base + OFF_QDO + uint32_t(s) * PAIR_BYTES; };
+  auto sDO = [&](int s) { return base + OFF_QDO + uint32_t(s) * PAIR_BYTES + ATOM_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int inner = heads * DH;
@@ -87,20 +98,37 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
   const int units = kStream ? items * ntile : items;
   const int my_units = int(blockIdx.x) < units ? (units - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
   const int G = my_units * nb;
-  struct Blk { int item, kt, qt, j; };
+  // Operand pairs are loaded ONCE per use span and released after their last use.  Resident: (K, V) of key tile kt in slot
+  // kt for the blocks (kt, *), (Q, dO) of query tile qt in slot qt for the blocks (*, qt) -- every tile of an item is
+  // loaded once, and the next item's tiles arrive while this item's later blocks run.  Streamed: (K, V) once per unit
+  // (slots alternate per unit), (Q, dO) per block (slots alternate per block).
+  struct Blk { int item, kt, qt, j, kvs, qs; uint32_t kvph, qph; bool kv_first, kv_last, q_first, q_last; };
   auto block_of = [&](int g) {
-    const int u = int(blockIdx.x) + (g / nb) * int(gridDim.x), j = g % nb;
+    const int un = g / nb, u = int(blockIdx.x) + un * int(gridDim.x), j = g - un * nb;
     Blk b;
     b.j = j;
-    if (kStream) { b.item = u / ntile; b.kt = u - b.item * ntile; b.qt = j; }
-    else { b.item = u; b.kt = j / ntile; b.qt = j - b.kt * ntile; }
+    if (kStream) {
+      b.item = u / ntile; b.kt = u - b.item * ntile; b.qt = j;
+      b.kvs = un & 1; b.kvph = uint32_t(un >> 1) & 1u; b.kv_first = j == 0; b.kv_last = j == nb - 1;
+      b.qs = g & 1; b.qph = uint32_t(g >> 1) & 1u; b.q_first = true; b.q_last = true;
+    } else {
+      b.item = u; b.kt = j / ntile; b.qt = j - b.kt * ntile;
+      b.kv_first = b.qt == 0; b.kv_last = b.qt == ntile - 1;
+      b.q_first = b.kt == 0;  b.q_last = b.kt == ntile - 1;
+      if (ntile == 1) {          // one block per item: the two slots alternate between items
+        b.kvs = b.qs = un & 1; b.kvph = b.qph = uint32_t(un >> 1) & 1u;
+      } else {
+        b.kvs = b.kt; b.qs = b.qt; b.kvph = b.qph = uint32_t(un) & 1u;
+      }
+    }
     return b;
   };
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKV); prefetch_tmap(&tmDO); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(set_full0 + 8 * i, 1);   mbar_init(set_empty0 + 8 * i, 1);
+      mbar_init(kv_full0 + 8 * i, 1);    mbar_init(kv_empty0 + 8 * i, 1);
+      mbar_init(qdo_full0 + 8 * i, 1);   mbar_init(qdo_empty0 + 8 * i, 1);
       mbar_init(sdp_ready0 + 8 * i, 1);  mbar_init(sdp_free0 + 8 * i, 8);
       mbar_init(ds_free0 + 8 * i, 1);
     }
@@ -123,13 +151,20 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
       for (int g = 0; g < G; ++g) {
         const Blk bk = block_of(g);
         const int kt = bk.kt, qt = bk.qt;
-        const int b = bk.item / heads, h = bk.item - b * heads, s = g & 1;
-        mbar_wait(set_empty0 + 8u * s, (uint32_t(g >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(set_full0 + 8u * s, SET_BYTES);
-        tma_load_3d(sQ(s), &tmQKV, set_full0 + 8u * s, h * DH, qt * BT, b);
-        tma_load_3d(sDO(s), &tmDO, set_full0 + 8u * s, h * DH, qt * BT, b);
-        tma_load_3d(sK(s), &tmQKV, set_full0 + 8u * s, inner + h * DH, kt * BT, b);
-        tma_load_3d(sV(s), &tmQKV, set_full0 + 8u * s, 2 * inner + h * DH, kt * BT, b);
+        const int b = bk.item / heads, h = bk.item - b * heads;
+        if (bk.kv_first) {
+          mbar_wait(kv_empty0 + 8u * bk.kvs, bk.kvph ^ 1u);
+          TRACEB(10, g);
+          mbar_arrive_expect_tx(kv_full0 + 8u * bk.kvs, PAIR_BYTES);
+          tma_load_3d(sK(bk.kvs), &tmQKV, kv_full0 + 8u * bk.kvs, inner + h * DH, kt * BT, b);
+          tma_load_3d(sV(bk.kvs), &tmQKV, kv_full0 + 8u * bk.kvs, 2 * inner + h * DH, kt * BT, b);
+        }
+        if (bk.q_first) {
+          mbar_wait(qdo_empty0 + 8u * bk.qs, bk.qph ^ 1u);
+          mbar_arrive_expect_tx(qdo_full0 + 8u * bk.qs, PAIR_BYTES);
+          tma_load_3d(sQ(bk.qs), &tmQKV, qdo_full0 + 8u * bk.qs, h * DH, qt * BT, b);
+          tma_load_3d(sDO(bk.qs), &tmDO, qdo_full0 + 8u * bk.qs, h * DH, qt * BT, b);
+        }
       }
     }
     __syncwarp();
@@ -142,42 +177,47 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
       constexpr uint32_t idesc_q = umma_idesc_16(BT, DH, fmt, 1, 0);          // A K-major, B MN-major: dQ
       // half hf (64 keys) of S = Q_q K_k^T and dP = dO_q V_k^T of block g, once the math warps have read the previous block's
       auto issue_half = [&](int g, int hf) {
-        const int kt = block_of(g).kt, s = g & 1;
+        const Blk nx = block_of(g);
+        const int kt = nx.kt;
         const uint32_t bph = uint32_t(g & 1);
+        if (hf == 0) {                                                        // the block's operand pairs have arrived
+          mbar_wait(kv_full0 + 8u * nx.kvs, nx.kvph);
+          mbar_wait(qdo_full0 + 8u * nx.qs, nx.qph);
+        }
         const int nkh = max(0, min(64, ext(kt) - 64 * hf));                   // keys of this half: 64, 16 (T = 197 tail) or 0
         mbar_wait(sdp_free0 + 8u * hf, bph ^ 1u);
         if (nkh > 0) {
-          const uint32_t k0 = sK(s) + hf * 8192, v0 = sV(s) + hf * 8192, q0 = sQ(s), do0 = sDO(s);
+          const uint32_t k_lo = umma_desc_lo(sK(nx.kvs) + hf * 8192), v_lo = umma_desc_lo(sV(nx.kvs) + hf * 8192),
+                         q_lo = umma_desc_lo(sQ(nx.qs)), do_lo = umma_desc_lo(sDO(nx.qs));
           const uint32_t idesc_s = umma_idesc_16(BT, nkh, fmt, 0, 0);         // [128 q] x [nkh keys], both K-major
           tc_fence_after();
-          // the k-steps of the two products alternate: consecutive MMAs into ONE accumulator serialise on it (a
-          // 128 x 64 x 16 step is ~30 cycles of tensor work behind a much longer pipeline), independent accumulators overlap
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            umma_bf16_ss<1>(d_s + 64 * hf, umma_desc_k_sw128(q0 + k * 32), umma_desc_k_sw128(k0 + k * 32), idesc_s, k != 0 ? 1u : 0u);
-            umma_bf16_ss<1>(d_dp + 64 * hf, umma_desc_k_sw128(do0 + k * 32), umma_desc_k_sw128(v0 + k * 32), idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < DH / 16; ++k) {                                 // 16 features = 32 B along the swizzled row
+            umma_bf16_ss_lo(d_s + 64 * hf, q_lo + 2 * k, k_lo + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            umma_bf16_ss_lo(d_dp + 64 * hf, do_lo + 2 * k, v_lo + 2 * k, idesc_s, k != 0 ? 1u : 0u);
           }
         }
         umma_commit(sdp_ready0 + 8u * hf);
       };
       int kti = 0;
       if (G > 0) {
-        mbar_wait(set_full0, 0u);
         issue_half(0, 0);
         issue_half(0, 1);
       }
       for (int g = 0; g < G; ++g) {
         const Blk bk = block_of(g);
-        const int it = g / nb, j = bk.j, kt = bk.kt, qt = bk.qt, s = g & 1;
+        const int it = g / nb, j = bk.j, kt = bk.kt, qt = bk.qt;
         const int nk = ext(kt), nq = ext(qt);
         const uint32_t bph = uint32_t(g & 1);
         const uint32_t ds_tile = sDS + uint32_t(g & 1) * 2 * ATOM_BYTES;
         // the next block's first half as soon as this block's has been read, its second half right after this block's math
         if (g + 1 < G) {
-          mbar_wait(set_full0 + 8u * ((g + 1) & 1), uint32_t((g + 1) >> 1) & 1u);
+          TRACEB(11, g + 1);
           issue_half(g + 1, 0);
         }
+        TRACEB(0, g);
         mbar_wait(pds_ready, bph);                         // P and dS of this block are in shared memory
+        TRACEB(1, g);
         // Order of issue (one tcgen05.mma costs the issuing thread ~50 cycles whatever its size --
         // profiles/microbench/mma_chain.cu -- so a block's 40 are ~2 k cycles): dV first, so that the single P tile is
         // released to the next block's math warps early; then the next block's second half of S / dP; dK and dQ last (the
@@ -187,11 +227,18 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
         // ---- dV_k += P^T dO_q : A = the P tile read MN-major (M = key, K = query), B = dO_q MN-major ----
         if (qt == 0) { mbar_wait(dkv_free, uint32_t(kti & 1) ^ 1u); }         // the previous key tile's dK / dV were drained
         tc_fence_after();
-        for (int kk = 0; kk < nq / 16; ++kk)
-          umma_bf16_ss<1>(d_dv, umma_desc_mn_sw128_wide(sP + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(sDO(s) + kk * 2048),
-                          idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
+        // descriptor low words: a k-step of 16 queries / keys is 2048 B further in an MN-major tile (+128), the dS tile read
+        // K-major advances 32 B inside its 64-key atom (+2) and one atom (+1024) every four steps
+        const uint32_t p_lo = umma_desc_lo(sP, ATOM_BYTES), ds_mn_lo = umma_desc_lo(ds_tile, ATOM_BYTES), ds_k_lo = umma_desc_lo(ds_tile),
+                       do_lo = umma_desc_lo(sDO(bk.qs)), q_lo = umma_desc_lo(sQ(bk.qs)), kmn_lo = umma_desc_lo(sK(bk.kvs));
+        const int nqs = nq / 16, nks = nk / 16;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (kk < nqs) umma_bf16_ss_lo(d_dv, p_lo + 128 * kk, do_lo + 128 * kk, idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
         umma_commit(p_free);
+        TRACEB(2, g);
         if (g + 1 < G) issue_half(g + 1, 1);
+        TRACEB(3, g);
         // ---- dK_k += dS^T Q_q (A = the dS tile read MN-major) and dQ_q += dS K_k (A = the dS tile read K-major, B = K_k
         //      MN-major).  dQ: resident = one accumulator per query tile, kept over the item's key tiles; streamed = a fresh
         //      accumulator per block, two alternating, drained by the epilogue warps a block later
@@ -200,19 +247,18 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
         else if (j == 0) mbar_wait(dq_free0, uint32_t(it & 1) ^ 1u);          // the previous item's dQ was drained
         const bool dq_fresh = kStream || kt == 0;
         tc_fence_after();
+#pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          if (kk < nq / 16)
-            umma_bf16_ss<1>(d_dk, umma_desc_mn_sw128_wide(ds_tile + kk * 2048, ATOM_BYTES), umma_desc_mn_sw128(sQ(s) + kk * 2048),
-                            idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
-          if (kk < nk / 16)
-            umma_bf16_ss<1>(d_dq, umma_desc_k_sw128(ds_tile + (kk >> 2) * ATOM_BYTES + (kk & 3) * 32),
-                            umma_desc_mn_sw128(sK(s) + kk * 2048), idesc_q, (!dq_fresh || kk != 0) ? 1u : 0u);
+          if (kk < nqs) umma_bf16_ss_lo(d_dk, ds_mn_lo + 128 * kk, q_lo + 128 * kk, idesc_t, (qt != 0 || kk != 0) ? 1u : 0u);
+          if (kk < nks) umma_bf16_ss_lo(d_dq, ds_k_lo + 1024 * (kk >> 2) + 2 * (kk & 3), kmn_lo + 128 * kk, idesc_q, (!dq_fresh || kk != 0) ? 1u : 0u);
         }
         umma_commit(ds_free0 + 8u * uint32_t(g & 1));
-        umma_commit(set_empty0 + 8u * uint32_t(s));        // the block's operand tiles may be overwritten
+        if (bk.kv_last) umma_commit(kv_empty0 + 8u * uint32_t(bk.kvs));    // the last block that reads this (K, V) pair
+        if (bk.q_last) umma_commit(qdo_empty0 + 8u * uint32_t(bk.qs));     // ... this (Q, dO) pair
         if (qt == ntile - 1) { umma_commit(dkv_ready); ++kti; }
         if (kStream) umma_commit(dq_ready0 + 8u * uint32_t(g & 1));
         else if (j == nb - 1) umma_commit(dq_ready0);
+        TRACEB(4, g);
       }
     }
     __syncwarp();
@@ -251,6 +297,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
             const int wcols = nkh / 2;                     // this warp's share of the half: 32, 8 (T = 197 tail) or 0
             const int cw = 64 * hf + half * wcols;         // first of this warp's columns
             mbar_wait(sdp_ready0 + 8u * hf, bph);
+            if (w == 0 && lane == 0) TRACEB(hf == 0 ? 5 : 8, blk);
             tc_fence_after();
             // the block has no key or row past T (warp-uniform): no masking selects in the inner loop
             const bool full = __all_sync(0xffffffffu, row_ok) && kt * BT + 64 * hf + nkh <= T;
@@ -290,9 +337,11 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
                 dk[e >> 1] = pack2<kDT>(d0, d1);
               }
               if (!tiles_free) {
+                if (w == 0 && lane == 0) TRACEB(6, blk);
                 mbar_wait(p_free, bph ^ 1u);               // the previous block's dV MMAs have read the P tile
                 mbar_wait(ds_free0 + 8u * uint32_t(blk & 1), (uint32_t(blk >> 1) & 1u) ^ 1u);   // dK / dQ of two blocks ago this dS tile
                 tiles_free = true;
+                if (w == 0 && lane == 0) TRACEB(7, blk);
               }
 #pragma unroll
               for (int g = 0; g < NN / 8; ++g) {           // 8 key columns -> one 16-byte chunk of each tile
@@ -313,6 +362,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
           fence_proxy_async_smem();                        // generic-proxy tile writes -> the MMAs' async-proxy reads
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_ready);
+          if (w == 0 && lane == 0) TRACEB(9, blk);
         }
       }
     }
@@ -452,6 +502,14 @@ int launch_t(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, co
 }
 
 }  // namespace
+
+#ifdef VITB200_TRACE
+}  // namespace vb
+extern "C" int vitb200_debug_attention_bwd_trace(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, vb::g_trace_bwd, sizeof(long long) * (n < 12 * 64 ? n : 12 * 64)) == cudaSuccess ? 0 : -2;
+}
+namespace vb {
+#endif
 
 bool attention_bwd_tc5_supports(int T) { return T >= 1 && T <= ROWS_MAX; }
 

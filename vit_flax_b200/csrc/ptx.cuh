@@ -359,6 +359,25 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_wide(uint32_t addr, uint3
   return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
          (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// The same descriptors split into words, for issue loops that walk an operand by a constant stride: only the low
+// word changes (start address >> 4 in bits [0,14), LBO >> 4 in [16,30)), so the k-th descriptor is `lo + k * (stride >> 4)`
+// -- one uniform add per operand in front of the tcgen05.mma instead of the shift / mask / or chain (the issuing thread
+// pays for every instruction of that chain: profiles/microbench/mma_chain.cu, profiles/r02_attention_bwd.md).
+constexpr uint32_t UMMA_DESC_HI_SW128 = 0x40004040u;   // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t addr, uint32_t lbo_bytes = 16) {
+  return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+// D[tmem] (+)= A * B, both from shared memory, descriptors given by their low words (SWIZZLE_128B, cta_group::1)
+__device__ __forceinline__ void umma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128) : "memory");
+}
+
 // kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32; operand majors selectable.
 // `fmt`: 0 = F16, 1 = BF16 (UMMA F16F32Format).
 __host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fmt, int b_mn_major = 0, int a_mn_major = 0) {
