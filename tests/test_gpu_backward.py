@@ -47,7 +47,8 @@ def rel_err(got, want):
 
 
 @pytest.mark.parametrize("batch,T,heads", [(2, 197, 3), (1, 208, 1), (3, 64, 2), (2, 17, 2), (1, 100, 1), (40, 197, 12),
-                                           (2, 257, 2), (1, 1025, 1), (3, 300, 2), (2, 209, 1)])
+                                           (2, 257, 2), (1, 1025, 1), (3, 300, 2), (2, 209, 1),
+                                           (30, 257, 8), (5, 1025, 7), (150, 128, 3)])   # several units of work per CTA
 @pytest.mark.parametrize("fmt", ["fp16", "bf16"])
 @pytest.mark.parametrize("impl", ["auto", "flash", "hmma"])
 def test_attention_bwd(lib, batch, T, heads, fmt, impl, monkeypatch):
