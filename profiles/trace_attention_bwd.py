@@ -26,13 +26,13 @@ _lib.check(lib.vitb200_attention_tc(st, qkv.data_ptr(), out.data_ptr(), batch, T
 for _ in range(2):
     _lib.check(lib.vitb200_attention_bwd(st, qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), dqkv.data_ptr(), batch, T, heads, _lib.DT_F16))
 torch.cuda.synchronize()
-tr = np.zeros((12, 64), np.int64)
+tr = np.zeros((16, 64), np.int64)
 lib.vitb200_debug_attention_bwd_trace.argtypes = [C.c_void_p, C.c_int]
 assert lib.vitb200_debug_attention_bwd_trace(tr.ctypes.data, tr.size) == 0
 names = ["iss_wait", "pds_seen", "dV_done", "half1_iss", "blk_done", "m_h0_rdy", "m_h0_calc", "m_tiles", "m_h1_rdy", "m_publish",
-         "load_iss", "half0_iss"]
+         "load_iss", "half0_iss", "m_h0_ld", "m_h1_ld", "m_h1_calc", "m_stored"]
 t0 = tr[10, 0]
 print("blk  " + " ".join(f"{n:>9s}" for n in names))
 for i in range(0, 40):
-    print(f"{i:4d} " + " ".join(f"{int(tr[e, i] - t0):9d}" for e in range(12)))
+    print(f"{i:4d} " + " ".join(f"{int(tr[e, i] - t0):9d}" for e in range(16)))
 print("per-block period (cycles):", (tr[9, 36] - tr[9, 12]) / 24.0)

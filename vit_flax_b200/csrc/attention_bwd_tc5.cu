@@ -44,7 +44,7 @@ namespace vb {
 
 #ifdef VITB200_TRACE
 // debug timeline of CTA 0: g_trace_bwd[event][block] = clock64 at the event (profiles/trace_attention_bwd.py)
-__device__ long long g_trace_bwd[12][64];
+__device__ long long g_trace_bwd[16][64];
 #define TRACEB(ev, i) do { if (blockIdx.x == 0 && (i) < 64) g_trace_bwd[ev][i] = clock64(); } while (0)
 #else
 #define TRACEB(ev, i) do { } while (0)
@@ -147,7 +147,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
 
   if (warp == 0) {
     // ===================== TMA producer: the four operand tiles of every block, one block ahead =====================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int g = 0; g < G; ++g) {
         const Blk bk = block_of(g);
         const int kt = bk.kt, qt = bk.qt;
@@ -170,7 +170,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr int fmt = kDT == DT_F16 ? 0 : 1;
       const uint32_t d_s = tmem_base + COL_S, d_dp = tmem_base + COL_DP, d_dv = tmem_base + COL_DV, d_dk = tmem_base + COL_DK;
       constexpr uint32_t idesc_t = umma_idesc_16(BT, DH, fmt, 1, 1);          // A and B MN-major: dV, dK
@@ -313,6 +313,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
                 tmem_ld_32x32b_x8(t_lane + COL_DP + c0, dv);
               }
               tmem_ld_wait();
+              if (w == 0 && lane == 0) TRACEB(hf == 0 ? 12 : 13, blk);
               if (release) {                               // the warp's last values of this half are in registers:
                 tc_fence_before();                         // the next block's half may be computed
                 __syncwarp();
@@ -343,6 +344,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
                 tiles_free = true;
                 if (w == 0 && lane == 0) TRACEB(7, blk);
               }
+              if (w == 0 && lane == 0 && hf == 1) TRACEB(14, blk);
 #pragma unroll
               for (int g = 0; g < NN / 8; ++g) {           // 8 key columns -> one 16-byte chunk of each tile
                 const int c = c0 + g * 8;
@@ -359,6 +361,7 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
               if (lane == 0) mbar_arrive(sdp_free0 + 8u * hf);
             }
           }
+          if (w == 0 && lane == 0) TRACEB(15, blk);
           fence_proxy_async_smem();                        // generic-proxy tile writes -> the MMAs' async-proxy reads
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_ready);
@@ -377,12 +380,16 @@ attention_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV,   // qkv [B,
       tmem_ld_32x32b_x32p(t_lane + col + 32, v + 32);
       tmem_ld_wait();
       if (dst != nullptr) {
+        // 32-byte stores (STG.256): every lane writes its own row, so a warp-wide store touches 32 lines whatever its
+        // width -- half as many requests as 16-byte ones in front of the math warps' tile stores in the same LSU
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          reinterpret_cast<uint4*>(dst)[g] = make_uint4(pack2<kDT>(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])),
-                                                        pack2<kDT>(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
-                                                        pack2<kDT>(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
-                                                        pack2<kDT>(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = pack2<kDT>(__uint_as_float(v[g * 16 + 2 * e]), __uint_as_float(v[g * 16 + 2 * e + 1]));
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + g * 16), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                       "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        }
       }
     };
     // dK / dV of a finished key tile -> 16-bit rows of dqkv
@@ -506,7 +513,7 @@ int launch_t(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, co
 #ifdef VITB200_TRACE
 }  // namespace vb
 extern "C" int vitb200_debug_attention_bwd_trace(long long* host, int n) {
-  return cudaMemcpyFromSymbol(host, vb::g_trace_bwd, sizeof(long long) * (n < 12 * 64 ? n : 12 * 64)) == cudaSuccess ? 0 : -2;
+  return cudaMemcpyFromSymbol(host, vb::g_trace_bwd, sizeof(long long) * (n < 16 * 64 ? n : 16 * 64)) == cudaSuccess ? 0 : -2;
 }
 namespace vb {
 #endif

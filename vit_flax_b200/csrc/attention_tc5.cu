@@ -185,7 +185,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
     // ===================== TMA producer =====================
     // Loads are issued in the order they are needed (K, Q, V of an item); every ring slot it
     // waits for was released at least one item ago, so the producer runs well ahead.
-    if (lane == 0) {
+    if (elect_one()) {
       for (int i = 0; i < n; ++i) {
         const int64_t item = first + i;
         const int bh = int(item / nqt), qt = int(item - int64_t(bh) * nqt);
@@ -219,7 +219,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I]
     // columns.  The O accumulator is shared by both slots: PV(i) waits until the epilogue of item
     // i-1 has pulled its O into registers (o_free), which also orders the two issuers' products.
     // Every wait is a blocking mbarrier wait (hardware suspend): no polling next to the softmax warps.
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr int fmt = kDT == DT_F16 ? 0 : 1;
       constexpr uint32_t idesc_s = umma_idesc_16(QT, KP, fmt, 0);   // B = K, K-major
       constexpr uint32_t idesc_o = umma_idesc_16(QT, DH, fmt, 1);   // B = V, MN-major

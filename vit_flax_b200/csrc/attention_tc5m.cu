@@ -159,7 +159,7 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int i0 = 0; i0 < n; i0 += 2) {
         const int ni = (i0 + 1 < n) ? 2 : 1;             // items of this pair
         int bb[2], hh[2];
@@ -190,7 +190,7 @@ attention_tc5m_kernel(const __grid_constant__ CUtensorMap tmQ,    // qkv [B,T,3I
     __syncwarp();
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers: warp 1 drives slot 0, warp 3 slot 1 =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr int fmt = kDT == DT_F16 ? 0 : 1;
       constexpr uint32_t idesc_s = umma_idesc_16(QT, KP, fmt, 0);   // B = K, K-major
       constexpr uint32_t idesc_o = umma_idesc_16(QT, DH, fmt, 1);   // B = V, MN-major

@@ -196,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -257,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only in pair mode) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_16(TILE_M, BN, kDT == DT_F16 ? 0 : 1, kMN ? 1 : 0, kMN ? 1 : 0);
       const uint16_t pair_mask = uint16_t(0x3u << lead);               // both CTAs of this pair
       const uint16_t all_mask = uint16_t((1u << CL) - 1u);             // every CTA whose smem the stage's loads touch

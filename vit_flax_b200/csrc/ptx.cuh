@@ -13,6 +13,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// One lane of a CONVERGED warp.  Unlike `lane == 0`, the compiler knows that exactly one lane is inside the branch: single-
+// thread instructions (tcgen05.mma / commit, TMA) are emitted as they are, on the uniform datapath, instead of each inside an
+// ELECT / PLOP3 / BRA.U.ANY loop over the possibly-active lanes (7 instead of 10-16 SASS instructions per tcgen05.mma, and the
+// issuing thread is latency-bound on exactly that chain: profiles/r02_attention_bwd.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ------------------------------------------- programmatic dependent launch
 // Every kernel of the forward is launched with programmatic stream serialization: its CTAs may
