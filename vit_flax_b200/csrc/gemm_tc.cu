@@ -509,7 +509,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
             const float* pos_row = aux + int64_t(tok) * N;
             uint16_t* x16_row = kLnOut ? static_cast<uint16_t*>(ln.x16) + int64_t(m_row0 + lrow) * N : nullptr;
             const bool row_ok = m_row0 + lrow < M;
-            uint32_t h0 = 0, h1 = 0;                   // 16-bit pairs of the previous 4-column chunk
+            uint32_t hx[8];                            // 16-bit pairs of up to four 4-column chunks: 16 values = one 32-byte store
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {              // 4 fp32 columns -> one 16-byte chunk
@@ -541,10 +541,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                 // the 16-bit copy of the raw row, the A operand of the GEMM that follows it
                 st1 += (o0 + o1) + (o2 + o3);
                 st2 = fmaf(o0, o0, fmaf(o1, o1, fmaf(o2, o2, fmaf(o3, o3, st2))));
-                if ((j & 1) == 0) {
-                  h0 = pack2<kDT>(o0, o1); h1 = pack2<kDT>(o2, o3);
-                } else if (row_ok && nb - 4 < N) {
-                  *reinterpret_cast<uint4*>(x16_row + nb - 4) = make_uint4(h0, h1, pack2<kDT>(o0, o1), pack2<kDT>(o2, o3));
+                hx[(j & 3) * 2] = pack2<kDT>(o0, o1);
+                hx[(j & 3) * 2 + 1] = pack2<kDT>(o2, o3);
+                // every lane writes its own row, so a warp-wide store touches 32 lines whatever its width: 32-byte stores
+                // (STG.256) are half the requests of 16-byte ones; N is a multiple of 8, so a row can end on a 16-byte piece
+                if ((j & 3) == 3 && row_ok) {
+                  if (nb + 4 <= N && (N & 15) == 0)          // rows of N 16-bit values start 32-byte aligned
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x16_row + nb - 12), "r"(hx[0]), "r"(hx[1]),
+                                 "r"(hx[2]), "r"(hx[3]), "r"(hx[4]), "r"(hx[5]), "r"(hx[6]), "r"(hx[7]) : "memory");
+                  else {
+                    if (nb - 4 <= N) *reinterpret_cast<uint4*>(x16_row + nb - 12) = make_uint4(hx[0], hx[1], hx[2], hx[3]);
+                    if (nb + 4 <= N) *reinterpret_cast<uint4*>(x16_row + nb - 4) = make_uint4(hx[4], hx[5], hx[6], hx[7]);
+                  }
                 }
               }
             }
