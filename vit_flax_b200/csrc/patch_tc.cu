@@ -93,7 +93,7 @@ patch_embed_im2col_kernel(const __grid_constant__ CUtensorMap tmImg,   // im2col
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -116,7 +116,7 @@ patch_embed_im2col_kernel(const __grid_constant__ CUtensorMap tmImg,   // im2col
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_16(PM, PN, kDT == DT_F16 ? 0 : 1);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
