@@ -45,12 +45,7 @@ dqkv = torch.empty_like(qkv)
 o = torch.randn((R, heads * 64), device="cuda").to(tdt)
 timeit("attention_bwd batch 256, T 197, 12 heads",
        lambda: _lib.check(lib.vitb200_attention_bwd(st(), qkv.data_ptr(), o.data_ptr(), do.data_ptr(), dqkv.data_ptr(), B, T, heads, dt)),
-       flops=5 * 2 * T * T * 64 * B * heads)   # useful flops: 5 matmuls (the kernel runs 6)
-os.environ["VITB200_ATTN_BWD"] = "flash"
-timeit("attention_bwd (streamed kernels), same problem",
-       lambda: _lib.check(lib.vitb200_attention_bwd(st(), qkv.data_ptr(), o.data_ptr(), do.data_ptr(), dqkv.data_ptr(), B, T, heads, dt)),
-       flops=5 * 2 * T * T * 64 * B * heads)
-os.environ.pop("VITB200_ATTN_BWD")
+       flops=5 * 2 * T * T * 64 * B * heads)   # per-kernel entry point: includes the forward kernel re-run for the log-sum-exp
 for (M, N, name) in ((D, 3 * D, "to_qkv"), (D, D, "to_out"), (D, H, "ff1"), (H, D, "ff2")):
     X = torch.randn((R, M), device="cuda").to(tdt)
     dY = torch.randn((R, N), device="cuda").to(tdt)

@@ -50,19 +50,10 @@ def rel_err(got, want):
                                            (2, 257, 2), (1, 1025, 1), (3, 300, 2), (2, 209, 1),
                                            (30, 257, 8), (5, 1025, 7), (150, 128, 3)])   # several units of work per CTA
 @pytest.mark.parametrize("fmt", ["fp16", "bf16"])
-@pytest.mark.parametrize("impl", ["auto", "flash", "hmma"])
-def test_attention_bwd(lib, batch, T, heads, fmt, impl, monkeypatch):
-    """Adjoint of vit.py:69-79 per (image, head): dq, dk, dv from (q, k, v, d_out), all 16-bit.  auto = the tcgen05
-    kernel (attention_bwd_tc5.cu; the row log-sum-exp it needs comes from the statistics kernel here, from the forward
-    in the model path): resident form up to T = 208, streamed form (dQ summed in an fp32 buffer) beyond; flash forces the
-    streamed mma.sync kernels at every shape, hmma the first shared-memory-resident mma.sync kernel (T <= 208): all
-    implementations are checked wherever they exist."""
-    if impl in ("flash", "hmma"):
-        if T > 208 and impl == "hmma":
-            pytest.skip("the resident mma.sync kernel stops at 208 tokens")
-        monkeypatch.setenv("VITB200_ATTN_BWD", impl)
-    else:
-        monkeypatch.delenv("VITB200_ATTN_BWD", raising=False)
+def test_attention_bwd(lib, batch, T, heads, fmt):
+    """Adjoint of vit.py:69-79 per (image, head): dq, dk, dv from (q, k, v, d_out), all 16-bit, on tcgen05
+    (attention_bwd_tc5.cu): resident form up to T = 208, streamed form (dQ summed in an fp32 buffer) beyond.  This per-kernel
+    entry point has no log-sum-exp from a forward pass: it re-runs the forward kernel for it (the model path keeps it)."""
     dt, tdt = DT16[fmt]
     inner = heads * 64
     g = torch.Generator().manual_seed(T * 7 + heads)

@@ -196,14 +196,9 @@ def test_layernorm(lib, rows, dim, out):
 @pytest.mark.parametrize("batch,T,heads", [(2, 65, 16), (3, 197, 12), (2, 257, 16), (1, 1025, 4), (2, 16, 1), (1, 1, 2), (1, 130, 3),
                                                (40, 197, 12), (1, 208, 1), (2, 128, 2), (3, 64, 5)])
 @pytest.mark.parametrize("fmt", ["bf16", "fp16"])
-@pytest.mark.parametrize("impl", ["auto", "hmma"])
-def test_attention_tc(lib, batch, T, heads, fmt, impl, monkeypatch):
-    """auto = tcgen05/TMEM kernel when T <= 208 else the streamed-KV mma.sync kernel; hmma forces
-    the latter (both generations stay covered at every shape)."""
-    if impl == "hmma":
-        monkeypatch.setenv("VITB200_ATTENTION", "hmma")
-    else:
-        monkeypatch.delenv("VITB200_ATTENTION", raising=False)
+def test_attention_tc(lib, batch, T, heads, fmt):
+    """The fused attention on tcgen05 / TMEM: one key block when T <= 208 (attention_tc5.cu), streamed key blocks with an
+    online softmax beyond (attention_tc5m.cu)."""
     dt, tdt, ulp = DT16[fmt]
     rng = np.random.default_rng(T + heads)
     inner = heads * 64
@@ -227,7 +222,6 @@ def test_attention_tc_every_image_of_a_full_batch(lib, batch, T, heads, fmt, mon
     """BASELINE-size batch: EVERY (image, head) is checked (torch fp32 reference on the GPU, in
     chunks), several launches back to back.  Regression test for a K-ring release race that
     corrupted a handful of (image, head) tiles only when all 148 persistent CTAs were busy."""
-    monkeypatch.delenv("VITB200_ATTENTION", raising=False)
     dt, tdt, ulp = DT16[fmt]
     inner = heads * 64
     g = torch.Generator(device="cuda").manual_seed(batch + T)

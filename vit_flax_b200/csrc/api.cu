@@ -1025,11 +1025,7 @@ int ensure_train(vitb200_model* m, cudaStream_t st) {
   if ((rc = ts->dx.alloc(R * D)) || (rc = ts->pooled_ln.alloc(B * D)) || (rc = ts->dpl.alloc(B * D))) return rc;
   if ((rc = ts->dy16.alloc(R * D)) || (rc = ts->dhid16.alloc(R * H)) || (rc = ts->dxn16.alloc(R * D)) ||
       (rc = ts->do16.alloc(R * I)) || (rc = ts->dqkv16.alloc(R * 3 * I))) return rc;
-  if (attention_bwd_needs_workspace(m->T)) {
-    if ((rc = ts->attn_ws.alloc(attention_bwd_flash_workspace_floats(c.max_batch, m->T, c.heads)))) return rc;
-  } else if ((rc = ts->attn_ws.alloc(size_t(round_up(int64_t(c.max_batch) * c.heads * m->T, 64))))) {   // D of the tcgen05 adjoint
-    return rc;
-  }
+  if ((rc = ts->attn_ws.alloc(attention_bwd_workspace_floats(c.max_batch, m->T, c.heads)))) return rc;   // D (+ fp32 dQ beyond 208 tokens)
   const size_t dx_max = std::max(std::max(H, D), std::max(I, size_t(m->K0pad))), dy_max = std::max(std::max(H, D), 3 * I);
   if ((rc = ts->tA.alloc(dx_max * Rpad)) || (rc = ts->tB.alloc(dy_max * Rpad))) return rc;
   const size_t nz = std::max(std::max(dx_max, dy_max), size_t(c.num_classes));

@@ -486,6 +486,22 @@ attn_bwd_rowdot_kernel(const uint16_t* __restrict__ d_out, const uint16_t* __res
   }
 }
 
+// fp32 dQ accumulator [rows, inner] -> the q third of dqkv (16 bits)
+template <int kDT>
+__global__ void __launch_bounds__(256)
+dq_convert_kernel(const float* __restrict__ dq_acc, uint16_t* __restrict__ dqkv, int64_t rows, int inner) {
+  const int per_row = inner >> 3;
+  const int64_t total = rows * per_row;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / per_row;
+    const int c = int(i - r * per_row) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(dq_acc + r * inner + c), b = *reinterpret_cast<const float4*>(dq_acc + r * inner + c + 4);
+    uint4 o;
+    o.x = pack2<kDT>(a.x, a.y); o.y = pack2<kDT>(a.z, a.w); o.z = pack2<kDT>(b.x, b.y); o.w = pack2<kDT>(b.z, b.w);
+    *reinterpret_cast<uint4*>(dqkv + r * 3 * inner + c) = o;
+  }
+}
+
 template <int kDT, bool kStream>
 int launch_t(cudaStream_t st, const void* qkv, const void* d_out, void* dqkv, const float* lse2, const float* dsum,
              float* dq_acc, int batch, int T, int heads) {
@@ -517,6 +533,16 @@ extern "C" int vitb200_debug_attention_bwd_trace(long long* host, int n) {
 }
 namespace vb {
 #endif
+
+// fp32 dQ accumulator [rows, inner] -> the q third of dqkv (16-bit)
+int launch_dq_convert(cudaStream_t st, const float* dq_acc, void* dqkv, int64_t rows, int inner, int dtype) {
+  const unsigned cgrid = unsigned(std::min<int64_t>((rows * (inner / 8) + 255) / 256, int64_t(sm_count()) * 16));
+  if (dtype == DT_F16) dq_convert_kernel<DT_F16><<<cgrid, 256, 0, st>>>(dq_acc, static_cast<uint16_t*>(dqkv), rows, inner);
+  else if (dtype == DT_BF16) dq_convert_kernel<DT_BF16><<<cgrid, 256, 0, st>>>(dq_acc, static_cast<uint16_t*>(dqkv), rows, inner);
+  else return fail(VITB200_ERR_INVALID, "attention_bwd: dtype must be bf16 or fp16");
+  VB_LAUNCH_CHECK("dq_convert_kernel");
+  return 0;
+}
 
 bool attention_bwd_tc5_supports(int T) { return T >= 1 && T <= ROWS_MAX; }
 

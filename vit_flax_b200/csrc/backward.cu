@@ -2,7 +2,7 @@
 //
 // The reference never differentiates its forward (nothing in vit_flax trains), so there is no
 // reference code to cite beyond the forward lines each kernel is the adjoint of:
-//   attention_bwd_kernel   adjoint of vit.py:69-79 (softmax(q k^T / 8) v per image and head)
+//   (the attention adjoint, vit.py:69-79, is attention_bwd_tc5.cu; launch_attention_bwd below only routes to it)
 //   ln_bwd_kernel          adjoint of nn.LayerNorm() (vit.py:31,163)
 //   gelu_fwd / gelu_bwd    nn.gelu (tanh form, vit.py:49) on the stored pre-activation
 //   pool_ln_bwd_kernel     adjoint of vit.py:159-163 (cls / mean pool + LayerNorm)
@@ -471,276 +471,6 @@ cls_bias_grad_kernel(const float* __restrict__ dpos, float* __restrict__ dcls, f
   if (blockIdx.y == 0 && cls_off && dcls) dcls[d] += dpos[d];
 }
 
-// ------------------------------------------------------------------ attention backward
-// One CTA per (image, head), T <= 208.  q, k, v, dO tiles and the T x T probability matrix live in
-// shared memory; all five matmuls run on mma.sync with ldmatrix operands:
-//   A   P = softmax(q k^T / 8)                       -> smem (16-bit)
-//   A2  dV = P^T dO                                  (P read transposed)
-//   B   dP = dO v^T;  D_i = sum_j P_ij dP_ij;  dS = P o (dP - D) / 8 -> smem (over P);  dQ = dS k
-//   C   dK = dS^T q
-// Padded query rows carry dO = 0, padded key columns P = 0, so neither contributes.
-constexpr int DH = 64;
-constexpr int ROW_BYTES = DH * 2;
-constexpr int ABW_MAX_T = 208;
-constexpr int ABW_MAX_NT = ABW_MAX_T / 8;     // 26 score n-tiles of 8 keys
-
-__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
-  return base + uint32_t(row) * ROW_BYTES + (uint32_t(chunk ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ void load_rows(uint32_t sbase, const uint16_t* g, int64_t ld, int nrows, int row_limit) {
-  for (int i = threadIdx.x; i < nrows * 8; i += blockDim.x) {
-    const int r = i >> 3, c = i & 7;
-    const bool ok = r < row_limit;
-    cp_async16(swz(sbase, r, c), g + int64_t(ok ? r : 0) * ld + c * 8, ok);
-  }
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
-// acc[8][4] (16 rows x 64 columns) = M^T[rows m0.., all q] . X[q, 64], M = the smem score matrix
-template <int kDT>
-__device__ __forceinline__ void mma_transposed_scores(float (&acc)[8][4], uint32_t sP, int pitch, int m0, uint32_t sX,
-                                                      int nblk, int lane) {
-  const int mi = lane >> 3, r = lane & 7;
-  for (int qs = 0; qs < nblk; ++qs) {
-    uint32_t a[4];
-    ldmatrix_x4_trans(sP + uint32_t(qs * 16 + (mi >> 1) * 8 + r) * pitch + uint32_t(m0 + (mi & 1) * 8) * 2, a[0], a[1], a[2], a[3]);
-#pragma unroll
-    for (int dp = 0; dp < 4; ++dp) {
-      uint32_t b0, b1, b2, b3;
-      ldmatrix_x4_trans(swz(sX, qs * 16 + (mi & 1) * 8 + r, dp * 2 + (mi >> 1)), b0, b1, b2, b3);
-      mma_16816<kDT>(acc[2 * dp], a, b0, b1);
-      mma_16816<kDT>(acc[2 * dp + 1], a, b2, b3);
-    }
-  }
-}
-
-template <int kDT>
-__device__ __forceinline__ void store_tile_16x64(const float (&acc)[8][4], uint16_t* gbase, int64_t ld, int row0, int T,
-                                                 int lane) {
-  const int g = lane >> 2, tg = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int c = nt * 8 + 2 * tg;
-    if (row0 + g < T) *reinterpret_cast<uint32_t*>(gbase + int64_t(row0 + g) * ld + c) = pack2<kDT>(acc[nt][0], acc[nt][1]);
-    if (row0 + g + 8 < T) *reinterpret_cast<uint32_t*>(gbase + int64_t(row0 + g + 8) * ld + c) = pack2<kDT>(acc[nt][2], acc[nt][3]);
-  }
-}
-
-// One 64-key chunk of a 16-row score block: acc[8][4] = rows(sA frag af) . X[keys ch*64 .. +63]^T
-template <int kDT>
-__device__ __forceinline__ void score_chunk(float (&acc)[8][4], const uint32_t (&af)[4][4], uint32_t sX, int ch, int nblk,
-                                            int lane) {
-  const int mi = lane >> 3, r8 = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    if (ch * 4 + p < nblk) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1, b2, b3;
-        ldmatrix_x4(swz(sX, (ch * 4 + p) * 16 + (mi >> 1) * 8 + r8, ks * 2 + (mi & 1)), b0, b1, b2, b3);
-        mma_16816<kDT>(acc[2 * p], af[ks], b0, b1);
-        mma_16816<kDT>(acc[2 * p + 1], af[ks], b2, b3);
-      }
-    }
-  }
-}
-
-// One warp per 16-row block (13 at T = 197).  Phase A keeps its 16 x T score block in registers; phase B
-// works on 64-key chunks with D_i = sum_d dO_id O_id taken from the attention output kept by the forward
-// (instead of a full row of dP), so the kernel fits 13 warps (allocated as 16: 128 registers each).
-template <int kDT>
-__global__ void __launch_bounds__(416, 1)
-attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ o_fwd, const uint16_t* __restrict__ d_out,
-                     uint16_t* __restrict__ dqkv, int T, int heads, int TP, int pitch) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, tg = lane & 3, mi = lane >> 3, r8 = lane & 7;
-  const int bh = blockIdx.x, b = bh / heads, h = bh - b * heads;
-  const int inner = heads * DH;
-  const int64_t ld = 3 * int64_t(inner);
-  const uint16_t* qbase = qkv + int64_t(b) * T * ld + h * DH;
-  uint16_t* dqbase = dqkv + int64_t(b) * T * ld + h * DH;
-  const uint32_t sQ = smem_u32(smem);
-  const uint32_t sK = sQ + uint32_t(TP) * ROW_BYTES, sV = sK + uint32_t(TP) * ROW_BYTES;
-  const uint32_t sD = sV + uint32_t(TP) * ROW_BYTES, sP = sD + uint32_t(TP) * ROW_BYTES;
-  load_rows(sQ, qbase, ld, TP, T);
-  load_rows(sK, qbase + inner, ld, TP, T);
-  cp_async_commit();
-  load_rows(sV, qbase + 2 * inner, ld, TP, T);     // v and dO land while phase A runs on q and k
-  load_rows(sD, d_out + int64_t(b) * T * inner + h * DH, inner, TP, T);
-  cp_async_commit();
-  cp_async_wait<1>();
-  __syncthreads();
-  const int nblk = TP >> 4, nch = (TP + 63) >> 6;
-  const float sl2 = 0.125f * 1.4426950408889634f;   // dim_head^-0.5 * log2(e)
-
-  // ---- A: P = softmax(q k^T / 8) -> smem ----
-  for (int qb = warp; qb < nblk; qb += nw) {
-    uint32_t qf[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-      ldmatrix_x4(swz(sQ, qb * 16 + (mi & 1) * 8 + r8, ks * 2 + (mi >> 1)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-    // the whole 16 x TP score block lives in registers (104 at T = 197..208): one q k^T, one exp sweep
-    float s[ABW_MAX_NT][4];
-#pragma unroll
-    for (int nt = 0; nt < ABW_MAX_NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
-#pragma unroll
-    for (int p = 0; p < ABW_MAX_NT / 2; ++p) {
-      if (p < nblk) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(swz(sK, p * 16 + (mi >> 1) * 8 + r8, ks * 2 + (mi & 1)), b0, b1, b2, b3);
-          mma_16816<kDT>(s[2 * p], qf[ks], b0, b1);
-          mma_16816<kDT>(s[2 * p + 1], qf[ks], b2, b3);
-        }
-      }
-    }
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < 2 * nblk) {
-        const int c0 = nt * 8 + 2 * tg;
-        if (c0 >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-        if (c0 + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-      }
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < 2 * nblk) {
-        s[nt][0] = ex2_approx((s[nt][0] - m0) * sl2);
-        s[nt][1] = ex2_approx((s[nt][1] - m0) * sl2);
-        s[nt][2] = ex2_approx((s[nt][2] - m1) * sl2);
-        s[nt][3] = ex2_approx((s[nt][3] - m1) * sl2);
-        l0 += s[nt][0] + s[nt][1];
-        l1 += s[nt][2] + s[nt][3];
-      }
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.f / l0, i1 = 1.f / l1;
-    const uint32_t pa = sP + uint32_t(qb * 16 + g) * pitch + uint32_t(2 * tg) * 2, pb = pa + 8u * pitch;
-#pragma unroll
-    for (int nt = 0; nt < ABW_MAX_NT; ++nt) {
-      if (nt < 2 * nblk) {
-        sts32(pa + nt * 16, pack2<kDT>(s[nt][0] * i0, s[nt][1] * i0));
-        sts32(pb + nt * 16, pack2<kDT>(s[nt][2] * i1, s[nt][3] * i1));
-      }
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-
-  // ---- A2: dV = P^T dO ----
-  for (int kb = warp; kb < nblk; kb += nw) {
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-    mma_transposed_scores<kDT>(acc, sP, pitch, kb * 16, sD, nblk, lane);
-    store_tile_16x64<kDT>(acc, dqbase + 2 * inner, ld, kb * 16, T, lane);
-  }
-  __syncthreads();
-
-  // ---- B: dP = dO v^T, dS = P o (dP - D) / 8 (over P, own rows), dQ = dS k ----
-  for (int qb = warp; qb < nblk; qb += nw) {
-    uint32_t dof[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-      ldmatrix_x4(swz(sD, qb * 16 + (mi & 1) * 8 + r8, ks * 2 + (mi >> 1)), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
-    // D_i = sum_d dO[i, d] O[i, d] for rows g and g + 8 of the block (quad = one row pair, 16 columns per lane)
-    float d0 = 0.f, d1 = 0.f;
-    {
-      const int ra = qb * 16 + g, rb = ra + 8;
-      const uint16_t* oa = o_fwd + (int64_t(b) * T + ra) * inner + h * DH;
-      const uint16_t* ob = o_fwd + (int64_t(b) * T + rb) * inner + h * DH;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        float x0, x1, y0, y1;
-        if (ra < T) {
-          unpack2<kDT>(lds32(swz(sD, ra, nt) + uint32_t(tg) * 4), x0, x1);
-          unpack2<kDT>(*reinterpret_cast<const uint32_t*>(oa + nt * 8 + 2 * tg), y0, y1);
-          d0 += x0 * y0 + x1 * y1;
-        }
-        if (rb < T) {
-          unpack2<kDT>(lds32(swz(sD, rb, nt) + uint32_t(tg) * 4), x0, x1);
-          unpack2<kDT>(*reinterpret_cast<const uint32_t*>(ob + nt * 8 + 2 * tg), y0, y1);
-          d1 += x0 * y0 + x1 * y1;
-        }
-      }
-      d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-      d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-      d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
-      d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    }
-    const uint32_t pa = sP + uint32_t(qb * 16 + g) * pitch + uint32_t(2 * tg) * 2, pb = pa + 8u * pitch;
-    float dq[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
-    for (int ch = 0; ch < nch; ++ch) {
-      float dp[8][4];
-      score_chunk<kDT>(dp, dof, sV, ch, nblk, lane);
-      uint32_t dsf[4][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        uint32_t va = 0u, vb = 0u;
-        if (ch * 64 + nt * 8 < TP) {
-          const uint32_t off = uint32_t(ch * 64 + nt * 8) * 2;
-          float p0, p1, p2, p3;
-          unpack2<kDT>(lds32(pa + off), p0, p1);
-          unpack2<kDT>(lds32(pb + off), p2, p3);
-          va = pack2<kDT>(p0 * (dp[nt][0] - d0) * 0.125f, p1 * (dp[nt][1] - d0) * 0.125f);
-          vb = pack2<kDT>(p2 * (dp[nt][2] - d1) * 0.125f, p3 * (dp[nt][3] - d1) * 0.125f);
-          sts32(pa + off, va);
-          sts32(pb + off, vb);
-        }
-        if ((nt & 1) == 0) { dsf[nt >> 1][0] = va; dsf[nt >> 1][1] = vb; }
-        else               { dsf[nt >> 1][2] = va; dsf[nt >> 1][3] = vb; }
-      }
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        if (ch * 4 + p < nblk) {
-#pragma unroll
-          for (int dpi = 0; dpi < 4; ++dpi) {
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4_trans(swz(sK, (ch * 4 + p) * 16 + (mi & 1) * 8 + r8, dpi * 2 + (mi >> 1)), b0, b1, b2, b3);
-            mma_16816<kDT>(dq[2 * dpi], dsf[p], b0, b1);
-            mma_16816<kDT>(dq[2 * dpi + 1], dsf[p], b2, b3);
-          }
-        }
-      }
-    }
-    store_tile_16x64<kDT>(dq, dqbase, ld, qb * 16, T, lane);
-  }
-  __syncthreads();
-
-  // ---- C: dK = dS^T q ----
-  for (int kb = warp; kb < nblk; kb += nw) {
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-    mma_transposed_scores<kDT>(acc, sP, pitch, kb * 16, sQ, nblk, lane);
-    store_tile_16x64<kDT>(acc, dqbase + inner, ld, kb * 16, T, lane);
-  }
-}
-
 inline unsigned grid_for(int64_t work_items, int per_block) {
   return unsigned(std::min<int64_t>((work_items + per_block - 1) / per_block, int64_t(sm_count()) * 16));
 }
@@ -905,76 +635,48 @@ int launch_token_grads(cudaStream_t st, const float* dx, float* dpos, float* dcl
   return 0;
 }
 
-int attention_bwd_max_tokens() { return ABW_MAX_T; }
+// Adjoint of vit.py:69-79 on tcgen05 (attention_bwd_tc5.cu): resident form up to 208 tokens, streamed form beyond.
+// `lse2` = the forward's row log-sum-exp (train_forward keeps it); `workspace` = attention_bwd_workspace_floats floats.
+// The per-kernel C entry point has neither: it re-runs the forward kernel into scratch for the log-sum-exp.
+bool attention_bwd_needs_workspace(int T) { return !attention_bwd_tc5_supports(T); }
 
-// Default: the tcgen05 kernel (attention_bwd_tc5.cu), resident form when T <= 208 and streamed form beyond.
-// VITB200_ATTN_BWD=flash forces the streamed mma.sync kernels everywhere, =hmma the first, shared-memory-resident mma.sync
-// kernel (A/B tests).
-static int attn_bwd_force_flash() {
-  const char* e = getenv("VITB200_ATTN_BWD");
-  return e && e[0] == 'f';
+size_t attention_bwd_workspace_floats(int batch, int T, int heads) {
+  // D per (image, head, token) [+ beyond 208 tokens: the fp32 dQ accumulator [batch * T, heads * 64]]
+  const size_t n = size_t(round_up(int64_t(batch) * heads * T, 64));
+  return attention_bwd_needs_workspace(T) ? n + size_t(batch) * T * heads * 64 : n;
 }
-static int attn_bwd_force_hmma() {
-  const char* e = getenv("VITB200_ATTN_BWD");
-  return e && e[0] == 'h';
-}
-
-bool attention_bwd_needs_workspace(int T) { return T > ABW_MAX_T || attn_bwd_force_flash(); }
 
 int launch_attention_bwd(cudaStream_t st, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv, int batch, int T,
                          int heads, int dtype, float* workspace, const float* lse2) {
   if (batch <= 0 || T <= 0 || heads <= 0) return fail(VITB200_ERR_INVALID, "attention_bwd: empty problem");
-  if (!attention_bwd_needs_workspace(T) && !attn_bwd_force_hmma() && attention_bwd_tc5_supports(T)) {
-    const size_t n = size_t(round_up(int64_t(batch) * heads * T, 64));
-    if (lse2 != nullptr && workspace != nullptr) {   // model path: lse2 from the forward, D by one HBM-bound pass
-      int rc = launch_attention_bwd_rowdot(st, d_out, o_fwd, workspace, batch, T, heads, dtype);
-      if (rc) return rc;
-      return launch_attention_bwd_tc5(st, qkv, d_out, dqkv, lse2, workspace, batch, T, heads, dtype);
-    }
-    // per-kernel entry point: no log-sum-exp from the forward -- the streamed statistics kernel makes it (and D) first
-    float* ws = nullptr;
-    VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * n * sizeof(float), st));
-    int rc = lse2 ? launch_attention_bwd_rowdot(st, d_out, o_fwd, ws + n, batch, T, heads, dtype)
-                  : launch_attention_bwd_stats(st, qkv, o_fwd, d_out, ws, ws + n, batch, T, heads, dtype);
-    if (!rc) rc = launch_attention_bwd_tc5(st, qkv, d_out, dqkv, lse2 ? lse2 : ws, ws + n, batch, T, heads, dtype);
-    cudaFreeAsync(ws, st);
-    return rc;
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(VITB200_ERR_INVALID, "attention_bwd: dtype must be bf16 or fp16");
+  const size_t n = size_t(round_up(int64_t(batch) * heads * T, 64));
+  const size_t ws_floats = attention_bwd_workspace_floats(batch, T, heads);
+  float* ws = workspace;
+  float* lse_tmp = nullptr;
+  uint16_t* o_tmp = nullptr;
+  int rc = 0;
+  if (ws == nullptr) VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), ws_floats * sizeof(float), st));
+  if (lse2 == nullptr) {   // per-kernel entry point: the forward kernel again, for its log-sum-exp (its output goes to scratch)
+    const size_t o_elems = size_t(batch) * T * heads * 64;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&lse_tmp), n * sizeof(float), st) != cudaSuccess ||
+        cudaMallocAsync(reinterpret_cast<void**>(&o_tmp), o_elems * sizeof(uint16_t), st) != cudaSuccess)
+      rc = fail(VITB200_ERR_CUDA, "attention_bwd: scratch allocation failed");
+    if (!rc) rc = launch_attention_tc(st, qkv, o_tmp, batch, T, heads, dtype, lse_tmp);
+    lse2 = lse_tmp;
   }
-  if (attention_bwd_needs_workspace(T)) {
-    // beyond 208 tokens: the tcgen05 kernel in its streamed form (dQ summed in an fp32 buffer); VITB200_ATTN_BWD=flash
-    // keeps the mma.sync kernels of attention_bwd_flash.cu (A/B tests).  Workspace layout of both: lse2 | D | dq_acc.
-    float* ws = workspace;
-    if (ws == nullptr)                       // per-kernel entry point: stream-ordered scratch
-      VB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), attention_bwd_flash_workspace_floats(batch, T, heads) * sizeof(float), st));
-    int rc;
-    if (attn_bwd_force_flash()) {
-      rc = launch_attention_bwd_flash(st, qkv, o_fwd, d_out, dqkv, ws, batch, T, heads, dtype);
-    } else {
-      const size_t n = size_t(round_up(int64_t(batch) * heads * T, 64));
-      float* dsum = ws + n;
-      float* dq_acc = ws + 2 * n;
-      // the row log-sum-exp: from the forward when it kept it (train_forward), else from the statistics kernel (with D)
-      rc = lse2 ? launch_attention_bwd_rowdot(st, d_out, o_fwd, dsum, batch, T, heads, dtype)
-                : launch_attention_bwd_stats(st, qkv, o_fwd, d_out, ws, dsum, batch, T, heads, dtype);
-      if (!rc) rc = launch_attention_bwd_tc5_stream(st, qkv, d_out, dqkv, lse2 ? lse2 : ws, dsum, dq_acc, batch, T, heads, dtype);
-    }
-    if (workspace == nullptr) cudaFreeAsync(ws, st);
-    return rc;
+  float* dsum = ws;
+  if (!rc) rc = launch_attention_bwd_rowdot(st, d_out, o_fwd, dsum, batch, T, heads, dtype);
+  if (!rc) {
+    if (attention_bwd_needs_workspace(T))
+      rc = launch_attention_bwd_tc5_stream(st, qkv, d_out, dqkv, lse2, dsum, ws + n, batch, T, heads, dtype);
+    else
+      rc = launch_attention_bwd_tc5(st, qkv, d_out, dqkv, lse2, dsum, batch, T, heads, dtype);
   }
-  const int TP = (T + 15) / 16 * 16, pitch = TP * 2 + 16;
-  const int nblk = TP / 16, nw = nblk;                        // one warp per 16-row block (<= 13)
-  const size_t smem = size_t(4) * TP * ROW_BYTES + size_t(TP) * pitch;
-  static PerDevice<bool> configured_on;   // the smem opt-in is per (function, device)
-  if (bool& configured = configured_on.here(); !configured) {
-    VB_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VB_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
-  VB_DT16_DISPATCH(dtype, (attention_bwd_kernel<kDT><<<unsigned(batch * heads), nw * 32, smem, st>>>(
-                              static_cast<const uint16_t*>(qkv), static_cast<const uint16_t*>(o_fwd),
-                              static_cast<const uint16_t*>(d_out), static_cast<uint16_t*>(dqkv), T, heads, TP, pitch)));
-  VB_LAUNCH_CHECK("attention_bwd_kernel");
-  return 0;
+  if (o_tmp) cudaFreeAsync(o_tmp, st);
+  if (lse_tmp) cudaFreeAsync(lse_tmp, st);
+  if (workspace == nullptr) cudaFreeAsync(ws, st);
+  return rc;
 }
 
 }  // namespace vb

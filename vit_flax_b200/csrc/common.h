@@ -185,32 +185,24 @@ int launch_head_bwd(cudaStream_t stream, const float* pl, const float* dl, const
                     float* dbias, float* dpl, int batch, int dim, int classes);
 int launch_token_grads(cudaStream_t stream, const float* dx, float* dpos, float* dcls, float* dbias, int batch,
                        int T, int dim, int cls_off);
-int attention_bwd_max_tokens();
-// o_fwd: the attention output of the forward pass (rowsum(dO o O) replaces a full row of dP)
-// T <= 208: one CTA per (image, head) with everything in shared memory; beyond (or VITB200_ATTN_BWD=flash): the
-// streamed kernels of attention_bwd_flash.cu, which need `workspace` (attention_bwd_flash_workspace_floats floats;
-// null = stream-ordered scratch allocated per call)
+// Adjoint of the fused attention (vit.py:69-79) on tcgen05 (attention_bwd_tc5.cu).  o_fwd: the attention output of the forward
+// pass (D = rowsum(dO o O) replaces a full row of dP); lse2: the forward's row log-sum-exp (launch_attention_tc's `lse`; null =
+// the forward kernel is run again into scratch for it); workspace: attention_bwd_workspace_floats floats (null = stream-ordered
+// scratch allocated per call).  T <= 208: dQ accumulates in TMEM; beyond: in an fp32 buffer of the workspace.
+bool attention_bwd_needs_workspace(int T);      // beyond the resident form: the workspace also holds the fp32 dQ accumulator
+size_t attention_bwd_workspace_floats(int batch, int T, int heads);
 int launch_attention_bwd(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
                          int batch, int T, int heads, int dtype, float* workspace = nullptr, const float* lse2 = nullptr);
-// `lse2` (the forward's row log-sum-exp, launch_attention_tc's `lse`): with it and T <= 208 the adjoint runs on tcgen05
-// (attention_bwd_tc5.cu); without it the per-kernel entry point computes it first (statistics kernel, stream-ordered scratch)
-bool attention_bwd_tc5_supports(int T);
+bool attention_bwd_tc5_supports(int T);         // the resident form
 int launch_attention_bwd_tc5(cudaStream_t stream, const void* qkv, const void* d_out, void* dqkv, const float* lse2,
                              const float* dsum, int batch, int T, int heads, int dtype);
-// the same kernel for any T (attention_bwd_tc5.cu, streamed mode): dQ contributions are summed in dq_acc (fp32
-// [batch * T, heads * 64]) and converted into dqkv at the end
+// the same kernel for any T (streamed mode): dQ contributions are summed in dq_acc (fp32 [batch * T, heads * 64]) and
+// converted into dqkv at the end
 int launch_attention_bwd_tc5_stream(cudaStream_t stream, const void* qkv, const void* d_out, void* dqkv, const float* lse2,
                                     const float* dsum, float* dq_acc, int batch, int T, int heads, int dtype);
 int launch_dq_convert(cudaStream_t stream, const float* dq_acc, void* dqkv, int64_t rows, int inner, int dtype);
 // dsum [batch*heads, T] = rowsum(dO o O) per (image, head, token): the D of the softmax adjoint
 int launch_attention_bwd_rowdot(cudaStream_t stream, const void* d_out, const void* o_fwd, float* dsum, int batch, int T,
                                 int heads, int dtype);
-// lse2 [batch*heads, T] (and dsum, same shape) by the streamed statistics kernel of attention_bwd_flash.cu
-int launch_attention_bwd_stats(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, float* lse2,
-                               float* dsum, int batch, int T, int heads, int dtype);
-bool attention_bwd_needs_workspace(int T);
-size_t attention_bwd_flash_workspace_floats(int batch, int T, int heads);
-int launch_attention_bwd_flash(cudaStream_t stream, const void* qkv, const void* o_fwd, const void* d_out, void* dqkv,
-                               float* workspace, int batch, int T, int heads, int dtype);
 
 }  // namespace vb
