@@ -30,13 +30,13 @@
 // warp instruction and SMSP plus the fp32 -> 16-bit pack F2FP at 4: 20 cycles per pair of scores -- is 2.08 k cycles
 // per item; the tensor side is 0.64 k (S: four dependent UTCHMMA of N = 208) + 0.73 k (P V: thirteen of N = 64, paced by
 // the ~50-cycle issue cost of one tcgen05.mma, not by the pipe: profiles/microbench/mma_chain.cu); the kernel runs at
-// ~3.2 k cycles per item because a TMEM slot goes round a LATENCY loop -- S 0.6-1.1 k, pass 1 0.7 k, pass 2 2.6 k (a
+// ~3.0 k cycles per item (79 us per launch at ViT-B/16 batch 256) because a TMEM slot goes round a LATENCY loop -- S 0.6-1.1 k, pass 1 0.7 k, pass 2 2.6 k (a
 // single warp issues in order and ptxas batches a chunk's MUFUs apart from its FFMA2 / FADD2 / F2FP work), store drain
 // 0.4 k, last P V part + next S issue 0.5-1.0 k -- and 512 TMEM columns hold two slots, no more.  The exponential phases
 // of the two groups are offset per SMSP (xu_done[q]: warp q hands over to warp q of the other group one chunk before
 // it finishes; free-running or earlier hand-offs measure the same within 2 %, strict alternation is 12 % slower).
 // Round-2 experiments that did NOT pay and were removed: all eight softmax warps on every item with the key columns
-// split between the two warps of a lane quarter (no phase overlap between items: 118 us against 84); the bf16 pack on
+// split between the two warps of a lane quarter (no phase overlap between items: 118 us against 84 at the time); the bf16 pack on
 // the integer pipe (add 0x8000 + PRMT: 97 against 88 us -- the softmax warps are short of issue slots, not of XU
 // cycles); hand-ordered volatile-asm interleaving of MUFU and FMA work (ptxas reschedules it to the same SASS); round
 // 1's polynomial ex2 on the FMA pipe.
